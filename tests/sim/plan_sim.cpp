@@ -1,0 +1,161 @@
+// TEST INFRASTRUCTURE ONLY -- CPU interpreter of a UnitPlan (tensor-fft_b200/csrc/unit_plan.h).
+// Walks the exact index maps the CUDA kernel uses (load items, operand layouts, MMA tiles /
+// TMEM lanes, epilogue destinations, staging, store items) in double precision, optionally
+// rounding to fp16 where the kernel does, and counts shared-memory bank conflicts of every
+// 16-byte access pattern.  Lets `pytest -m "not gpu"` prove the plan algebra == DFT.
+#include <cmath>
+#include <complex>
+#include <cstdint>
+#include <cstdio>
+#include <vector>
+#include "../../tensor-fft_b200/csrc/unit_plan.h"
+
+using namespace tfft;
+typedef std::complex<double> cd;
+static const double kPi = 3.14159265358979323846264338327950288;
+static inline double rh(double v, bool on) { return on ? (double)(_Float16)v : v; }
+static inline cd twd(int64_t e, int64_t n) {
+  e %= n; if (e < 0) e += n;
+  double a = -2.0 * kPi * (double)e / (double)n;
+  return cd(std::cos(a), std::sin(a));
+}
+static uint32_t bitsum(uint32_t q, const uint32_t* c, int nbits) {
+  uint32_t s = 0;
+  for (int i = 0; i < nbits; ++i) if (q >> i & 1) s += c[i];
+  return s;
+}
+// conflicts of one quarter-warp of 16-byte accesses: max lanes per 16-byte bank group - 1
+static int qw_conflict(const uint32_t* addr) {
+  int cnt[8] = {0};
+  int worst = 0;
+  for (int i = 0; i < 8; ++i) { int g = (addr[i] >> 4) & 7; if (++cnt[g] > worst) worst = cnt[g]; }
+  return worst - 1;
+}
+
+extern "C" {
+
+// Runs `n_units` units.  in/out are planar double arrays (element offsets as the plan says).
+// Returns the total number of bank conflicts found (negative = plan error).
+// conflicts[0..3] = load stores, epilogue stores, store-phase loads, (unused)
+int plansim_run(int log2_len, int log2_units, int in_mode, int out_mode, const int64_t* strides9,
+                int pass1_log2n, int n_units, const double* in_re, const double* in_im,
+                double* out_re, double* out_im, int emulate_fp16, int* conflicts) {
+  UnitShape shape; shape.log2_len = log2_len; shape.log2_units = log2_units;
+  shape.in_mode = (AxisMode)in_mode; shape.out_mode = (AxisMode)out_mode;
+  UnitPlan P; PlanBuildInfo info;
+  if (!build_unit_plan(shape, &P, &info)) { fprintf(stderr, "plan error: %s\n", info.error.c_str()); return -1; }
+  UnitStrides st;
+  st.in_tstride = strides9[0]; st.in_nstride = strides9[1]; st.out_tstride = strides9[2]; st.out_nstride = strides9[3];
+  st.in_batch_stride = strides9[4]; st.in_unit_stride = strides9[5]; st.out_batch_stride = strides9[6];
+  st.out_unit_stride = strides9[7]; st.units_per_batch = (uint32_t)strides9[8]; st.col_base_stride = 1u << log2_units;
+  st.pass1_log2n = pass1_log2n;
+  fill_strides(st, info, &P);
+  const bool h = emulate_fp16 != 0;
+  const int T = 1 << P.log2_tail, s = P.stages, rowbits = P.log2_elems - 4;
+  const int64_t L = int64_t(1) << P.log2_len;
+  conflicts[0] = conflicts[1] = conflicts[2] = conflicts[3] = 0;
+  const uint32_t smem_halves = std::max(P.plane_bytes, P.stage_plane_bytes) / 2;
+  for (int unit = 0; unit < n_units; ++unit) {
+    const int64_t ibase = (unit / P.units_per_batch) * P.in_batch_stride + (unit % P.units_per_batch) * P.in_unit_stride;
+    const int64_t obase = (unit / P.units_per_batch) * P.out_batch_stride + (unit % P.units_per_batch) * P.out_unit_stride;
+    const uint32_t col_base = (unit % P.units_per_batch) * P.col_base_stride;
+    std::vector<double> sre(smem_halves, NAN), sim(smem_halves, NAN);
+    // ---------------- load
+    const uint32_t n_items = 1u << P.load_item_bits;
+    for (uint32_t q0 = 0; q0 < n_items; q0 += 8) {
+      uint32_t addr[8];
+      for (uint32_t dq = 0; dq < 8; ++dq) {
+        uint32_t q = q0 + dq;
+        uint32_t g = bitsum(q, P.load_gofs, P.load_item_bits);
+        uint32_t so = bitsum(q, P.load_sofs, P.load_item_bits);
+        uint32_t r = bitsum(q, P.load_rval, P.load_item_bits);
+        addr[dq] = so;
+        for (int e = 0; e < 8; ++e) {
+          cd x[8];
+          for (int j = 0; j < T; ++j) {
+            int64_t a = ibase + g + (int64_t)j * P.load_gj + e;
+            x[j] = cd(rh(in_re[a], h), rh(in_im[a], h));
+          }
+          uint32_t re_ = r + e * P.load_estep;
+          for (int k0 = 0; k0 < T; ++k0) {
+            cd acc = 0;
+            for (int j = 0; j < T; ++j) acc += x[j] * twd((int64_t)j * k0, T);
+            acc *= twd((int64_t)k0 * re_, L) * (double)P.load_scale;
+            uint32_t o = (so + P.load_sk0[k0]) / 2 + e;
+            sre[o] = rh(acc.real(), h); sim[o] = rh(acc.imag(), h);
+          }
+        }
+      }
+      conflicts[0] += qw_conflict(addr);
+    }
+    // ---------------- MMA stages
+    for (int t = 1; t <= s; ++t) {
+      const UnitPlan::Epi& E = P.epi[t - 1];
+      const uint32_t dst_bytes = t < s ? P.plane_bytes : P.stage_plane_bytes;
+      std::vector<double> nre(smem_halves, NAN), nim(smem_halves, NAN);
+      const uint32_t rows = 1u << rowbits;
+      for (uint32_t row0 = 0; row0 < rows; row0 += 8) {
+        uint32_t addr[8];
+        for (uint32_t dr = 0; dr < 8; ++dr) {
+          uint32_t row = row0 + dr;
+          // A operand read exactly as the UMMA descriptor addresses it
+          cd a[16];
+          for (int kap = 0; kap < 16; ++kap) {
+            uint32_t off = (row >> 3) * kRowChunkStride + (kap >> 3) * kKGroupStride + (kap & 7) * 16 + (row & 7) * 2;
+            a[kap] = cd(sre[off / 2], sim[off / 2]);
+          }
+          cd y[16];
+          for (int k = 0; k < 16; ++k) {
+            cd acc = 0;
+            for (int kap = 0; kap < 16; ++kap) {
+              cd f = twd(kap * k, 16);
+              if (h) f = cd(rh(f.real(), true), rh(f.imag(), true));
+              acc += a[kap] * f;
+            }
+            y[k] = acc / 16.0;
+          }
+          uint32_t dst = bitsum(row, E.dst, rowbits);
+          uint32_t aux = bitsum(row, E.aux, rowbits);
+          uint32_t col = bitsum(row, E.col, rowbits);
+          addr[dr] = dst;
+          if (dst + 16 > dst_bytes || dst + E.dst_khi + 16 > dst_bytes) { fprintf(stderr, "dst out of range\n"); return -2; }
+          for (int k = 0; k < 16; ++k) {
+            cd v = y[k];
+            if (E.tw_mode == 1) v *= twd((int64_t)aux * k, int64_t(1) << E.tw_log2n);
+            if (E.tw_mode == 2) v *= twd(((int64_t)aux + (int64_t)k * E.tw_kw) * (int64_t)(col_base + col), int64_t(1) << E.tw_log2n);
+            uint32_t o = (dst + (k >= 8 ? E.dst_khi : 0)) / 2 + (k & 7);
+            if (!std::isnan(nre[o])) { fprintf(stderr, "stage %d: destination written twice\n", t); return -3; }
+            nre[o] = rh(v.real(), h); nim[o] = rh(v.imag(), h);
+          }
+        }
+        conflicts[1] += qw_conflict(addr);
+      }
+      sre.swap(nre); sim.swap(nim);
+    }
+    // ---------------- store
+    const uint32_t n_sitems = 1u << P.store_item_bits;
+    for (uint32_t q0 = 0; q0 < n_sitems; q0 += 8) {
+      for (int x = 0; x < 8; ++x) {
+        uint32_t addr[8];
+        for (uint32_t dq = 0; dq < 8; ++dq) {
+          uint32_t q = q0 + dq;
+          uint32_t so = bitsum(q, P.store_sofs, P.store_item_bits) + bitsum(x, P.store_xs, 3);
+          uint32_t g = bitsum(q, P.store_gofs, P.store_item_bits);
+          addr[dq] = so;
+          for (int c = 0; c < 8; ++c) {
+            int64_t a = obase + g + x + bitsum(c, P.store_cg, 3);
+            double vr = sre[so / 2 + c], vi = sim[so / 2 + c];
+            if (std::isnan(vr)) { fprintf(stderr, "store reads an unwritten staging slot\n"); return -4; }
+            out_re[a] = vr; out_im[a] = vi;
+          }
+        }
+        conflicts[2] += qw_conflict(addr);
+      }
+    }
+  }
+  return conflicts[0] + conflicts[1] + conflicts[2];
+}
+
+int plansim_plan_bytes() { return (int)sizeof(UnitPlan); }
+
+}  // extern "C"
