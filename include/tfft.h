@@ -1,0 +1,95 @@
+/* tfft -- B200-native fp16 complex-to-complex FFT, drop-in C ABI for the plan/execute path of
+ * CPestka/Tensor-FFT (src/base).  The reference is header-only C++ with no C ABI of its own; each
+ * entry point below names the reference interface it replaces (paths relative to the reference
+ * root).  Conventions are the reference's: forward transform exp(-2*pi*i*n*k/N), result scaled
+ * by 1/N, natural order in and out, PLANAR fp16 (one array of real parts, one of imaginary
+ * parts), N a power of two >= 256 (src/base/Plan.h:85-96).
+ *
+ * All pointers are plain device (or, for the *_host entry points, host) pointers to IEEE
+ * binary16 values; no CUDA or torch types appear in the signatures.  `stream` is a cudaStream_t
+ * passed as void* (NULL = default stream).  Functions return 0 on success, a negative
+ * TFFT_E_* code for library errors and a positive cudaError_t value for CUDA errors.
+ * There is no CPU fallback: without a CUDA device every exec call fails with an error.
+ */
+#ifndef TFFT_H_
+#define TFFT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tfft_plan_s* tfft_plan_t;
+
+enum {
+  TFFT_OK = 0,
+  TFFT_E_INVALID_SIZE = -1,   /* not a power of two, < 256 or > 2^24 (Plan.h:85-96 prints + nullopt) */
+  TFFT_E_INVALID_ARG = -2,    /* null pointer, misaligned pointer or stride */
+  TFFT_E_NO_DEVICE = -3,      /* no sm_100 device: the product has no CPU path */
+  TFFT_E_UNSUPPORTED = -4,
+  TFFT_E_NOMEM = -5
+};
+
+/* flags for tfft_plan_create */
+enum {
+  TFFT_DEFAULT = 0,
+  /* multi-pass sizes (N > 32768) overwrite the input planes like the reference does
+   * (src/base/ComputeFFT.h:89-145 ping-pongs between input and result buffers); set this flag
+   * to make the plan own a scratch buffer instead and leave the input intact. */
+  TFFT_PRESERVE_INPUT = 1
+};
+
+typedef struct tfft_plan_info_s {
+  int64_t n;                 /* transform length                          (Plan.h:19 fft_length_) */
+  int64_t batch;             /* transforms per exec                                                */
+  int32_t r16_stages;        /* tensor-core radix-16 stages per pass                               */
+  int32_t tail_radix;        /* 1, 2, 4 or 8: CUDA-core radix fused into the load phase            */
+  int32_t passes;            /* HBM round trips: 1 for N <= 32768, 2 (four-step) above             */
+  int32_t results_in_results;/* always 1: results land in the output planes (Plan.h:25)            */
+  int32_t amount_of_r16_steps; /* reference-compatible: log2(N)/4 - 1   (Plan.h:99)                */
+  int32_t amount_of_r2_steps;  /* reference-compatible: log2(N) % 4     (Plan.h:100)               */
+  int32_t transforms_per_cta;  /* pass 1 (or the only pass)                                        */
+  int32_t smem_bytes;          /* dynamic shared memory per CTA, largest pass                      */
+  int32_t tmem_columns;        /* tensor-memory columns per CTA, largest pass                      */
+  int64_t grid;                /* CTAs of the first pass                                           */
+  int64_t workspace_bytes;     /* device scratch owned by the plan                                 */
+  int64_t algorithmic_bytes;   /* 8 * n * batch * passes                            */
+} tfft_plan_info_t;
+
+/* Replaces CreatePlan(fft_length, ...) (src/base/Plan.h:77-194) + PlanWorksOnDevice
+ * (Plan.h:257-296).  `batch` replaces the amount_of_ffts_ of DataBatchHandler
+ * (src/base/DataHandler.h:88-89).  The plan is immutable afterwards; exec calls on one plan
+ * may be issued from several host threads / streams (except with workspace-owning plans). */
+int tfft_plan_create(tfft_plan_t* plan, int64_t n, int64_t batch, uint32_t flags);
+
+/* Plan for `batch` 2-D transforms of ny rows x nx columns (row-major planar images), scale
+ * 1/(ny*nx).  The reference has no 2-D path. */
+int tfft_plan_create_2d(tfft_plan_t* plan, int64_t ny, int64_t nx, int64_t batch, uint32_t flags);
+
+int tfft_plan_info(tfft_plan_t plan, tfft_plan_info_t* info);
+int tfft_plan_destroy(tfft_plan_t plan);
+
+/* Replaces ComputeFFT(plan, DataHandler) and ComputeFFT(plan, DataBatchHandler)
+ * (src/base/ComputeFFT.h:54-151, :162-293).  Transform b reads in_re + b*in_stride,
+ * in_im + b*in_stride and writes out_re + b*out_stride, out_im + b*out_stride (strides in
+ * elements, multiples of 8; pointers 16-byte aligned).  The reference batch layout
+ * [RE_0|IM_0|RE_1|IM_1|...] (DataHandler.h:105-114) is in_im = in_re + n, stride = 2n.
+ * Asynchronous on `stream`; one kernel launch per pass for the whole batch. */
+int tfft_exec(tfft_plan_t plan, const void* in_re, const void* in_im, void* out_re, void* out_im,
+              int64_t in_stride, int64_t out_stride, void* stream);
+
+/* Whole reference call sequence with HOST buffers: CopyDataHostToDevice -> ComputeFFT ->
+ * CopyResultsDeviceToHost (src/base/DataHandler.h:45-70,124-153).  host_in / host_out hold,
+ * per transform, [RE(n) | IM(n)] halves (2*n*batch values each).  Uses plan-owned device
+ * buffers; synchronises before returning like the reference's batch overload does. */
+int tfft_exec_host(tfft_plan_t plan, const void* host_in, void* host_out);
+
+const char* tfft_error_string(int code);
+int tfft_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TFFT_H_ */

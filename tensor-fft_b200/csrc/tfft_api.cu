@@ -1,0 +1,319 @@
+// C ABI of the B200-native fp16 FFT (include/tfft.h): plan construction, pass scheduling and
+// kernel launches.  Host logic mirrors the reference's plan/execute split
+// (src/base/Plan.h:77-194 CreatePlan, src/base/ComputeFFT.h:54-293 ComputeFFT) but one exec is
+// one kernel launch per HBM pass for the WHOLE batch (the reference issues
+// batch x (1 + r16 + 2^r2 - 1) launches on `batch` freshly created streams,
+// ComputeFFT.h:167-284).  There is no CPU path: every exec needs an sm_100 device.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "../../include/tfft.h"
+#include "fft_unit_kernel.cuh"
+
+namespace {
+
+using namespace tfft;
+
+struct Pass {
+  UnitPlan plan;           // layout decisions (strides filled per exec)
+  PlanBuildInfo info;
+  UnitStrides strides;     // plan-time part of the addressing
+  int log2t = 0;
+  dim3 grid;
+  uint32_t smem = 0;
+  int src = 0, dst = 0;    // 0 = user input planes, 1 = user output planes, 2 = plan workspace
+  bool in_stride_is_user = false, out_stride_is_user = false;
+};
+
+int ilog2_exact(int64_t n) {
+  if (n <= 0 || (n & (n - 1))) return -1;
+  int l = 0;
+  while ((int64_t(1) << l) < n) ++l;
+  return l;
+}
+
+typedef void (*KernelFn)(const UnitPlan, const __half*, const __half*, __half*, __half*);
+KernelFn kernel_for(int log2t) {
+  switch (log2t) {
+    case 0: return fft_unit_kernel<0>;
+    case 1: return fft_unit_kernel<1>;
+    case 2: return fft_unit_kernel<2>;
+    default: return fft_unit_kernel<3>;
+  }
+}
+
+std::once_flag g_attr_once;
+int g_attr_err = 0;
+void set_kernel_attrs() {
+  for (int t = 0; t < 4; ++t) {
+    cudaError_t e = cudaFuncSetAttribute(kernel_for(t), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) g_attr_err = static_cast<int>(e);
+  }
+}
+
+}  // namespace
+
+struct tfft_plan_s {
+  int64_t n = 0, batch = 0, ny = 0, nx = 0;
+  uint32_t flags = 0;
+  int lg = 0;
+  std::vector<Pass> passes;
+  __half* workspace = nullptr;   // 2 * n * batch halves when TFFT_PRESERVE_INPUT on multi-pass sizes
+  int64_t workspace_bytes = 0;
+  __half* host_path_buf = nullptr;   // lazily allocated [in | out] for tfft_exec_host
+  int device = 0;
+};
+
+namespace {
+
+// transforms per unit for a row/row pass: fill ~16K elements, at least 2K, never more than the batch needs
+int pick_log2_units(int lg, int64_t batch, int target_log2_elems) {
+  int ups = target_log2_elems - lg;
+  if (ups < 0) ups = 0;
+  while (ups > 0 && lg + ups > 11 && (int64_t(1) << (ups - 1)) >= batch) --ups;  // do not over-pad small batches
+  if (lg + ups < 11) ups = 11 - lg;
+  return ups;
+}
+
+bool add_pass(tfft_plan_s* p, const UnitShape& shape, const UnitStrides& st, dim3 grid, int src, int dst,
+              bool in_user, bool out_user) {
+  Pass ps;
+  if (!build_unit_plan(shape, &ps.plan, &ps.info)) {
+    fprintf(stderr, "tfft: plan error: %s\n", ps.info.error.c_str());
+    return false;
+  }
+  ps.strides = st;
+  ps.log2t = shape.log2_len % 4;
+  ps.grid = grid;
+  ps.smem = smem_layout(ps.plan).total;
+  ps.src = src;
+  ps.dst = dst;
+  ps.in_stride_is_user = in_user;
+  ps.out_stride_is_user = out_user;
+  p->passes.push_back(ps);
+  return true;
+}
+
+int build_1d(tfft_plan_s* p) {
+  const int lg = p->lg;
+  const int64_t n = p->n, batch = p->batch;
+  if (lg <= 15) {
+    UnitShape sh;
+    sh.log2_len = lg;
+    sh.log2_units = pick_log2_units(lg, batch, lg == 15 ? 15 : 14);
+    UnitStrides st;
+    st.n_transforms = static_cast<uint32_t>(batch);
+    st.units_per_batch = 0x7FFFFFFFu;   // unit base = unit * unit_stride
+    const int64_t U = int64_t(1) << sh.log2_units;
+    dim3 grid(static_cast<unsigned>((batch + U - 1) / U), 1, 1);
+    return add_pass(p, sh, st, grid, 0, 1, true, true) ? TFFT_OK : TFFT_E_UNSUPPORTED;
+  }
+  // four-step: n = N1 * N2, element n1*N2 + n2.  Pass 1: N2 strided length-N1 transforms (column
+  // mode, in place on the source), times exp(-2*pi*i*k1*n2/n).  Pass 2: N1 contiguous length-N2
+  // transforms stored transposed: X[k1 + N1*k2].   
+  const int lg1 = (lg + 1) / 2, lg2 = lg - lg1;
+  if (lg1 > 12 || lg2 < 8) return TFFT_E_INVALID_SIZE;
+  const int64_t N1 = int64_t(1) << lg1, N2 = int64_t(1) << lg2;
+  const bool preserve = (p->flags & TFFT_PRESERVE_INPUT) != 0;
+  {
+    UnitShape sh;
+    sh.log2_len = lg1;
+    sh.log2_units = (lg1 >= 12 ? 15 : 14) - lg1;
+    sh.in_mode = kColMode;
+    sh.out_mode = kColMode;
+    const int64_t U = int64_t(1) << sh.log2_units;
+    UnitStrides st;
+    st.in_nstride = N2; st.out_nstride = N2;
+    st.in_unit_stride = U; st.out_unit_stride = U;
+    st.units_per_batch = static_cast<uint32_t>(N2 / U);
+    st.col_base_stride = static_cast<uint32_t>(U);
+    st.pass1_log2n = lg;
+    dim3 grid(static_cast<unsigned>(batch * (N2 / U)), 1, 1);
+    // batch stride: user's input stride (source) ; destination = source (in place) or workspace
+    if (!add_pass(p, sh, st, grid, 0, preserve ? 2 : 0, true, !preserve)) return TFFT_E_UNSUPPORTED;
+  }
+  {
+    UnitShape sh;
+    sh.log2_len = lg2;
+    sh.log2_units = (lg2 >= 12 ? 15 : 14) - lg2;
+    sh.in_mode = kRowMode;
+    sh.out_mode = kColMode;
+    const int64_t U = int64_t(1) << sh.log2_units;
+    UnitStrides st;
+    st.in_tstride = N2; st.in_unit_stride = U * N2;
+    st.out_nstride = N1; st.out_unit_stride = U;
+    st.units_per_batch = static_cast<uint32_t>(N1 / U);
+    dim3 grid(static_cast<unsigned>(batch * (N1 / U)), 1, 1);
+    if (!add_pass(p, sh, st, grid, preserve ? 2 : 0, 1, !preserve, true)) return TFFT_E_UNSUPPORTED;
+  }
+  if (preserve) {
+    p->workspace_bytes = 2 * n * batch * static_cast<int64_t>(sizeof(__half));
+    if (cudaMalloc(&p->workspace, p->workspace_bytes) != cudaSuccess) {
+      cudaGetLastError();
+      return TFFT_E_NOMEM;
+    }
+  }
+  return TFFT_OK;
+}
+
+int launch_pass(const tfft_plan_s* p, const Pass& ps, const __half* src_re, const __half* src_im, __half* dst_re,
+                __half* dst_im, int64_t in_stride, int64_t out_stride, cudaStream_t stream) {
+  UnitStrides st = ps.strides;
+  const int64_t U = int64_t(1) << ps.plan.log2_units;
+  if (ps.plan.in_mode == kRowMode && ps.plan.out_mode == kRowMode) {   // batched 1-D, one pass
+    st.in_tstride = in_stride; st.out_tstride = out_stride;
+    st.in_unit_stride = U * in_stride; st.out_unit_stride = U * out_stride;
+  } else {   // four-step passes: the batch level carries the user's (or workspace) transform stride
+    st.in_batch_stride = in_stride;
+    st.out_batch_stride = out_stride;
+  }
+  UnitPlan plan = ps.plan;
+  fill_strides(st, ps.info, &plan);
+  KernelFn fn = kernel_for(ps.log2t);
+  void* args[] = {&plan, &src_re, &src_im, &dst_re, &dst_im};
+  cudaError_t e = cudaLaunchKernel(reinterpret_cast<const void*>(fn), ps.grid, dim3(kThreads), args, ps.smem, stream);
+  (void)p;
+  return e == cudaSuccess ? TFFT_OK : static_cast<int>(e);
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+
+extern "C" {
+
+int tfft_version(void) { return 100; }
+
+const char* tfft_error_string(int code) {
+  switch (code) {
+    case TFFT_OK: return "success";
+    case TFFT_E_INVALID_SIZE: return "transform length must be a power of two in [256, 2^24]";
+    case TFFT_E_INVALID_ARG: return "invalid argument (null / misaligned pointer or stride)";
+    case TFFT_E_NO_DEVICE: return "no sm_100 CUDA device (this library has no CPU path)";
+    case TFFT_E_UNSUPPORTED: return "unsupported configuration";
+    case TFFT_E_NOMEM: return "device memory allocation failed";
+    default: return code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "unknown tfft error";
+  }
+}
+
+int tfft_plan_create(tfft_plan_t* out, int64_t n, int64_t batch, uint32_t flags) {
+  if (!out) return TFFT_E_INVALID_ARG;
+  *out = nullptr;
+  const int lg = ilog2_exact(n);
+  if (lg < 8 || lg > 24) return TFFT_E_INVALID_SIZE;
+  if (batch < 1 || batch > (int64_t(1) << 30)) return TFFT_E_INVALID_ARG;
+  tfft_plan_s* p = new (std::nothrow) tfft_plan_s;
+  if (!p) return TFFT_E_NOMEM;
+  p->n = n; p->batch = batch; p->flags = flags; p->lg = lg;
+  int rc = build_1d(p);
+  if (rc != TFFT_OK) {
+    delete p;
+    return rc;
+  }
+  *out = p;
+  return TFFT_OK;
+}
+
+int tfft_plan_create_2d(tfft_plan_t* out, int64_t ny, int64_t nx, int64_t batch, uint32_t flags) {
+  (void)ny; (void)nx; (void)batch; (void)flags;
+  if (out) *out = nullptr;
+  return TFFT_E_UNSUPPORTED;
+}
+
+int tfft_plan_info(tfft_plan_t p, tfft_plan_info_t* info) {
+  if (!p || !info) return TFFT_E_INVALID_ARG;
+  std::memset(info, 0, sizeof(*info));
+  info->n = p->n;
+  info->batch = p->batch;
+  const Pass& first = p->passes.front();
+  info->r16_stages = static_cast<int32_t>(first.plan.stages);
+  info->tail_radix = 1 << first.plan.log2_tail;
+  info->passes = static_cast<int32_t>(p->passes.size());
+  info->results_in_results = 1;
+  info->amount_of_r16_steps = p->lg / 4 - 1;
+  info->amount_of_r2_steps = p->lg % 4;
+  info->transforms_per_cta = 1 << first.plan.log2_units;
+  for (const Pass& ps : p->passes) {
+    if (static_cast<int32_t>(ps.smem) > info->smem_bytes) info->smem_bytes = static_cast<int32_t>(ps.smem);
+    const int32_t tc = static_cast<int32_t>(tmem_cols(ps.plan));
+    if (tc > info->tmem_columns) info->tmem_columns = tc;
+  }
+  info->grid = first.grid.x;
+  info->workspace_bytes = p->workspace_bytes;
+  info->algorithmic_bytes = 8 * p->n * p->batch * static_cast<int64_t>(p->passes.size());
+  return TFFT_OK;
+}
+
+int tfft_plan_destroy(tfft_plan_t p) {
+  if (!p) return TFFT_E_INVALID_ARG;
+  if (p->workspace) cudaFree(p->workspace);
+  if (p->host_path_buf) cudaFree(p->host_path_buf);
+  delete p;
+  return TFFT_OK;
+}
+
+int tfft_exec(tfft_plan_t p, const void* in_re, const void* in_im, void* out_re, void* out_im, int64_t in_stride,
+              int64_t out_stride, void* stream_) {
+  if (!p || !in_re || !in_im || !out_re || !out_im) return TFFT_E_INVALID_ARG;
+  if (!aligned16(in_re) || !aligned16(in_im) || !aligned16(out_re) || !aligned16(out_im)) return TFFT_E_INVALID_ARG;
+  if (in_stride < 0 || out_stride < 0 || (in_stride & 7) || (out_stride & 7)) return TFFT_E_INVALID_ARG;
+  if (p->batch > 1 && (in_stride < p->n || out_stride < p->n)) return TFFT_E_INVALID_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return TFFT_E_NO_DEVICE;
+  }
+  std::call_once(g_attr_once, set_kernel_attrs);
+  if (g_attr_err) return g_attr_err == static_cast<int>(cudaErrorInvalidDeviceFunction) ? TFFT_E_NO_DEVICE : g_attr_err;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const __half* ire = static_cast<const __half*>(in_re);
+  const __half* iim = static_cast<const __half*>(in_im);
+  __half* ore = static_cast<__half*>(out_re);
+  __half* oim = static_cast<__half*>(out_im);
+  for (const Pass& ps : p->passes) {
+    const __half *sre, *sim;
+    __half *dre, *dim;
+    int64_t is, os;
+    auto pick = [&](int which, const __half** re, const __half** im, int64_t* stride) {
+      if (which == 0) { *re = ire; *im = iim; *stride = in_stride; }
+      else if (which == 1) { *re = ore; *im = oim; *stride = out_stride; }
+      else { *re = p->workspace; *im = p->workspace + p->n; *stride = 2 * p->n; }
+    };
+    const __half *tre, *tim;
+    pick(ps.src, &sre, &sim, &is);
+    pick(ps.dst, &tre, &tim, &os);
+    dre = const_cast<__half*>(tre);
+    dim = const_cast<__half*>(tim);
+    int rc = launch_pass(p, ps, sre, sim, dre, dim, is, os, stream);
+    if (rc != TFFT_OK) return rc;
+  }
+  return TFFT_OK;
+}
+
+int tfft_exec_host(tfft_plan_t p, const void* host_in, void* host_out) {
+  if (!p || !host_in || !host_out) return TFFT_E_INVALID_ARG;
+  const int64_t halves = 2 * p->n * p->batch;
+  if (!p->host_path_buf) {
+    cudaError_t e = cudaMalloc(&p->host_path_buf, 2 * halves * sizeof(__half));
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return e == cudaErrorMemoryAllocation ? TFFT_E_NOMEM : (e == cudaErrorNoDevice ? TFFT_E_NO_DEVICE : static_cast<int>(e));
+    }
+  }
+  __half* din = p->host_path_buf;
+  __half* dout = p->host_path_buf + halves;
+  cudaError_t e = cudaMemcpyAsync(din, host_in, halves * sizeof(__half), cudaMemcpyHostToDevice, 0);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  int rc = tfft_exec(p, din, din + p->n, dout, dout + p->n, 2 * p->n, 2 * p->n, nullptr);
+  if (rc != TFFT_OK) return rc;
+  e = cudaMemcpyAsync(host_out, dout, halves * sizeof(__half), cudaMemcpyDeviceToHost, 0);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  e = cudaStreamSynchronize(0);
+  return e == cudaSuccess ? TFFT_OK : static_cast<int>(e);
+}
+
+}  // extern "C"

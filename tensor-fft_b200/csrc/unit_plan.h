@@ -63,6 +63,7 @@ struct UnitPlan {
   uint32_t load_estep;                // r increment between the 8 elements of a chunk (1 or 0)
   uint32_t load_gj;                   // global element stride of the tail digit j
   uint32_t load_sk0[8];               // shared byte offset of output k_0
+  uint32_t load_uval[kMaxItemBits];   // contribution to the unit-local transform index u
   // ---- epilogues
   struct Epi {
     uint32_t dst[kMaxRowBits];   // byte contribution of row bit i to the destination chunk
@@ -79,11 +80,15 @@ struct UnitPlan {
   uint32_t store_gofs[kMaxRowBits];   // global element offset contribution
   uint32_t store_xs[3];               // staging byte offsets of the 3 transposed bits
   uint32_t store_cg[3];               // global element offsets of chunk-internal bits k_s[0..2]
+  uint32_t store_uval[kMaxRowBits];   // contribution to the unit-local transform index u
+  uint32_t n_transforms;              // != 0 (row/row passes): transforms >= n_transforms are masked
   // ---- global addressing (elements)
   int64_t in_batch_stride, in_unit_stride;     // unit base = (unit / upb) * batch_stride + (unit % upb) * unit_stride
   int64_t out_batch_stride, out_unit_stride;
   uint32_t units_per_batch;
-  uint32_t col_base_stride;   // tw_mode 2: col_base = (unit % upb) * col_base_stride
+  uint32_t col_base_stride;   // tw_mode 2: col_base = ((unit % upb) / col_div) * col_base_stride
+  uint32_t col_div;
+  int64_t in_outer_stride, out_outer_stride;   // blockIdx.y level (2-D images)
   float load_scale;           // 1/T
 };
 
@@ -234,6 +239,7 @@ inline bool build_unit_plan(const UnitShape& shape, UnitPlan* plan, PlanBuildInf
     for (size_t i = 0; i < lb.size(); ++i) {
       plan->load_sofs[i] = smem_contrib(lb[i]);
       plan->load_rval[i] = lb[i].kind == LBit::R ? (1u << lb[i].idx) : 0u;
+      plan->load_uval[i] = lb[i].kind == LBit::U ? (1u << lb[i].idx) : 0u;
       // gofs filled by fill_strides
     }
     plan->load_estep = shape.in_mode == kRowMode ? 1u : 0u;
@@ -353,7 +359,10 @@ inline bool build_unit_plan(const UnitShape& shape, UnitPlan* plan, PlanBuildInf
       sb.push_back(b);
     }
     plan->store_item_bits = static_cast<uint32_t>(sb.size());
-    for (size_t i = 0; i < sb.size(); ++i) plan->store_sofs[i] = staging_contrib(sb[i]);
+    for (size_t i = 0; i < sb.size(); ++i) {
+      plan->store_sofs[i] = staging_contrib(sb[i]);
+      plan->store_uval[i] = sb[i].kind == LBit::U ? (1u << sb[i].idx) : 0u;
+    }
     for (int i = 0; i < 3; ++i) plan->store_xs[i] = staging_contrib(info->store_x[i]);
   }
   return true;
@@ -366,6 +375,10 @@ struct UnitStrides {
   int64_t in_batch_stride = 0, in_unit_stride = 0, out_batch_stride = 0, out_unit_stride = 0;
   uint32_t units_per_batch = 1;
   uint32_t col_base_stride = 0;
+  uint32_t col_div = 1;
+  bool col_from_u = true;    // tw_mode 2 column index includes the unit-local transform index u
+  int64_t in_outer_stride = 0, out_outer_stride = 0;
+  uint32_t n_transforms = 0;
   uint32_t pass1_log2n = 0;  // != 0: multiply outputs by exp(-2*pi*i*o*(col_base+u)/2^pass1_log2n)
 };
 
@@ -393,6 +406,11 @@ inline void fill_strides(const UnitStrides& st, const PlanBuildInfo& info, UnitP
   plan->out_batch_stride = st.out_batch_stride; plan->out_unit_stride = st.out_unit_stride;
   plan->units_per_batch = st.units_per_batch;
   plan->col_base_stride = st.col_base_stride;
+  plan->col_div = st.col_div ? st.col_div : 1;
+  plan->in_outer_stride = st.in_outer_stride; plan->out_outer_stride = st.out_outer_stride;
+  plan->n_transforms = st.n_transforms;
+  if (!st.col_from_u)
+    for (int i = 0; i < kMaxRowBits; ++i) plan->epi[s - 1].col[i] = 0;
   if (st.pass1_log2n) {
     plan->epi[s - 1].tw_mode = 2;
     plan->epi[s - 1].tw_log2n = st.pass1_log2n;

@@ -1,0 +1,305 @@
+"""tfft -- Python host side of the B200-native fp16 FFT (product code).
+
+A thin ctypes binding of the C ABI in include/tfft.h plus a mirror of the reference's host
+interface (same names and call sequence as /root/reference/src/base):
+
+    plan = create_plan(n)                       # CreatePlan            Plan.h:77-194
+    plan_works_on_device(plan, 0)               # PlanWorksOnDevice     Plan.h:257-296
+    h = DataHandler(n)  / DataBatchHandler(n, b)  #                     DataHandler.h:22-166
+    h.copy_data_host_to_device(host)            # CopyDataHostToDevice  DataHandler.h:45-53
+    err = compute_fft(plan, h)                  # ComputeFFT            ComputeFFT.h:54-293
+    h.copy_results_device_to_host(out, plan.results_in_results_)
+
+PyTorch is used only for device memory and streams.  There is no CPU fallback: importing works
+anywhere (so plan logic can be tested on CPU) but every compute call raises if the CUDA
+library or a GPU is missing.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from dataclasses import dataclass
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libtfft.so")
+_lib = None
+
+MODE_256 = 0      # BaseFFTMode::Mode_256   (Plan.h:14)
+MODE_4096 = 1     # BaseFFTMode::Mode_4096
+
+TFFT_PRESERVE_INPUT = 1
+
+
+class TfftError(RuntimeError):
+    pass
+
+
+class _PlanInfo(ctypes.Structure):
+    _fields_ = [
+        ("n", ctypes.c_int64), ("batch", ctypes.c_int64), ("r16_stages", ctypes.c_int32),
+        ("tail_radix", ctypes.c_int32), ("passes", ctypes.c_int32), ("results_in_results", ctypes.c_int32),
+        ("amount_of_r16_steps", ctypes.c_int32), ("amount_of_r2_steps", ctypes.c_int32),
+        ("transforms_per_cta", ctypes.c_int32), ("smem_bytes", ctypes.c_int32), ("tmem_columns", ctypes.c_int32),
+        ("grid", ctypes.c_int64), ("workspace_bytes", ctypes.c_int64), ("algorithmic_bytes", ctypes.c_int64),
+    ]
+
+
+EXPORTS = ("tfft_plan_create", "tfft_plan_create_2d", "tfft_plan_info", "tfft_plan_destroy", "tfft_exec",
+           "tfft_exec_host", "tfft_error_string", "tfft_version")
+
+
+def lib() -> ctypes.CDLL:
+    """Load tensor-fft_b200/tfft/libtfft.so (built by __graft_entry__.build()). Fails loudly if absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise TfftError(f"{_LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                            "(there is no CPU fallback)")
+        L = ctypes.CDLL(_LIB_PATH)
+        vp, i64, u32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint32
+        L.tfft_plan_create.argtypes = [ctypes.POINTER(vp), i64, i64, u32]
+        L.tfft_plan_create_2d.argtypes = [ctypes.POINTER(vp), i64, i64, i64, u32]
+        L.tfft_plan_info.argtypes = [vp, ctypes.POINTER(_PlanInfo)]
+        L.tfft_plan_destroy.argtypes = [vp]
+        L.tfft_exec.argtypes = [vp, vp, vp, vp, vp, i64, i64, vp]
+        L.tfft_exec_host.argtypes = [vp, vp, vp]
+        L.tfft_error_string.argtypes = [ctypes.c_int]
+        L.tfft_error_string.restype = ctypes.c_char_p
+        _lib = L
+    return _lib
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise TfftError(f"tfft error {rc}: {lib().tfft_error_string(rc).decode()}")
+
+
+class NativePlan:
+    """Owner of a tfft_plan_t."""
+
+    def __init__(self, n: int, batch: int = 1, flags: int = 0, shape2d: Optional[tuple] = None):
+        self._h = ctypes.c_void_p()
+        if shape2d is None:
+            _check(lib().tfft_plan_create(ctypes.byref(self._h), n, batch, flags))
+        else:
+            _check(lib().tfft_plan_create_2d(ctypes.byref(self._h), shape2d[0], shape2d[1], batch, flags))
+        info = _PlanInfo()
+        _check(lib().tfft_plan_info(self._h, ctypes.byref(info)))
+        self.info = {k: getattr(info, k) for k, _ in _PlanInfo._fields_}
+        self.n, self.batch = n, batch
+
+    def exec(self, in_re, in_im, out_re, out_im, in_stride: int, out_stride: int, stream=None) -> None:
+        """Launch on torch CUDA tensors (fp16). Strides in elements between consecutive transforms."""
+        import torch
+        for t in (in_re, in_im, out_re, out_im):
+            if not (t.is_cuda and t.dtype == torch.float16):
+                raise TfftError("tfft exec needs CUDA float16 tensors (no CPU fallback)")
+        s = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        _check(lib().tfft_exec(self._h, in_re.data_ptr(), in_im.data_ptr(), out_re.data_ptr(), out_im.data_ptr(),
+                               in_stride, out_stride, ctypes.c_void_p(s)))
+
+    def exec_host(self, host_in, host_out) -> None:
+        """numpy float16 arrays of 2*n*batch values laid out [RE|IM] per transform."""
+        _check(lib().tfft_exec_host(self._h, host_in.ctypes.data_as(ctypes.c_void_p),
+                                    host_out.ctypes.data_as(ctypes.c_void_p)))
+
+    def close(self) -> None:
+        if self._h:
+            lib().tfft_plan_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# --------------------------------------------------------------------------------------------
+# Mirror of the reference host interface (src/base/Plan.h, DataHandler.h, ComputeFFT.h)
+# --------------------------------------------------------------------------------------------
+@dataclass
+class Plan:
+    """Plan<Integer> (Plan.h:18-39). Launch-shape fields are informational for the new kernels."""
+    fft_length_: int
+    amount_of_r16_steps_: int
+    amount_of_r2_steps_: int
+    base_fft_mode_: int
+    results_in_results_: bool
+    base_fft_warps_per_block_: int
+    base_fft_blocksize_: int
+    base_fft_gridsize_: int
+    base_fft_shared_mem_in_bytes_: int
+    r16_warps_per_block_: int
+    r16_blocksize_: int
+    r16_gridsize_: int
+    r16_shared_mem_in_bytes_: int
+    r2_blocksize_: int
+
+
+def is_power_of_2(x: int) -> bool:
+    """IsPowerOf2 (Plan.h:41-47)."""
+    return x != 0 and (x & (x - 1)) == 0
+
+
+def exact_log2(x: int) -> int:
+    """ExactLog2 (Plan.h:50-67), without the reference's 32-bit truncation."""
+    return x.bit_length() - 1
+
+
+def create_plan(fft_length: int, mode: int = MODE_256, base_fft_warps_per_block: int = 8,
+                r16_warps_per_block: int = 8, r2_blocksize: int = 256) -> Optional[Plan]:
+    """CreatePlan (Plan.h:77-194): same validation and error behaviour (message on stdout, None).
+
+    The tuning arguments are validated like the reference validates them, so callers that pass
+    reference tuner values keep working, but they do not steer the B200 kernels.
+    """
+    if not is_power_of_2(fft_length):
+        print("Error! Input size has to be a power of 2!")
+        return None
+    lg = exact_log2(fft_length)
+    if lg < 8:
+        print("Error! Input size has to be larger than 256 i.e. 16^2")
+        return None
+    if mode == MODE_4096 and fft_length < 4096:
+        print("Error! Baselayer fft length cant be longer that fft_length.")
+        return None
+    r16, r2 = lg // 4 - 1, lg % 4
+    total_warps = fft_length // 256
+    if total_warps < base_fft_warps_per_block:
+        base_w = total_warps
+    else:
+        if total_warps % base_fft_warps_per_block != 0:
+            print("Error! Total amount of warps (fft_length/256) has to be evenly devisable by "
+                  "base_fft_warps_per_block.")
+            return None
+        base_w = 16 if mode == MODE_4096 else base_fft_warps_per_block
+    if total_warps < r16_warps_per_block:
+        r16_w = total_warps
+    else:
+        if total_warps % r16_warps_per_block != 0:
+            print("Error! Total amount of warps (fft_length/256) has to be evenly devisable by "
+                  "amount_of_r16_warps_per_block.")
+            return None
+        r16_w = r16_warps_per_block
+    if (fft_length >> r2) % r2_blocksize != 0:
+        print("Error! smallest_r2_subfft_length i.e. pow(2,(log2_of_fft_lenght / 4)) has to be evenly "
+              "devisable by r2_blocksize.")
+        return None
+    return Plan(fft_length_=fft_length, amount_of_r16_steps_=r16, amount_of_r2_steps_=r2, base_fft_mode_=mode,
+                results_in_results_=True,   # the fused kernels always write the results planes
+                base_fft_warps_per_block_=base_w, base_fft_blocksize_=base_w * 32,
+                base_fft_gridsize_=total_warps // base_w, base_fft_shared_mem_in_bytes_=base_w * 1024 * 2,
+                r16_warps_per_block_=r16_w, r16_blocksize_=r16_w * 32, r16_gridsize_=total_warps // r16_w,
+                r16_shared_mem_in_bytes_=r16_w * 768 * 2, r2_blocksize_=r2_blocksize)
+
+
+def create_plan_from_file(fft_length: int, tuner_results_file: str) -> Optional[Plan]:
+    """CreatePlan(N, tuner_file) (Plan.h:197-255): line format `N mode base_warps r16_warps r2_block`."""
+    try:
+        with open(tuner_results_file) as f:
+            for line in f:
+                parts = line.split()
+                if parts and int(float(parts[0])) == fft_length:
+                    mode = MODE_256 if int(parts[1]) == 256 else MODE_4096
+                    return create_plan(fft_length, mode, int(parts[2]), int(parts[3]), int(parts[4]))
+    except OSError:
+        print("Error! Failed to open tuner file.")
+        return None
+    print("Error! Tuner file didnt contain requested fft length.")
+    return None
+
+
+def get_max_no_optin_shared_mem(device_id: int = 0) -> int:
+    """GetMaxNoOptInSharedMem (Plan.h:298-303)."""
+    import torch
+    return int(torch.cuda.get_device_properties(device_id).shared_memory_per_block)
+
+
+def plan_works_on_device(plan: Plan, device_id: int = 0) -> bool:
+    """PlanWorksOnDevice (Plan.h:257-296), for the B200 kernels: needs compute capability 10.x."""
+    import torch
+    if not torch.cuda.is_available():
+        print("Error! No CUDA device.")
+        return False
+    major, _ = torch.cuda.get_device_capability(device_id)
+    if major != 10:
+        print("Error! Compute capability 10.x (sm_100a) is required.")
+        return False
+    return True
+
+
+class DataHandler:
+    """DataHandler<Integer> (DataHandler.h:22-82): one allocation of 4*N halves
+    [in_RE | in_IM | out_RE | out_IM]."""
+
+    def __init__(self, fft_length: int, device: str = "cuda"):
+        import torch
+        self.fft_length_ = fft_length
+        self.amount_of_ffts_ = 1
+        self.dptr_data_ = torch.empty(4 * fft_length, dtype=torch.float16, device=device)
+        n = fft_length
+        self.dptr_input_RE_ = self.dptr_data_[0:n]
+        self.dptr_input_IM_ = self.dptr_data_[n:2 * n]
+        self.dptr_results_RE_ = self.dptr_data_[2 * n:3 * n]
+        self.dptr_results_IM_ = self.dptr_data_[3 * n:4 * n]
+
+    def peak_at_last_error(self) -> Optional[str]:
+        return None
+
+    def copy_data_host_to_device(self, data) -> Optional[str]:
+        import torch
+        src = torch.from_numpy(data).view(torch.float16).reshape(-1)
+        self.dptr_data_[:2 * self.fft_length_ * self.amount_of_ffts_].copy_(src)
+        return None
+
+    def copy_results_device_to_host(self, data, results_in_results: bool) -> Optional[str]:
+        import torch
+        k = 2 * self.fft_length_ * self.amount_of_ffts_
+        src = self.dptr_data_[k:2 * k] if results_in_results else self.dptr_data_[:k]
+        torch.from_numpy(data).view(torch.float16).reshape(-1).copy_(src)
+        return None
+
+
+class DataBatchHandler(DataHandler):
+    """DataBatchHandler<Integer> (DataHandler.h:86-166): inputs [RE_0|IM_0|RE_1|IM_1|...] then the
+    results in the same order."""
+
+    def __init__(self, fft_length: int, amount_of_ffts: int, device: str = "cuda"):
+        import torch
+        self.fft_length_ = fft_length
+        self.amount_of_ffts_ = amount_of_ffts
+        n, b = fft_length, amount_of_ffts
+        self.dptr_data_ = torch.empty(4 * n * b, dtype=torch.float16, device=device)
+        self.dptr_input_RE_ = [self.dptr_data_[2 * i * n:(2 * i + 1) * n] for i in range(b)]
+        self.dptr_input_IM_ = [self.dptr_data_[(2 * i + 1) * n:(2 * i + 2) * n] for i in range(b)]
+        off = 2 * n * b
+        self.dptr_results_RE_ = [self.dptr_data_[off + 2 * i * n:off + (2 * i + 1) * n] for i in range(b)]
+        self.dptr_results_IM_ = [self.dptr_data_[off + (2 * i + 1) * n:off + (2 * i + 2) * n] for i in range(b)]
+
+
+_plan_cache: dict = {}
+
+
+def compute_fft(fft_plan: Plan, data: DataHandler, max_no_optin_shared_mem: int = 32768) -> Optional[str]:
+    """ComputeFFT (ComputeFFT.h:54-151 single, :162-293 batch). Returns None on success, else the
+    error string -- the reference's std::optional<std::string> convention. Asynchronous for the
+    single handler, synchronised for the batch handler, like the reference."""
+    import torch
+    n, b = fft_plan.fft_length_, data.amount_of_ffts_
+    if n != data.fft_length_:
+        return "plan / data handler length mismatch"
+    try:
+        key = (n, b, data.dptr_data_.device.index)
+        native = _plan_cache.get(key)
+        if native is None:
+            native = _plan_cache[key] = NativePlan(n, b)
+        buf = data.dptr_data_
+        half = 2 * n * b
+        native.exec(buf[0:], buf[n:], buf[half:], buf[half + n:], 2 * n, 2 * n)
+        if b > 1:
+            torch.cuda.synchronize()
+    except TfftError as e:
+        return str(e)
+    return None
