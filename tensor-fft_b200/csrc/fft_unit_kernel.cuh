@@ -2,19 +2,20 @@
 // (U transforms of length L = T*16^s, E = U*L <= 32768 complex elements) and touches HBM
 // exactly once: planar fp16 in, planar fp16 out.
 //
-//   load    16-byte LDG -> radix-T butterfly + twiddle in fp32 registers -> 16-byte STS into
-//           the stage-1 tensor-core operand layout (replaces the reference's digit-reversal
-//           gather src/base/TensorFFT256.cu:125-171 and its Radix2Kernel launches
-//           src/base/Radix2.cu:20-77, src/base/ComputeFFT.h:123-145)
-//   stage   radix-16 DFT as tcgen05.mma (M=128 rows of data x N=32 [re|im] x K=16), fp32
-//           accumulation in tensor memory; epilogue tcgen05.ld -> fp32 twiddle -> fp16 ->
-//           16-byte STS into the next stage's operand layout (replaces the wmma stages of
-//           src/base/TensorFFT256.cu:191-275 and src/base/TensorRadix16.cu:101-213, which
-//           accumulate in fp16 and pay one HBM round trip per radix-16 step)
+//   load    16-byte cp.async global->shared straight into the stage-1 tensor-core operand layout
+//           (replaces the reference's digit-reversal gather, src/base/TensorFFT256.cu:125-171)
+//   stage   radix-16/32/64 DFT as tcgen05.mma (M=128 rows of data x N=2R [re|im] x K=16 steps),
+//           fp32 accumulation in tensor memory; epilogue tcgen05.ld -> packed-fp32 twiddle ->
+//           fp16 -> 16-byte STS into the next stage's operand layout (replaces the wmma stages
+//           of src/base/TensorFFT256.cu:191-275 and src/base/TensorRadix16.cu:101-213, which
+//           accumulate in fp16 and pay one HBM round trip per radix-16 step, and the
+//           Radix2Kernel launches of src/base/Radix2.cu:20-77 / ComputeFFT.h:123-145: the
+//           non-power-of-16 factor is folded into a radix-32/64 tensor stage)
 //   store   16-byte LDS -> 8x8 in-register transpose -> 16-byte coalesced STG.
-// All index maps come from the host-side UnitPlan (unit_plan.h).  Scaling: 1/T in the load
-// phase and 1/16 folded into the fp16 DFT matrix (exact powers of two), total 1/L like the
-// reference's "sequential scaling" (TensorFFT256.cu:167-171, TensorRadix16.cu:133-136).
+// CTAs are persistent (grid = min(units, resident CTAs)) and loop over units.
+// All index maps come from the host-side UnitPlan (unit_plan.h).  Scaling: 1/R_t is folded
+// into each fp16 DFT matrix (exact powers of two), total 1/L like the reference's "sequential
+// scaling" (TensorFFT256.cu:167-171, TensorRadix16.cu:133-136, Radix2.cu:64-76).
 #pragma once
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -25,7 +26,54 @@
 namespace tfft {
 
 constexpr int kThreads = 256;
-constexpr uint32_t kBMatBytes = 1024;   // one 16 x 32 fp16 B operand
+constexpr uint32_t kTwTableBytes = 512 + 4096;   // [TWlo: 64 float2 | TWhi: 512 float2]
+
+// ---------------------------------------------------------------- packed fp32 pairs (FFMA2)
+// Blackwell issues two fp32 FMAs per lane per instruction on 64-bit register pairs
+// (fma.rn.f32x2); the kernel is issue-bound, so all twiddle arithmetic runs on pairs of
+// neighbouring elements.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 neg2(f32x2 a) { return a ^ 0x8000000080000000ull; }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { return add2(a, neg2(b)); }
+__device__ __forceinline__ uint32_t pack_half2_pair(f32x2 v) {
+  float lo, hi;
+  upk(v, lo, hi);
+  return ptx::pack_half2(lo, hi);
+}
+// two complex numbers, planar: re = (re0, re1), im = (im0, im1)
+struct C2 {
+  f32x2 re, im;
+};
+__device__ __forceinline__ C2 cmul2(C2 a, C2 b) {
+  return {fma2(neg2(a.im), b.im, mul2(a.re, b.re)), fma2(a.im, b.re, mul2(a.re, b.im))};
+}
+__device__ __forceinline__ C2 cadd2(C2 a, C2 b) { return {add2(a.re, b.re), add2(a.im, b.im)}; }
+__device__ __forceinline__ C2 csub2(C2 a, C2 b) { return {sub2(a.re, b.re), sub2(a.im, b.im)}; }
+__device__ __forceinline__ C2 cmul2_mi(C2 a) { return {a.im, neg2(a.re)}; }   // * (-i)
+__device__ __forceinline__ C2 cbcast(float re, float im) { return {pk(re, re), pk(im, im)}; }
 
 struct Cplx {
   float re, im;
@@ -33,9 +81,6 @@ struct Cplx {
 __device__ __forceinline__ Cplx cmul(Cplx a, Cplx b) {
   return {fmaf(a.re, b.re, -a.im * b.im), fmaf(a.re, b.im, a.im * b.re)};
 }
-__device__ __forceinline__ Cplx cadd(Cplx a, Cplx b) { return {a.re + b.re, a.im + b.im}; }
-__device__ __forceinline__ Cplx csub(Cplx a, Cplx b) { return {a.re - b.re, a.im - b.im}; }
-__device__ __forceinline__ Cplx cmul_mi(Cplx a) { return {a.im, -a.re}; }  // a * (-i)
 // exp(-2*pi*i * x / 2^log2n) for an integer phase x (already reduced mod 2^log2n or small)
 __device__ __forceinline__ Cplx twiddle(uint32_t x, uint32_t log2n) {
   float s, c;
@@ -44,43 +89,15 @@ __device__ __forceinline__ Cplx twiddle(uint32_t x, uint32_t log2n) {
   return {c, s};
 }
 
-// in-register forward DFT of size T (T = 2, 4, 8), unscaled
-template <int T>
-__device__ __forceinline__ void small_dft(Cplx (&x)[T]) {
-  if constexpr (T == 2) {
-    Cplx a = x[0], b = x[1];
-    x[0] = cadd(a, b);
-    x[1] = csub(a, b);
-  } else if constexpr (T == 4) {
-    Cplx a = cadd(x[0], x[2]), b = csub(x[0], x[2]), c = cadd(x[1], x[3]), d = cmul_mi(csub(x[1], x[3]));
-    x[0] = cadd(a, c);
-    x[1] = cadd(b, d);
-    x[2] = csub(a, c);
-    x[3] = csub(b, d);
-  } else if constexpr (T == 8) {
-    Cplx e[4] = {x[0], x[2], x[4], x[6]}, o[4] = {x[1], x[3], x[5], x[7]};
-    small_dft<4>(e);
-    small_dft<4>(o);
-    const float h = 0.70710678118654752f;
-    Cplx o1 = {h * (o[1].re + o[1].im), h * (o[1].im - o[1].re)};    // * exp(-i*pi/4)
-    Cplx o2 = cmul_mi(o[2]);                                          // * (-i)
-    Cplx o3 = {h * (o[3].im - o[3].re), -h * (o[3].re + o[3].im)};   // * exp(-3i*pi/4)
-    x[0] = cadd(e[0], o[0]); x[4] = csub(e[0], o[0]);
-    x[1] = cadd(e[1], o1);   x[5] = csub(e[1], o1);
-    x[2] = cadd(e[2], o2);   x[6] = csub(e[2], o2);
-    x[3] = cadd(e[3], o3);   x[7] = csub(e[3], o3);
-  }
-}
-
 __device__ __forceinline__ uint32_t bit_sum(uint32_t q, const uint32_t* contrib, int first, int count) {
   uint32_t s = 0;
 #pragma unroll
   for (int i = 0; i < count; ++i)
-    if ((q >> (first + i)) & 1u) s += contrib[first + i];
+    if ((q >> i) & 1u) s += contrib[first + i];
   return s;
 }
 
-__device__ __forceinline__ uint4 ldg128(const __half* p) {
+__device__ __forceinline__ uint4 ldg128(const void* p) {
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
@@ -92,268 +109,406 @@ __device__ __forceinline__ void stg128(__half* p, uint4 v) {
                "r"(v.w)
                : "memory");
 }
-__device__ __forceinline__ float2 unpack_half2(uint32_t v) {
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr));
+  return r;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ f32x2 unpack_half2(uint32_t v) {
   __half2 h = *reinterpret_cast<__half2*>(&v);
-  return __half22float2(h);
+  float2 f = __half22float2(h);
+  return pk(f.x, f.y);
 }
 
-// Dynamic shared memory carve-up (bytes): [plane_re | plane_im | B1 | B2 | mbar | tmem slot]
+// Device tables (built on the host, tfft_api.cu make_tables; staged into shared memory once per CTA):
+//   [0, 512)    TWlo[j]  = exp(-2*pi*i * j / L),        j < 64
+//   [512, 4608) TWhi[j]  = exp(-2*pi*i * 64*j / L),     j < L/64 <= 512
+//   then for every distinct radix R of the plan the B operands B1 = [Fr | Fi] / R and
+//   B2 = [-Fi | Fr] / R (fp16, K-major SWIZZLE_NONE: Bmath[kappa][n] at
+//   (n>>3)*16R + (kappa>>3)*128 + (n&7)*16 + (kappa&7)*2 bytes), F = exp(-2*pi*i*kappa*k/R).
+struct TableLayout {
+  uint32_t b_off[kMaxStages];   // byte offset of B1 of stage t (B2 follows at + 4*R*R)
+  uint32_t total;               // multiple of 16
+};
+__host__ __device__ inline TableLayout table_layout(const UnitPlan& p) {
+  TableLayout l;
+  uint32_t off = kTwTableBytes;
+  for (uint32_t t = 0; t < kMaxStages; ++t) l.b_off[t] = 0;
+  for (uint32_t t = 0; t < p.stages; ++t) {
+    bool found = false;
+    for (uint32_t u = 0; u < t; ++u)
+      if (p.log2_radix[u] == p.log2_radix[t]) { l.b_off[t] = l.b_off[u]; found = true; break; }
+    if (!found) {
+      l.b_off[t] = off;
+      off += 8u << (2 * p.log2_radix[t]);   // 2 matrices of 2R x R halves
+    }
+  }
+  l.total = off;
+  return l;
+}
+
+// Dynamic shared memory carve-up (bytes): [plane_re | plane_im | tables | mbar | tmem slot]
 struct SmemLayout {
-  uint32_t plane_stride, b1_off, b2_off, bar_off, slot_off, total;
+  uint32_t plane_stride, table_off, bar_off, slot_off, total;
 };
 __host__ __device__ inline SmemLayout smem_layout(const UnitPlan& p) {
   SmemLayout l;
-  uint32_t pb = p.plane_bytes > p.stage_plane_bytes ? p.plane_bytes : p.stage_plane_bytes;
-  l.plane_stride = (pb + 127u) & ~127u;
-  l.b1_off = 2 * l.plane_stride;
-  l.b2_off = l.b1_off + kBMatBytes;
-  l.bar_off = l.b2_off + kBMatBytes;
+  l.plane_stride = p.plane_bytes;
+  l.table_off = 2 * l.plane_stride;
+  l.bar_off = l.table_off + table_layout(p).total;
   l.slot_off = l.bar_off + 8;
   l.total = l.slot_off + 8;
   return l;
 }
-__host__ __device__ inline uint32_t tmem_cols(const UnitPlan& p) {
-  uint32_t need = p.n_tiles * 32, c = 32;
-  while (c < need) c <<= 1;
-  return c;
+
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* gptr, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(saddr), "l"(gptr), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
-template <int LOG2T>
-__global__ void __launch_bounds__(kThreads) fft_unit_kernel(const __grid_constant__ UnitPlan P,
-                                                            const __half* __restrict__ in_re,
-                                                            const __half* __restrict__ in_im,
-                                                            __half* __restrict__ out_re,
-                                                            __half* __restrict__ out_im) {
+// exp(-2*pi*i * x / L) from the two-level shared-memory table, x < L
+__device__ __forceinline__ Cplx tw_lookup(const float2* tw_table, uint32_t x) {
+  const float2 lo = tw_table[x & 63u], hi = tw_table[64u + (x >> 6)];
+  return cmul({lo.x, lo.y}, {hi.x, hi.y});
+}
+
+// Optional phase trace (developer builds, -DTFFT_TRACE): thread 0 of every CTA records clock64 at
+// phase boundaries of its first units into a global buffer (tools/trace_phases.py).
+#ifdef TFFT_TRACE
+#define TFFT_TRACE_MARK(slot)                                                                  \
+  do {                                                                                          \
+    if (threadIdx.x == 0 && trace != nullptr && trace_unit < 4)                                 \
+      trace[(static_cast<size_t>(blockIdx.x) * 4 + trace_unit) * 16 + (slot)] = clock64();      \
+  } while (0)
+#else
+#define TFFT_TRACE_MARK(slot) do {} while (0)
+#endif
+
+struct KernelCtx {
+  uint32_t sbase, s_re, s_im, taddr, lane_row, wgroup, lane_base;
+  const float2* tw_table;
+  uint32_t col_base;
+};
+
+// sum of the contributions of the set bits of a COMPILE-TIME index: folds into constant-bank adds
+template <uint32_t Q, int COUNT>
+__device__ __forceinline__ uint32_t bit_sum_c(const uint32_t* contrib, int first) {
+  uint32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < COUNT; ++i)
+    if ((Q >> i) & 1u) s += contrib[first + i];
+  return s;
+}
+
+// Epilogue of work item (2*II + wgroup) of stage ST: one 128-row tile x 16 output columns.
+//   RHO: log2 radix, LAST: final stage (no inter-stage twiddle), items are numbered
+//   item = tile * G + g (G = R/16 column groups per tile); bit 0 of the item index is the warp group.
+template <int RHO, uint32_t II>
+__device__ __forceinline__ void epilogue_load(const KernelCtx& c, uint32_t (&are)[16], uint32_t (&aim)[16]) {
+  constexpr uint32_t R = 1u << RHO, G = R / 16;
+  constexpr uint32_t kTileHi = (G == 1) ? (2 * II) : (G == 2 ? II : II / 2);
+  constexpr uint32_t kGHi = (G == 4) ? 2 * (II % 2) : 0;
+  const uint32_t tile = kTileHi + (G == 1 ? c.wgroup : 0u);
+  const uint32_t g = kGHi + (G == 1 ? 0u : c.wgroup);
+  const uint32_t tcol = c.taddr + c.lane_base + tile * 2 * R + g * 16;
+  ptx::tmem_ld_32x32b_x16(tcol, are);
+  ptx::tmem_ld_32x32b_x16(tcol + R, aim);
+}
+
+template <int ST, int RHO, bool LAST, uint32_t II>
+__device__ __forceinline__ void epilogue_item(const UnitPlan& P, const KernelCtx& c, uint32_t dst_thr, uint32_t aux_thr,
+                                              uint32_t col_thr, const uint32_t (&are)[16], const uint32_t (&aim)[16]) {
   using namespace ptx;
-  constexpr int T = 1 << LOG2T;
+  constexpr uint32_t R = 1u << RHO, G = R / 16;
+  const UnitPlan::Epi& E = P.epi[ST];
+  // item = 2*II + wgroup;  tile = item / G, g = item % G
+  constexpr uint32_t kTileHi = (G == 1) ? (2 * II) : (G == 2 ? II : II / 2);   // compile-time part of the tile index
+  constexpr uint32_t kGHi = (G == 4) ? 2 * (II % 2) : 0;                       // compile-time part of g
+  const uint32_t g = kGHi + (G == 1 ? 0u : c.wgroup);
+  // dst_thr / aux_thr already hold the per-thread part including the warp-group bit
+  uint32_t dst = dst_thr + bit_sum_c<kTileHi, kMaxRowBits - 7>(E.dst, 7);
+  if (G == 4) dst += bit_sum_c<(kGHi >> 1), 1>(E.dst_k, 2);   // k_t[5]
+  uint32_t pre[8], pim[8];
+  bool plain = LAST && E.tw_mode == 0;
+  if (plain) {
+#pragma unroll
+    for (int k = 0; k < 16; k += 2) {
+      pre[k >> 1] = pack_half2(__uint_as_float(are[k]), __uint_as_float(are[k + 1]));
+      pim[k >> 1] = pack_half2(__uint_as_float(aim[k]), __uint_as_float(aim[k + 1]));
+    }
+  } else {
+    const uint32_t aux = aux_thr + bit_sum_c<kTileHi, kMaxRowBits - 7>(E.aux, 7);
+    Cplx t0, t1, s2;
+    if (!LAST) {
+      const uint32_t idx = aux << E.tw_shift;                       // unit angle 2*pi/L
+      const Cplx w1 = tw_lookup(c.tw_table, idx);
+      s2 = cmul(w1, w1);
+      if (G == 1) {
+        t0 = {1.f, 0.f};
+        t1 = w1;
+      } else {
+        t0 = tw_lookup(c.tw_table, (idx * 16u * g) & ((1u << P.log2_len) - 1u));
+        t1 = cmul(t0, w1);
+      }
+    } else {
+      const uint32_t col = col_thr + bit_sum_c<kTileHi, kMaxRowBits - 7>(E.col, 7) + c.col_base;
+      const uint32_t mask = (1u << E.tw_log2n) - 1u;
+      const Cplx w1 = twiddle((E.tw_kw * col) & mask, E.tw_log2n);
+      t0 = twiddle(((aux + 16u * g * E.tw_kw) * col) & mask, E.tw_log2n);
+      t1 = cmul(t0, w1);
+      s2 = cmul(w1, w1);
+    }
+    // twiddles of columns (k, k+1) as packed pairs; nim = -im carried to avoid sign flips
+    f32x2 tre = pk(t0.re, t1.re), tim = pk(t0.im, t1.im), tnim = pk(-t0.im, -t1.im);
+    const f32x2 sre = pk(s2.re, s2.re), sim = pk(s2.im, s2.im), snim = pk(-s2.im, -s2.im);
+#pragma unroll
+    for (int k = 0; k < 16; k += 2) {
+      const f32x2 xr = pk(__uint_as_float(are[k]), __uint_as_float(are[k + 1]));
+      const f32x2 xi = pk(__uint_as_float(aim[k]), __uint_as_float(aim[k + 1]));
+      pre[k >> 1] = pack_half2_pair(fma2(xi, tnim, mul2(xr, tre)));
+      pim[k >> 1] = pack_half2_pair(fma2(xi, tre, mul2(xr, tim)));
+      if (k < 14) {
+        const f32x2 nre = fma2(tnim, sim, mul2(tre, sre));
+        const f32x2 nim = fma2(tim, sre, mul2(tre, sim));
+        tnim = fma2(tnim, sre, mul2(tre, snim));
+        tre = nre;
+        tim = nim;
+      }
+    }
+  }
+  sts128(c.s_re + dst, make_uint4(pre[0], pre[1], pre[2], pre[3]));
+  sts128(c.s_re + dst + E.dst_k[0], make_uint4(pre[4], pre[5], pre[6], pre[7]));
+  sts128(c.s_im + dst, make_uint4(pim[0], pim[1], pim[2], pim[3]));
+  sts128(c.s_im + dst + E.dst_k[0], make_uint4(pim[4], pim[5], pim[6], pim[7]));
+}
+
+// Software-pipelined item loop: the tensor-memory load of item II+1 is in flight while item II is
+// processed (tcgen05.wait::ld waits for ALL outstanding loads, so the next load is issued right after
+// the wait and before the arithmetic).
+template <int ST, int RHO, bool LAST, int LOG2E, uint32_t II = 0>
+__device__ __forceinline__ void epilogue_items(const UnitPlan& P, const KernelCtx& c, uint32_t dst_thr,
+                                               uint32_t aux_thr, uint32_t col_thr, uint32_t (&cre)[16],
+                                               uint32_t (&cim)[16], uint32_t (&nre)[16], uint32_t (&nim)[16]) {
+  constexpr uint32_t kItemsPerGroup = (1u << LOG2E) / 2048 / 2;   // E/2048 work items per stage, two warp groups
+  if constexpr (II < kItemsPerGroup) {
+    ptx::tmem_ld_wait();                                            // item II has landed in (cre, cim)
+    if constexpr (II + 1 < kItemsPerGroup) epilogue_load<RHO, II + 1>(c, nre, nim);
+    epilogue_item<ST, RHO, LAST, II>(P, c, dst_thr, aux_thr, col_thr, cre, cim);
+    epilogue_items<ST, RHO, LAST, LOG2E, II + 1>(P, c, dst_thr, aux_thr, col_thr, nre, nim, cre, cim);
+  }
+}
+
+// One tensor-core stage: all UMMAs (one thread), wait, then the epilogue on all 8 warps.
+template <int ST, int RHO, bool LAST, int LOG2E>
+__device__ __forceinline__ void run_stage(const UnitPlan& P, const KernelCtx& c, uint32_t b1_saddr, uint64_t* bar,
+                                          uint32_t& phase, int warp, int lane, long long* trace,
+                                          uint32_t trace_unit) {
+  using namespace ptx;
+  constexpr uint32_t R = 1u << RHO, G = R / 16, kSteps = R / 16;
+  constexpr uint32_t S = 16 * R + 16;                       // chunk stride of this stage's operand layout
+  constexpr uint32_t kTiles = (1u << LOG2E) / R / 128;
+  fence_proxy_async_smem();   // generic-proxy / cp.async operand writes -> visible to the tensor core
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  TFFT_TRACE_MARK(9 + 2 * ST);
+  if (warp == 0) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(128, 2 * R, /*a_mn=*/1, /*b_mn=*/0);
+      // descriptors differ only in the 14-bit start-address field (units of 16 bytes): add offsets there
+      const uint64_t da_re = make_smem_desc(c.s_re, kKGroupStride, S);
+      const uint64_t da_im = make_smem_desc(c.s_im, kKGroupStride, S);
+      const uint64_t db1 = make_smem_desc(b1_saddr, kKGroupStride, 16 * R);
+      const uint64_t db2 = make_smem_desc(b1_saddr + 4 * R * R, kKGroupStride, 16 * R);
+#pragma unroll
+      for (uint32_t tile = 0; tile < kTiles; ++tile) {
+        const uint32_t d = c.taddr + tile * 2 * R;
+#pragma unroll
+        for (uint32_t j = 0; j < kSteps; ++j)
+          umma_f16_ss(d, da_re + (tile * S + j * 16), db1 + j * 16, idesc, j > 0 ? 1u : 0u);
+#pragma unroll
+        for (uint32_t j = 0; j < kSteps; ++j)
+          umma_f16_ss(d, da_im + (tile * S + j * 16), db2 + j * 16, idesc, 1u);
+      }
+      umma_commit(bar);
+      mbar_wait(bar, phase & 1u);
+    }
+    __syncwarp();
+  }
+  phase++;
+  __syncthreads();            // all MMAs of this stage are complete: operand planes are free
+  tc_fence_after_sync();
+  TFFT_TRACE_MARK(10 + 2 * ST);
+  // per-thread parts of the bit-linear row maps: 7 lane-row bits + the warp-group bit of the item index
+  const UnitPlan::Epi& E = P.epi[ST];
+  uint32_t dst_thr = bit_sum(c.lane_row, E.dst, 0, 7);
+  uint32_t aux_thr = bit_sum(c.lane_row, E.aux, 0, 7);
+  uint32_t col_thr = LAST ? bit_sum(c.lane_row, E.col, 0, 7) : 0u;
+  if (c.wgroup) {
+    if (G == 1) {          // the warp group selects tile bit 0 = row bit 7
+      dst_thr += E.dst[7];
+      aux_thr += E.aux[7];
+      if (LAST) col_thr += E.col[7];
+    } else {               // the warp group selects g bit 0 = k_t[4]
+      dst_thr += E.dst_k[1];
+    }
+  }
+  uint32_t ra[16], rb[16], rc[16], rd[16];
+  epilogue_load<RHO, 0>(c, ra, rb);
+  epilogue_items<ST, RHO, LAST, LOG2E>(P, c, dst_thr, aux_thr, col_thr, ra, rb, rc, rd);
+}
+
+template <int LOG2E, int RHO0, int RHO1, int RHO2>
+__global__ void __launch_bounds__(kThreads, (LOG2E == 15 ? 1 : 2))
+fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ in_re,
+                const __half* __restrict__ in_im, __half* __restrict__ out_re, __half* __restrict__ out_im,
+                const uint4* __restrict__ tables, long long* __restrict__ trace) {
+  using namespace ptx;
   extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int kStages = RHO2 ? 3 : 2;
   const SmemLayout SL = smem_layout(P);
-  uint8_t* plane_re = smem;
-  uint8_t* plane_im = smem + SL.plane_stride;
+  const TableLayout TL = table_layout(P);
+  KernelCtx c;
+  c.sbase = smem_u32(smem);
+  c.s_re = c.sbase;
+  c.s_im = c.sbase + SL.plane_stride;
+  c.tw_table = reinterpret_cast<const float2*>(smem + SL.table_off);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + SL.bar_off);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SL.slot_off);
+  const uint32_t table_base = c.sbase + SL.table_off;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t unit = blockIdx.x;
-  const uint32_t ub = unit / P.units_per_batch, uu = unit % P.units_per_batch;
-  const int64_t in_base = static_cast<int64_t>(ub) * P.in_batch_stride + static_cast<int64_t>(uu) * P.in_unit_stride +
-                          static_cast<int64_t>(blockIdx.y) * P.in_outer_stride;
-  const int64_t out_base = static_cast<int64_t>(ub) * P.out_batch_stride +
-                           static_cast<int64_t>(uu) * P.out_unit_stride +
-                           static_cast<int64_t>(blockIdx.y) * P.out_outer_stride;
-  // row/row passes with a ragged batch: transforms past the end are loaded as zeros, never stored
-  const uint32_t u_limit = P.n_transforms ? P.n_transforms - min(P.n_transforms, unit << P.log2_units) : 0xFFFFFFFFu;
-  const uint32_t ncols = tmem_cols(P);
+  c.lane_row = static_cast<uint32_t>((warp & 3) * 32 + lane);
+  c.lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+  c.wgroup = static_cast<uint32_t>(warp >> 2);
+  uint32_t trace_unit = 0;
+  (void)trace_unit;
 
-  // ------------------------------------------------------------------ setup
+  // ------------------------------------------------------------------ setup (once per CTA)
   if (warp == 0) {
-    tmem_alloc(tmem_slot, ncols);
+    tmem_alloc(tmem_slot, P.tmem_cols);
     tmem_relinquish();
   }
   if (tid == 32) {
     mbar_init(bar, 1);
     fence_mbar_init();
   }
-  {
-    // B operands, K-major SWIZZLE_NONE: Bmath[k][n] at (n>>3)*256 + (k>>3)*128 + (n&7)*16 + (k&7)*2
-    // B1 = [Fr | Fi] / 16, B2 = [-Fi | Fr] / 16, F[k][n] = exp(-2*pi*i*k*n/16)
-    __half* b1 = reinterpret_cast<__half*>(smem + SL.b1_off);
-    __half* b2 = reinterpret_cast<__half*>(smem + SL.b2_off);
-    for (int e = tid; e < 512; e += kThreads) {
-      int k = e >> 5, n = e & 31, nn = n & 15;
-      float s, c;
-      sincospif(-static_cast<float>((k * nn) & 15) * 0.125f, &s, &c);
-      float fr = c * 0.0625f, fi = s * 0.0625f;
-      uint32_t off = (n >> 3) * 128 + (k >> 3) * 64 + (n & 7) * 8 + (k & 7);  // in halves
-      b1[off] = __float2half_rn(n < 16 ? fr : fi);
-      b2[off] = __float2half_rn(n < 16 ? -fi : fr);
-    }
-  }
-
-  // ------------------------------------------------------------------ load phase
-  {
-    const uint32_t n_items = 1u << P.load_item_bits;
-    const __half* gre = in_re + in_base;
-    const __half* gim = in_im + in_base;
-    Cplx delta = {1.f, 0.f};
-    if (T > 1 && P.load_estep) delta = twiddle(1u, P.log2_len);
-    for (uint32_t q = tid; q < n_items; q += kThreads) {
-      const uint32_t g = bit_sum(q, P.load_gofs, 0, kMaxItemBits);
-      const uint32_t so = bit_sum(q, P.load_sofs, 0, kMaxItemBits);
-      const bool live = bit_sum(q, P.load_uval, 0, kMaxItemBits) < u_limit;
-      if constexpr (T == 1) {
-        uint4 vr = make_uint4(0, 0, 0, 0), vi = vr;
-        if (live) {
-          vr = ldg128(gre + g);
-          vi = ldg128(gim + g);
-        }
-        *reinterpret_cast<uint4*>(plane_re + so) = vr;
-        *reinterpret_cast<uint4*>(plane_im + so) = vi;
-      } else {
-        const uint32_t r0 = bit_sum(q, P.load_rval, 0, kMaxItemBits);
-        uint4 vr[T], vi[T];
-#pragma unroll
-        for (int j = 0; j < T; ++j) {
-          vr[j] = vi[j] = make_uint4(0, 0, 0, 0);
-          if (live) {
-            vr[j] = ldg128(gre + g + j * P.load_gj);
-            vi[j] = ldg128(gim + g + j * P.load_gj);
-          }
-        }
-        uint32_t ore[T][4], oim[T][4];
-        Cplx w1 = twiddle(r0, P.log2_len);  // exp(-2*pi*i*r/L) of chunk element 0
-#pragma unroll
-        for (int e2 = 0; e2 < 4; ++e2) {      // two chunk elements per iteration (one packed register)
-          float yre[T][2], yim[T][2];
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            Cplx x[T];
-#pragma unroll
-            for (int j = 0; j < T; ++j) {
-              const uint32_t wr = reinterpret_cast<const uint32_t*>(&vr[j])[e2];
-              const uint32_t wi = reinterpret_cast<const uint32_t*>(&vi[j])[e2];
-              float2 fr = unpack_half2(wr), fi = unpack_half2(wi);
-              x[j] = {h ? fr.y : fr.x, h ? fi.y : fi.x};
-            }
-            small_dft<T>(x);
-            Cplx wk = {P.load_scale, 0.f};
-            const Cplx w1s = w1;
-#pragma unroll
-            for (int k0 = 0; k0 < T; ++k0) {
-              Cplx y = cmul(x[k0], wk);
-              yre[k0][h] = y.re;
-              yim[k0][h] = y.im;
-              wk = cmul(wk, w1s);
-            }
-            w1 = cmul(w1, delta);
-          }
-#pragma unroll
-          for (int k0 = 0; k0 < T; ++k0) {
-            ore[k0][e2] = pack_half2(yre[k0][0], yre[k0][1]);
-            oim[k0][e2] = pack_half2(yim[k0][0], yim[k0][1]);
-          }
-        }
-#pragma unroll
-        for (int k0 = 0; k0 < T; ++k0) {
-          const uint32_t o = so + P.load_sk0[k0];
-          *reinterpret_cast<uint4*>(plane_re + o) = make_uint4(ore[k0][0], ore[k0][1], ore[k0][2], ore[k0][3]);
-          *reinterpret_cast<uint4*>(plane_im + o) = make_uint4(oim[k0][0], oim[k0][1], oim[k0][2], oim[k0][3]);
-        }
-      }
-    }
-  }
-
-  // ------------------------------------------------------------------ radix-16 stages
-  const uint32_t lane_row = static_cast<uint32_t>((warp & 3) * 32 + lane);
-  uint32_t taddr = 0;
-  for (uint32_t t = 0; t < P.stages; ++t) {
-    fence_proxy_async_smem();   // generic-proxy operand stores -> visible to the tensor core
-    tc_fence_before_sync();
-    __syncthreads();
-    tc_fence_after_sync();
-    taddr = *tmem_slot;
-    if (tid == 0) {
-      const uint32_t idesc = make_idesc_f16(128, 32, /*a_mn=*/1, /*b_mn=*/0);
-      const uint32_t sbase = smem_u32(smem);
-      const uint64_t db1 = make_smem_desc(sbase + SL.b1_off, 128, 256);
-      const uint64_t db2 = make_smem_desc(sbase + SL.b2_off, 128, 256);
-      for (uint32_t tile = 0; tile < P.n_tiles; ++tile) {
-        const uint32_t a_off = tile * 16 * kRowChunkStride;
-        const uint64_t da_re = make_smem_desc(sbase + a_off, kKGroupStride, kRowChunkStride);
-        const uint64_t da_im = make_smem_desc(sbase + SL.plane_stride + a_off, kKGroupStride, kRowChunkStride);
-        umma_f16_ss(taddr + tile * 32, da_re, db1, idesc, 0);
-        umma_f16_ss(taddr + tile * 32, da_im, db2, idesc, 1);
-      }
-      umma_commit(bar);
-    }
-    mbar_wait(bar, t & 1);
-    tc_fence_after_sync();
-
-    const UnitPlan::Epi& E = P.epi[t];
-    const uint32_t dst_lo = bit_sum(lane_row, E.dst, 0, 7);
-    const uint32_t aux_lo = bit_sum(lane_row, E.aux, 0, 7);
-    const uint32_t col_lo = bit_sum(lane_row, E.col, 0, 7);
-    for (uint32_t tile = warp >> 2; tile < P.n_tiles; tile += kThreads / 128) {
-      uint32_t acc[32];
-      tmem_ld_32x32b_x32(taddr + (static_cast<uint32_t>((warp & 3) * 32) << 16) + tile * 32, acc);
-      const uint32_t dst = dst_lo + bit_sum(tile, E.dst + 7, 0, kMaxRowBits - 7);
-      const uint32_t aux = aux_lo + bit_sum(tile, E.aux + 7, 0, kMaxRowBits - 7);
-      Cplx tw = {1.f, 0.f}, step = {1.f, 0.f};
-      if (E.tw_mode == 1) {
-        step = twiddle(aux, E.tw_log2n);
-      } else if (E.tw_mode == 2) {
-        const uint32_t col = col_lo + bit_sum(tile, E.col + 7, 0, kMaxRowBits - 7) + (uu / P.col_div) * P.col_base_stride;
-        const uint32_t mask = (1u << E.tw_log2n) - 1u;
-        tw = twiddle((aux * col) & mask, E.tw_log2n);
-        step = twiddle((E.tw_kw * col) & mask, E.tw_log2n);
-      }
-      tmem_ld_wait();
-      uint32_t pre[8], pim[8];
-      if (E.tw_mode == 0) {
-#pragma unroll
-        for (int k = 0; k < 16; k += 2) {
-          pre[k >> 1] = pack_half2(__uint_as_float(acc[k]), __uint_as_float(acc[k + 1]));
-          pim[k >> 1] = pack_half2(__uint_as_float(acc[16 + k]), __uint_as_float(acc[17 + k]));
-        }
-      } else {
-        float vre[16], vim[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          Cplx y = cmul({__uint_as_float(acc[k]), __uint_as_float(acc[16 + k])}, tw);
-          vre[k] = y.re;
-          vim[k] = y.im;
-          tw = cmul(tw, step);
-        }
-#pragma unroll
-        for (int k = 0; k < 16; k += 2) {
-          pre[k >> 1] = pack_half2(vre[k], vre[k + 1]);
-          pim[k >> 1] = pack_half2(vim[k], vim[k + 1]);
-        }
-      }
-      *reinterpret_cast<uint4*>(plane_re + dst) = make_uint4(pre[0], pre[1], pre[2], pre[3]);
-      *reinterpret_cast<uint4*>(plane_re + dst + E.dst_khi) = make_uint4(pre[4], pre[5], pre[6], pre[7]);
-      *reinterpret_cast<uint4*>(plane_im + dst) = make_uint4(pim[0], pim[1], pim[2], pim[3]);
-      *reinterpret_cast<uint4*>(plane_im + dst + E.dst_khi) = make_uint4(pim[4], pim[5], pim[6], pim[7]);
-    }
-  }
+  for (uint32_t o = tid * 16; o < TL.total; o += kThreads * 16) sts128(table_base + o, ldg128(tables + (o >> 4)));
   tc_fence_before_sync();
   __syncthreads();
+  tc_fence_after_sync();
+  c.taddr = *tmem_slot;
+  uint32_t phase = 0;
 
-  // ------------------------------------------------------------------ store phase
-  {
-    const uint32_t n_items = 1u << P.store_item_bits;
-    __half* gre = out_re + out_base;
-    __half* gim = out_im + out_base;
-    for (uint32_t q = tid; q < n_items; q += kThreads) {
-      const uint32_t so = bit_sum(q, P.store_sofs, 0, kMaxRowBits);
-      const uint32_t g = bit_sum(q, P.store_gofs, 0, kMaxRowBits);
-      if (bit_sum(q, P.store_uval, 0, kMaxRowBits) >= u_limit) continue;
+  // per-thread constant parts of the bit-linear load / store maps (item q = tid + 256*i)
+  constexpr uint32_t kLoadItems = (1u << LOG2E) / 8 / kThreads;    // 16-byte chunks per thread and plane
+  constexpr uint32_t kStoreBlocks = (1u << LOG2E) / 64;            // 8x8 blocks per plane
+  constexpr uint32_t kStoreItems = kStoreBlocks >= kThreads ? kStoreBlocks / kThreads : 1;
+  const uint32_t ld_g_lo = bit_sum(tid, P.load_gofs, 0, 8), ld_s_lo = bit_sum(tid, P.load_sofs, 0, 8);
+  const uint32_t ld_u_lo = bit_sum(tid, P.load_uval, 0, 8);
+  const uint32_t st_s_lo = bit_sum(tid, P.store_sofs, 0, 8), st_g_lo = bit_sum(tid, P.store_gofs, 0, 8);
+  const uint32_t st_u_lo = bit_sum(tid, P.store_uval, 0, 8);
+
+  for (uint32_t unit = blockIdx.x; unit < P.n_units; unit += gridDim.x) {
+    const uint32_t ub = unit / P.units_per_batch, uu = unit % P.units_per_batch;
+    const int64_t in_base =
+        static_cast<int64_t>(ub) * P.in_batch_stride + static_cast<int64_t>(uu) * P.in_unit_stride;
+    const int64_t out_base =
+        static_cast<int64_t>(ub) * P.out_batch_stride + static_cast<int64_t>(uu) * P.out_unit_stride;
+    // row/row passes with a ragged batch: transforms past the end are loaded as zeros, never stored
+    const uint32_t u_limit =
+        P.n_transforms ? P.n_transforms - min(P.n_transforms, unit << P.log2_units) : 0xFFFFFFFFu;
+    c.col_base = (uu / P.col_div) * P.col_base_stride;
+
+    // ---------------------------------------------------------------- load phase
+    TFFT_TRACE_MARK(0);
+    {
+      const __half* gre = in_re + in_base;
+      const __half* gim = in_im + in_base;
+      if (u_limit == 0xFFFFFFFFu) {
 #pragma unroll
-      for (int plane = 0; plane < 2; ++plane) {
-        const uint8_t* sp = plane ? plane_im : plane_re;
-        __half* gp = plane ? gim : gre;
-        uint4 a[8];
+        for (uint32_t i = 0; i < kLoadItems; ++i) {
+          const uint32_t g = ld_g_lo + bit_sum(i, P.load_gofs, 8, kMaxItemBits - 8);
+          const uint32_t so = ld_s_lo + bit_sum(i, P.load_sofs, 8, kMaxItemBits - 8);
+          cp_async16(c.s_re + so, gre + g, 16u);
+          cp_async16(c.s_im + so, gim + g, 16u);
+        }
+      } else {
 #pragma unroll
-        for (int x = 0; x < 8; ++x)
-          a[x] = *reinterpret_cast<const uint4*>(sp + so + bit_sum(static_cast<uint32_t>(x), P.store_xs, 0, 3));
+        for (uint32_t i = 0; i < kLoadItems; ++i) {
+          const uint32_t g = ld_g_lo + bit_sum(i, P.load_gofs, 8, kMaxItemBits - 8);
+          const uint32_t so = ld_s_lo + bit_sum(i, P.load_sofs, 8, kMaxItemBits - 8);
+          const bool live = ld_u_lo + bit_sum(i, P.load_uval, 8, kMaxItemBits - 8) < u_limit;
+          cp_async16(c.s_re + so, gre + (live ? g : 0u), live ? 16u : 0u);
+          cp_async16(c.s_im + so, gim + (live ? g : 0u), live ? 16u : 0u);
+        }
+      }
+      TFFT_TRACE_MARK(1);
+      cp_async_wait_all();
+    }
+    TFFT_TRACE_MARK(2);
+
+    // ---------------------------------------------------------------- tensor-core stages
+    run_stage<0, RHO0, false, LOG2E>(P, c, table_base + TL.b_off[0], bar, phase, warp, lane, trace, trace_unit);
+    TFFT_TRACE_MARK(3);
+    run_stage<1, RHO1, kStages == 2, LOG2E>(P, c, table_base + TL.b_off[1], bar, phase, warp, lane, trace,
+                                            trace_unit);
+    TFFT_TRACE_MARK(4);
+    if constexpr (kStages == 3)
+      run_stage<2, (RHO2 ? RHO2 : 4), true, LOG2E>(P, c, table_base + TL.b_off[2], bar, phase, warp, lane, trace,
+                                                   trace_unit);
+    TFFT_TRACE_MARK(5);
+    __syncthreads();
+    TFFT_TRACE_MARK(6);
+
+    // ---------------------------------------------------------------- store phase
+    {
+      __half* gre = out_re + out_base;
+      __half* gim = out_im + out_base;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint32_t sel = (c & 1) ? 0x7632u : 0x5410u;
-          uint32_t w[4];
+      for (uint32_t i = 0; i < kStoreItems; ++i) {
+        const uint32_t so = st_s_lo + bit_sum(i, P.store_sofs, 8, kMaxItemBits - 8);
+        const uint32_t g = st_g_lo + bit_sum(i, P.store_gofs, 8, kMaxItemBits - 8);
+        if (kStoreBlocks < kThreads && tid >= static_cast<int>(kStoreBlocks)) continue;
+        if (st_u_lo + bit_sum(i, P.store_uval, 8, kMaxItemBits - 8) >= u_limit) continue;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const uint32_t lo = reinterpret_cast<const uint32_t*>(&a[2 * i])[c >> 1];
-            const uint32_t hi = reinterpret_cast<const uint32_t*>(&a[2 * i + 1])[c >> 1];
-            w[i] = __byte_perm(lo, hi, sel);
+        for (int plane = 0; plane < 2; ++plane) {
+          const uint32_t sp = plane ? c.s_im : c.s_re;
+          __half* gp = plane ? gim : gre;
+          uint4 a[8];
+#pragma unroll
+          for (int x = 0; x < 8; ++x) a[x] = lds128(sp + so + bit_sum(static_cast<uint32_t>(x), P.store_xs, 0, 3));
+#pragma unroll
+          for (int cc = 0; cc < 8; ++cc) {
+            const uint32_t sel = (cc & 1) ? 0x7632u : 0x5410u;
+            uint32_t w[4];
+#pragma unroll
+            for (int i2 = 0; i2 < 4; ++i2) {
+              const uint32_t lo = reinterpret_cast<const uint32_t*>(&a[2 * i2])[cc >> 1];
+              const uint32_t hi = reinterpret_cast<const uint32_t*>(&a[2 * i2 + 1])[cc >> 1];
+              w[i2] = __byte_perm(lo, hi, sel);
+            }
+            stg128(gp + g + bit_sum(static_cast<uint32_t>(cc), P.store_cg, 0, 3), make_uint4(w[0], w[1], w[2], w[3]));
           }
-          stg128(gp + g + bit_sum(static_cast<uint32_t>(c), P.store_cg, 0, 3), make_uint4(w[0], w[1], w[2], w[3]));
         }
       }
     }
+    TFFT_TRACE_MARK(7);
+    __syncthreads();   // staging fully read before the next unit's loads overwrite it
+    TFFT_TRACE_MARK(8);
+    trace_unit++;
   }
 
   // ------------------------------------------------------------------ teardown
-  if (warp == 0) tmem_dealloc(taddr, ncols);
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(c.taddr, P.tmem_cols);
 }
 
 }  // namespace tfft

@@ -5,7 +5,10 @@
 // batch x (1 + r16 + 2^r2 - 1) launches on `batch` freshly created streams,
 // ComputeFFT.h:167-284).  There is no CPU path: every exec needs an sm_100 device.
 #include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -22,8 +25,10 @@ struct Pass {
   UnitPlan plan;           // layout decisions (strides filled per exec)
   PlanBuildInfo info;
   UnitStrides strides;     // plan-time part of the addressing
-  int log2t = 0;
-  dim3 grid;
+  uint32_t n_units = 0;
+  std::vector<uint8_t> tables;            // host image
+  mutable uint4* d_tables[16] = {};       // per-device copies, uploaded at first use
+  mutable int resident_ctas[16] = {};     // persistent grid size per device
   uint32_t smem = 0;
   int src = 0, dst = 0;    // 0 = user input planes, 1 = user output planes, 2 = plan workspace
   bool in_stride_is_user = false, out_stride_is_user = false;
@@ -36,21 +41,84 @@ int ilog2_exact(int64_t n) {
   return l;
 }
 
-typedef void (*KernelFn)(const UnitPlan, const __half*, const __half*, __half*, __half*);
-KernelFn kernel_for(int log2t) {
-  switch (log2t) {
-    case 0: return fft_unit_kernel<0>;
-    case 1: return fft_unit_kernel<1>;
-    case 2: return fft_unit_kernel<2>;
-    default: return fft_unit_kernel<3>;
+// Host image of the per-plan constant tables the kernel stages into shared memory
+// (layout: fft_unit_kernel.cuh "Device tables"): two-level twiddle table for unit angle 2*pi/L and
+// the fp16 DFT matrices [Fr|Fi]/R, [-Fi|Fr]/R of every radix the plan uses.
+std::vector<uint8_t> make_tables(const UnitPlan& plan) {
+  const TableLayout TL = table_layout(plan);
+  std::vector<uint8_t> host(TL.total, 0);
+  const double pi = 3.14159265358979323846264338327950288;
+  const int64_t L = int64_t(1) << plan.log2_len;
+  auto unit = [&](int64_t e, int64_t n, double* c, double* s) {   // exp(-2*pi*i*e/n), exact on the axes
+    e %= n;
+    if (e == 0) { *c = 1; *s = 0; return; }
+    if (4 * e == n) { *c = 0; *s = -1; return; }
+    if (2 * e == n) { *c = -1; *s = 0; return; }
+    if (4 * e == 3 * n) { *c = 0; *s = 1; return; }
+    const double a = -2.0 * pi * static_cast<double>(e) / static_cast<double>(n);
+    *c = std::cos(a); *s = std::sin(a);
+  };
+  float2* tw = reinterpret_cast<float2*>(host.data());
+  for (int j = 0; j < 64; ++j) {
+    double c, s;
+    unit(j, L, &c, &s);
+    tw[j] = make_float2(static_cast<float>(c), static_cast<float>(s));
   }
+  for (int64_t j = 0; j < 512; ++j) {
+    double c, s;
+    unit((64 * j) % L, L, &c, &s);
+    tw[64 + j] = make_float2(static_cast<float>(c), static_cast<float>(s));
+  }
+  for (uint32_t t = 0; t < plan.stages; ++t) {
+    const int rho = static_cast<int>(plan.log2_radix[t]), R = 1 << rho;
+    __half* b1 = reinterpret_cast<__half*>(host.data() + TL.b_off[t]);
+    __half* b2 = b1 + 2 * R * R;
+    for (int kap = 0; kap < R; ++kap)
+      for (int n = 0; n < 2 * R; ++n) {
+        double c, s;
+        unit(static_cast<int64_t>(kap) * (n % R), R, &c, &s);
+        const float fr = static_cast<float>(c / R), fi = static_cast<float>(s / R);
+        const uint32_t off = (n >> 3) * (8 * R) + (kap >> 3) * 64 + (n & 7) * 8 + (kap & 7);   // in halves
+        b1[off] = __float2half_rn(n < R ? fr : fi);
+        b2[off] = __float2half_rn(n < R ? -fi : fr);
+      }
+  }
+  return host;
+}
+
+long long* g_trace = nullptr;   // developer phase trace buffer (tfft_debug_set_trace)
+std::mutex g_upload_mutex;
+// Kernel instantiations: one per (unit size, radix schedule) the planner can produce.
+typedef void (*KernelFn)(const UnitPlan, const __half*, const __half*, __half*, __half*, const uint4*, long long*);
+struct KernelEntry {
+  int log2e, r0, r1, r2;
+  KernelFn fn;
+};
+#define TFFT_K(E, A, B, C) {E, A, B, C, fft_unit_kernel<E, A, B, C>}
+const KernelEntry g_kernels[] = {
+    TFFT_K(13, 4, 4, 0), TFFT_K(14, 4, 4, 0),                       // L = 2^8
+    TFFT_K(13, 4, 5, 0), TFFT_K(14, 4, 5, 0),                       // 2^9
+    TFFT_K(13, 5, 5, 0), TFFT_K(14, 5, 5, 0),                       // 2^10
+    TFFT_K(13, 5, 6, 0), TFFT_K(14, 5, 6, 0),                       // 2^11
+    TFFT_K(13, 6, 6, 0), TFFT_K(14, 6, 6, 0), TFFT_K(15, 6, 6, 0),  // 2^12
+    TFFT_K(13, 4, 4, 5), TFFT_K(14, 4, 4, 5),                       // 2^13
+    TFFT_K(14, 4, 5, 5),                                            // 2^14
+    TFFT_K(15, 5, 5, 5),                                            // 2^15
+};
+#undef TFFT_K
+KernelFn kernel_for(const UnitPlan& p) {
+  for (const KernelEntry& k : g_kernels)
+    if (k.log2e == static_cast<int>(p.log2_elems) && k.r0 == static_cast<int>(p.log2_radix[0]) &&
+        k.r1 == static_cast<int>(p.log2_radix[1]) && k.r2 == static_cast<int>(p.stages == 3 ? p.log2_radix[2] : 0))
+      return k.fn;
+  return nullptr;
 }
 
 std::once_flag g_attr_once;
 int g_attr_err = 0;
 void set_kernel_attrs() {
-  for (int t = 0; t < 4; ++t) {
-    cudaError_t e = cudaFuncSetAttribute(kernel_for(t), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  for (const KernelEntry& k : g_kernels) {
+    cudaError_t e = cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) g_attr_err = static_cast<int>(e);
   }
 }
@@ -70,16 +138,22 @@ struct tfft_plan_s {
 
 namespace {
 
-// transforms per unit for a row/row pass: fill ~16K elements, at least 2K, never more than the batch needs
-int pick_log2_units(int lg, int64_t batch, int target_log2_elems) {
-  int ups = target_log2_elems - lg;
-  if (ups < 0) ups = 0;
-  while (ups > 0 && lg + ups > 11 && (int64_t(1) << (ups - 1)) >= batch) --ups;  // do not over-pad small batches
-  if (lg + ups < 11) ups = 11 - lg;
+// log2 of the unit size (elements resident per CTA) for transforms of length 2^lg: 16K elements
+// (256 tensor-memory columns, two CTAs per SM) unless the length or its tables need otherwise.
+int unit_log2_elems(int lg) {
+  if (lg == 15) return 15;
+  if (lg == 11) return 13;   // radix 32 + 64 matrices (40 KiB): keep two CTAs per SM
+  return 14;
+}
+// transforms per unit for a row/row pass, never padding a small batch beyond the 8K-element minimum
+int pick_log2_units(int lg, int64_t batch) {
+  int ups = unit_log2_elems(lg) - lg;
+  while (ups > 0 && lg + ups > 13 && (int64_t(1) << (ups - 1)) >= batch) --ups;
+  if (lg + ups < 13) ups = 13 - lg;
   return ups;
 }
 
-bool add_pass(tfft_plan_s* p, const UnitShape& shape, const UnitStrides& st, dim3 grid, int src, int dst,
+bool add_pass(tfft_plan_s* p, const UnitShape& shape, const UnitStrides& st, uint32_t n_units, int src, int dst,
               bool in_user, bool out_user) {
   Pass ps;
   if (!build_unit_plan(shape, &ps.plan, &ps.info)) {
@@ -87,9 +161,10 @@ bool add_pass(tfft_plan_s* p, const UnitShape& shape, const UnitStrides& st, dim
     return false;
   }
   ps.strides = st;
-  ps.log2t = shape.log2_len % 4;
-  ps.grid = grid;
+  ps.strides.n_units = n_units;
+  ps.n_units = n_units;
   ps.smem = smem_layout(ps.plan).total;
+  ps.tables = make_tables(ps.plan);
   ps.src = src;
   ps.dst = dst;
   ps.in_stride_is_user = in_user;
@@ -104,13 +179,13 @@ int build_1d(tfft_plan_s* p) {
   if (lg <= 15) {
     UnitShape sh;
     sh.log2_len = lg;
-    sh.log2_units = pick_log2_units(lg, batch, lg == 15 ? 15 : 14);
+    sh.log2_units = pick_log2_units(lg, batch);
     UnitStrides st;
     st.n_transforms = static_cast<uint32_t>(batch);
     st.units_per_batch = 0x7FFFFFFFu;   // unit base = unit * unit_stride
     const int64_t U = int64_t(1) << sh.log2_units;
-    dim3 grid(static_cast<unsigned>((batch + U - 1) / U), 1, 1);
-    return add_pass(p, sh, st, grid, 0, 1, true, true) ? TFFT_OK : TFFT_E_UNSUPPORTED;
+    return add_pass(p, sh, st, static_cast<uint32_t>((batch + U - 1) / U), 0, 1, true, true) ? TFFT_OK
+                                                                                             : TFFT_E_UNSUPPORTED;
   }
   // four-step: n = N1 * N2, element n1*N2 + n2.  Pass 1: N2 strided length-N1 transforms (column
   // mode, in place on the source), times exp(-2*pi*i*k1*n2/n).  Pass 2: N1 contiguous length-N2
@@ -122,7 +197,7 @@ int build_1d(tfft_plan_s* p) {
   {
     UnitShape sh;
     sh.log2_len = lg1;
-    sh.log2_units = (lg1 >= 12 ? 15 : 14) - lg1;
+    sh.log2_units = std::max(3, unit_log2_elems(lg1) - lg1);
     sh.in_mode = kColMode;
     sh.out_mode = kColMode;
     const int64_t U = int64_t(1) << sh.log2_units;
@@ -132,14 +207,14 @@ int build_1d(tfft_plan_s* p) {
     st.units_per_batch = static_cast<uint32_t>(N2 / U);
     st.col_base_stride = static_cast<uint32_t>(U);
     st.pass1_log2n = lg;
-    dim3 grid(static_cast<unsigned>(batch * (N2 / U)), 1, 1);
     // batch stride: user's input stride (source) ; destination = source (in place) or workspace
-    if (!add_pass(p, sh, st, grid, 0, preserve ? 2 : 0, true, !preserve)) return TFFT_E_UNSUPPORTED;
+    if (!add_pass(p, sh, st, static_cast<uint32_t>(batch * (N2 / U)), 0, preserve ? 2 : 0, true, !preserve))
+      return TFFT_E_UNSUPPORTED;
   }
   {
     UnitShape sh;
     sh.log2_len = lg2;
-    sh.log2_units = (lg2 >= 12 ? 15 : 14) - lg2;
+    sh.log2_units = std::max(3, unit_log2_elems(lg2) - lg2);
     sh.in_mode = kRowMode;
     sh.out_mode = kColMode;
     const int64_t U = int64_t(1) << sh.log2_units;
@@ -147,8 +222,8 @@ int build_1d(tfft_plan_s* p) {
     st.in_tstride = N2; st.in_unit_stride = U * N2;
     st.out_nstride = N1; st.out_unit_stride = U;
     st.units_per_batch = static_cast<uint32_t>(N1 / U);
-    dim3 grid(static_cast<unsigned>(batch * (N1 / U)), 1, 1);
-    if (!add_pass(p, sh, st, grid, preserve ? 2 : 0, 1, !preserve, true)) return TFFT_E_UNSUPPORTED;
+    if (!add_pass(p, sh, st, static_cast<uint32_t>(batch * (N1 / U)), preserve ? 2 : 0, 1, !preserve, true))
+      return TFFT_E_UNSUPPORTED;
   }
   if (preserve) {
     p->workspace_bytes = 2 * n * batch * static_cast<int64_t>(sizeof(__half));
@@ -173,9 +248,42 @@ int launch_pass(const tfft_plan_s* p, const Pass& ps, const __half* src_re, cons
   }
   UnitPlan plan = ps.plan;
   fill_strides(st, ps.info, &plan);
-  KernelFn fn = kernel_for(ps.log2t);
-  void* args[] = {&plan, &src_re, &src_im, &dst_re, &dst_im};
-  cudaError_t e = cudaLaunchKernel(reinterpret_cast<const void*>(fn), ps.grid, dim3(kThreads), args, ps.smem, stream);
+  KernelFn fn = kernel_for(plan);
+  if (!fn) return TFFT_E_UNSUPPORTED;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  if (dev < 0 || dev >= 16) return TFFT_E_UNSUPPORTED;
+  {
+    std::lock_guard<std::mutex> lock(g_upload_mutex);
+    if (!ps.d_tables[dev]) {
+      uint4* d = nullptr;
+      e = cudaMalloc(&d, ps.tables.size());
+      if (e != cudaSuccess) { cudaGetLastError(); return e == cudaErrorMemoryAllocation ? TFFT_E_NOMEM : static_cast<int>(e); }
+      e = cudaMemcpy(d, ps.tables.data(), ps.tables.size(), cudaMemcpyHostToDevice);
+      if (e != cudaSuccess) { cudaFree(d); return static_cast<int>(e); }
+      int per_sm = 0, sms = 0, smem_sm = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, ps.smem);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+      if (getenv("TFFT_DEBUG")) fprintf(stderr, "tfft: occupancy api=%d smem/sm=%d\n", per_sm, smem_sm);
+      const int by_smem = smem_sm / static_cast<int>(ps.smem + 1024);
+      if (per_sm < by_smem) per_sm = std::min(by_smem, 2);   // the API can under-report before the carve-out is set
+      const int tmem_limit = 512 / static_cast<int>(plan.tmem_cols);   // tensor memory: 512 columns per SM
+      if (per_sm > tmem_limit) per_sm = tmem_limit;
+      if (per_sm < 1 || sms < 1) { cudaFree(d); return TFFT_E_UNSUPPORTED; }
+      ps.resident_ctas[dev] = per_sm * sms;
+      ps.d_tables[dev] = d;
+    }
+  }
+  const uint4* tables = ps.d_tables[dev];
+  const unsigned grid = std::min<unsigned>(ps.n_units, static_cast<unsigned>(ps.resident_ctas[dev]));
+  long long* trace = g_trace;
+  void* args[] = {&plan, &src_re, &src_im, &dst_re, &dst_im, &tables, &trace};
+  if (getenv("TFFT_DEBUG"))
+    fprintf(stderr, "tfft: launch grid=%u units=%u smem=%u tmem=%u resident=%d\n", grid, ps.n_units, ps.smem,
+            plan.tmem_cols, ps.resident_ctas[dev]);
+  e = cudaLaunchKernel(reinterpret_cast<const void*>(fn), dim3(grid), dim3(kThreads), args, ps.smem, stream);
   (void)p;
   return e == cudaSuccess ? TFFT_OK : static_cast<int>(e);
 }
@@ -187,6 +295,9 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 extern "C" {
 
 int tfft_version(void) { return 100; }
+
+// developer hook (not in tfft.h): device buffer of gridDim*4*16 int64 for -DTFFT_TRACE builds
+void tfft_debug_set_trace(long long* buf) { g_trace = buf; }
 
 const char* tfft_error_string(int code) {
   switch (code) {
@@ -231,7 +342,7 @@ int tfft_plan_info(tfft_plan_t p, tfft_plan_info_t* info) {
   info->batch = p->batch;
   const Pass& first = p->passes.front();
   info->r16_stages = static_cast<int32_t>(first.plan.stages);
-  info->tail_radix = 1 << first.plan.log2_tail;
+  info->tail_radix = 1 << (first.plan.log2_radix[first.plan.stages - 1] - 4);
   info->passes = static_cast<int32_t>(p->passes.size());
   info->results_in_results = 1;
   info->amount_of_r16_steps = p->lg / 4 - 1;
@@ -239,10 +350,10 @@ int tfft_plan_info(tfft_plan_t p, tfft_plan_info_t* info) {
   info->transforms_per_cta = 1 << first.plan.log2_units;
   for (const Pass& ps : p->passes) {
     if (static_cast<int32_t>(ps.smem) > info->smem_bytes) info->smem_bytes = static_cast<int32_t>(ps.smem);
-    const int32_t tc = static_cast<int32_t>(tmem_cols(ps.plan));
+    const int32_t tc = static_cast<int32_t>(ps.plan.tmem_cols);
     if (tc > info->tmem_columns) info->tmem_columns = tc;
   }
-  info->grid = first.grid.x;
+  info->grid = first.n_units;
   info->workspace_bytes = p->workspace_bytes;
   info->algorithmic_bytes = 8 * p->n * p->batch * static_cast<int64_t>(p->passes.size());
   return TFFT_OK;
@@ -252,6 +363,9 @@ int tfft_plan_destroy(tfft_plan_t p) {
   if (!p) return TFFT_E_INVALID_ARG;
   if (p->workspace) cudaFree(p->workspace);
   if (p->host_path_buf) cudaFree(p->host_path_buf);
+  for (Pass& ps : p->passes)
+    for (int d = 0; d < 16; ++d)
+      if (ps.d_tables[d]) cudaFree(ps.d_tables[d]);
   delete p;
   return TFFT_OK;
 }

@@ -22,7 +22,7 @@ from dataclasses import dataclass
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libtfft.so")
+_LIB_PATH = os.environ.get("TFFT_LIB", os.path.join(_HERE, "libtfft.so"))   # TFFT_LIB: developer override
 _lib = None
 
 MODE_256 = 0      # BaseFFTMode::Mode_256   (Plan.h:14)

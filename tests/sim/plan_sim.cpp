@@ -48,19 +48,20 @@ int plansim_run(int log2_len, int log2_units, int in_mode, int out_mode, const i
   st.in_tstride = strides9[0]; st.in_nstride = strides9[1]; st.out_tstride = strides9[2]; st.out_nstride = strides9[3];
   st.in_batch_stride = strides9[4]; st.in_unit_stride = strides9[5]; st.out_batch_stride = strides9[6];
   st.out_unit_stride = strides9[7]; st.units_per_batch = (uint32_t)strides9[8]; st.col_base_stride = 1u << log2_units;
+  st.n_units = (uint32_t)n_units;
   st.pass1_log2n = pass1_log2n;
   fill_strides(st, info, &P);
   const bool h = emulate_fp16 != 0;
-  const int T = 1 << P.log2_tail, s = P.stages, rowbits = P.log2_elems - 4;
+  const int s = P.stages;
   const int64_t L = int64_t(1) << P.log2_len;
   conflicts[0] = conflicts[1] = conflicts[2] = conflicts[3] = 0;
-  const uint32_t smem_halves = std::max(P.plane_bytes, P.stage_plane_bytes) / 2;
+  const uint32_t smem_halves = P.plane_bytes / 2;
   for (int unit = 0; unit < n_units; ++unit) {
     const int64_t ibase = (unit / P.units_per_batch) * P.in_batch_stride + (unit % P.units_per_batch) * P.in_unit_stride;
     const int64_t obase = (unit / P.units_per_batch) * P.out_batch_stride + (unit % P.units_per_batch) * P.out_unit_stride;
-    const uint32_t col_base = (unit % P.units_per_batch) * P.col_base_stride;
+    const uint32_t col_base = ((unit % P.units_per_batch) / P.col_div) * P.col_base_stride;
     std::vector<double> sre(smem_halves, NAN), sim(smem_halves, NAN);
-    // ---------------- load
+    // ---------------- load (pure copy of 16-byte chunks)
     const uint32_t n_items = 1u << P.load_item_bits;
     for (uint32_t q0 = 0; q0 < n_items; q0 += 8) {
       uint32_t addr[8];
@@ -68,22 +69,12 @@ int plansim_run(int log2_len, int log2_units, int in_mode, int out_mode, const i
         uint32_t q = q0 + dq;
         uint32_t g = bitsum(q, P.load_gofs, P.load_item_bits);
         uint32_t so = bitsum(q, P.load_sofs, P.load_item_bits);
-        uint32_t r = bitsum(q, P.load_rval, P.load_item_bits);
         addr[dq] = so;
+        if (so + 16 > P.plane_bytes) { fprintf(stderr, "load dst out of range\n"); return -2; }
         for (int e = 0; e < 8; ++e) {
-          cd x[8];
-          for (int j = 0; j < T; ++j) {
-            int64_t a = ibase + g + (int64_t)j * P.load_gj + e;
-            x[j] = cd(rh(in_re[a], h), rh(in_im[a], h));
-          }
-          uint32_t re_ = r + e * P.load_estep;
-          for (int k0 = 0; k0 < T; ++k0) {
-            cd acc = 0;
-            for (int j = 0; j < T; ++j) acc += x[j] * twd((int64_t)j * k0, T);
-            acc *= twd((int64_t)k0 * re_, L) * (double)P.load_scale;
-            uint32_t o = (so + P.load_sk0[k0]) / 2 + e;
-            sre[o] = rh(acc.real(), h); sim[o] = rh(acc.imag(), h);
-          }
+          if (!std::isnan(sre[so / 2 + e])) { fprintf(stderr, "load: destination written twice\n"); return -3; }
+          sre[so / 2 + e] = rh(in_re[ibase + g + e], h);
+          sim[so / 2 + e] = rh(in_im[ibase + g + e], h);
         }
       }
       conflicts[0] += qw_conflict(addr);
@@ -91,39 +82,43 @@ int plansim_run(int log2_len, int log2_units, int in_mode, int out_mode, const i
     // ---------------- MMA stages
     for (int t = 1; t <= s; ++t) {
       const UnitPlan::Epi& E = P.epi[t - 1];
-      const uint32_t dst_bytes = t < s ? P.plane_bytes : P.stage_plane_bytes;
+      const int rho = P.log2_radix[t - 1], R = 1 << rho;
+      const int rowbits = P.log2_elems - rho;
+      const uint32_t S = P.chunk_stride[t - 1];
       std::vector<double> nre(smem_halves, NAN), nim(smem_halves, NAN);
       const uint32_t rows = 1u << rowbits;
+      if (rows != P.n_tiles[t - 1] * 128) { fprintf(stderr, "tile count mismatch\n"); return -5; }
       for (uint32_t row0 = 0; row0 < rows; row0 += 8) {
         uint32_t addr[8];
         for (uint32_t dr = 0; dr < 8; ++dr) {
           uint32_t row = row0 + dr;
-          // A operand read exactly as the UMMA descriptor addresses it
-          cd a[16];
-          for (int kap = 0; kap < 16; ++kap) {
-            uint32_t off = (row >> 3) * kRowChunkStride + (kap >> 3) * kKGroupStride + (kap & 7) * 16 + (row & 7) * 2;
+          // A operand read exactly as the UMMA descriptors address it
+          std::vector<cd> a(R), y(R);
+          for (int kap = 0; kap < R; ++kap) {
+            uint32_t off = (row >> 3) * S + (kap >> 3) * kKGroupStride + (kap & 7) * 16 + (row & 7) * 2;
             a[kap] = cd(sre[off / 2], sim[off / 2]);
+            if (std::isnan(sre[off / 2])) { fprintf(stderr, "stage %d reads an unwritten operand slot\n", t); return -6; }
           }
-          cd y[16];
-          for (int k = 0; k < 16; ++k) {
+          for (int k = 0; k < R; ++k) {
             cd acc = 0;
-            for (int kap = 0; kap < 16; ++kap) {
-              cd f = twd(kap * k, 16);
+            for (int kap = 0; kap < R; ++kap) {
+              cd f = twd((int64_t)kap * k, R) / (double)R;
               if (h) f = cd(rh(f.real(), true), rh(f.imag(), true));
               acc += a[kap] * f;
             }
-            y[k] = acc / 16.0;
+            y[k] = acc;
           }
           uint32_t dst = bitsum(row, E.dst, rowbits);
           uint32_t aux = bitsum(row, E.aux, rowbits);
           uint32_t col = bitsum(row, E.col, rowbits);
           addr[dr] = dst;
-          if (dst + 16 > dst_bytes || dst + E.dst_khi + 16 > dst_bytes) { fprintf(stderr, "dst out of range\n"); return -2; }
-          for (int k = 0; k < 16; ++k) {
+          for (int k = 0; k < R; ++k) {
             cd v = y[k];
-            if (E.tw_mode == 1) v *= twd((int64_t)aux * k, int64_t(1) << E.tw_log2n);
+            if (E.tw_mode == 1) v *= twd(((int64_t)aux << E.tw_shift) * k, L);
             if (E.tw_mode == 2) v *= twd(((int64_t)aux + (int64_t)k * E.tw_kw) * (int64_t)(col_base + col), int64_t(1) << E.tw_log2n);
-            uint32_t o = (dst + (k >= 8 ? E.dst_khi : 0)) / 2 + (k & 7);
+            uint32_t o = dst + bitsum((uint32_t)(k >> 3), E.dst_k, 3);
+            if (o + 16 > P.plane_bytes) { fprintf(stderr, "dst out of range\n"); return -2; }
+            o = o / 2 + (k & 7);
             if (!std::isnan(nre[o])) { fprintf(stderr, "stage %d: destination written twice\n", t); return -3; }
             nre[o] = rh(v.real(), h); nim[o] = rh(v.imag(), h);
           }

@@ -38,7 +38,8 @@ def test_plan_info_matches_reference_plan_table():
 
 def test_config2_plan_shape():
     p = tfft.NativePlan(16384, 4096)
-    assert p.info["tail_radix"] == 4 and p.info["r16_stages"] == 3 and p.info["grid"] == 4096
+    # 16384 = 16 * 32 * 32: three tensor-core stages, the non-power-of-16 factor 4 is folded into them
+    assert p.info["tail_radix"] == 2 and p.info["r16_stages"] == 3 and p.info["grid"] == 4096
     assert p.info["algorithmic_bytes"] == 536870912
 
 

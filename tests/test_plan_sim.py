@@ -38,7 +38,7 @@ def _rows(sim, lg, ups, n_units=2, h=0, tstride=None):
     return rc, list(conf)[:3], np.linalg.norm(got - want) / np.linalg.norm(want)
 
 
-SHAPES = [(lg, ups) for lg in range(8, 16) for ups in range(0, 8) if 11 <= lg + ups <= 15]
+SHAPES = [(lg, ups) for lg in range(8, 16) for ups in range(0, 8) if 13 <= lg + ups <= 15]
 
 
 @pytest.mark.parametrize("lg,ups", SHAPES)
@@ -53,13 +53,13 @@ def test_reference_batch_layout_stride(sim):
     assert rc == 0 and err < 1e-13
 
 
-@pytest.mark.parametrize("lg,ups,ref_level", [(8, 4, 5.1e-4), (12, 2, 6.6e-4), (14, 0, 8.0e-4)])
+@pytest.mark.parametrize("lg,ups,ref_level", [(8, 5, 5.1e-4), (12, 2, 6.6e-4), (14, 0, 8.0e-4)])
 def test_predicted_fp16_error_below_reference(sim, lg, ups, ref_level):
     rc, _, err = _rows(sim, lg, ups, h=1)
     assert rc == 0 and err < ref_level
 
 
-@pytest.mark.parametrize("lg1,lg2,u1,u2", [(8, 8, 3, 3), (8, 8, 6, 6), (10, 10, 4, 4), (11, 11, 3, 3),
+@pytest.mark.parametrize("lg1,lg2,u1,u2", [(8, 8, 5, 5), (8, 8, 6, 6), (10, 10, 4, 4), (11, 11, 3, 3),
                                            (12, 12, 3, 3), (9, 8, 5, 6), (12, 9, 3, 5)])
 def test_four_step_passes(sim, lg1, lg2, u1, u2):
     """N = N1*N2: column pass (+ exp(-2 pi i k1 n2/N)) then row pass with transposed store."""
