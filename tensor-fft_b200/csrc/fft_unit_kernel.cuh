@@ -56,7 +56,12 @@ __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
 }
-__device__ __forceinline__ f32x2 neg2(f32x2 a) { return a ^ 0x8000000080000000ull; }
+// negation through the scalar halves: ptxas folds it into the operand modifier of FFMA2 / FMUL2
+__device__ __forceinline__ f32x2 neg2(f32x2 a) {
+  float lo, hi;
+  upk(a, lo, hi);
+  return pk(-lo, -hi);
+}
 __device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { return add2(a, neg2(b)); }
 __device__ __forceinline__ uint32_t pack_half2_pair(f32x2 v) {
   float lo, hi;
@@ -184,7 +189,7 @@ __device__ __forceinline__ Cplx tw_lookup(const float2* tw_table, uint32_t x) {
 #define TFFT_TRACE_MARK(slot)                                                                  \
   do {                                                                                          \
     if (threadIdx.x == 0 && trace != nullptr && trace_unit < 4)                                 \
-      trace[(static_cast<size_t>(blockIdx.x) * 4 + trace_unit) * 16 + (slot)] = clock64();      \
+      trace[(static_cast<size_t>(blockIdx.x) * 4 + trace_unit) * 32 + (slot)] = clock64();      \
   } while (0)
 #else
 #define TFFT_TRACE_MARK(slot) do {} while (0)
@@ -264,21 +269,19 @@ __device__ __forceinline__ void epilogue_item(const UnitPlan& P, const KernelCtx
       t1 = cmul(t0, w1);
       s2 = cmul(w1, w1);
     }
-    // twiddles of columns (k, k+1) as packed pairs; nim = -im carried to avoid sign flips
-    f32x2 tre = pk(t0.re, t1.re), tim = pk(t0.im, t1.im), tnim = pk(-t0.im, -t1.im);
-    const f32x2 sre = pk(s2.re, s2.re), sim = pk(s2.im, s2.im), snim = pk(-s2.im, -s2.im);
+    // twiddles of columns (k, k+1) as packed pairs, advanced by step^2 = (sre, sim) per pair
+    f32x2 tre = pk(t0.re, t1.re), tim = pk(t0.im, t1.im);
+    const f32x2 sre = pk(s2.re, s2.re), sim = pk(s2.im, s2.im);
 #pragma unroll
     for (int k = 0; k < 16; k += 2) {
       const f32x2 xr = pk(__uint_as_float(are[k]), __uint_as_float(are[k + 1]));
       const f32x2 xi = pk(__uint_as_float(aim[k]), __uint_as_float(aim[k + 1]));
-      pre[k >> 1] = pack_half2_pair(fma2(xi, tnim, mul2(xr, tre)));
+      pre[k >> 1] = pack_half2_pair(fma2(neg2(xi), tim, mul2(xr, tre)));
       pim[k >> 1] = pack_half2_pair(fma2(xi, tre, mul2(xr, tim)));
       if (k < 14) {
-        const f32x2 nre = fma2(tnim, sim, mul2(tre, sre));
-        const f32x2 nim = fma2(tim, sre, mul2(tre, sim));
-        tnim = fma2(tnim, sre, mul2(tre, snim));
+        const f32x2 nre = fma2(neg2(tim), sim, mul2(tre, sre));
+        tim = fma2(tim, sre, mul2(tre, sim));
         tre = nre;
-        tim = nim;
       }
     }
   }
@@ -294,13 +297,16 @@ __device__ __forceinline__ void epilogue_item(const UnitPlan& P, const KernelCtx
 template <int ST, int RHO, bool LAST, int LOG2E, uint32_t II = 0>
 __device__ __forceinline__ void epilogue_items(const UnitPlan& P, const KernelCtx& c, uint32_t dst_thr,
                                                uint32_t aux_thr, uint32_t col_thr, uint32_t (&cre)[16],
-                                               uint32_t (&cim)[16], uint32_t (&nre)[16], uint32_t (&nim)[16]) {
+                                               uint32_t (&cim)[16], uint32_t (&nre)[16], uint32_t (&nim)[16],
+                                               long long* trace, uint32_t trace_unit) {
   constexpr uint32_t kItemsPerGroup = (1u << LOG2E) / 2048 / 2;   // E/2048 work items per stage, two warp groups
   if constexpr (II < kItemsPerGroup) {
     ptx::tmem_ld_wait();                                            // item II has landed in (cre, cim)
+    if (ST == 0 && II < 4) TFFT_TRACE_MARK(16 + 2 * II);
     if constexpr (II + 1 < kItemsPerGroup) epilogue_load<RHO, II + 1>(c, nre, nim);
     epilogue_item<ST, RHO, LAST, II>(P, c, dst_thr, aux_thr, col_thr, cre, cim);
-    epilogue_items<ST, RHO, LAST, LOG2E, II + 1>(P, c, dst_thr, aux_thr, col_thr, nre, nim, cre, cim);
+    if (ST == 0 && II < 4) TFFT_TRACE_MARK(17 + 2 * II);
+    epilogue_items<ST, RHO, LAST, LOG2E, II + 1>(P, c, dst_thr, aux_thr, col_thr, nre, nim, cre, cim, trace, trace_unit);
   }
 }
 
@@ -361,7 +367,7 @@ __device__ __forceinline__ void run_stage(const UnitPlan& P, const KernelCtx& c,
   }
   uint32_t ra[16], rb[16], rc[16], rd[16];
   epilogue_load<RHO, 0>(c, ra, rb);
-  epilogue_items<ST, RHO, LAST, LOG2E>(P, c, dst_thr, aux_thr, col_thr, ra, rb, rc, rd);
+  epilogue_items<ST, RHO, LAST, LOG2E>(P, c, dst_thr, aux_thr, col_thr, ra, rb, rc, rd, trace, trace_unit);
 }
 
 template <int LOG2E, int RHO0, int RHO1, int RHO2>
