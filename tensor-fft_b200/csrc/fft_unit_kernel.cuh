@@ -17,6 +17,7 @@
 // into each fp16 DFT matrix (exact powers of two), total 1/L like the reference's "sequential
 // scaling" (TensorFFT256.cu:167-171, TensorRadix16.cu:133-136, Radix2.cu:64-76).
 #pragma once
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -158,16 +159,25 @@ __host__ __device__ inline TableLayout table_layout(const UnitPlan& p) {
 
 // Dynamic shared memory carve-up (bytes): [plane_re | plane_im | tables | mbar | tmem slot]
 struct SmemLayout {
-  uint32_t plane_stride, table_off, bar_off, slot_off, total;
+  uint32_t plane_stride, table_off, bar_off, load_bar_off, slot_off, total;
 };
 __host__ __device__ inline SmemLayout smem_layout(const UnitPlan& p) {
   SmemLayout l;
-  l.plane_stride = p.plane_bytes;
+  l.plane_stride = (p.plane_bytes + 1023u) & ~1023u;   // SWIZZLE_128B atoms need 1024-byte alignment
   l.table_off = 2 * l.plane_stride;
   l.bar_off = l.table_off + table_layout(p).total;
-  l.slot_off = l.bar_off + 8;
+  l.load_bar_off = l.bar_off + 8;
+  l.slot_off = l.load_bar_off + 8;
   l.total = l.slot_off + 8;
   return l;
+}
+
+// 4-D TMA tile load {64 rows, R kappa, M/64, U transforms} -> SWIZZLE_128B stage-1 operand plane
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t c3, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %2, %2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(0), "r"(c3), "r"(ptx::smem_u32(bar))
+      : "memory");
 }
 
 __device__ __forceinline__ void cp_async16(uint32_t saddr, const void* gptr, uint32_t src_bytes) {
@@ -199,7 +209,14 @@ struct KernelCtx {
   uint32_t sbase, s_re, s_im, taddr, lane_row, wgroup, lane_base;
   const float2* tw_table;
   uint32_t col_base;
+  uint32_t a_re, a_im;     // stage-1 operand planes (== s_re / s_im unless a separate landing buffer is used)
+  uint32_t bar_id;         // 0: the 256 threads are the whole CTA (__syncthreads); else named barrier of a slot
+  uint64_t* landing_free;  // two-slot kernel: arrives when the stage-1 MMAs have consumed the landing buffer
 };
+__device__ __forceinline__ void group_sync(const KernelCtx& c) {
+  if (c.bar_id == 0) __syncthreads();
+  else asm volatile("bar.sync %0, %1;" ::"r"(c.bar_id), "r"(kThreads) : "memory");
+}
 
 // sum of the contributions of the set bits of a COMPILE-TIME index: folds into constant-bank adds
 template <uint32_t Q, int COUNT>
@@ -311,7 +328,7 @@ __device__ __forceinline__ void epilogue_items(const UnitPlan& P, const KernelCt
 }
 
 // One tensor-core stage: all UMMAs (one thread), wait, then the epilogue on all 8 warps.
-template <int ST, int RHO, bool LAST, int LOG2E>
+template <int ST, int RHO, bool LAST, int LOG2E, bool SW128 = false>
 __device__ __forceinline__ void run_stage(const UnitPlan& P, const KernelCtx& c, uint32_t b1_saddr, uint64_t* bar,
                                           uint32_t& phase, int warp, int lane, long long* trace,
                                           uint32_t trace_unit) {
@@ -321,15 +338,21 @@ __device__ __forceinline__ void run_stage(const UnitPlan& P, const KernelCtx& c,
   constexpr uint32_t kTiles = (1u << LOG2E) / R / 128;
   fence_proxy_async_smem();   // generic-proxy / cp.async operand writes -> visible to the tensor core
   tc_fence_before_sync();
-  __syncthreads();
+  group_sync(c);
   tc_fence_after_sync();
   TFFT_TRACE_MARK(9 + 2 * ST);
   if (warp == 0) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_f16(128, 2 * R, /*a_mn=*/1, /*b_mn=*/0);
       // descriptors differ only in the 14-bit start-address field (units of 16 bytes): add offsets there
-      const uint64_t da_re = make_smem_desc(c.s_re, kKGroupStride, S);
-      const uint64_t da_im = make_smem_desc(c.s_im, kKGroupStride, S);
+      // A operand: SWIZZLE_NONE padded chunks (written by cp.async / epilogues), or for a TMA-loaded
+      // stage 1 SWIZZLE_128B atoms of 64 rows (LBO = atom stride 128R, SBO = K-group stride 1024)
+      constexpr uint64_t kSw128 = uint64_t(2) << 61;
+      const uint32_t pa_re = ST == 0 ? c.a_re : c.s_re, pa_im = ST == 0 ? c.a_im : c.s_im;
+      const uint64_t da_re = SW128 ? (make_smem_desc(pa_re, 128 * R, 1024) | kSw128) : make_smem_desc(pa_re, kKGroupStride, S);
+      const uint64_t da_im = SW128 ? (make_smem_desc(pa_im, 128 * R, 1024) | kSw128) : make_smem_desc(pa_im, kKGroupStride, S);
+      constexpr uint32_t kTileStep = SW128 ? (2 * 128 * R) / 16 : S;   // descriptor address units (16 B) per tile
+      constexpr uint32_t kKStep = SW128 ? 2048 / 16 : 16;              // ... per 16-wide K step
       const uint64_t db1 = make_smem_desc(b1_saddr, kKGroupStride, 16 * R);
       const uint64_t db2 = make_smem_desc(b1_saddr + 4 * R * R, kKGroupStride, 16 * R);
 #pragma unroll
@@ -337,18 +360,19 @@ __device__ __forceinline__ void run_stage(const UnitPlan& P, const KernelCtx& c,
         const uint32_t d = c.taddr + tile * 2 * R;
 #pragma unroll
         for (uint32_t j = 0; j < kSteps; ++j)
-          umma_f16_ss(d, da_re + (tile * S + j * 16), db1 + j * 16, idesc, j > 0 ? 1u : 0u);
+          umma_f16_ss(d, da_re + (tile * kTileStep + j * kKStep), db1 + j * 16, idesc, j > 0 ? 1u : 0u);
 #pragma unroll
         for (uint32_t j = 0; j < kSteps; ++j)
-          umma_f16_ss(d, da_im + (tile * S + j * 16), db2 + j * 16, idesc, 1u);
+          umma_f16_ss(d, da_im + (tile * kTileStep + j * kKStep), db2 + j * 16, idesc, 1u);
       }
       umma_commit(bar);
+      if (ST == 0 && c.landing_free != nullptr) umma_commit(c.landing_free);
       mbar_wait(bar, phase & 1u);
     }
     __syncwarp();
   }
   phase++;
-  __syncthreads();            // all MMAs of this stage are complete: operand planes are free
+  group_sync(c);              // all MMAs of this stage are complete: operand planes are free
   tc_fence_after_sync();
   TFFT_TRACE_MARK(10 + 2 * ST);
   // per-thread parts of the bit-linear row maps: 7 lane-row bits + the warp-group bit of the item index
@@ -370,11 +394,47 @@ __device__ __forceinline__ void run_stage(const UnitPlan& P, const KernelCtx& c,
   epilogue_items<ST, RHO, LAST, LOG2E>(P, c, dst_thr, aux_thr, col_thr, ra, rb, rc, rd, trace, trace_unit);
 }
 
-template <int LOG2E, int RHO0, int RHO1, int RHO2>
+// Store phase: 16-byte shared loads of 8 staging chunks, 8x8 in-register transpose, 16-byte global stores.
+template <int LOG2E>
+__device__ __forceinline__ void store_phase(const UnitPlan& P, const KernelCtx& c, __half* gre, __half* gim, int tid,
+                                            uint32_t st_s_lo, uint32_t st_g_lo, uint32_t st_u_lo, uint32_t u_limit) {
+  constexpr uint32_t kStoreBlocks = (1u << LOG2E) / 64;            // 8x8 blocks per plane
+  constexpr uint32_t kStoreItems = kStoreBlocks >= kThreads ? kStoreBlocks / kThreads : 1;
+#pragma unroll
+  for (uint32_t i = 0; i < kStoreItems; ++i) {
+    const uint32_t so = st_s_lo + bit_sum(i, P.store_sofs, 8, kMaxItemBits - 8);
+    const uint32_t g = st_g_lo + bit_sum(i, P.store_gofs, 8, kMaxItemBits - 8);
+    if (kStoreBlocks < kThreads && tid >= static_cast<int>(kStoreBlocks)) continue;
+    if (st_u_lo + bit_sum(i, P.store_uval, 8, kMaxItemBits - 8) >= u_limit) continue;
+#pragma unroll
+    for (int plane = 0; plane < 2; ++plane) {
+      const uint32_t sp = plane ? c.s_im : c.s_re;
+      __half* gp = plane ? gim : gre;
+      uint4 a[8];
+#pragma unroll
+      for (int x = 0; x < 8; ++x) a[x] = lds128(sp + so + bit_sum(static_cast<uint32_t>(x), P.store_xs, 0, 3));
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) {
+        const uint32_t sel = (cc & 1) ? 0x7632u : 0x5410u;
+        uint32_t w[4];
+#pragma unroll
+        for (int i2 = 0; i2 < 4; ++i2) {
+          const uint32_t lo = reinterpret_cast<const uint32_t*>(&a[2 * i2])[cc >> 1];
+          const uint32_t hi = reinterpret_cast<const uint32_t*>(&a[2 * i2 + 1])[cc >> 1];
+          w[i2] = __byte_perm(lo, hi, sel);
+        }
+        stg128(gp + g + bit_sum(static_cast<uint32_t>(cc), P.store_cg, 0, 3), make_uint4(w[0], w[1], w[2], w[3]));
+      }
+    }
+  }
+}
+
+template <int LOG2E, int RHO0, int RHO1, int RHO2, bool TMA>
 __global__ void __launch_bounds__(kThreads, (LOG2E == 15 ? 1 : 2))
 fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ in_re,
                 const __half* __restrict__ in_im, __half* __restrict__ out_re, __half* __restrict__ out_im,
-                const uint4* __restrict__ tables, long long* __restrict__ trace) {
+                const uint4* __restrict__ tables, long long* __restrict__ trace,
+                const __grid_constant__ CUtensorMap tmap_re, const __grid_constant__ CUtensorMap tmap_im) {
   using namespace ptx;
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int kStages = RHO2 ? 3 : 2;
@@ -386,6 +446,7 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
   c.s_im = c.sbase + SL.plane_stride;
   c.tw_table = reinterpret_cast<const float2*>(smem + SL.table_off);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + SL.bar_off);
+  uint64_t* load_bar = reinterpret_cast<uint64_t*>(smem + SL.load_bar_off);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SL.slot_off);
   const uint32_t table_base = c.sbase + SL.table_off;
 
@@ -393,6 +454,10 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
   c.lane_row = static_cast<uint32_t>((warp & 3) * 32 + lane);
   c.lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
   c.wgroup = static_cast<uint32_t>(warp >> 2);
+  c.a_re = c.s_re;
+  c.a_im = c.s_im;
+  c.bar_id = 0;
+  c.landing_free = nullptr;
   uint32_t trace_unit = 0;
   (void)trace_unit;
 
@@ -403,6 +468,7 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
   }
   if (tid == 32) {
     mbar_init(bar, 1);
+    mbar_init(load_bar, 1);
     fence_mbar_init();
   }
   for (uint32_t o = tid * 16; o < TL.total; o += kThreads * 16) sts128(table_base + o, ldg128(tables + (o >> 4)));
@@ -410,12 +476,10 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
   __syncthreads();
   tc_fence_after_sync();
   c.taddr = *tmem_slot;
-  uint32_t phase = 0;
+  uint32_t phase = 0, load_phase = 0;
 
   // per-thread constant parts of the bit-linear load / store maps (item q = tid + 256*i)
   constexpr uint32_t kLoadItems = (1u << LOG2E) / 8 / kThreads;    // 16-byte chunks per thread and plane
-  constexpr uint32_t kStoreBlocks = (1u << LOG2E) / 64;            // 8x8 blocks per plane
-  constexpr uint32_t kStoreItems = kStoreBlocks >= kThreads ? kStoreBlocks / kThreads : 1;
   const uint32_t ld_g_lo = bit_sum(tid, P.load_gofs, 0, 8), ld_s_lo = bit_sum(tid, P.load_sofs, 0, 8);
   const uint32_t ld_u_lo = bit_sum(tid, P.load_uval, 0, 8);
   const uint32_t st_s_lo = bit_sum(tid, P.store_sofs, 0, 8), st_g_lo = bit_sum(tid, P.store_gofs, 0, 8);
@@ -434,7 +498,19 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
 
     // ---------------------------------------------------------------- load phase
     TFFT_TRACE_MARK(0);
-    {
+    if constexpr (TMA) {
+      // one tensor tile per plane: {64 rows, R kappa, M/64, U transforms}; transforms past the end of
+      // the batch are out of bounds of the tensor map and arrive as zeros
+      if (tid == 0) {
+        fence_proxy_async_smem();   // earlier generic-proxy reads of the planes precede the async-proxy writes
+        mbar_arrive_expect_tx(load_bar, 4u << LOG2E);
+        tma_load_4d(c.s_re, &tmap_re, unit << P.log2_units, load_bar);
+        tma_load_4d(c.s_im, &tmap_im, unit << P.log2_units, load_bar);
+      }
+      TFFT_TRACE_MARK(1);
+      mbar_wait(load_bar, load_phase & 1u);
+      load_phase++;
+    } else {
       const __half* gre = in_re + in_base;
       const __half* gim = in_im + in_base;
       if (u_limit == 0xFFFFFFFFu) {
@@ -461,7 +537,7 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
     TFFT_TRACE_MARK(2);
 
     // ---------------------------------------------------------------- tensor-core stages
-    run_stage<0, RHO0, false, LOG2E>(P, c, table_base + TL.b_off[0], bar, phase, warp, lane, trace, trace_unit);
+    run_stage<0, RHO0, false, LOG2E, TMA>(P, c, table_base + TL.b_off[0], bar, phase, warp, lane, trace, trace_unit);
     TFFT_TRACE_MARK(3);
     run_stage<1, RHO1, kStages == 2, LOG2E>(P, c, table_base + TL.b_off[1], bar, phase, warp, lane, trace,
                                             trace_unit);
@@ -474,37 +550,7 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
     TFFT_TRACE_MARK(6);
 
     // ---------------------------------------------------------------- store phase
-    {
-      __half* gre = out_re + out_base;
-      __half* gim = out_im + out_base;
-#pragma unroll
-      for (uint32_t i = 0; i < kStoreItems; ++i) {
-        const uint32_t so = st_s_lo + bit_sum(i, P.store_sofs, 8, kMaxItemBits - 8);
-        const uint32_t g = st_g_lo + bit_sum(i, P.store_gofs, 8, kMaxItemBits - 8);
-        if (kStoreBlocks < kThreads && tid >= static_cast<int>(kStoreBlocks)) continue;
-        if (st_u_lo + bit_sum(i, P.store_uval, 8, kMaxItemBits - 8) >= u_limit) continue;
-#pragma unroll
-        for (int plane = 0; plane < 2; ++plane) {
-          const uint32_t sp = plane ? c.s_im : c.s_re;
-          __half* gp = plane ? gim : gre;
-          uint4 a[8];
-#pragma unroll
-          for (int x = 0; x < 8; ++x) a[x] = lds128(sp + so + bit_sum(static_cast<uint32_t>(x), P.store_xs, 0, 3));
-#pragma unroll
-          for (int cc = 0; cc < 8; ++cc) {
-            const uint32_t sel = (cc & 1) ? 0x7632u : 0x5410u;
-            uint32_t w[4];
-#pragma unroll
-            for (int i2 = 0; i2 < 4; ++i2) {
-              const uint32_t lo = reinterpret_cast<const uint32_t*>(&a[2 * i2])[cc >> 1];
-              const uint32_t hi = reinterpret_cast<const uint32_t*>(&a[2 * i2 + 1])[cc >> 1];
-              w[i2] = __byte_perm(lo, hi, sel);
-            }
-            stg128(gp + g + bit_sum(static_cast<uint32_t>(cc), P.store_cg, 0, 3), make_uint4(w[0], w[1], w[2], w[3]));
-          }
-        }
-      }
-    }
+    store_phase<LOG2E>(P, c, out_re + out_base, out_im + out_base, tid, st_s_lo, st_g_lo, st_u_lo, u_limit);
     TFFT_TRACE_MARK(7);
     __syncthreads();   // staging fully read before the next unit's loads overwrite it
     TFFT_TRACE_MARK(8);
@@ -515,6 +561,130 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(c.taddr, P.tmem_cols);
+}
+
+// ==========================================================================================
+// Two-slot kernel (16K-element units, TMA input): one CTA per SM runs TWO units at a time.
+// 512 threads = 2 slots x 256 threads; each slot is the single-unit program above on its own working
+// planes, tensor-memory half and named barrier.  Both slots share the constant tables and ONE landing
+// buffer: the TMA tile of a unit lands there, the unit's stage-1 MMAs read it, and as soon as those
+// MMAs have completed (tcgen05.commit on `landing_free`) the next unit's tile is requested -- the
+// global load of unit q+1 overlaps stages 2..s and the store of unit q instead of serialising with
+// them.  Landing uses are strictly sequential: use q belongs to slot q & 1.
+// Shared memory: [W0_re | W0_im | W1_re | W1_im | L_re | L_im | tables | barriers]
+struct Smem2Layout {
+  uint32_t plane_stride, land_off, land_stride, table_off, bar_off, total;
+};
+__host__ __device__ inline Smem2Layout smem2_layout(const UnitPlan& p) {
+  Smem2Layout l;
+  l.plane_stride = (p.plane_bytes + 1023u) & ~1023u;
+  l.land_off = 4 * l.plane_stride;
+  l.land_stride = 2u << p.log2_elems;   // dense SWIZZLE_128B plane: 2 bytes per element
+  l.table_off = l.land_off + 2 * l.land_stride;
+  l.bar_off = l.table_off + table_layout(p).total;
+  l.total = l.bar_off + 64;
+  return l;
+}
+
+template <int RHO0, int RHO1, int RHO2>
+__global__ void __launch_bounds__(2 * kThreads, 1)
+fft_unit_kernel_2slot(const __grid_constant__ UnitPlan P, __half* __restrict__ out_re, __half* __restrict__ out_im,
+                      const uint4* __restrict__ tables, const __grid_constant__ CUtensorMap tmap_re,
+                      const __grid_constant__ CUtensorMap tmap_im) {
+  using namespace ptx;
+  constexpr int LOG2E = 14;
+  constexpr int kStages = RHO2 ? 3 : 2;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const Smem2Layout SL = smem2_layout(P);
+  const TableLayout TL = table_layout(P);
+  const int tid_cta = threadIdx.x;
+  const uint32_t slot = static_cast<uint32_t>(tid_cta >> 8);
+  const int tid = tid_cta & (kThreads - 1), warp = tid >> 5, lane = tid & 31;
+  long long* trace = nullptr;
+  uint32_t trace_unit = 0;
+  (void)trace; (void)trace_unit;
+
+  KernelCtx c;
+  c.sbase = smem_u32(smem);
+  c.s_re = c.sbase + (2 * slot) * SL.plane_stride;
+  c.s_im = c.s_re + SL.plane_stride;
+  c.a_re = c.sbase + SL.land_off;
+  c.a_im = c.a_re + SL.land_stride;
+  c.tw_table = reinterpret_cast<const float2*>(smem + SL.table_off);
+  c.lane_row = static_cast<uint32_t>((warp & 3) * 32 + lane);
+  c.lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+  c.wgroup = static_cast<uint32_t>(warp >> 2);
+  c.bar_id = 1 + slot;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SL.bar_off);
+  uint64_t* mma_bar = bars + slot;          // per slot: UMMA completion
+  uint64_t* land_full = bars + 2;           // TMA tile landed
+  uint64_t* land_free = bars + 3;           // stage-1 MMAs consumed the landing buffer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  c.landing_free = land_free;
+  const uint32_t table_base = c.sbase + SL.table_off;
+
+  // ------------------------------------------------------------------ setup (once per CTA)
+  if (tid_cta < 32) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  if (tid_cta == 32) {
+    mbar_init(bars + 0, 1);
+    mbar_init(bars + 1, 1);
+    mbar_init(land_full, 1);
+    mbar_init(land_free, 1);
+    fence_mbar_init();
+  }
+  for (uint32_t o = tid_cta * 16; o < TL.total; o += 2 * kThreads * 16) sts128(table_base + o, ldg128(tables + (o >> 4)));
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  c.taddr = *tmem_slot + slot * 256;
+  uint32_t phase = 0;
+
+  const uint32_t st_s_lo = bit_sum(tid, P.store_sofs, 0, 8), st_g_lo = bit_sum(tid, P.store_gofs, 0, 8);
+  const uint32_t st_u_lo = bit_sum(tid, P.store_uval, 0, 8);
+
+  // landing use q (q = 0, 1, 2, ...) carries unit blockIdx.x + q * gridDim.x and belongs to slot q & 1
+  auto unit_of = [&](uint32_t q) { return blockIdx.x + q * gridDim.x; };
+  auto request = [&](uint32_t q) {   // one thread: wait until use q-1 has been consumed, then start the TMA of use q
+    if (q > 0) mbar_wait(land_free, (q - 1) & 1u);
+    fence_proxy_async_smem();
+    mbar_arrive_expect_tx(land_full, 4u << LOG2E);
+    tma_load_4d(c.a_re, &tmap_re, unit_of(q) << P.log2_units, land_full);
+    tma_load_4d(c.a_im, &tmap_im, unit_of(q) << P.log2_units, land_full);
+  };
+  if (tid == 0 && unit_of(slot) < P.n_units) request(slot);   // slot 1 blocks here until slot 0's first stage-1 MMAs finish
+  group_sync(c);   // parity waits on land_full are only valid once this slot's own request has been issued
+
+  for (uint32_t q = slot; unit_of(q) < P.n_units; q += 2) {
+    const uint32_t unit = unit_of(q);
+    const uint32_t ub = unit / P.units_per_batch, uu = unit % P.units_per_batch;
+    const int64_t out_base =
+        static_cast<int64_t>(ub) * P.out_batch_stride + static_cast<int64_t>(uu) * P.out_unit_stride;
+    const uint32_t u_limit =
+        P.n_transforms ? P.n_transforms - min(P.n_transforms, unit << P.log2_units) : 0xFFFFFFFFu;
+    c.col_base = (uu / P.col_div) * P.col_base_stride;
+
+    mbar_wait(land_full, q & 1u);   // this unit's tile has landed
+
+    run_stage<0, RHO0, false, LOG2E, true>(P, c, table_base + TL.b_off[0], mma_bar, phase, warp, lane, trace, trace_unit);
+    run_stage<1, RHO1, kStages == 2, LOG2E>(P, c, table_base + TL.b_off[1], mma_bar, phase, warp, lane, trace,
+                                            trace_unit);
+    if constexpr (kStages == 3)
+      run_stage<2, (RHO2 ? RHO2 : 4), true, LOG2E>(P, c, table_base + TL.b_off[2], mma_bar, phase, warp, lane, trace,
+                                                   trace_unit);
+    // request this slot's next tile: the other slot's stage-1 MMAs (use q+1) normally completed long ago
+    if (tid == 0 && unit_of(q + 2) < P.n_units) request(q + 2);
+    group_sync(c);
+    store_phase<LOG2E>(P, c, out_re + out_base, out_im + out_base, tid, st_s_lo, st_g_lo, st_u_lo, u_limit);
+    group_sync(c);   // staging fully read before the next unit's epilogues overwrite the working planes
+  }
+
+  // ------------------------------------------------------------------ teardown
+  tc_fence_before_sync();
+  __syncthreads();
+  if (tid_cta < 32) tmem_dealloc(*tmem_slot, 512);
 }
 
 }  // namespace tfft

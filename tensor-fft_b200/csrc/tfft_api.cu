@@ -89,36 +89,85 @@ std::vector<uint8_t> make_tables(const UnitPlan& plan) {
 long long* g_trace = nullptr;   // developer phase trace buffer (tfft_debug_set_trace)
 std::mutex g_upload_mutex;
 // Kernel instantiations: one per (unit size, radix schedule) the planner can produce.
-typedef void (*KernelFn)(const UnitPlan, const __half*, const __half*, __half*, __half*, const uint4*, long long*);
+typedef void (*KernelFn)(const UnitPlan, const __half*, const __half*, __half*, __half*, const uint4*, long long*,
+                         const CUtensorMap, const CUtensorMap);
 struct KernelEntry {
   int log2e, r0, r1, r2;
-  KernelFn fn;
+  KernelFn fn, fn_tma;   // fn_tma: stage-1 operand loaded by TMA (row-mode input, >= 64 rows per K line)
 };
-#define TFFT_K(E, A, B, C) {E, A, B, C, fft_unit_kernel<E, A, B, C>}
+#define TFFT_K(E, A, B, C) {E, A, B, C, fft_unit_kernel<E, A, B, C, false>, nullptr}
+#define TFFT_KT(E, A, B, C) {E, A, B, C, fft_unit_kernel<E, A, B, C, false>, fft_unit_kernel<E, A, B, C, true>}
 const KernelEntry g_kernels[] = {
     TFFT_K(13, 4, 4, 0), TFFT_K(14, 4, 4, 0),                       // L = 2^8
     TFFT_K(13, 4, 5, 0), TFFT_K(14, 4, 5, 0),                       // 2^9
     TFFT_K(13, 5, 5, 0), TFFT_K(14, 5, 5, 0),                       // 2^10
-    TFFT_K(13, 5, 6, 0), TFFT_K(14, 5, 6, 0),                       // 2^11
-    TFFT_K(13, 6, 6, 0), TFFT_K(14, 6, 6, 0), TFFT_K(15, 6, 6, 0),  // 2^12
-    TFFT_K(13, 4, 4, 5), TFFT_K(14, 4, 4, 5),                       // 2^13
-    TFFT_K(14, 4, 5, 5),                                            // 2^14
-    TFFT_K(15, 5, 5, 5),                                            // 2^15
+    TFFT_KT(13, 5, 6, 0), TFFT_KT(14, 5, 6, 0),                        // 2^11
+    TFFT_KT(13, 6, 6, 0), TFFT_KT(14, 6, 6, 0), TFFT_KT(15, 6, 6, 0),  // 2^12
+    TFFT_KT(13, 4, 4, 5), TFFT_KT(14, 4, 4, 5),                        // 2^13
+    TFFT_KT(14, 4, 5, 5),                                              // 2^14
+    TFFT_KT(15, 5, 5, 5),                                              // 2^15
 };
 #undef TFFT_K
+#undef TFFT_KT
 KernelFn kernel_for(const UnitPlan& p) {
   for (const KernelEntry& k : g_kernels)
     if (k.log2e == static_cast<int>(p.log2_elems) && k.r0 == static_cast<int>(p.log2_radix[0]) &&
         k.r1 == static_cast<int>(p.log2_radix[1]) && k.r2 == static_cast<int>(p.stages == 3 ? p.log2_radix[2] : 0))
-      return k.fn;
+      return p.tma_load ? k.fn_tma : k.fn;
   return nullptr;
+}
+
+// Two-slot variant (one CTA per SM, two units in flight, shared landing buffer) for 16K-element units
+typedef void (*Kernel2Fn)(const UnitPlan, __half*, __half*, const uint4*, const CUtensorMap, const CUtensorMap);
+Kernel2Fn kernel2_for(const UnitPlan& p) {
+  if (!p.tma_load || p.log2_elems != 14 || p.stages != 3 || getenv("TFFT_NO_2SLOT")) return nullptr;
+  if (p.log2_radix[0] == 4 && p.log2_radix[1] == 4 && p.log2_radix[2] == 5) return fft_unit_kernel_2slot<4, 4, 5>;
+  if (p.log2_radix[0] == 4 && p.log2_radix[1] == 5 && p.log2_radix[2] == 5) return fft_unit_kernel_2slot<4, 5, 5>;
+  return nullptr;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+// Tensor map of one input plane for the TMA load: dims (fastest first) {64 rows, R kappa (stride M),
+// M/64 (stride 64), transforms (stride tstride)}, box {64, R, M/64, U}, 128-byte swizzle.
+int make_input_tensor_map(const UnitPlan& plan, const __half* base, int64_t tstride, int64_t n_transforms,
+                          CUtensorMap* out) {
+  EncodeTiledFn encode = get_encode_fn();
+  if (!encode) return TFFT_E_UNSUPPORTED;
+  const uint64_t L = uint64_t(1) << plan.log2_len, R = uint64_t(1) << plan.log2_radix[0], M = L / R;
+  const uint64_t U = uint64_t(1) << plan.log2_units;
+  cuuint64_t gdim[4] = {64, R, M / 64, static_cast<cuuint64_t>(n_transforms)};
+  cuuint64_t gstride[3] = {M * 2, 128, static_cast<cuuint64_t>(tstride) * 2};
+  cuuint32_t box[4] = {64, static_cast<cuuint32_t>(R), static_cast<cuuint32_t>(M / 64), static_cast<cuuint32_t>(U)};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(base), gdim, gstride, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? TFFT_OK : TFFT_E_INVALID_ARG;
 }
 
 std::once_flag g_attr_once;
 int g_attr_err = 0;
 void set_kernel_attrs() {
-  for (const KernelEntry& k : g_kernels) {
-    cudaError_t e = cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  for (const KernelEntry& k : g_kernels)
+    for (KernelFn fn : {k.fn, k.fn_tma}) {
+      if (!fn) continue;
+      cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) g_attr_err = static_cast<int>(e);
+    }
+  for (Kernel2Fn fn : {static_cast<Kernel2Fn>(fft_unit_kernel_2slot<4, 4, 5>), static_cast<Kernel2Fn>(fft_unit_kernel_2slot<4, 5, 5>)}) {
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) g_attr_err = static_cast<int>(e);
   }
 }
@@ -180,6 +229,11 @@ int build_1d(tfft_plan_s* p) {
     UnitShape sh;
     sh.log2_len = lg;
     sh.log2_units = pick_log2_units(lg, batch);
+    {
+      int rho[kMaxStages];
+      radix_schedule(lg, rho);
+      sh.tma_load = (lg - rho[0]) >= 6 && getenv("TFFT_NO_TMA") == nullptr;
+    }
     UnitStrides st;
     st.n_transforms = static_cast<uint32_t>(batch);
     st.units_per_batch = 0x7FFFFFFFu;   // unit base = unit * unit_stride
@@ -279,7 +333,29 @@ int launch_pass(const tfft_plan_s* p, const Pass& ps, const __half* src_re, cons
   const uint4* tables = ps.d_tables[dev];
   const unsigned grid = std::min<unsigned>(ps.n_units, static_cast<unsigned>(ps.resident_ctas[dev]));
   long long* trace = g_trace;
-  void* args[] = {&plan, &src_re, &src_im, &dst_re, &dst_im, &tables, &trace};
+  alignas(64) CUtensorMap tmap_re, tmap_im;
+  std::memset(&tmap_re, 0, sizeof(tmap_re));
+  std::memset(&tmap_im, 0, sizeof(tmap_im));
+  if (plan.tma_load) {
+    // row-mode input: transform t of the launch starts at src + t * tstride, or, for four-step row
+    // passes, at src + (t / upb) * batch_stride + (t % upb) * tstride == t * tstride when contiguous
+    const int64_t n_tr = static_cast<int64_t>(ps.n_units) << plan.log2_units;
+    int rc = make_input_tensor_map(plan, src_re, st.in_tstride, plan.n_transforms ? plan.n_transforms : n_tr, &tmap_re);
+    if (rc == TFFT_OK) rc = make_input_tensor_map(plan, src_im, st.in_tstride, plan.n_transforms ? plan.n_transforms : n_tr, &tmap_im);
+    if (rc != TFFT_OK) return rc;
+  }
+  if (Kernel2Fn fn2 = kernel2_for(plan)) {
+    const Smem2Layout S2 = smem2_layout(plan);
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (S2.total <= 227 * 1024 && sms > 0) {
+      const unsigned grid2 = std::min<unsigned>(ps.n_units, static_cast<unsigned>(sms));
+      void* args2[] = {&plan, &dst_re, &dst_im, &tables, &tmap_re, &tmap_im};
+      e = cudaLaunchKernel(reinterpret_cast<const void*>(fn2), dim3(grid2), dim3(2 * kThreads), args2, S2.total, stream);
+      return e == cudaSuccess ? TFFT_OK : static_cast<int>(e);
+    }
+  }
+  void* args[] = {&plan, &src_re, &src_im, &dst_re, &dst_im, &tables, &trace, &tmap_re, &tmap_im};
   if (getenv("TFFT_DEBUG"))
     fprintf(stderr, "tfft: launch grid=%u units=%u smem=%u tmem=%u resident=%d\n", grid, ps.n_units, ps.smem,
             plan.tmem_cols, ps.resident_ctas[dev]);

@@ -46,6 +46,7 @@ struct UnitShape {
   int log2_units = 0;   // log2(U): transforms per unit
   AxisMode in_mode = kRowMode;   // kRowMode: transform elements contiguous; kColMode: 8+ transforms interleaved
   AxisMode out_mode = kRowMode;
+  bool tma_load = false;   // stage-1 operand written by a TMA tensor load (SWIZZLE_128B, natural row order)
 };
 
 // Device-visible description of one kernel pass (passed by value as a kernel parameter).
@@ -59,6 +60,9 @@ struct UnitPlan {
   uint32_t chunk_stride[kMaxStages];       // S_t
   uint32_t plane_bytes;                    // bytes of one operand plane, max over stages and staging
   uint32_t tmem_cols;                      // power of two >= E/64
+  uint32_t tma_load;                       // 1: stage-1 operand = SWIZZLE_128B MN-major atoms of 64 rows filled by TMA:
+                                           //    element (row, kappa) at (row>>6)*128R + (kappa>>3)*1024 + (kappa&7)*128
+                                           //    + ((((row>>3)&7) ^ (kappa&7))<<4) + (row&7)*2   (verified by probe/tma_probe.cu)
   // ---- load phase: chunk q (bit-linear) -> offsets
   uint32_t load_item_bits;
   uint32_t load_gofs[kMaxItemBits];   // global element offset contribution of item bit i
@@ -156,6 +160,10 @@ inline bool build_unit_plan(const UnitShape& shape, UnitPlan* plan, PlanBuildInf
   }
   plan->log2_len = lg; plan->log2_units = ups; plan->stages = s;
   plan->log2_elems = eps; plan->in_mode = shape.in_mode; plan->out_mode = shape.out_mode;
+  if (shape.tma_load && (shape.in_mode != kRowMode || (lg - rho[0]) < 6)) {
+    info->error = "TMA load needs row mode and >= 64 contiguous rows per K line"; return false;
+  }
+  plan->tma_load = shape.tma_load ? 1u : 0u;
   {
     int lo = lg;
     for (int t = 0; t < s; ++t) { lo -= rho[t]; info->lo_bit[t] = lo; }
@@ -229,6 +237,7 @@ inline bool build_unit_plan(const UnitShape& shape, UnitPlan* plan, PlanBuildInf
     }
     for (auto& v : writer_varying) {
       int p;
+      if (t == 1 && shape.tma_load) break;   // TMA writes the layout: natural row order (m, then u)
       if (is_kbit_of_stage(v, t, &p) || find_bit(rb, v) >= 0) continue;
       p = 0;
       while (p < 3 && (res_used[p] || slot_has[p])) ++p;

@@ -37,11 +37,12 @@ extern "C" {
 // Runs `n_units` units.  in/out are planar double arrays (element offsets as the plan says).
 // Returns the total number of bank conflicts found (negative = plan error).
 // conflicts[0..3] = load stores, epilogue stores, store-phase loads, (unused)
-int plansim_run(int log2_len, int log2_units, int in_mode, int out_mode, const int64_t* strides9,
+int plansim_run(int log2_len, int log2_units, int in_mode_flags, int out_mode, const int64_t* strides9,
                 int pass1_log2n, int n_units, const double* in_re, const double* in_im,
                 double* out_re, double* out_im, int emulate_fp16, int* conflicts) {
   UnitShape shape; shape.log2_len = log2_len; shape.log2_units = log2_units;
-  shape.in_mode = (AxisMode)in_mode; shape.out_mode = (AxisMode)out_mode;
+  const int in_mode = in_mode_flags & 1;
+  shape.in_mode = (AxisMode)in_mode; shape.out_mode = (AxisMode)out_mode; shape.tma_load = (in_mode_flags & 2) != 0;
   UnitPlan P; PlanBuildInfo info;
   if (!build_unit_plan(shape, &P, &info)) { fprintf(stderr, "plan error: %s\n", info.error.c_str()); return -1; }
   UnitStrides st;
@@ -61,8 +62,22 @@ int plansim_run(int log2_len, int log2_units, int in_mode, int out_mode, const i
     const int64_t obase = (unit / P.units_per_batch) * P.out_batch_stride + (unit % P.units_per_batch) * P.out_unit_stride;
     const uint32_t col_base = ((unit % P.units_per_batch) / P.col_div) * P.col_base_stride;
     std::vector<double> sre(smem_halves, NAN), sim(smem_halves, NAN);
-    // ---------------- load (pure copy of 16-byte chunks)
-    const uint32_t n_items = 1u << P.load_item_bits;
+    // ---------------- load: TMA tensor tile {64 rows, R kappa, M/64, U} with 128-byte swizzle ...
+    if (P.tma_load) {
+      const int R = 1 << P.log2_radix[0];
+      const int64_t M = L / R, U = int64_t(1) << P.log2_units;
+      for (int64_t u = 0; u < U; ++u)
+        for (int64_t m = 0; m < M; ++m)
+          for (int kap = 0; kap < R; ++kap) {
+            const int64_t row = u * M + m;
+            const uint32_t off = (uint32_t)((row >> 6) * 128 * R + (kap >> 3) * 1024 + (kap & 7) * 128 +
+                                            ((((row >> 3) & 7) ^ (kap & 7)) << 4) + (row & 7) * 2);
+            const int64_t a = ibase + u * strides9[0] + kap * M + m;
+            sre[off / 2] = rh(in_re[a], h); sim[off / 2] = rh(in_im[a], h);
+          }
+    }
+    // ... or a pure copy of 16-byte chunks (cp.async)
+    const uint32_t n_items = P.tma_load ? 0u : (1u << P.load_item_bits);
     for (uint32_t q0 = 0; q0 < n_items; q0 += 8) {
       uint32_t addr[8];
       for (uint32_t dq = 0; dq < 8; ++dq) {
@@ -96,6 +111,8 @@ int plansim_run(int log2_len, int log2_units, int in_mode, int out_mode, const i
           std::vector<cd> a(R), y(R);
           for (int kap = 0; kap < R; ++kap) {
             uint32_t off = (row >> 3) * S + (kap >> 3) * kKGroupStride + (kap & 7) * 16 + (row & 7) * 2;
+            if (t == 1 && P.tma_load)
+              off = (row >> 6) * 128 * R + (kap >> 3) * 1024 + (kap & 7) * 128 + ((((row >> 3) & 7) ^ (kap & 7)) << 4) + (row & 7) * 2;
             a[kap] = cd(sre[off / 2], sim[off / 2]);
             if (std::isnan(sre[off / 2])) { fprintf(stderr, "stage %d reads an unwritten operand slot\n", t); return -6; }
           }
