@@ -80,6 +80,13 @@ int tfft_plan_destroy(tfft_plan_t plan);
 int tfft_exec(tfft_plan_t plan, const void* in_re, const void* in_im, void* out_re, void* out_im,
               int64_t in_stride, int64_t out_stride, void* stream);
 
+/* Batched transform fused with the inter-pass twiddle of a four-/six-step decomposition: transform b
+ * additionally multiplies its output k by exp(-2*pi*i * k * (first_col + b) / 2^log2_total).  Used by
+ * the multi-GPU 1-D transform (one huge transform = columns pass + all-to-all + rows pass; the
+ * reference has no multi-GPU path).  Only for n <= 32768. */
+int tfft_exec_twiddled(tfft_plan_t plan, const void* in_re, const void* in_im, void* out_re, void* out_im,
+                       int64_t in_stride, int64_t out_stride, int32_t log2_total, int64_t first_col, void* stream);
+
 /* Whole reference call sequence with HOST buffers: CopyDataHostToDevice -> ComputeFFT ->
  * CopyResultsDeviceToHost (src/base/DataHandler.h:45-70,124-153).  host_in / host_out hold,
  * per transform, [RE(n) | IM(n)] halves (2*n*batch values each).  Uses plan-owned device

@@ -95,6 +95,15 @@ __device__ __forceinline__ Cplx twiddle(uint32_t x, uint32_t log2n) {
   return {c, s};
 }
 
+// same for phases up to 2^30: the low 12 bits and the rest are looked up separately so that both
+// fractions are exact in fp32
+__device__ __forceinline__ Cplx twiddle64(uint64_t x, uint32_t log2n) {
+  if (log2n <= 24) return twiddle(static_cast<uint32_t>(x), log2n);
+  const Cplx hi = twiddle(static_cast<uint32_t>(x >> 12), log2n - 12);
+  const Cplx lo = twiddle(static_cast<uint32_t>(x & 0xFFFu), log2n);
+  return cmul(hi, lo);
+}
+
 __device__ __forceinline__ uint32_t bit_sum(uint32_t q, const uint32_t* contrib, int first, int count) {
   uint32_t s = 0;
 #pragma unroll
@@ -279,10 +288,10 @@ __device__ __forceinline__ void epilogue_item(const UnitPlan& P, const KernelCtx
         t1 = cmul(t0, w1);
       }
     } else {
-      const uint32_t col = col_thr + bit_sum_c<kTileHi, kMaxRowBits - 7>(E.col, 7) + c.col_base;
-      const uint32_t mask = (1u << E.tw_log2n) - 1u;
-      const Cplx w1 = twiddle((E.tw_kw * col) & mask, E.tw_log2n);
-      t0 = twiddle(((aux + 16u * g * E.tw_kw) * col) & mask, E.tw_log2n);
+      const uint64_t col = col_thr + bit_sum_c<kTileHi, kMaxRowBits - 7>(E.col, 7) + c.col_base;
+      const uint64_t mask = (uint64_t(1) << E.tw_log2n) - 1u;
+      const Cplx w1 = twiddle64((E.tw_kw * col) & mask, E.tw_log2n);
+      t0 = twiddle64(((aux + 16u * g * E.tw_kw) * col) & mask, E.tw_log2n);
       t1 = cmul(t0, w1);
       s2 = cmul(w1, w1);
     }
@@ -494,7 +503,7 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
     // row/row passes with a ragged batch: transforms past the end are loaded as zeros, never stored
     const uint32_t u_limit =
         P.n_transforms ? P.n_transforms - min(P.n_transforms, unit << P.log2_units) : 0xFFFFFFFFu;
-    c.col_base = (uu / P.col_div) * P.col_base_stride;
+    c.col_base = (uu / P.col_div) * P.col_base_stride + P.col_first;
 
     // ---------------------------------------------------------------- load phase
     TFFT_TRACE_MARK(0);
@@ -664,7 +673,7 @@ fft_unit_kernel_2slot(const __grid_constant__ UnitPlan P, __half* __restrict__ o
         static_cast<int64_t>(ub) * P.out_batch_stride + static_cast<int64_t>(uu) * P.out_unit_stride;
     const uint32_t u_limit =
         P.n_transforms ? P.n_transforms - min(P.n_transforms, unit << P.log2_units) : 0xFFFFFFFFu;
-    c.col_base = (uu / P.col_div) * P.col_base_stride;
+    c.col_base = (uu / P.col_div) * P.col_base_stride + P.col_first;
 
     mbar_wait(land_full, q & 1u);   // this unit's tile has landed
 

@@ -290,8 +290,14 @@ int build_1d(tfft_plan_s* p) {
 }
 
 int launch_pass(const tfft_plan_s* p, const Pass& ps, const __half* src_re, const __half* src_im, __half* dst_re,
-                __half* dst_im, int64_t in_stride, int64_t out_stride, cudaStream_t stream) {
+                __half* dst_im, int64_t in_stride, int64_t out_stride, cudaStream_t stream, int tw_log2 = 0,
+                int64_t tw_first_col = 0) {
   UnitStrides st = ps.strides;
+  if (tw_log2) {   // fused output twiddle: column index of transform b = first_col + b
+    st.pass1_log2n = static_cast<uint32_t>(tw_log2);
+    st.col_base_stride = 1u << ps.plan.log2_units;
+    st.col_div = 1;
+  }
   const int64_t U = int64_t(1) << ps.plan.log2_units;
   if (ps.plan.in_mode == kRowMode && ps.plan.out_mode == kRowMode) {   // batched 1-D, one pass
     st.in_tstride = in_stride; st.out_tstride = out_stride;
@@ -302,6 +308,7 @@ int launch_pass(const tfft_plan_s* p, const Pass& ps, const __half* src_re, cons
   }
   UnitPlan plan = ps.plan;
   fill_strides(st, ps.info, &plan);
+  plan.col_first = static_cast<uint32_t>(tw_first_col);
   KernelFn fn = kernel_for(plan);
   if (!fn) return TFFT_E_UNSUPPORTED;
   int dev = 0;
@@ -482,6 +489,25 @@ int tfft_exec(tfft_plan_t p, const void* in_re, const void* in_im, void* out_re,
     if (rc != TFFT_OK) return rc;
   }
   return TFFT_OK;
+}
+
+int tfft_exec_twiddled(tfft_plan_t p, const void* in_re, const void* in_im, void* out_re, void* out_im,
+                       int64_t in_stride, int64_t out_stride, int32_t log2_total, int64_t first_col, void* stream_) {
+  if (!p || !in_re || !in_im || !out_re || !out_im) return TFFT_E_INVALID_ARG;
+  if (p->passes.size() != 1 || log2_total < p->lg || log2_total > 30) return TFFT_E_UNSUPPORTED;
+  if (first_col < 0 || first_col + p->batch > (int64_t(1) << (log2_total - p->lg))) return TFFT_E_INVALID_ARG;
+  if (!aligned16(in_re) || !aligned16(in_im) || !aligned16(out_re) || !aligned16(out_im)) return TFFT_E_INVALID_ARG;
+  if ((in_stride & 7) || (out_stride & 7) || in_stride < p->n || out_stride < p->n) return TFFT_E_INVALID_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return TFFT_E_NO_DEVICE;
+  }
+  std::call_once(g_attr_once, set_kernel_attrs);
+  if (g_attr_err) return g_attr_err;
+  return launch_pass(p, p->passes[0], static_cast<const __half*>(in_re), static_cast<const __half*>(in_im),
+                     static_cast<__half*>(out_re), static_cast<__half*>(out_im), in_stride, out_stride,
+                     static_cast<cudaStream_t>(stream_), log2_total, first_col);
 }
 
 int tfft_exec_host(tfft_plan_t p, const void* host_in, void* host_out) {

@@ -95,6 +95,7 @@ struct UnitPlan {
   uint32_t n_transforms;                       // != 0 (row/row passes): transforms >= n_transforms are masked
   uint32_t col_base_stride;   // tw_mode 2: col_base = ((unit % upb) / col_div) * col_base_stride
   uint32_t col_div;
+  uint32_t col_first;         // tw_mode 2: added to every column index (tfft_exec_twiddled)
 };
 
 // ------------------------------------------------------------------------------------------

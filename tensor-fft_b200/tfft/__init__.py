@@ -46,7 +46,7 @@ class _PlanInfo(ctypes.Structure):
 
 
 EXPORTS = ("tfft_plan_create", "tfft_plan_create_2d", "tfft_plan_info", "tfft_plan_destroy", "tfft_exec",
-           "tfft_exec_host", "tfft_error_string", "tfft_version")
+           "tfft_exec_twiddled", "tfft_exec_host", "tfft_error_string", "tfft_version")
 
 
 def lib() -> ctypes.CDLL:
@@ -63,6 +63,7 @@ def lib() -> ctypes.CDLL:
         L.tfft_plan_info.argtypes = [vp, ctypes.POINTER(_PlanInfo)]
         L.tfft_plan_destroy.argtypes = [vp]
         L.tfft_exec.argtypes = [vp, vp, vp, vp, vp, i64, i64, vp]
+        L.tfft_exec_twiddled.argtypes = [vp, vp, vp, vp, vp, i64, i64, ctypes.c_int32, i64, vp]
         L.tfft_exec_host.argtypes = [vp, vp, vp]
         L.tfft_error_string.argtypes = [ctypes.c_int]
         L.tfft_error_string.restype = ctypes.c_char_p
@@ -98,6 +99,18 @@ class NativePlan:
         s = torch.cuda.current_stream().cuda_stream if stream is None else stream
         _check(lib().tfft_exec(self._h, in_re.data_ptr(), in_im.data_ptr(), out_re.data_ptr(), out_im.data_ptr(),
                                in_stride, out_stride, ctypes.c_void_p(s)))
+
+    def exec_twiddled(self, in_re, in_im, out_re, out_im, in_stride: int, out_stride: int, log2_total: int,
+                      first_col: int, stream=None) -> None:
+        """exec + output k of transform b times exp(-2 pi i k (first_col + b) / 2^log2_total)."""
+        import torch
+        for t in (in_re, in_im, out_re, out_im):
+            if not (t.is_cuda and t.dtype == torch.float16):
+                raise TfftError("tfft exec needs CUDA float16 tensors (no CPU fallback)")
+        s = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        _check(lib().tfft_exec_twiddled(self._h, in_re.data_ptr(), in_im.data_ptr(), out_re.data_ptr(),
+                                        out_im.data_ptr(), in_stride, out_stride, log2_total, first_col,
+                                        ctypes.c_void_p(s)))
 
     def exec_host(self, host_in, host_out) -> None:
         """numpy float16 arrays of 2*n*batch values laid out [RE|IM] per transform."""
