@@ -174,18 +174,19 @@ __host__ __device__ inline SmemLayout smem_layout(const UnitPlan& p) {
   SmemLayout l;
   l.plane_stride = (p.plane_bytes + 1023u) & ~1023u;   // SWIZZLE_128B atoms need 1024-byte alignment
   l.table_off = 2 * l.plane_stride;
-  l.bar_off = l.table_off + table_layout(p).total;
-  l.load_bar_off = l.bar_off + 8;
+  l.bar_off = l.table_off + table_layout(p).total;   // two MMA barriers
+  l.load_bar_off = l.bar_off + 16;
   l.slot_off = l.load_bar_off + 8;
   l.total = l.slot_off + 8;
   return l;
 }
 
 // 4-D TMA tile load {64 rows, R kappa, M/64, U transforms} -> SWIZZLE_128B stage-1 operand plane
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t c3, uint64_t* bar) {
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t c2, uint32_t c3,
+                                            uint64_t* bar) {
   asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %2, %2, %3}], [%4];"
-      ::"r"(dst), "l"(map), "r"(0), "r"(c3), "r"(ptx::smem_u32(bar))
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %2, %3, %4}], [%5];"
+      ::"r"(dst), "l"(map), "r"(0), "r"(c2), "r"(c3), "r"(ptx::smem_u32(bar))
       : "memory");
 }
 
@@ -205,10 +206,17 @@ __device__ __forceinline__ Cplx tw_lookup(const float2* tw_table, uint32_t x) {
 // Optional phase trace (developer builds, -DTFFT_TRACE): thread 0 of every CTA records clock64 at
 // phase boundaries of its first units into a global buffer (tools/trace_phases.py).
 #ifdef TFFT_TRACE
-#define TFFT_TRACE_MARK(slot)                                                                  \
-  do {                                                                                          \
-    if (threadIdx.x == 0 && trace != nullptr && trace_unit < 4)                                 \
-      trace[(static_cast<size_t>(blockIdx.x) * 4 + trace_unit) * 32 + (slot)] = clock64();      \
+#define TFFT_TRACE_TID0 ((threadIdx.x & 255) == 0 && threadIdx.x < 512)
+#define TFFT_TRACE_SLOT (threadIdx.x >> 8)
+#ifndef TFFT_TRACE_FIRST
+#define TFFT_TRACE_FIRST 0
+#endif
+#define TFFT_TRACE_MARK(slot)                                                                       \
+  do {                                                                                               \
+    if (TFFT_TRACE_TID0 && trace != nullptr && trace_unit >= TFFT_TRACE_FIRST &&            \
+        trace_unit < TFFT_TRACE_FIRST + 4)                                                           \
+      trace[((static_cast<size_t>(blockIdx.x) * 2 + TFFT_TRACE_SLOT) * 4 + trace_unit -           \
+             TFFT_TRACE_FIRST) * 32 + (slot)] = clock64();                                           \
   } while (0)
 #else
 #define TFFT_TRACE_MARK(slot) do {} while (0)
@@ -220,11 +228,12 @@ struct KernelCtx {
   uint32_t col_base;
   uint32_t a_re, a_im;     // stage-1 operand planes (== s_re / s_im unless a separate landing buffer is used)
   uint32_t bar_id;         // 0: the 256 threads are the whole CTA (__syncthreads); else named barrier of a slot
-  uint64_t* landing_free;  // two-slot kernel: arrives when the stage-1 MMAs have consumed the landing buffer
+  uint32_t sync_threads;   // threads of the slot's named barrier
+  int mma_warp;            // warp that issues the UMMAs: 0 (it also runs epilogues) or a dedicated 9th warp (8)
 };
 __device__ __forceinline__ void group_sync(const KernelCtx& c) {
   if (c.bar_id == 0) __syncthreads();
-  else asm volatile("bar.sync %0, %1;" ::"r"(c.bar_id), "r"(kThreads) : "memory");
+  else asm volatile("bar.sync %0, %1;" ::"r"(c.bar_id), "r"(c.sync_threads) : "memory");
 }
 
 // sum of the contributions of the set bits of a COMPILE-TIME index: folds into constant-bank adds
@@ -317,73 +326,96 @@ __device__ __forceinline__ void epilogue_item(const UnitPlan& P, const KernelCtx
   sts128(c.s_im + dst + E.dst_k[0], make_uint4(pim[4], pim[5], pim[6], pim[7]));
 }
 
-// Software-pipelined item loop: the tensor-memory load of item II+1 is in flight while item II is
-// processed (tcgen05.wait::ld waits for ALL outstanding loads, so the next load is issued right after
-// the wait and before the arithmetic).
-template <int ST, int RHO, bool LAST, int LOG2E, uint32_t II = 0>
-__device__ __forceinline__ void epilogue_items(const UnitPlan& P, const KernelCtx& c, uint32_t dst_thr,
+// Software-pipelined item loop over items [II, END): the tensor-memory load of item II+1 is in flight
+// while item II is processed (tcgen05.wait::ld waits for ALL outstanding loads, so the next load is
+// issued right after the wait and before the arithmetic).
+template <int ST, int RHO, bool LAST, uint32_t II, uint32_t END>
+__device__ __forceinline__ void epilogue_range(const UnitPlan& P, const KernelCtx& c, uint32_t dst_thr,
                                                uint32_t aux_thr, uint32_t col_thr, uint32_t (&cre)[16],
-                                               uint32_t (&cim)[16], uint32_t (&nre)[16], uint32_t (&nim)[16],
-                                               long long* trace, uint32_t trace_unit) {
-  constexpr uint32_t kItemsPerGroup = (1u << LOG2E) / 2048 / 2;   // E/2048 work items per stage, two warp groups
-  if constexpr (II < kItemsPerGroup) {
+                                               uint32_t (&cim)[16], uint32_t (&nre)[16], uint32_t (&nim)[16]) {
+  if constexpr (II < END) {
     ptx::tmem_ld_wait();                                            // item II has landed in (cre, cim)
-    if (ST == 0 && II < 4) TFFT_TRACE_MARK(16 + 2 * II);
-    if constexpr (II + 1 < kItemsPerGroup) epilogue_load<RHO, II + 1>(c, nre, nim);
+    if constexpr (II + 1 < END) epilogue_load<RHO, II + 1>(c, nre, nim);
     epilogue_item<ST, RHO, LAST, II>(P, c, dst_thr, aux_thr, col_thr, cre, cim);
-    if (ST == 0 && II < 4) TFFT_TRACE_MARK(17 + 2 * II);
-    epilogue_items<ST, RHO, LAST, LOG2E, II + 1>(P, c, dst_thr, aux_thr, col_thr, nre, nim, cre, cim, trace, trace_unit);
+    epilogue_range<ST, RHO, LAST, II + 1, END>(P, c, dst_thr, aux_thr, col_thr, nre, nim, cre, cim);
   }
 }
 
-// One tensor-core stage: all UMMAs (one thread), wait, then the epilogue on all 8 warps.
-template <int ST, int RHO, bool LAST, int LOG2E, bool SW128 = false>
+// every warp waits for the MMA barrier itself (one polling lane per warp)
+__device__ __forceinline__ void warp_wait(uint64_t* bar, uint32_t parity, int lane) {
+  if (lane == 0) ptx::mbar_wait(bar, parity);
+  __syncwarp();
+  ptx::tc_fence_after_sync();
+}
+
+// One tensor-core stage: all UMMAs (one thread), then the epilogue on all 8 warps.
+// PIPE: the UMMAs are committed in two halves (by tile) and the epilogue of the first half overlaps
+// the tensor-core work of the second half.  Only legal when the first-half epilogue cannot touch
+// operand bytes the second-half MMAs still read: stage 1 reading a separate landing buffer, or a plan
+// built with pipe_stage2 (checked on the CPU by tests/sim/plan_sim.cpp).
+// Hooks of the MMA-issuing thread (warp 0, lane 0): before it issues the UMMAs of tile half h, and once it
+// has observed their completion.  The two-slot kernel uses them for its landing-buffer ring.
+struct NoHook {
+  __device__ __forceinline__ void before_half(int) const {}
+  __device__ __forceinline__ void after_half(int) const {}
+};
+template <int ST, int RHO, bool LAST, int LOG2E, bool SW128 = false, bool PIPE = false, class Hook = NoHook>
 __device__ __forceinline__ void run_stage(const UnitPlan& P, const KernelCtx& c, uint32_t b1_saddr, uint64_t* bar,
-                                          uint32_t& phase, int warp, int lane, long long* trace,
-                                          uint32_t trace_unit) {
+                                          uint32_t (&phase)[2], int warp, int lane, long long* trace,
+                                          uint32_t trace_unit, Hook hook = Hook()) {
   using namespace ptx;
   constexpr uint32_t R = 1u << RHO, G = R / 16, kSteps = R / 16;
   constexpr uint32_t S = 16 * R + 16;                       // chunk stride of this stage's operand layout
   constexpr uint32_t kTiles = (1u << LOG2E) / R / 128;
+  constexpr uint32_t kItemsPerGroup = (1u << LOG2E) / 2048 / 2;   // E/2048 work items per stage, two warp groups
+  constexpr bool kPipe = PIPE && kTiles >= 2 && kItemsPerGroup >= 2;
   fence_proxy_async_smem();   // generic-proxy / cp.async operand writes -> visible to the tensor core
   tc_fence_before_sync();
   group_sync(c);
   tc_fence_after_sync();
   TFFT_TRACE_MARK(9 + 2 * ST);
-  if (warp == 0) {
+  if (warp == c.mma_warp && lane == 0) {
+    constexpr uint32_t idesc = make_idesc_f16(128, 2 * R, /*a_mn=*/1, /*b_mn=*/0);
+    // descriptors differ only in the 14-bit start-address field (units of 16 bytes): add offsets there
+    // A operand: SWIZZLE_NONE padded chunks (written by cp.async / epilogues), or for a TMA-loaded
+    // stage 1 SWIZZLE_128B atoms of 64 rows (LBO = atom stride 128R, SBO = K-group stride 1024)
+    constexpr uint64_t kSw128 = uint64_t(2) << 61;
+    const uint32_t pa_re = ST == 0 ? c.a_re : c.s_re, pa_im = ST == 0 ? c.a_im : c.s_im;
+    const uint64_t da_re = SW128 ? (make_smem_desc(pa_re, 128 * R, 1024) | kSw128) : make_smem_desc(pa_re, kKGroupStride, S);
+    const uint64_t da_im = SW128 ? (make_smem_desc(pa_im, 128 * R, 1024) | kSw128) : make_smem_desc(pa_im, kKGroupStride, S);
+    constexpr uint32_t kTileStep = SW128 ? (2 * 128 * R) / 16 : S;   // descriptor address units (16 B) per tile
+    constexpr uint32_t kKStep = SW128 ? 2048 / 16 : 16;              // ... per 16-wide K step
+    const uint64_t db1 = make_smem_desc(b1_saddr, kKGroupStride, 16 * R);
+    const uint64_t db2 = make_smem_desc(b1_saddr + 4 * R * R, kKGroupStride, 16 * R);
+#pragma unroll
+    for (uint32_t tile = 0; tile < kTiles; ++tile) {
+      const uint32_t d = c.taddr + tile * 2 * R;
+      if (tile == 0) hook.before_half(0);
+      if (tile == (kTiles + 1) / 2) hook.before_half(1);
+      if (kTiles == 1 && tile == 0) hook.before_half(1);
+#pragma unroll
+      for (uint32_t j = 0; j < kSteps; ++j)
+        umma_f16_ss(d, da_re + (tile * kTileStep + j * kKStep), db1 + j * 16, idesc, j > 0 ? 1u : 0u);
+#pragma unroll
+      for (uint32_t j = 0; j < kSteps; ++j)
+        umma_f16_ss(d, da_im + (tile * kTileStep + j * kKStep), db2 + j * 16, idesc, 1u);
+      if (kPipe && tile + 1 == kTiles / 2) umma_commit(bar);     // first half of the tiles
+    }
+    umma_commit(kPipe ? bar + 1 : bar);   // separate barriers: a parity wait must never fall two phases behind
+  }
+  if (warp >= 8) {   // dedicated MMA warp: observe the completions (landing-ring hooks), no epilogue work
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(128, 2 * R, /*a_mn=*/1, /*b_mn=*/0);
-      // descriptors differ only in the 14-bit start-address field (units of 16 bytes): add offsets there
-      // A operand: SWIZZLE_NONE padded chunks (written by cp.async / epilogues), or for a TMA-loaded
-      // stage 1 SWIZZLE_128B atoms of 64 rows (LBO = atom stride 128R, SBO = K-group stride 1024)
-      constexpr uint64_t kSw128 = uint64_t(2) << 61;
-      const uint32_t pa_re = ST == 0 ? c.a_re : c.s_re, pa_im = ST == 0 ? c.a_im : c.s_im;
-      const uint64_t da_re = SW128 ? (make_smem_desc(pa_re, 128 * R, 1024) | kSw128) : make_smem_desc(pa_re, kKGroupStride, S);
-      const uint64_t da_im = SW128 ? (make_smem_desc(pa_im, 128 * R, 1024) | kSw128) : make_smem_desc(pa_im, kKGroupStride, S);
-      constexpr uint32_t kTileStep = SW128 ? (2 * 128 * R) / 16 : S;   // descriptor address units (16 B) per tile
-      constexpr uint32_t kKStep = SW128 ? 2048 / 16 : 16;              // ... per 16-wide K step
-      const uint64_t db1 = make_smem_desc(b1_saddr, kKGroupStride, 16 * R);
-      const uint64_t db2 = make_smem_desc(b1_saddr + 4 * R * R, kKGroupStride, 16 * R);
-#pragma unroll
-      for (uint32_t tile = 0; tile < kTiles; ++tile) {
-        const uint32_t d = c.taddr + tile * 2 * R;
-#pragma unroll
-        for (uint32_t j = 0; j < kSteps; ++j)
-          umma_f16_ss(d, da_re + (tile * kTileStep + j * kKStep), db1 + j * 16, idesc, j > 0 ? 1u : 0u);
-#pragma unroll
-        for (uint32_t j = 0; j < kSteps; ++j)
-          umma_f16_ss(d, da_im + (tile * kTileStep + j * kKStep), db2 + j * 16, idesc, 1u);
-      }
-      umma_commit(bar);
-      if (ST == 0 && c.landing_free != nullptr) umma_commit(c.landing_free);
-      mbar_wait(bar, phase & 1u);
+      mbar_wait(bar, phase[0] & 1u);
+      hook.after_half(0);
+      if (kPipe) mbar_wait(bar + 1, phase[1] & 1u);
+      hook.after_half(1);
     }
     __syncwarp();
+    phase[0]++;
+    if (kPipe) phase[1]++;
+    return;
   }
-  phase++;
-  group_sync(c);              // all MMAs of this stage are complete: operand planes are free
-  tc_fence_after_sync();
-  TFFT_TRACE_MARK(10 + 2 * ST);
+  const bool run_hooks = c.mma_warp == 0 && warp == 0 && lane == 0;
   // per-thread parts of the bit-linear row maps: 7 lane-row bits + the warp-group bit of the item index
   const UnitPlan::Epi& E = P.epi[ST];
   uint32_t dst_thr = bit_sum(c.lane_row, E.dst, 0, 7);
@@ -399,8 +431,42 @@ __device__ __forceinline__ void run_stage(const UnitPlan& P, const KernelCtx& c,
     }
   }
   uint32_t ra[16], rb[16], rc[16], rd[16];
-  epilogue_load<RHO, 0>(c, ra, rb);
-  epilogue_items<ST, RHO, LAST, LOG2E>(P, c, dst_thr, aux_thr, col_thr, ra, rb, rc, rd, trace, trace_unit);
+#ifdef TFFT_DEBUG_SKIP
+  if (true) {   // developer experiment: no epilogue work, only the barrier protocol
+    warp_wait(bar, phase[0] & 1u, lane);
+    if (run_hooks) hook.after_half(0);
+    if (kPipe) warp_wait(bar + 1, phase[1] & 1u, lane);
+    if (run_hooks) hook.after_half(1);
+    phase[0]++;
+    if (kPipe) phase[1]++;
+    return;
+  }
+#endif
+  if constexpr (kPipe) {
+    // items [0, half) only touch tiles of the first half for every radix (item = 2*II + wgroup)
+    constexpr uint32_t kHalf = kItemsPerGroup / 2;
+    warp_wait(bar, phase[0] & 1u, lane);
+    if (run_hooks) hook.after_half(0);
+    TFFT_TRACE_MARK(10 + 2 * ST);
+    epilogue_load<RHO, 0>(c, ra, rb);
+    epilogue_range<ST, RHO, LAST, 0, kHalf>(P, c, dst_thr, aux_thr, col_thr, ra, rb, rc, rd);
+    warp_wait(bar + 1, phase[1] & 1u, lane);
+    if (run_hooks) hook.after_half(1);
+    epilogue_load<RHO, kHalf>(c, ra, rb);
+    epilogue_range<ST, RHO, LAST, kHalf, kItemsPerGroup>(P, c, dst_thr, aux_thr, col_thr, ra, rb, rc, rd);
+    phase[0]++;
+    phase[1]++;
+  } else {
+    warp_wait(bar, phase[0] & 1u, lane);
+    if (run_hooks) {
+      hook.after_half(0);
+      hook.after_half(1);
+    }
+    TFFT_TRACE_MARK(10 + 2 * ST);
+    epilogue_load<RHO, 0>(c, ra, rb);
+    epilogue_range<ST, RHO, LAST, 0, kItemsPerGroup>(P, c, dst_thr, aux_thr, col_thr, ra, rb, rc, rd);
+    phase[0]++;
+  }
 }
 
 // Store phase: 16-byte shared loads of 8 staging chunks, 8x8 in-register transpose, 16-byte global stores.
@@ -466,7 +532,8 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
   c.a_re = c.s_re;
   c.a_im = c.s_im;
   c.bar_id = 0;
-  c.landing_free = nullptr;
+  c.sync_threads = kThreads;
+  c.mma_warp = 0;
   uint32_t trace_unit = 0;
   (void)trace_unit;
 
@@ -477,6 +544,7 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
   }
   if (tid == 32) {
     mbar_init(bar, 1);
+    mbar_init(bar + 1, 1);
     mbar_init(load_bar, 1);
     fence_mbar_init();
   }
@@ -485,7 +553,7 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
   __syncthreads();
   tc_fence_after_sync();
   c.taddr = *tmem_slot;
-  uint32_t phase = 0, load_phase = 0;
+  uint32_t phase[2] = {0, 0}, load_phase = 0;
 
   // per-thread constant parts of the bit-linear load / store maps (item q = tid + 256*i)
   constexpr uint32_t kLoadItems = (1u << LOG2E) / 8 / kThreads;    // 16-byte chunks per thread and plane
@@ -513,8 +581,8 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
       if (tid == 0) {
         fence_proxy_async_smem();   // earlier generic-proxy reads of the planes precede the async-proxy writes
         mbar_arrive_expect_tx(load_bar, 4u << LOG2E);
-        tma_load_4d(c.s_re, &tmap_re, unit << P.log2_units, load_bar);
-        tma_load_4d(c.s_im, &tmap_im, unit << P.log2_units, load_bar);
+        tma_load_4d(c.s_re, &tmap_re, 0, unit << P.log2_units, load_bar);
+        tma_load_4d(c.s_im, &tmap_im, 0, unit << P.log2_units, load_bar);
       }
       TFFT_TRACE_MARK(1);
       mbar_wait(load_bar, load_phase & 1u);
@@ -581,6 +649,10 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
 // global load of unit q+1 overlaps stages 2..s and the store of unit q instead of serialising with
 // them.  Landing uses are strictly sequential: use q belongs to slot q & 1.
 // Shared memory: [W0_re | W0_im | W1_re | W1_im | L_re | L_im | tables | barriers]
+// A dedicated 9th MMA / TMA warp per slot was measured slower (153 us vs 137 us at C2: the 576-thread CTA
+// caps registers at 96 and spills), so the slot's warp 0 issues the UMMAs and also runs epilogues.
+constexpr bool kDedicatedMmaWarp = false;
+constexpr int kSlotThreads = kThreads + (kDedicatedMmaWarp ? 32 : 0);
 struct Smem2Layout {
   uint32_t plane_stride, land_off, land_stride, table_off, bar_off, total;
 };
@@ -596,10 +668,10 @@ __host__ __device__ inline Smem2Layout smem2_layout(const UnitPlan& p) {
 }
 
 template <int RHO0, int RHO1, int RHO2>
-__global__ void __launch_bounds__(2 * kThreads, 1)
+__global__ void __launch_bounds__(2 * kSlotThreads, 1)
 fft_unit_kernel_2slot(const __grid_constant__ UnitPlan P, __half* __restrict__ out_re, __half* __restrict__ out_im,
                       const uint4* __restrict__ tables, const __grid_constant__ CUtensorMap tmap_re,
-                      const __grid_constant__ CUtensorMap tmap_im) {
+                      const __grid_constant__ CUtensorMap tmap_im, long long* __restrict__ trace) {
   using namespace ptx;
   constexpr int LOG2E = 14;
   constexpr int kStages = RHO2 ? 3 : 2;
@@ -607,11 +679,15 @@ fft_unit_kernel_2slot(const __grid_constant__ UnitPlan P, __half* __restrict__ o
   const Smem2Layout SL = smem2_layout(P);
   const TableLayout TL = table_layout(P);
   const int tid_cta = threadIdx.x;
-  const uint32_t slot = static_cast<uint32_t>(tid_cta >> 8);
-  const int tid = tid_cta & (kThreads - 1), warp = tid >> 5, lane = tid & 31;
-  long long* trace = nullptr;
+  // CTA warps 0-7: epilogue warps of slot 0, 8-15: of slot 1 (tcgen05.ld reaches the tensor-memory lane
+  // quarter given by the CTA warp index mod 4, so each slot's epilogue warps start at a multiple of 4);
+  // warps 16 / 17: the dedicated MMA warps of slot 0 / 1 (warp 8 of their slot)
+  const uint32_t slot = tid_cta < 2 * kThreads ? static_cast<uint32_t>(tid_cta >> 8)
+                                               : static_cast<uint32_t>((tid_cta - 2 * kThreads) >> 5);
+  const int tid = tid_cta < 2 * kThreads ? (tid_cta & (kThreads - 1)) : kThreads + (tid_cta & 31);
+  const int warp = tid >> 5, lane = tid & 31;
   uint32_t trace_unit = 0;
-  (void)trace; (void)trace_unit;
+  (void)trace_unit;
 
   KernelCtx c;
   c.sbase = smem_u32(smem);
@@ -624,12 +700,12 @@ fft_unit_kernel_2slot(const __grid_constant__ UnitPlan P, __half* __restrict__ o
   c.lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
   c.wgroup = static_cast<uint32_t>(warp >> 2);
   c.bar_id = 1 + slot;
+  c.sync_threads = kSlotThreads;
+  c.mma_warp = kDedicatedMmaWarp ? 8 : 0;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SL.bar_off);
-  uint64_t* mma_bar = bars + slot;          // per slot: UMMA completion
-  uint64_t* land_full = bars + 2;           // TMA tile landed
-  uint64_t* land_free = bars + 3;           // stage-1 MMAs consumed the landing buffer
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
-  c.landing_free = land_free;
+  uint64_t* mma_bar = bars + 2 * slot;      // per slot: UMMA completion (two barriers: tile halves)
+  uint64_t* land_full = bars + 4;           // land_full[2*s + h]: tile half h for slot s has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   const uint32_t table_base = c.sbase + SL.table_off;
 
   // ------------------------------------------------------------------ setup (once per CTA)
@@ -640,31 +716,40 @@ fft_unit_kernel_2slot(const __grid_constant__ UnitPlan P, __half* __restrict__ o
   if (tid_cta == 32) {
     mbar_init(bars + 0, 1);
     mbar_init(bars + 1, 1);
-    mbar_init(land_full, 1);
-    mbar_init(land_free, 1);
+    mbar_init(bars + 2, 1);
+    mbar_init(bars + 3, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(land_full + i, 1);
     fence_mbar_init();
   }
-  for (uint32_t o = tid_cta * 16; o < TL.total; o += 2 * kThreads * 16) sts128(table_base + o, ldg128(tables + (o >> 4)));
+  for (uint32_t o = tid_cta * 16; o < TL.total; o += 2 * kSlotThreads * 16) sts128(table_base + o, ldg128(tables + (o >> 4)));
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   c.taddr = *tmem_slot + slot * 256;
-  uint32_t phase = 0;
+  uint32_t phase[2] = {0, 0};
 
   const uint32_t st_s_lo = bit_sum(tid, P.store_sofs, 0, 8), st_g_lo = bit_sum(tid, P.store_gofs, 0, 8);
   const uint32_t st_u_lo = bit_sum(tid, P.store_uval, 0, 8);
 
-  // landing use q (q = 0, 1, 2, ...) carries unit blockIdx.x + q * gridDim.x and belongs to slot q & 1
+  // landing use q (q = 0, 1, 2, ...) carries unit blockIdx.x + q * gridDim.x and belongs to slot q & 1.
+  // The landing buffer is a ring of two half tiles (the first / second half of the stage-1 MMA tiles).
+  // Half h of use q+1 is requested by the thread that observes the completion of the half-h MMAs of use q
+  // (that half of the buffer is free from that moment), so loads are in flight almost all the time.
   auto unit_of = [&](uint32_t q) { return blockIdx.x + q * gridDim.x; };
-  auto request = [&](uint32_t q) {   // one thread: wait until use q-1 has been consumed, then start the TMA of use q
-    if (q > 0) mbar_wait(land_free, (q - 1) & 1u);
-    fence_proxy_async_smem();
-    mbar_arrive_expect_tx(land_full, 4u << LOG2E);
-    tma_load_4d(c.a_re, &tmap_re, unit_of(q) << P.log2_units, land_full);
-    tma_load_4d(c.a_im, &tmap_im, unit_of(q) << P.log2_units, land_full);
+  const uint32_t half_c2 = P.log2_units ? 0u : ((1u << (P.log2_len - P.log2_radix[0])) >> 7);   // (M/64)/2
+  const uint32_t half_c3 = P.log2_units ? ((1u << P.log2_units) >> 1) : 0u;
+  auto request = [&](uint32_t q, uint32_t h) {
+    if (unit_of(q) >= P.n_units) return;
+    uint64_t* full = land_full + 2 * (q & 1u) + h;
+    mbar_arrive_expect_tx(full, 2u << LOG2E);
+    const uint32_t off = h << LOG2E;   // half a plane: E bytes
+    tma_load_4d(c.a_re + off, &tmap_re, h * half_c2, (unit_of(q) << P.log2_units) + h * half_c3, full);
+    tma_load_4d(c.a_im + off, &tmap_im, h * half_c2, (unit_of(q) << P.log2_units) + h * half_c3, full);
   };
-  if (tid == 0 && unit_of(slot) < P.n_units) request(slot);   // slot 1 blocks here until slot 0's first stage-1 MMAs finish
-  group_sync(c);   // parity waits on land_full are only valid once this slot's own request has been issued
+  if (tid_cta == 0) {
+    request(0, 0);
+    request(0, 1);
+  }
 
   for (uint32_t q = slot; unit_of(q) < P.n_units; q += 2) {
     const uint32_t unit = unit_of(q);
@@ -674,20 +759,44 @@ fft_unit_kernel_2slot(const __grid_constant__ UnitPlan P, __half* __restrict__ o
     const uint32_t u_limit =
         P.n_transforms ? P.n_transforms - min(P.n_transforms, unit << P.log2_units) : 0xFFFFFFFFu;
     c.col_base = (uu / P.col_div) * P.col_base_stride + P.col_first;
+    TFFT_TRACE_MARK(0);
+    TFFT_TRACE_MARK(1);
+    TFFT_TRACE_MARK(2);
 
-    mbar_wait(land_full, q & 1u);   // this unit's tile has landed
-
-    run_stage<0, RHO0, false, LOG2E, true>(P, c, table_base + TL.b_off[0], mma_bar, phase, warp, lane, trace, trace_unit);
-    run_stage<1, RHO1, kStages == 2, LOG2E>(P, c, table_base + TL.b_off[1], mma_bar, phase, warp, lane, trace,
-                                            trace_unit);
+    // stage 1 reads the landing buffer and writes the working planes: overlap is always legal;
+    // stage 2 works in place: overlap needs a plan built with pipe_stage2
+    struct LandingHook {
+      uint64_t* full;
+      uint32_t parity, q;
+      decltype(request)& req;
+      __device__ __forceinline__ void before_half(int h) const { mbar_wait(full + h, parity); }   // tile half landed
+      __device__ __forceinline__ void after_half(int h) const { req(q + 1, static_cast<uint32_t>(h)); }
+    };
+    LandingHook hook{land_full + 2 * slot, (q >> 1) & 1u, q, request};
+    run_stage<0, RHO0, false, LOG2E, true, true>(P, c, table_base + TL.b_off[0], mma_bar, phase, warp, lane, trace,
+                                                 trace_unit, hook);
+    TFFT_TRACE_MARK(3);
+#ifndef TFFT_DEBUG_SKIP
+    if (kStages == 3 && P.pipe_stage2)
+      run_stage<1, RHO1, kStages == 2, LOG2E, false, true>(P, c, table_base + TL.b_off[1], mma_bar, phase, warp, lane,
+                                                           trace, trace_unit);
+    else
+      run_stage<1, RHO1, kStages == 2, LOG2E>(P, c, table_base + TL.b_off[1], mma_bar, phase, warp, lane, trace,
+                                              trace_unit);
+    TFFT_TRACE_MARK(4);
     if constexpr (kStages == 3)
       run_stage<2, (RHO2 ? RHO2 : 4), true, LOG2E>(P, c, table_base + TL.b_off[2], mma_bar, phase, warp, lane, trace,
                                                    trace_unit);
-    // request this slot's next tile: the other slot's stage-1 MMAs (use q+1) normally completed long ago
-    if (tid == 0 && unit_of(q + 2) < P.n_units) request(q + 2);
+#endif
+    TFFT_TRACE_MARK(5);
     group_sync(c);
-    store_phase<LOG2E>(P, c, out_re + out_base, out_im + out_base, tid, st_s_lo, st_g_lo, st_u_lo, u_limit);
+    TFFT_TRACE_MARK(6);
+    if (warp < 8)
+      store_phase<LOG2E>(P, c, out_re + out_base, out_im + out_base, tid, st_s_lo, st_g_lo, st_u_lo, u_limit);
+    TFFT_TRACE_MARK(7);
     group_sync(c);   // staging fully read before the next unit's epilogues overwrite the working planes
+    TFFT_TRACE_MARK(8);
+    trace_unit++;
   }
 
   // ------------------------------------------------------------------ teardown

@@ -118,7 +118,8 @@ KernelFn kernel_for(const UnitPlan& p) {
 }
 
 // Two-slot variant (one CTA per SM, two units in flight, shared landing buffer) for 16K-element units
-typedef void (*Kernel2Fn)(const UnitPlan, __half*, __half*, const uint4*, const CUtensorMap, const CUtensorMap);
+typedef void (*Kernel2Fn)(const UnitPlan, __half*, __half*, const uint4*, const CUtensorMap, const CUtensorMap,
+                          long long*);
 Kernel2Fn kernel2_for(const UnitPlan& p) {
   if (!p.tma_load || p.log2_elems != 14 || p.stages != 3 || getenv("TFFT_NO_2SLOT")) return nullptr;
   if (p.log2_radix[0] == 4 && p.log2_radix[1] == 4 && p.log2_radix[2] == 5) return fft_unit_kernel_2slot<4, 4, 5>;
@@ -142,7 +143,7 @@ EncodeTiledFn get_encode_fn() {
 // Tensor map of one input plane for the TMA load: dims (fastest first) {64 rows, R kappa (stride M),
 // M/64 (stride 64), transforms (stride tstride)}, box {64, R, M/64, U}, 128-byte swizzle.
 int make_input_tensor_map(const UnitPlan& plan, const __half* base, int64_t tstride, int64_t n_transforms,
-                          CUtensorMap* out) {
+                          CUtensorMap* out, bool half_box = false) {
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) return TFFT_E_UNSUPPORTED;
   const uint64_t L = uint64_t(1) << plan.log2_len, R = uint64_t(1) << plan.log2_radix[0], M = L / R;
@@ -150,6 +151,10 @@ int make_input_tensor_map(const UnitPlan& plan, const __half* base, int64_t tstr
   cuuint64_t gdim[4] = {64, R, M / 64, static_cast<cuuint64_t>(n_transforms)};
   cuuint64_t gstride[3] = {M * 2, 128, static_cast<cuuint64_t>(tstride) * 2};
   cuuint32_t box[4] = {64, static_cast<cuuint32_t>(R), static_cast<cuuint32_t>(M / 64), static_cast<cuuint32_t>(U)};
+  if (half_box) {   // two-slot kernel: one box = half of a unit's stage-1 tiles
+    if (U >= 2) box[3] = static_cast<cuuint32_t>(U / 2);
+    else box[2] = static_cast<cuuint32_t>(M / 128);
+  }
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(base), gdim, gstride, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -233,6 +238,7 @@ int build_1d(tfft_plan_s* p) {
       int rho[kMaxStages];
       radix_schedule(lg, rho);
       sh.tma_load = (lg - rho[0]) >= 6 && getenv("TFFT_NO_TMA") == nullptr;
+      sh.pipe_stage2 = sh.tma_load && lg >= 13 && getenv("TFFT_NO_PIPE") == nullptr;
     }
     UnitStrides st;
     st.n_transforms = static_cast<uint32_t>(batch);
@@ -347,8 +353,10 @@ int launch_pass(const tfft_plan_s* p, const Pass& ps, const __half* src_re, cons
     // row-mode input: transform t of the launch starts at src + t * tstride, or, for four-step row
     // passes, at src + (t / upb) * batch_stride + (t % upb) * tstride == t * tstride when contiguous
     const int64_t n_tr = static_cast<int64_t>(ps.n_units) << plan.log2_units;
-    int rc = make_input_tensor_map(plan, src_re, st.in_tstride, plan.n_transforms ? plan.n_transforms : n_tr, &tmap_re);
-    if (rc == TFFT_OK) rc = make_input_tensor_map(plan, src_im, st.in_tstride, plan.n_transforms ? plan.n_transforms : n_tr, &tmap_im);
+    const bool half_box = kernel2_for(plan) != nullptr;
+    int rc = make_input_tensor_map(plan, src_re, st.in_tstride, plan.n_transforms ? plan.n_transforms : n_tr, &tmap_re, half_box);
+    if (rc == TFFT_OK)
+      rc = make_input_tensor_map(plan, src_im, st.in_tstride, plan.n_transforms ? plan.n_transforms : n_tr, &tmap_im, half_box);
     if (rc != TFFT_OK) return rc;
   }
   if (Kernel2Fn fn2 = kernel2_for(plan)) {
@@ -357,8 +365,8 @@ int launch_pass(const tfft_plan_s* p, const Pass& ps, const __half* src_re, cons
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (S2.total <= 227 * 1024 && sms > 0) {
       const unsigned grid2 = std::min<unsigned>(ps.n_units, static_cast<unsigned>(sms));
-      void* args2[] = {&plan, &dst_re, &dst_im, &tables, &tmap_re, &tmap_im};
-      e = cudaLaunchKernel(reinterpret_cast<const void*>(fn2), dim3(grid2), dim3(2 * kThreads), args2, S2.total, stream);
+      void* args2[] = {&plan, &dst_re, &dst_im, &tables, &tmap_re, &tmap_im, &trace};
+      e = cudaLaunchKernel(reinterpret_cast<const void*>(fn2), dim3(grid2), dim3(2 * kSlotThreads), args2, S2.total, stream);
       return e == cudaSuccess ? TFFT_OK : static_cast<int>(e);
     }
   }

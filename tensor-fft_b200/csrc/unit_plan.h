@@ -47,6 +47,9 @@ struct UnitShape {
   AxisMode in_mode = kRowMode;   // kRowMode: transform elements contiguous; kColMode: 8+ transforms interleaved
   AxisMode out_mode = kRowMode;
   bool tma_load = false;   // stage-1 operand written by a TMA tensor load (SWIZZLE_128B, natural row order)
+  bool pipe_stage2 = false;  // 3-stage plans: make the top row bit of stages 2 and 3 the same logical bit (k_1's
+                             // top bit), so that the epilogue of the first half of stage 2's tiles only writes into
+                             // the already consumed first half of the operand planes (MMA / epilogue overlap)
 };
 
 // Device-visible description of one kernel pass (passed by value as a kernel parameter).
@@ -60,6 +63,7 @@ struct UnitPlan {
   uint32_t chunk_stride[kMaxStages];       // S_t
   uint32_t plane_bytes;                    // bytes of one operand plane, max over stages and staging
   uint32_t tmem_cols;                      // power of two >= E/64
+  uint32_t pipe_stage2;                    // 1: stage 2 may overlap its second-half MMAs with its first-half epilogue
   uint32_t tma_load;                       // 1: stage-1 operand = SWIZZLE_128B MN-major atoms of 64 rows filled by TMA:
                                            //    element (row, kappa) at (row>>6)*128R + (kappa>>3)*1024 + (kappa&7)*128
                                            //    + ((((row>>3)&7) ^ (kappa&7))<<4) + (row&7)*2   (verified by probe/tma_probe.cu)
@@ -165,6 +169,7 @@ inline bool build_unit_plan(const UnitShape& shape, UnitPlan* plan, PlanBuildInf
     info->error = "TMA load needs row mode and >= 64 contiguous rows per K line"; return false;
   }
   plan->tma_load = shape.tma_load ? 1u : 0u;
+  plan->pipe_stage2 = (shape.pipe_stage2 && s == 3) ? 1u : 0u;
   {
     int lo = lg;
     for (int t = 0; t < s; ++t) { lo -= rho[t]; info->lo_bit[t] = lo; }
@@ -255,6 +260,13 @@ inline bool build_unit_plan(const UnitShape& shape, UnitPlan* plan, PlanBuildInf
     }
     for (auto& b : rest) rb.push_back(b);
     if ((int)rb.size() != eps - rho[t - 1]) { info->error = "row bit count mismatch"; return false; }
+    if (shape.pipe_stage2 && s == 3 && t >= 2) {
+      const LBit hbit = {LBit::K, 1, (uint8_t)(rho[0] - 1)};
+      const int pos = find_bit(rb, hbit);
+      if (pos < 6) { info->error = "pipeline bit is not free"; return false; }
+      rb.erase(rb.begin() + pos);
+      rb.push_back(hbit);
+    }
     writer_varying.assign(rb.begin(), rb.begin() + 3);  // the epilogue of this stage writes the next layout
   }
 

@@ -43,6 +43,7 @@ int plansim_run(int log2_len, int log2_units, int in_mode_flags, int out_mode, c
   UnitShape shape; shape.log2_len = log2_len; shape.log2_units = log2_units;
   const int in_mode = in_mode_flags & 1;
   shape.in_mode = (AxisMode)in_mode; shape.out_mode = (AxisMode)out_mode; shape.tma_load = (in_mode_flags & 2) != 0;
+  shape.pipe_stage2 = (in_mode_flags & 4) != 0;
   UnitPlan P; PlanBuildInfo info;
   if (!build_unit_plan(shape, &P, &info)) { fprintf(stderr, "plan error: %s\n", info.error.c_str()); return -1; }
   UnitStrides st;
@@ -129,6 +130,13 @@ int plansim_run(int log2_len, int log2_units, int in_mode_flags, int out_mode, c
           uint32_t aux = bitsum(row, E.aux, rowbits);
           uint32_t col = bitsum(row, E.col, rowbits);
           addr[dr] = dst;
+          // MMA / epilogue overlap of stage 2: first-half rows may only write into the consumed first half
+          if (P.pipe_stage2 && t == 2 && row < rows / 2) {
+            const uint32_t half_bytes = (rows / 16) * S;
+            uint32_t hi = dst;
+            for (int j = 0; j < 3; ++j) hi += E.dst_k[j];
+            if (hi + 16 > half_bytes) { fprintf(stderr, "pipeline hazard: first-half epilogue writes beyond the consumed half\n"); return -7; }
+          }
           for (int k = 0; k < R; ++k) {
             cd v = y[k];
             if (E.tw_mode == 1) v *= twd(((int64_t)aux << E.tw_shift) * k, L);
