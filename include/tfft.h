@@ -25,7 +25,7 @@ typedef struct tfft_plan_s* tfft_plan_t;
 
 enum {
   TFFT_OK = 0,
-  TFFT_E_INVALID_SIZE = -1,   /* not a power of two, < 256 or > 2^24 (Plan.h:85-96 prints + nullopt) */
+  TFFT_E_INVALID_SIZE = -1,   /* not a power of two, < 256 or > 2^30 (Plan.h:85-96 prints + nullopt) */
   TFFT_E_INVALID_ARG = -2,    /* null pointer, misaligned pointer or stride */
   TFFT_E_NO_DEVICE = -3,      /* no sm_100 device: the product has no CPU path */
   TFFT_E_UNSUPPORTED = -4,
@@ -46,7 +46,7 @@ typedef struct tfft_plan_info_s {
   int64_t batch;             /* transforms per exec                                                */
   int32_t r16_stages;        /* tensor-core radix-16 stages per pass                               */
   int32_t tail_radix;        /* 1, 2, 4 or 8: CUDA-core radix fused into the load phase            */
-  int32_t passes;            /* HBM round trips: 1 for N <= 32768, 2 (four-step) above             */
+  int32_t passes;            /* HBM round trips: 1 (N <= 2^15), 2 (<= 2^24), 3 above                */
   int32_t results_in_results;/* always 1: results land in the output planes (Plan.h:25)            */
   int32_t amount_of_r16_steps; /* reference-compatible: log2(N)/4 - 1   (Plan.h:99)                */
   int32_t amount_of_r2_steps;  /* reference-compatible: log2(N) % 4     (Plan.h:100)               */

@@ -32,6 +32,7 @@ struct Pass {
   uint32_t smem = 0;
   int src = 0, dst = 0;    // 0 = user input planes, 1 = user output planes, 2 = plan workspace
   bool in_stride_is_user = false, out_stride_is_user = false;
+  bool own_batch_strides = false;   // three-pass plans: the batch level of the unit addressing is internal
 };
 
 int ilog2_exact(int64_t n) {
@@ -186,6 +187,7 @@ struct tfft_plan_s {
   std::vector<Pass> passes;
   __half* workspace = nullptr;   // 2 * n * batch halves when TFFT_PRESERVE_INPUT on multi-pass sizes
   int64_t workspace_bytes = 0;
+  bool loop_batch = false;           // three-pass plans run one transform at a time
   __half* host_path_buf = nullptr;   // lazily allocated [in | out] for tfft_exec_host
   int device = 0;
 };
@@ -246,6 +248,58 @@ int build_1d(tfft_plan_s* p) {
     const int64_t U = int64_t(1) << sh.log2_units;
     return add_pass(p, sh, st, static_cast<uint32_t>((batch + U - 1) / U), 0, 1, true, true) ? TFFT_OK
                                                                                              : TFFT_E_UNSUPPORTED;
+  }
+  if (lg > 24) {
+    // three passes: n = N1 * Na * Nb (each 2^8 .. 2^12), one transform at a time (exec loops over the batch).
+    //   A: N2 = Na*Nb strided length-N1 transforms, times exp(-2*pi*i*k1*n2/n)            (column mode, in place)
+    //   B: for every k1, Nb strided length-Na transforms of row k1, times exp(-2*pi*i*ka*b/N2)   (column mode, in place)
+    //   C: for 8+ consecutive k1 and one ka, length-Nb transforms stored at k1 + N1*(ka + Na*kb)  (row in, column out)
+    int lg1 = (lg + 2) / 3;
+    if (lg1 < 8) lg1 = 8;
+    const int lg2 = lg - lg1, la = (lg2 + 1) / 2, lb = lg2 - la;
+    if (lg1 > 12 || la > 12 || lb < 8) return TFFT_E_INVALID_SIZE;
+    const int64_t N1 = int64_t(1) << lg1, N2 = int64_t(1) << lg2, Na = int64_t(1) << la, Nb = int64_t(1) << lb;
+    p->loop_batch = true;
+    {
+      UnitShape sh;
+      sh.log2_len = lg1; sh.log2_units = std::max(3, unit_log2_elems(lg1) - lg1);
+      sh.in_mode = kColMode; sh.out_mode = kColMode;
+      const int64_t U = int64_t(1) << sh.log2_units;
+      UnitStrides st;
+      st.in_nstride = N2; st.out_nstride = N2; st.in_unit_stride = U; st.out_unit_stride = U;
+      st.units_per_batch = static_cast<uint32_t>(N2 / U);
+      st.col_base_stride = static_cast<uint32_t>(U);
+      st.pass1_log2n = lg;
+      if (!add_pass(p, sh, st, static_cast<uint32_t>(N2 / U), 0, 0, true, true)) return TFFT_E_UNSUPPORTED;
+      p->passes.back().own_batch_strides = true;
+    }
+    {
+      UnitShape sh;
+      sh.log2_len = la; sh.log2_units = std::max(3, unit_log2_elems(la) - la);
+      sh.in_mode = kColMode; sh.out_mode = kColMode;
+      const int64_t U = int64_t(1) << sh.log2_units;
+      UnitStrides st;
+      st.in_nstride = Nb; st.out_nstride = Nb; st.in_unit_stride = U; st.out_unit_stride = U;
+      st.in_batch_stride = N2; st.out_batch_stride = N2;
+      st.units_per_batch = static_cast<uint32_t>(Nb / U);
+      st.col_base_stride = static_cast<uint32_t>(U);
+      st.pass1_log2n = lg2;
+      if (!add_pass(p, sh, st, static_cast<uint32_t>(N1 * (Nb / U)), 0, 0, true, true)) return TFFT_E_UNSUPPORTED;
+      p->passes.back().own_batch_strides = true;
+    }
+    {
+      UnitShape sh;
+      sh.log2_len = lb; sh.log2_units = std::max(3, unit_log2_elems(lb) - lb);
+      sh.in_mode = kRowMode; sh.out_mode = kColMode;
+      const int64_t U = int64_t(1) << sh.log2_units;
+      UnitStrides st;
+      st.in_tstride = N2; st.in_unit_stride = Nb; st.in_batch_stride = U * N2;
+      st.out_nstride = N1 * Na; st.out_unit_stride = N1; st.out_batch_stride = U;
+      st.units_per_batch = static_cast<uint32_t>(Na);
+      if (!add_pass(p, sh, st, static_cast<uint32_t>((N1 / U) * Na), 0, 1, true, true)) return TFFT_E_UNSUPPORTED;
+      p->passes.back().own_batch_strides = true;
+    }
+    return TFFT_OK;
   }
   // four-step: n = N1 * N2, element n1*N2 + n2.  Pass 1: N2 strided length-N1 transforms (column
   // mode, in place on the source), times exp(-2*pi*i*k1*n2/n).  Pass 2: N1 contiguous length-N2
@@ -308,7 +362,7 @@ int launch_pass(const tfft_plan_s* p, const Pass& ps, const __half* src_re, cons
   if (ps.plan.in_mode == kRowMode && ps.plan.out_mode == kRowMode) {   // batched 1-D, one pass
     st.in_tstride = in_stride; st.out_tstride = out_stride;
     st.in_unit_stride = U * in_stride; st.out_unit_stride = U * out_stride;
-  } else {   // four-step passes: the batch level carries the user's (or workspace) transform stride
+  } else if (!ps.own_batch_strides) {   // four-step passes: the batch level carries the user's (or workspace) transform stride
     st.in_batch_stride = in_stride;
     st.out_batch_stride = out_stride;
   }
@@ -393,7 +447,7 @@ void tfft_debug_set_trace(long long* buf) { g_trace = buf; }
 const char* tfft_error_string(int code) {
   switch (code) {
     case TFFT_OK: return "success";
-    case TFFT_E_INVALID_SIZE: return "transform length must be a power of two in [256, 2^24]";
+    case TFFT_E_INVALID_SIZE: return "transform length must be a power of two in [256, 2^30]";
     case TFFT_E_INVALID_ARG: return "invalid argument (null / misaligned pointer or stride)";
     case TFFT_E_NO_DEVICE: return "no sm_100 CUDA device (this library has no CPU path)";
     case TFFT_E_UNSUPPORTED: return "unsupported configuration";
@@ -406,7 +460,7 @@ int tfft_plan_create(tfft_plan_t* out, int64_t n, int64_t batch, uint32_t flags)
   if (!out) return TFFT_E_INVALID_ARG;
   *out = nullptr;
   const int lg = ilog2_exact(n);
-  if (lg < 8 || lg > 24) return TFFT_E_INVALID_SIZE;
+  if (lg < 8 || lg > 30) return TFFT_E_INVALID_SIZE;
   if (batch < 1 || batch > (int64_t(1) << 30)) return TFFT_E_INVALID_ARG;
   tfft_plan_s* p = new (std::nothrow) tfft_plan_s;
   if (!p) return TFFT_E_NOMEM;
@@ -475,11 +529,13 @@ int tfft_exec(tfft_plan_t p, const void* in_re, const void* in_im, void* out_re,
   std::call_once(g_attr_once, set_kernel_attrs);
   if (g_attr_err) return g_attr_err == static_cast<int>(cudaErrorInvalidDeviceFunction) ? TFFT_E_NO_DEVICE : g_attr_err;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const __half* ire = static_cast<const __half*>(in_re);
-  const __half* iim = static_cast<const __half*>(in_im);
-  __half* ore = static_cast<__half*>(out_re);
-  __half* oim = static_cast<__half*>(out_im);
+  const int64_t outer = p->loop_batch ? p->batch : 1;
+  for (int64_t ob = 0; ob < outer; ++ob)
   for (const Pass& ps : p->passes) {
+    const __half* ire = static_cast<const __half*>(in_re) + ob * in_stride;
+    const __half* iim = static_cast<const __half*>(in_im) + ob * in_stride;
+    __half* ore = static_cast<__half*>(out_re) + ob * out_stride;
+    __half* oim = static_cast<__half*>(out_im) + ob * out_stride;
     const __half *sre, *sim;
     __half *dre, *dim;
     int64_t is, os;

@@ -26,11 +26,11 @@ def test_header_symbols_are_exported():
 
 def test_plan_info_matches_reference_plan_table():
     # r16 = log2N/4 - 1, r2 = log2N % 4 (src/base/Plan.h:99-100)
-    for lg, r16, r2 in [(8, 1, 0), (9, 1, 1), (12, 2, 0), (14, 2, 2), (15, 2, 3), (16, 3, 0), (20, 4, 0), (24, 5, 0)]:
+    for lg, r16, r2 in [(8, 1, 0), (9, 1, 1), (12, 2, 0), (14, 2, 2), (15, 2, 3), (16, 3, 0), (20, 4, 0), (24, 5, 0), (25, 5, 1), (28, 6, 0)]:
         p = tfft.NativePlan(1 << lg, 2)
         assert (p.info["amount_of_r16_steps"], p.info["amount_of_r2_steps"]) == (r16, r2)
         assert p.info["results_in_results"] == 1
-        assert p.info["passes"] == (1 if lg <= 15 else 2)
+        assert p.info["passes"] == (1 if lg <= 15 else 2 if lg <= 24 else 3)
         assert p.info["algorithmic_bytes"] == 8 * (1 << lg) * 2 * p.info["passes"]
         assert p.info["smem_bytes"] <= 227 * 1024 and p.info["tmem_columns"] <= 512
         p.close()
@@ -43,7 +43,7 @@ def test_config2_plan_shape():
     assert p.info["algorithmic_bytes"] == 536870912
 
 
-@pytest.mark.parametrize("n", [0, 100, 128, 255, 3 << 10, 1 << 25])
+@pytest.mark.parametrize("n", [0, 100, 128, 255, 3 << 10, 1 << 31])
 def test_invalid_sizes_are_rejected(n):
     with pytest.raises(tfft.TfftError):
         tfft.NativePlan(n, 1)

@@ -48,7 +48,7 @@ def run_abi(re16, im16, flags=0, in_stride=None, separate_planes=False):
 
 
 @pytest.mark.parametrize("lg,batch", [(8, 64), (8, 1), (9, 5), (10, 33), (11, 16), (12, 1), (12, 9), (13, 4),
-                                      (14, 8), (15, 3), (16, 2), (17, 1), (18, 1), (20, 2), (22, 1), (24, 1)])
+                                      (14, 8), (15, 3), (16, 2), (17, 1), (18, 1), (20, 2), (22, 1), (24, 1), (25, 2), (26, 1)])
 def test_vs_fp64_oracle(lg, batch):
     n = 1 << lg
     re, im = O.gauss_fixture(n, batch, seed=100 + lg)
@@ -236,3 +236,16 @@ def test_config2_full_size_impulses_and_linearity():
     plan.exec(a.view(-1), a.view(-1)[n:], yb.view(-1), yb.view(-1)[n:], 2 * n, 2 * n)
     torch.cuda.synchronize()
     assert bool(torch.equal(ya, yb))
+
+
+@pytest.mark.parametrize("exe", ["shim_ExampleBatchFFT", "shim_ExampleSingleFFT"])
+def test_reference_examples_run_against_the_shim(exe):
+    """The reference's own example programs, compiled unmodified against compat/base (tests/test_compat_shim.py
+    builds them where /root/reference exists), run on the library: both mains `return true` on success."""
+    import subprocess
+    path = os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "_ref", exe)
+    if not os.path.exists(path):
+        pytest.skip("shim example binaries not built (needs /root/reference at build time)")
+    r = subprocess.run([path], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 1, (r.returncode, r.stdout[-500:], r.stderr[-500:])    # `return true;` from main
+    assert "rror" not in r.stdout
