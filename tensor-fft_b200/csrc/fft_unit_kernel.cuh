@@ -304,19 +304,29 @@ __device__ __forceinline__ void epilogue_item(const UnitPlan& P, const KernelCtx
       t1 = cmul(t0, w1);
       s2 = cmul(w1, w1);
     }
-    // twiddles of columns (k, k+1) as packed pairs, advanced by step^2 = (sre, sim) per pair
+    // twiddles of columns (k, k+1) as packed pairs P_j = (t_2j, t_2j+1).  P_1 = P_0 * step^2 is a full
+    // complex product; after that the three-term recurrence P_{j+1} = 2cos(2 theta) P_j - P_{j-1} (exact for
+    // a geometric sequence on the unit circle) advances a pair with ONE packed FMA per component instead
+    // of a packed complex product (two).  Seven steps from exact seeds: error <= ~50 ulp(fp32) ~ 3e-6.
     f32x2 tre = pk(t0.re, t1.re), tim = pk(t0.im, t1.im);
     const f32x2 sre = pk(s2.re, s2.re), sim = pk(s2.im, s2.im);
+    const f32x2 c2 = pk(2.f * s2.re, 2.f * s2.re);
+    f32x2 qre = tre, qim = tim;   // P_{j-1}
 #pragma unroll
     for (int k = 0; k < 16; k += 2) {
       const f32x2 xr = pk(__uint_as_float(are[k]), __uint_as_float(are[k + 1]));
       const f32x2 xi = pk(__uint_as_float(aim[k]), __uint_as_float(aim[k + 1]));
       pre[k >> 1] = pack_half2_pair(fma2(neg2(xi), tim, mul2(xr, tre)));
       pim[k >> 1] = pack_half2_pair(fma2(xi, tre, mul2(xr, tim)));
-      if (k < 14) {
-        const f32x2 nre = fma2(neg2(tim), sim, mul2(tre, sre));
-        tim = fma2(tim, sre, mul2(tre, sim));
+      if (k == 0) {
+        tre = fma2(neg2(qim), sim, mul2(qre, sre));
+        tim = fma2(qim, sre, mul2(qre, sim));
+      } else if (k < 14) {
+        const f32x2 nre = fma2(c2, tre, neg2(qre)), nim = fma2(c2, tim, neg2(qim));
+        qre = tre;
+        qim = tim;
         tre = nre;
+        tim = nim;
       }
     }
   }
@@ -374,7 +384,7 @@ __device__ __forceinline__ void run_stage(const UnitPlan& P, const KernelCtx& c,
   group_sync(c);
   tc_fence_after_sync();
   TFFT_TRACE_MARK(9 + 2 * ST);
-  if (warp == c.mma_warp && lane == 0) {
+  if (warp == c.mma_warp && elect_one()) {
     constexpr uint32_t idesc = make_idesc_f16(128, 2 * R, /*a_mn=*/1, /*b_mn=*/0);
     // descriptors differ only in the 14-bit start-address field (units of 16 bytes): add offsets there
     // A operand: SWIZZLE_NONE padded chunks (written by cp.async / epilogues), or for a TMA-loaded
@@ -415,7 +425,7 @@ __device__ __forceinline__ void run_stage(const UnitPlan& P, const KernelCtx& c,
     if (kPipe) phase[1]++;
     return;
   }
-  const bool run_hooks = c.mma_warp == 0 && warp == 0 && lane == 0;
+  const bool hook_warp = c.mma_warp == 0 && warp == 0;   // converged at every use below (after warp_wait)
   // per-thread parts of the bit-linear row maps: 7 lane-row bits + the warp-group bit of the item index
   const UnitPlan::Epi& E = P.epi[ST];
   uint32_t dst_thr = bit_sum(c.lane_row, E.dst, 0, 7);
@@ -434,9 +444,9 @@ __device__ __forceinline__ void run_stage(const UnitPlan& P, const KernelCtx& c,
 #ifdef TFFT_DEBUG_SKIP
   if (true) {   // developer experiment: no epilogue work, only the barrier protocol
     warp_wait(bar, phase[0] & 1u, lane);
-    if (run_hooks) hook.after_half(0);
+    if (hook_warp && elect_one()) hook.after_half(0);
     if (kPipe) warp_wait(bar + 1, phase[1] & 1u, lane);
-    if (run_hooks) hook.after_half(1);
+    if (hook_warp && elect_one()) hook.after_half(1);
     phase[0]++;
     if (kPipe) phase[1]++;
     return;
@@ -446,19 +456,19 @@ __device__ __forceinline__ void run_stage(const UnitPlan& P, const KernelCtx& c,
     // items [0, half) only touch tiles of the first half for every radix (item = 2*II + wgroup)
     constexpr uint32_t kHalf = kItemsPerGroup / 2;
     warp_wait(bar, phase[0] & 1u, lane);
-    if (run_hooks) hook.after_half(0);
+    if (hook_warp && elect_one()) hook.after_half(0);
     TFFT_TRACE_MARK(10 + 2 * ST);
     epilogue_load<RHO, 0>(c, ra, rb);
     epilogue_range<ST, RHO, LAST, 0, kHalf>(P, c, dst_thr, aux_thr, col_thr, ra, rb, rc, rd);
     warp_wait(bar + 1, phase[1] & 1u, lane);
-    if (run_hooks) hook.after_half(1);
+    if (hook_warp && elect_one()) hook.after_half(1);
     epilogue_load<RHO, kHalf>(c, ra, rb);
     epilogue_range<ST, RHO, LAST, kHalf, kItemsPerGroup>(P, c, dst_thr, aux_thr, col_thr, ra, rb, rc, rd);
     phase[0]++;
     phase[1]++;
   } else {
     warp_wait(bar, phase[0] & 1u, lane);
-    if (run_hooks) {
+    if (hook_warp && elect_one()) {
       hook.after_half(0);
       hook.after_half(1);
     }
