@@ -17,6 +17,7 @@
 // into each fp16 DFT matrix (exact powers of two), total 1/L like the reference's "sequential
 // scaling" (TensorFFT256.cu:167-171, TensorRadix16.cu:133-136, Radix2.cu:64-76).
 #pragma once
+#include <type_traits>
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -206,7 +207,10 @@ __device__ __forceinline__ Cplx tw_lookup(const float2* tw_table, uint32_t x) {
 // Optional phase trace (developer builds, -DTFFT_TRACE): thread 0 of every CTA records clock64 at
 // phase boundaries of its first units into a global buffer (tools/trace_phases.py).
 #ifdef TFFT_TRACE
-#define TFFT_TRACE_TID0 ((threadIdx.x & 255) == 0 && threadIdx.x < 512)
+#ifndef TFFT_TRACE_THREAD
+#define TFFT_TRACE_THREAD 0   // thread of each slot that records (0 = the UMMA-issuing thread)
+#endif
+#define TFFT_TRACE_TID0 ((threadIdx.x & 255) == TFFT_TRACE_THREAD && threadIdx.x < 512)
 #define TFFT_TRACE_SLOT (threadIdx.x >> 8)
 #ifndef TFFT_TRACE_FIRST
 #define TFFT_TRACE_FIRST 0
@@ -369,63 +373,97 @@ struct NoHook {
   __device__ __forceinline__ void before_half(int) const {}
   __device__ __forceinline__ void after_half(int) const {}
 };
-template <int ST, int RHO, bool LAST, int LOG2E, bool SW128 = false, bool PIPE = false, class Hook = NoHook>
+template <int RHO, int LOG2E, bool PIPE>
+struct StageShape {
+  static constexpr uint32_t R = 1u << RHO, G = R / 16, kSteps = R / 16;
+  static constexpr uint32_t S = 16 * R + 16;                       // chunk stride of this stage's operand layout
+  static constexpr uint32_t kTiles = (1u << LOG2E) / R / 128;
+  static constexpr uint32_t kItemsPerGroup = (1u << LOG2E) / 2048 / 2;   // E/2048 work items per stage, two warp groups
+  static constexpr bool kPipe = PIPE && kTiles >= 2 && kItemsPerGroup >= 2;
+};
+
+// All UMMAs of one stage, issued by ONE thread (under elect_one()).
+template <int ST, int RHO, int LOG2E, bool SW128, bool PIPE, class Hook>
+__device__ __forceinline__ void stage_issue(const KernelCtx& c, uint32_t b1_saddr, uint64_t* bar, const Hook& hook,
+                                            long long* trace, uint32_t trace_unit) {
+  using namespace ptx;
+  using SS = StageShape<RHO, LOG2E, PIPE>;
+  constexpr uint32_t R = SS::R, kSteps = SS::kSteps, S = SS::S, kTiles = SS::kTiles;
+  constexpr bool kPipe = SS::kPipe;
+  constexpr uint32_t idesc = make_idesc_f16(128, 2 * R, /*a_mn=*/1, /*b_mn=*/0);
+  // descriptors differ only in the 14-bit start-address field (units of 16 bytes): add offsets there
+  // A operand: SWIZZLE_NONE padded chunks (written by cp.async / epilogues), or for a TMA-loaded
+  // stage 1 SWIZZLE_128B atoms of 64 rows (LBO = atom stride 128R, SBO = K-group stride 1024)
+  constexpr uint64_t kSw128 = uint64_t(2) << 61;
+  const uint32_t pa_re = ST == 0 ? c.a_re : c.s_re, pa_im = ST == 0 ? c.a_im : c.s_im;
+  const uint64_t da_re = SW128 ? (make_smem_desc(pa_re, 128 * R, 1024) | kSw128) : make_smem_desc(pa_re, kKGroupStride, S);
+  const uint64_t da_im = SW128 ? (make_smem_desc(pa_im, 128 * R, 1024) | kSw128) : make_smem_desc(pa_im, kKGroupStride, S);
+  constexpr uint32_t kTileStep = SW128 ? (2 * 128 * R) / 16 : S;   // descriptor address units (16 B) per tile
+  constexpr uint32_t kKStep = SW128 ? 2048 / 16 : 16;              // ... per 16-wide K step
+  const uint64_t db1 = make_smem_desc(b1_saddr, kKGroupStride, 16 * R);
+  const uint64_t db2 = make_smem_desc(b1_saddr + 4 * R * R, kKGroupStride, 16 * R);
+#pragma unroll
+  for (uint32_t tile = 0; tile < kTiles; ++tile) {
+    const uint32_t d = c.taddr + tile * 2 * R;
+    if (tile == 0) {
+      hook.before_half(0);
+      TFFT_TRACE_MARK(16 + 4 * ST);
+    }
+    if (tile == (kTiles + 1) / 2) {
+      hook.before_half(1);
+      TFFT_TRACE_MARK(17 + 4 * ST);
+    }
+    if (kTiles == 1 && tile == 0) hook.before_half(1);
+#pragma unroll
+    for (uint32_t j = 0; j < kSteps; ++j)
+      umma_f16_ss(d, da_re + (tile * kTileStep + j * kKStep), db1 + j * 16, idesc, j > 0 ? 1u : 0u);
+#pragma unroll
+    for (uint32_t j = 0; j < kSteps; ++j)
+      umma_f16_ss(d, da_im + (tile * kTileStep + j * kKStep), db2 + j * 16, idesc, 1u);
+    if (kPipe && tile + 1 == kTiles / 2) umma_commit(bar);     // first half of the tiles
+  }
+  umma_commit(kPipe ? bar + 1 : bar);   // separate barriers: a parity wait must never fall two phases behind
+  TFFT_TRACE_MARK(18 + 4 * ST);
+}
+
+// Dedicated UMMA warp: observe the completions of a stage (one lane) and run the landing-ring hooks.
+template <int RHO, int LOG2E, bool PIPE, class Hook>
+__device__ __forceinline__ void stage_observe(uint64_t* bar, uint32_t (&phase)[2], const Hook& hook) {
+  constexpr bool kPipe = StageShape<RHO, LOG2E, PIPE>::kPipe;
+  if (ptx::elect_one()) {
+    ptx::mbar_wait(bar, phase[0] & 1u);
+    hook.after_half(0);
+    if (kPipe) ptx::mbar_wait(bar + 1, phase[1] & 1u);
+    hook.after_half(1);
+  }
+  __syncwarp();
+  phase[0]++;
+  if (kPipe) phase[1]++;
+}
+
+// ROLE 0: every warp runs the epilogue and warp 0 also issues the UMMAs.
+// ROLE 1: epilogue warp of a slot whose UMMAs are issued by a dedicated warp.  That warp issues the
+//         stage-1 UMMAs of a unit ahead of time (during the previous unit's store phase), so stage 1 has
+//         no leading barrier here.
+template <int ST, int RHO, bool LAST, int LOG2E, bool SW128 = false, bool PIPE = false, class Hook = NoHook,
+          int ROLE = 0>
 __device__ __forceinline__ void run_stage(const UnitPlan& P, const KernelCtx& c, uint32_t b1_saddr, uint64_t* bar,
                                           uint32_t (&phase)[2], int warp, int lane, long long* trace,
                                           uint32_t trace_unit, Hook hook = Hook()) {
   using namespace ptx;
-  constexpr uint32_t R = 1u << RHO, G = R / 16, kSteps = R / 16;
-  constexpr uint32_t S = 16 * R + 16;                       // chunk stride of this stage's operand layout
-  constexpr uint32_t kTiles = (1u << LOG2E) / R / 128;
-  constexpr uint32_t kItemsPerGroup = (1u << LOG2E) / 2048 / 2;   // E/2048 work items per stage, two warp groups
-  constexpr bool kPipe = PIPE && kTiles >= 2 && kItemsPerGroup >= 2;
-  fence_proxy_async_smem();   // generic-proxy / cp.async operand writes -> visible to the tensor core
-  tc_fence_before_sync();
-  group_sync(c);
-  tc_fence_after_sync();
+  using SS = StageShape<RHO, LOG2E, PIPE>;
+  constexpr uint32_t R = SS::R, G = SS::G, kItemsPerGroup = SS::kItemsPerGroup;
+  constexpr bool kPipe = SS::kPipe;
+  if (ROLE == 0 || ST > 0) {
+    fence_proxy_async_smem();   // generic-proxy / cp.async operand writes -> visible to the tensor core
+    tc_fence_before_sync();
+    group_sync(c);
+    tc_fence_after_sync();
+  }
   TFFT_TRACE_MARK(9 + 2 * ST);
-  if (warp == c.mma_warp && elect_one()) {
-    constexpr uint32_t idesc = make_idesc_f16(128, 2 * R, /*a_mn=*/1, /*b_mn=*/0);
-    // descriptors differ only in the 14-bit start-address field (units of 16 bytes): add offsets there
-    // A operand: SWIZZLE_NONE padded chunks (written by cp.async / epilogues), or for a TMA-loaded
-    // stage 1 SWIZZLE_128B atoms of 64 rows (LBO = atom stride 128R, SBO = K-group stride 1024)
-    constexpr uint64_t kSw128 = uint64_t(2) << 61;
-    const uint32_t pa_re = ST == 0 ? c.a_re : c.s_re, pa_im = ST == 0 ? c.a_im : c.s_im;
-    const uint64_t da_re = SW128 ? (make_smem_desc(pa_re, 128 * R, 1024) | kSw128) : make_smem_desc(pa_re, kKGroupStride, S);
-    const uint64_t da_im = SW128 ? (make_smem_desc(pa_im, 128 * R, 1024) | kSw128) : make_smem_desc(pa_im, kKGroupStride, S);
-    constexpr uint32_t kTileStep = SW128 ? (2 * 128 * R) / 16 : S;   // descriptor address units (16 B) per tile
-    constexpr uint32_t kKStep = SW128 ? 2048 / 16 : 16;              // ... per 16-wide K step
-    const uint64_t db1 = make_smem_desc(b1_saddr, kKGroupStride, 16 * R);
-    const uint64_t db2 = make_smem_desc(b1_saddr + 4 * R * R, kKGroupStride, 16 * R);
-#pragma unroll
-    for (uint32_t tile = 0; tile < kTiles; ++tile) {
-      const uint32_t d = c.taddr + tile * 2 * R;
-      if (tile == 0) hook.before_half(0);
-      if (tile == (kTiles + 1) / 2) hook.before_half(1);
-      if (kTiles == 1 && tile == 0) hook.before_half(1);
-#pragma unroll
-      for (uint32_t j = 0; j < kSteps; ++j)
-        umma_f16_ss(d, da_re + (tile * kTileStep + j * kKStep), db1 + j * 16, idesc, j > 0 ? 1u : 0u);
-#pragma unroll
-      for (uint32_t j = 0; j < kSteps; ++j)
-        umma_f16_ss(d, da_im + (tile * kTileStep + j * kKStep), db2 + j * 16, idesc, 1u);
-      if (kPipe && tile + 1 == kTiles / 2) umma_commit(bar);     // first half of the tiles
-    }
-    umma_commit(kPipe ? bar + 1 : bar);   // separate barriers: a parity wait must never fall two phases behind
-  }
-  if (warp >= 8) {   // dedicated MMA warp: observe the completions (landing-ring hooks), no epilogue work
-    if (lane == 0) {
-      mbar_wait(bar, phase[0] & 1u);
-      hook.after_half(0);
-      if (kPipe) mbar_wait(bar + 1, phase[1] & 1u);
-      hook.after_half(1);
-    }
-    __syncwarp();
-    phase[0]++;
-    if (kPipe) phase[1]++;
-    return;
-  }
-  const bool hook_warp = c.mma_warp == 0 && warp == 0;   // converged at every use below (after warp_wait)
+  if (ROLE == 0 && warp == 0 && elect_one())
+    stage_issue<ST, RHO, LOG2E, SW128, PIPE, Hook>(c, b1_saddr, bar, hook, trace, trace_unit);
+  const bool hook_warp = ROLE == 0 && warp == 0;   // converged at every use below (after warp_wait)
   // per-thread parts of the bit-linear row maps: 7 lane-row bits + the warp-group bit of the item index
   const UnitPlan::Epi& E = P.epi[ST];
   uint32_t dst_thr = bit_sum(c.lane_row, E.dst, 0, 7);
@@ -441,7 +479,7 @@ __device__ __forceinline__ void run_stage(const UnitPlan& P, const KernelCtx& c,
     }
   }
   uint32_t ra[16], rb[16], rc[16], rd[16];
-#ifdef TFFT_DEBUG_SKIP
+#if defined(TFFT_DEBUG_SKIP) || defined(TFFT_DEBUG_MMA_ONLY)
   if (true) {   // developer experiment: no epilogue work, only the barrier protocol
     warp_wait(bar, phase[0] & 1u, lane);
     if (hook_warp && elect_one()) hook.after_half(0);
@@ -659,10 +697,20 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
 // global load of unit q+1 overlaps stages 2..s and the store of unit q instead of serialising with
 // them.  Landing uses are strictly sequential: use q belongs to slot q & 1.
 // Shared memory: [W0_re | W0_im | W1_re | W1_im | L_re | L_im | tables | barriers]
-// A dedicated 9th MMA / TMA warp per slot was measured slower (153 us vs 137 us at C2: the 576-thread CTA
-// caps registers at 96 and spills), so the slot's warp 0 issues the UMMAs and also runs epilogues.
+// By default the slot's warp 0 issues the UMMAs and also runs epilogues.  -DTFFT_DEDICATED_MMA_WARP builds
+// the warp-specialised variant instead (a fifth warp group with one UMMA / TMA warp per slot, setmaxnreg
+// moving its registers to the epilogue warps, and the stage-1 UMMAs of the next unit issued during the
+// store phase).  Measured at C2 on B200: 127-130 us either way -- the slots are not latency-bound on the
+// issuing warp -- so the simpler program is the default.
+#ifdef TFFT_DEDICATED_MMA_WARP
+constexpr bool kDedicatedMmaWarp = true;
+#else
 constexpr bool kDedicatedMmaWarp = false;
+#endif
 constexpr int kSlotThreads = kThreads + (kDedicatedMmaWarp ? 32 : 0);
+// dedicated mode: a fifth warp group (warps 16-19) holds the two UMMA-issuing warps (two warps idle) so
+// that setmaxnreg can move its registers to the epilogue warp groups
+constexpr int kCta2Threads = kDedicatedMmaWarp ? 640 : 512;
 struct Smem2Layout {
   uint32_t plane_stride, land_off, land_stride, table_off, bar_off, total;
 };
@@ -678,7 +726,7 @@ __host__ __device__ inline Smem2Layout smem2_layout(const UnitPlan& p) {
 }
 
 template <int RHO0, int RHO1, int RHO2>
-__global__ void __launch_bounds__(2 * kSlotThreads, 1)
+__global__ void __launch_bounds__(kCta2Threads, 1)
 fft_unit_kernel_2slot(const __grid_constant__ UnitPlan P, __half* __restrict__ out_re, __half* __restrict__ out_im,
                       const uint4* __restrict__ tables, const __grid_constant__ CUtensorMap tmap_re,
                       const __grid_constant__ CUtensorMap tmap_im, long long* __restrict__ trace) {
@@ -693,7 +741,7 @@ fft_unit_kernel_2slot(const __grid_constant__ UnitPlan P, __half* __restrict__ o
   // quarter given by the CTA warp index mod 4, so each slot's epilogue warps start at a multiple of 4);
   // warps 16 / 17: the dedicated MMA warps of slot 0 / 1 (warp 8 of their slot)
   const uint32_t slot = tid_cta < 2 * kThreads ? static_cast<uint32_t>(tid_cta >> 8)
-                                               : static_cast<uint32_t>((tid_cta - 2 * kThreads) >> 5);
+                                               : static_cast<uint32_t>(((tid_cta - 2 * kThreads) >> 5) & 1);
   const int tid = tid_cta < 2 * kThreads ? (tid_cta & (kThreads - 1)) : kThreads + (tid_cta & 31);
   const int warp = tid >> 5, lane = tid & 31;
   uint32_t trace_unit = 0;
@@ -711,7 +759,7 @@ fft_unit_kernel_2slot(const __grid_constant__ UnitPlan P, __half* __restrict__ o
   c.wgroup = static_cast<uint32_t>(warp >> 2);
   c.bar_id = 1 + slot;
   c.sync_threads = kSlotThreads;
-  c.mma_warp = kDedicatedMmaWarp ? 8 : 0;
+  c.mma_warp = 0;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SL.bar_off);
   uint64_t* mma_bar = bars + 2 * slot;      // per slot: UMMA completion (two barriers: tile halves)
   uint64_t* land_full = bars + 4;           // land_full[2*s + h]: tile half h for slot s has landed
@@ -731,15 +779,12 @@ fft_unit_kernel_2slot(const __grid_constant__ UnitPlan P, __half* __restrict__ o
     for (int i = 0; i < 4; ++i) mbar_init(land_full + i, 1);
     fence_mbar_init();
   }
-  for (uint32_t o = tid_cta * 16; o < TL.total; o += 2 * kSlotThreads * 16) sts128(table_base + o, ldg128(tables + (o >> 4)));
+  for (uint32_t o = tid_cta * 16; o < TL.total; o += kCta2Threads * 16) sts128(table_base + o, ldg128(tables + (o >> 4)));
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   c.taddr = *tmem_slot + slot * 256;
   uint32_t phase[2] = {0, 0};
-
-  const uint32_t st_s_lo = bit_sum(tid, P.store_sofs, 0, 8), st_g_lo = bit_sum(tid, P.store_gofs, 0, 8);
-  const uint32_t st_u_lo = bit_sum(tid, P.store_uval, 0, 8);
 
   // landing use q (q = 0, 1, 2, ...) carries unit blockIdx.x + q * gridDim.x and belongs to slot q & 1.
   // The landing buffer is a ring of two half tiles (the first / second half of the stage-1 MMA tiles).
@@ -760,53 +805,110 @@ fft_unit_kernel_2slot(const __grid_constant__ UnitPlan P, __half* __restrict__ o
     request(0, 0);
     request(0, 1);
   }
+  struct LandingHook {
+    uint64_t* full;
+    uint32_t parity, q;
+    decltype(request)& req;
+    __device__ __forceinline__ void before_half(int h) const { mbar_wait(full + h, parity); }   // tile half landed
+    __device__ __forceinline__ void after_half(int h) const { req(q + 1, static_cast<uint32_t>(h)); }
+  };
+  const uint32_t b_saddr0 = table_base + TL.b_off[0], b_saddr1 = table_base + TL.b_off[1],
+                 b_saddr2 = table_base + TL.b_off[2];
+  // stage 1 reads the landing buffer and writes the working planes: MMA/epilogue overlap is always legal;
+  // stage 2 works in place: overlap needs a plan built with pipe_stage2
+  const bool pipe2 = kStages == 3 && P.pipe_stage2;
 
-  for (uint32_t q = slot; unit_of(q) < P.n_units; q += 2) {
-    const uint32_t unit = unit_of(q);
-    const uint32_t ub = unit / P.units_per_batch, uu = unit % P.units_per_batch;
-    const int64_t out_base =
-        static_cast<int64_t>(ub) * P.out_batch_stride + static_cast<int64_t>(uu) * P.out_unit_stride;
-    const uint32_t u_limit =
-        P.n_transforms ? P.n_transforms - min(P.n_transforms, unit << P.log2_units) : 0xFFFFFFFFu;
-    c.col_base = (uu / P.col_div) * P.col_base_stride + P.col_first;
-    TFFT_TRACE_MARK(0);
-    TFFT_TRACE_MARK(1);
-    TFFT_TRACE_MARK(2);
-
-    // stage 1 reads the landing buffer and writes the working planes: overlap is always legal;
-    // stage 2 works in place: overlap needs a plan built with pipe_stage2
-    struct LandingHook {
-      uint64_t* full;
-      uint32_t parity, q;
-      decltype(request)& req;
-      __device__ __forceinline__ void before_half(int h) const { mbar_wait(full + h, parity); }   // tile half landed
-      __device__ __forceinline__ void after_half(int h) const { req(q + 1, static_cast<uint32_t>(h)); }
-    };
-    LandingHook hook{land_full + 2 * slot, (q >> 1) & 1u, q, request};
-    run_stage<0, RHO0, false, LOG2E, true, true>(P, c, table_base + TL.b_off[0], mma_bar, phase, warp, lane, trace,
-                                                 trace_unit, hook);
-    TFFT_TRACE_MARK(3);
-#ifndef TFFT_DEBUG_SKIP
-    if (kStages == 3 && P.pipe_stage2)
-      run_stage<1, RHO1, kStages == 2, LOG2E, false, true>(P, c, table_base + TL.b_off[1], mma_bar, phase, warp, lane,
-                                                           trace, trace_unit);
-    else
-      run_stage<1, RHO1, kStages == 2, LOG2E>(P, c, table_base + TL.b_off[1], mma_bar, phase, warp, lane, trace,
-                                              trace_unit);
-    TFFT_TRACE_MARK(4);
-    if constexpr (kStages == 3)
-      run_stage<2, (RHO2 ? RHO2 : 4), true, LOG2E>(P, c, table_base + TL.b_off[2], mma_bar, phase, warp, lane, trace,
-                                                   trace_unit);
+  if (kDedicatedMmaWarp && tid_cta >= 2 * kThreads) {
+    // ---------------------------------------------------------------- UMMA / TMA warps (fifth warp group)
+    // The stage-1 UMMAs of a unit only need its landed tile and a free tensor-memory half, so they are
+    // issued as soon as the previous unit's last epilogue has drained the accumulators: the wait for the
+    // tile and the stage-1 tensor work overlap the previous unit's store phase.
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (tid_cta < 2 * kSlotThreads) {   // the other two warps of the group idle until the teardown
+      auto issue0 = [&](uint32_t q) {
+        if (unit_of(q) >= P.n_units) return;
+        LandingHook hook{land_full + 2 * slot, (q >> 1) & 1u, q, request};
+        if (elect_one())
+          stage_issue<0, RHO0, LOG2E, true, true, LandingHook>(c, b_saddr0, mma_bar, hook, trace, trace_unit);
+        __syncwarp();
+      };
+      issue0(slot);
+      for (uint32_t q = slot; unit_of(q) < P.n_units; q += 2) {
+        LandingHook hook{land_full + 2 * slot, (q >> 1) & 1u, q, request};
+        stage_observe<RHO0, LOG2E, true>(mma_bar, phase, hook);
+#if !defined(TFFT_DEBUG_SKIP)
+        tc_fence_before_sync();
+        group_sync(c);   // stage-1 epilogue complete: stage-2 operands in place
+        tc_fence_after_sync();
+        if (pipe2) {
+          if (elect_one()) stage_issue<1, RHO1, LOG2E, false, true, NoHook>(c, b_saddr1, mma_bar, NoHook(), trace, trace_unit);
+          __syncwarp();
+          stage_observe<RHO1, LOG2E, true>(mma_bar, phase, NoHook());
+        } else {
+          if (elect_one()) stage_issue<1, RHO1, LOG2E, false, false, NoHook>(c, b_saddr1, mma_bar, NoHook(), trace, trace_unit);
+          __syncwarp();
+          stage_observe<RHO1, LOG2E, false>(mma_bar, phase, NoHook());
+        }
+        if constexpr (kStages == 3) {
+          tc_fence_before_sync();
+          group_sync(c);
+          tc_fence_after_sync();
+          if (elect_one())
+            stage_issue<2, (RHO2 ? RHO2 : 4), LOG2E, false, false, NoHook>(c, b_saddr2, mma_bar, NoHook(), trace, trace_unit);
+          __syncwarp();
+          stage_observe<(RHO2 ? RHO2 : 4), LOG2E, false>(mma_bar, phase, NoHook());
+        }
 #endif
-    TFFT_TRACE_MARK(5);
-    group_sync(c);
-    TFFT_TRACE_MARK(6);
-    if (warp < 8)
+        tc_fence_before_sync();
+        group_sync(c);   // last epilogue complete: the accumulators are free
+        tc_fence_after_sync();
+        issue0(q + 2);
+        group_sync(c);   // store phase complete
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue / store warps
+    if (kDedicatedMmaWarp) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    constexpr int ROLE = kDedicatedMmaWarp ? 1 : 0;
+    const uint32_t st_s_lo = bit_sum(tid, P.store_sofs, 0, 8), st_g_lo = bit_sum(tid, P.store_gofs, 0, 8);
+    const uint32_t st_u_lo = bit_sum(tid, P.store_uval, 0, 8);
+    for (uint32_t q = slot; unit_of(q) < P.n_units; q += 2) {
+      const uint32_t unit = unit_of(q);
+      const uint32_t ub = unit / P.units_per_batch, uu = unit % P.units_per_batch;
+      const int64_t out_base =
+          static_cast<int64_t>(ub) * P.out_batch_stride + static_cast<int64_t>(uu) * P.out_unit_stride;
+      const uint32_t u_limit =
+          P.n_transforms ? P.n_transforms - min(P.n_transforms, unit << P.log2_units) : 0xFFFFFFFFu;
+      c.col_base = (uu / P.col_div) * P.col_base_stride + P.col_first;
+      TFFT_TRACE_MARK(0);
+      TFFT_TRACE_MARK(1);
+      TFFT_TRACE_MARK(2);
+      LandingHook hook{land_full + 2 * slot, (q >> 1) & 1u, q, request};
+      run_stage<0, RHO0, false, LOG2E, true, true, LandingHook, ROLE>(P, c, b_saddr0, mma_bar, phase, warp, lane, trace,
+                                                                      trace_unit, hook);
+      TFFT_TRACE_MARK(3);
+#if !defined(TFFT_DEBUG_SKIP)
+      if (pipe2)
+        run_stage<1, RHO1, kStages == 2, LOG2E, false, true, NoHook, ROLE>(P, c, b_saddr1, mma_bar, phase, warp, lane,
+                                                                           trace, trace_unit);
+      else
+        run_stage<1, RHO1, kStages == 2, LOG2E, false, false, NoHook, ROLE>(P, c, b_saddr1, mma_bar, phase, warp, lane,
+                                                                            trace, trace_unit);
+      TFFT_TRACE_MARK(4);
+      if constexpr (kStages == 3)
+        run_stage<2, (RHO2 ? RHO2 : 4), true, LOG2E, false, false, NoHook, ROLE>(P, c, b_saddr2, mma_bar, phase, warp,
+                                                                                 lane, trace, trace_unit);
+#endif
+      TFFT_TRACE_MARK(5);
+      tc_fence_before_sync();
+      group_sync(c);
+      TFFT_TRACE_MARK(6);
       store_phase<LOG2E>(P, c, out_re + out_base, out_im + out_base, tid, st_s_lo, st_g_lo, st_u_lo, u_limit);
-    TFFT_TRACE_MARK(7);
-    group_sync(c);   // staging fully read before the next unit's epilogues overwrite the working planes
-    TFFT_TRACE_MARK(8);
-    trace_unit++;
+      TFFT_TRACE_MARK(7);
+      group_sync(c);   // staging fully read before the next unit's epilogues overwrite the working planes
+      TFFT_TRACE_MARK(8);
+      trace_unit++;
+    }
   }
 
   // ------------------------------------------------------------------ teardown

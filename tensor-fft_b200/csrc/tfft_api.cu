@@ -420,7 +420,7 @@ int launch_pass(const tfft_plan_s* p, const Pass& ps, const __half* src_re, cons
     if (S2.total <= 227 * 1024 && sms > 0) {
       const unsigned grid2 = std::min<unsigned>(ps.n_units, static_cast<unsigned>(sms));
       void* args2[] = {&plan, &dst_re, &dst_im, &tables, &tmap_re, &tmap_im, &trace};
-      e = cudaLaunchKernel(reinterpret_cast<const void*>(fn2), dim3(grid2), dim3(2 * kSlotThreads), args2, S2.total, stream);
+      e = cudaLaunchKernel(reinterpret_cast<const void*>(fn2), dim3(grid2), dim3(kCta2Threads), args2, S2.total, stream);
       return e == cudaSuccess ? TFFT_OK : static_cast<int>(e);
     }
   }

@@ -27,5 +27,8 @@ for row in (0, 1, 2, 3, 294, 295):
 for st in range(3):
     a = t[:296, 1:3, 9 + 2 * st]; bdone = t[:296, 1:3, 10 + 2 * st]; end = t[:296, 1:3, 3 + st]; beg = t[:296, 1:3, 2 + st]
     print(f"stage{st}: pre-sync {int((a - beg).mean())}  mma-first-half-wait {int((bdone - a).mean())}  epilogue(+2nd half wait) {int((end - bdone).mean())}")
+for st in range(3):
+    a = t[:296, 1:3, 9 + 2 * st]
+    print(f"stage{st} mma thread: half0 ready +{int((t[:296,1:3,16+4*st]-a).mean())}  half1 ready +{int((t[:296,1:3,17+4*st]-a).mean())}  all issued +{int((t[:296,1:3,18+4*st]-a).mean())}  first-half done +{int((t[:296,1:3,10+2*st]-a).mean())}")
 tt = t[:296, 1:3, :9]
 print("mean (units 1-2):", {nm: int(v) for nm, v in zip(names, np.diff(tt, axis=2).mean(axis=(0, 1)))}, "total", int((tt[:, :, 8] - tt[:, :, 0]).mean()))
