@@ -156,7 +156,8 @@ __host__ __device__ inline TableLayout table_layout(const UnitPlan& p) {
   for (uint32_t t = 0; t < kMaxStages; ++t) l.b_off[t] = 0;
   for (uint32_t t = 0; t < p.stages; ++t) {
     bool found = false;
-    for (uint32_t u = 0; u < t; ++u)
+    const bool kron = p.kron_bits && t + 1 == p.stages;   // F_x (x) F_y: never shared with a plain stage
+    for (uint32_t u = 0; u < t && !kron; ++u)
       if (p.log2_radix[u] == p.log2_radix[t]) { l.b_off[t] = l.b_off[u]; found = true; break; }
     if (!found) {
       l.b_off[t] = off;
@@ -169,7 +170,7 @@ __host__ __device__ inline TableLayout table_layout(const UnitPlan& p) {
 
 // Dynamic shared memory carve-up (bytes): [plane_re | plane_im | tables | mbar | tmem slot]
 struct SmemLayout {
-  uint32_t plane_stride, table_off, bar_off, load_bar_off, slot_off, total;
+  uint32_t plane_stride, table_off, bar_off, load_bar_off, slot_off, ytw_off, total;
 };
 __host__ __device__ inline SmemLayout smem_layout(const UnitPlan& p) {
   SmemLayout l;
@@ -178,8 +179,18 @@ __host__ __device__ inline SmemLayout smem_layout(const UnitPlan& p) {
   l.bar_off = l.table_off + table_layout(p).total;   // two MMA barriers
   l.load_bar_off = l.bar_off + 16;
   l.slot_off = l.load_bar_off + 8;
-  l.total = l.slot_off + 8;
+  l.ytw_off = l.slot_off + 8;        // Kronecker units: 8 float2 row twiddles of the current unit
+  l.total = l.ytw_off + 64;
   return l;
+}
+
+// 5-D variant for Kronecker units: {64 rows, R kappa, M/64, y_lo, u + U*image}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t c3, uint32_t c4,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %2, %2, %3, %4}], [%5];"
+      ::"r"(dst), "l"(map), "r"(0), "r"(c3), "r"(c4), "r"(ptx::smem_u32(bar))
+      : "memory");
 }
 
 // 4-D TMA tile load {64 rows, R kappa, M/64, U transforms} -> SWIZZLE_128B stage-1 operand plane
@@ -229,6 +240,7 @@ __device__ __forceinline__ Cplx tw_lookup(const float2* tw_table, uint32_t x) {
 struct KernelCtx {
   uint32_t sbase, s_re, s_im, taddr, lane_row, wgroup, lane_base;
   const float2* tw_table;
+  const float2* ytw;       // Kronecker units: exp(-2*pi*i * k_y * y_lo / ny), k_y < 8, of the current unit
   uint32_t col_base;
   uint32_t a_re, a_im;     // stage-1 operand planes (== s_re / s_im unless a separate landing buffer is used)
   uint32_t bar_id;         // 0: the 256 threads are the whole CTA (__syncthreads); else named barrier of a slot
@@ -289,6 +301,24 @@ __device__ __forceinline__ void epilogue_item(const UnitPlan& P, const KernelCtx
   } else {
     const uint32_t aux = aux_thr + bit_sum_c<kTileHi, kMaxRowBits - 7>(E.aux, 7);
     Cplx t0, t1, s2;
+    if (LAST && E.tw_mode == 3) {
+      // Kronecker stage: columns k of this item belong to output row k_y = k >> tw_shift (tw_shift >= 3, so
+      // each 8-column chunk has one k_y); factor exp(-2*pi*i*k_y*y_lo/ny) from the per-unit table
+      const float2 w0 = c.ytw[(16u * g) >> E.tw_shift], w1 = c.ytw[(16u * g + 8u) >> E.tw_shift];
+#pragma unroll
+      for (int k = 0; k < 16; k += 2) {
+        const f32x2 wr = k < 8 ? pk(w0.x, w0.x) : pk(w1.x, w1.x), wi = k < 8 ? pk(w0.y, w0.y) : pk(w1.y, w1.y);
+        const f32x2 xr = pk(__uint_as_float(are[k]), __uint_as_float(are[k + 1]));
+        const f32x2 xi = pk(__uint_as_float(aim[k]), __uint_as_float(aim[k + 1]));
+        pre[k >> 1] = pack_half2_pair(fma2(neg2(xi), wi, mul2(xr, wr)));
+        pim[k >> 1] = pack_half2_pair(fma2(xi, wr, mul2(xr, wi)));
+      }
+      sts128(c.s_re + dst, make_uint4(pre[0], pre[1], pre[2], pre[3]));
+      sts128(c.s_re + dst + E.dst_k[0], make_uint4(pre[4], pre[5], pre[6], pre[7]));
+      sts128(c.s_im + dst, make_uint4(pim[0], pim[1], pim[2], pim[3]));
+      sts128(c.s_im + dst + E.dst_k[0], make_uint4(pim[4], pim[5], pim[6], pim[7]));
+      return;
+    }
     if (!LAST) {
       const uint32_t idx = aux << E.tw_shift;                       // unit angle 2*pi/L
       const Cplx w1 = tw_lookup(c.tw_table, idx);
@@ -582,6 +612,7 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
   c.bar_id = 0;
   c.sync_threads = kThreads;
   c.mma_warp = 0;
+  c.ytw = reinterpret_cast<const float2*>(smem + SL.ytw_off);
   uint32_t trace_unit = 0;
   (void)trace_unit;
 
@@ -620,6 +651,11 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
     const uint32_t u_limit =
         P.n_transforms ? P.n_transforms - min(P.n_transforms, unit << P.log2_units) : 0xFFFFFFFFu;
     c.col_base = (uu / P.col_div) * P.col_base_stride + P.col_first;
+    if (P.kron_bits && tid < 8) {   // row twiddles of this unit (read by the last epilogue, two barriers from here)
+      const Cplx w = twiddle((static_cast<uint32_t>(tid) * c.col_base) & ((1u << P.epi[kStages - 1].tw_log2n) - 1u),
+                             P.epi[kStages - 1].tw_log2n);
+      reinterpret_cast<float2*>(smem + SL.ytw_off)[tid] = make_float2(w.re, w.im);
+    }
 
     // ---------------------------------------------------------------- load phase
     TFFT_TRACE_MARK(0);
@@ -629,8 +665,13 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
       if (tid == 0) {
         fence_proxy_async_smem();   // earlier generic-proxy reads of the planes precede the async-proxy writes
         mbar_arrive_expect_tx(load_bar, 4u << LOG2E);
-        tma_load_4d(c.s_re, &tmap_re, 0, unit << P.log2_units, load_bar);
-        tma_load_4d(c.s_im, &tmap_im, 0, unit << P.log2_units, load_bar);
+        if (P.kron_bits) {
+          tma_load_5d(c.s_re, &tmap_re, uu, ub << P.log2_units, load_bar);
+          tma_load_5d(c.s_im, &tmap_im, uu, ub << P.log2_units, load_bar);
+        } else {
+          tma_load_4d(c.s_re, &tmap_re, 0, unit << P.log2_units, load_bar);
+          tma_load_4d(c.s_im, &tmap_im, 0, unit << P.log2_units, load_bar);
+        }
       }
       TFFT_TRACE_MARK(1);
       mbar_wait(load_bar, load_phase & 1u);
@@ -712,7 +753,7 @@ constexpr int kSlotThreads = kThreads + (kDedicatedMmaWarp ? 32 : 0);
 // that setmaxnreg can move its registers to the epilogue warp groups
 constexpr int kCta2Threads = kDedicatedMmaWarp ? 640 : 512;
 struct Smem2Layout {
-  uint32_t plane_stride, land_off, land_stride, table_off, bar_off, total;
+  uint32_t plane_stride, land_off, land_stride, table_off, bar_off, ytw_off, total;
 };
 __host__ __device__ inline Smem2Layout smem2_layout(const UnitPlan& p) {
   Smem2Layout l;
@@ -721,7 +762,8 @@ __host__ __device__ inline Smem2Layout smem2_layout(const UnitPlan& p) {
   l.land_stride = 2u << p.log2_elems;   // dense SWIZZLE_128B plane: 2 bytes per element
   l.table_off = l.land_off + 2 * l.land_stride;
   l.bar_off = l.table_off + table_layout(p).total;
-  l.total = l.bar_off + 64;
+  l.ytw_off = l.bar_off + 128;   // [0,64) barriers, [64,72) tensor-memory slot, [128,256) row twiddles of the two slots
+  l.total = l.bar_off + 256;
   return l;
 }
 
@@ -760,6 +802,7 @@ fft_unit_kernel_2slot(const __grid_constant__ UnitPlan P, __half* __restrict__ o
   c.bar_id = 1 + slot;
   c.sync_threads = kSlotThreads;
   c.mma_warp = 0;
+  c.ytw = reinterpret_cast<const float2*>(smem + SL.ytw_off + 64 * slot);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SL.bar_off);
   uint64_t* mma_bar = bars + 2 * slot;      // per slot: UMMA completion (two barriers: tile halves)
   uint64_t* land_full = bars + 4;           // land_full[2*s + h]: tile half h for slot s has landed
@@ -798,6 +841,12 @@ fft_unit_kernel_2slot(const __grid_constant__ UnitPlan P, __half* __restrict__ o
     uint64_t* full = land_full + 2 * (q & 1u) + h;
     mbar_arrive_expect_tx(full, 2u << LOG2E);
     const uint32_t off = h << LOG2E;   // half a plane: E bytes
+    if (P.kron_bits) {   // unit = (image, y_lo); tile halves split the U rows
+      const uint32_t uq = unit_of(q), c3 = uq % P.units_per_batch, c4 = ((uq / P.units_per_batch) << P.log2_units) + h * half_c3;
+      tma_load_5d(c.a_re + off, &tmap_re, c3, c4, full);
+      tma_load_5d(c.a_im + off, &tmap_im, c3, c4, full);
+      return;
+    }
     tma_load_4d(c.a_re + off, &tmap_re, h * half_c2, (unit_of(q) << P.log2_units) + h * half_c3, full);
     tma_load_4d(c.a_im + off, &tmap_im, h * half_c2, (unit_of(q) << P.log2_units) + h * half_c3, full);
   };
@@ -880,6 +929,11 @@ fft_unit_kernel_2slot(const __grid_constant__ UnitPlan P, __half* __restrict__ o
       const uint32_t u_limit =
           P.n_transforms ? P.n_transforms - min(P.n_transforms, unit << P.log2_units) : 0xFFFFFFFFu;
       c.col_base = (uu / P.col_div) * P.col_base_stride + P.col_first;
+      if (P.kron_bits && tid < 8) {   // row twiddles of this unit (read by the last epilogue, two barriers from here)
+        const Cplx w = twiddle((static_cast<uint32_t>(tid) * c.col_base) & ((1u << P.epi[kStages - 1].tw_log2n) - 1u),
+                               P.epi[kStages - 1].tw_log2n);
+        reinterpret_cast<float2*>(smem + SL.ytw_off + 64 * slot)[tid] = make_float2(w.re, w.im);
+      }
       TFFT_TRACE_MARK(0);
       TFFT_TRACE_MARK(1);
       TFFT_TRACE_MARK(2);

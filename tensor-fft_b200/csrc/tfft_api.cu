@@ -33,6 +33,7 @@ struct Pass {
   int src = 0, dst = 0;    // 0 = user input planes, 1 = user output planes, 2 = plan workspace
   bool in_stride_is_user = false, out_stride_is_user = false;
   bool own_batch_strides = false;   // three-pass plans: the batch level of the unit addressing is internal
+  int kind = 0;                     // 0: 1-D passes; 1: 2-D row pass (row mode, unit = U rows of one image); 2: 2-D column pass
 };
 
 int ilog2_exact(int64_t n) {
@@ -74,10 +75,16 @@ std::vector<uint8_t> make_tables(const UnitPlan& plan) {
     const int rho = static_cast<int>(plan.log2_radix[t]), R = 1 << rho;
     __half* b1 = reinterpret_cast<__half*>(host.data() + TL.b_off[t]);
     __half* b2 = b1 + 2 * R * R;
+    // Kronecker last stage (2-D row pass): K index = (kappa_x low, kappa_y high), output column = (k_x low, k_y high),
+    // F = F_x[kappa_x][k_x] * F_y[kappa_y][k_y]
+    const int ybits = (plan.kron_bits && t + 1 == plan.stages) ? static_cast<int>(plan.kron_bits) : 0;
+    const int Rx = R >> ybits, Ry = 1 << ybits;
     for (int kap = 0; kap < R; ++kap)
       for (int n = 0; n < 2 * R; ++n) {
         double c, s;
-        unit(static_cast<int64_t>(kap) * (n % R), R, &c, &s);
+        const int k = n % R;
+        // phase / R = kap_x*k_x/Rx + kap_y*k_y/Ry
+        unit(static_cast<int64_t>(kap % Rx) * (k % Rx) * Ry + static_cast<int64_t>(kap / Rx) * (k / Rx) * Rx, R, &c, &s);
         const float fr = static_cast<float>(c / R), fi = static_cast<float>(s / R);
         const uint32_t off = (n >> 3) * (8 * R) + (kap >> 3) * 64 + (n & 7) * 8 + (kap & 7);   // in halves
         b1[off] = __float2half_rn(n < R ? fr : fi);
@@ -163,6 +170,25 @@ int make_input_tensor_map(const UnitPlan& plan, const __half* base, int64_t tstr
   return r == CUDA_SUCCESS ? TFFT_OK : TFFT_E_INVALID_ARG;
 }
 
+// Kronecker units (2-D row pass): unit (image b, y_lo) reads rows y_lo + u*(ny/U), u < U, of image b.  Images are
+// contiguous (stride ny*nx), so row = y_lo + (ny/U)*(u + U*b): dims {64, R, M/64, y_lo (stride nx), u + U*b}.
+int make_kron_tensor_map(const UnitPlan& plan, const __half* base, int64_t ny, int64_t batch, CUtensorMap* out,
+                         bool half_box) {
+  EncodeTiledFn encode = get_encode_fn();
+  if (!encode) return TFFT_E_UNSUPPORTED;
+  const uint64_t L = uint64_t(1) << plan.log2_len, R = uint64_t(1) << plan.log2_radix[0], M = L / R;
+  const uint64_t U = uint64_t(1) << plan.log2_units;
+  cuuint64_t gdim[5] = {64, R, M / 64, static_cast<cuuint64_t>(ny) / U, U * static_cast<cuuint64_t>(batch)};
+  cuuint64_t gstride[4] = {M * 2, 128, L * 2, (static_cast<cuuint64_t>(ny) / U) * L * 2};
+  cuuint32_t box[5] = {64, static_cast<cuuint32_t>(R), static_cast<cuuint32_t>(M / 64), 1,
+                       static_cast<cuuint32_t>(half_box ? U / 2 : U)};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<__half*>(base), gdim, gstride, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? TFFT_OK : TFFT_E_INVALID_ARG;
+}
+
 std::once_flag g_attr_once;
 int g_attr_err = 0;
 void set_kernel_attrs() {
@@ -185,10 +211,20 @@ struct tfft_plan_s {
   uint32_t flags = 0;
   int lg = 0;
   std::vector<Pass> passes;
+  std::vector<Pass> passes_strided;   // 2-D plans: the same passes without TMA loads, built at the first exec whose
+                                      // images are not contiguous (the tensor maps need image stride == ny*nx)
+  int ybits = 0;                      // 2-D plans: rows per Kronecker unit = 2^ybits (0: plain row pass)
   __half* workspace = nullptr;   // 2 * n * batch halves when TFFT_PRESERVE_INPUT on multi-pass sizes
   int64_t workspace_bytes = 0;
   bool loop_batch = false;           // three-pass plans run one transform at a time
   __half* host_path_buf = nullptr;   // lazily allocated [in | out] for tfft_exec_host
+  // tfft_exec_host pipeline: the batch is cut into chunks; chunk i+1 uploads while chunk i transforms and
+  // chunk i-1 downloads (PCIe is full duplex), on three plan-owned streams
+  tfft_plan_s* host_chunk_plan = nullptr;   // plan for `host_chunk` transforms
+  tfft_plan_s* host_tail_plan = nullptr;    // plan for the ragged last chunk
+  int64_t host_chunk = 0;
+  cudaStream_t host_streams[3] = {nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> host_events;     // 2 per chunk: uploaded, transformed
   int device = 0;
 };
 
@@ -349,6 +385,73 @@ int build_1d(tfft_plan_s* p) {
   return TFFT_OK;
 }
 
+// 2-D transform of ny x nx row-major images (the reference has no 2-D path), two HBM passes:
+//   rows    : every unit holds U = 2^yb rows y_lo + u*(ny/U) of one image (yb = log2(ny) - 12, 0 for ny <= 4096),
+//             transforms them along x and -- when yb > 0 -- also across the U rows (first decimation-in-frequency
+//             step of the column transform, folded into the last tensor stage as F_x (x) F_y) and multiplies row
+//             k_y by exp(-2*pi*i*k_y*y_lo/ny); result row k_y of unit y_lo is stored at row y_lo*U + k_y of the output
+//   columns : for every k_y, 8+ adjacent columns: length-(ny/U) transforms over rows k_y + U*y_lo, in place;
+//             output index k' lands at row k_y + U*k' = the natural row of the 2-D transform.
+int build_2d(tfft_plan_s* p, std::vector<Pass>* passes, bool allow_tma) {
+  const int lgx = ilog2_exact(p->nx), lgy = ilog2_exact(p->ny);
+  if (lgx < 8 || lgy < 8 || lgx > 15) return TFFT_E_INVALID_SIZE;
+  auto yb_ok = [&](int yb) {
+    if (yb == 0) return lgy <= 12;
+    if (lgx + yb < 13 || lgx + yb > 15 || lgy - yb > 12 || lgy - yb < 8) return false;
+    int rho[kMaxStages];
+    const int s = radix_schedule(lgx + yb, rho);
+    return rho[s - 1] - yb >= 3;   // the Kronecker stage keeps >= 3 bits of the x index (16-byte store chunks)
+  };
+  int yb = lgy > 12 ? lgy - 12 : 0;
+  while (yb <= 3 && !yb_ok(yb)) ++yb;
+  if (const char* e = getenv("TFFT_2D_YBITS")) yb = atoi(e);   // developer override (e.g. 2 rows vs 4 rows per unit)
+  if (yb < 0 || yb > 3 || !yb_ok(yb)) return TFFT_E_UNSUPPORTED;
+  p->ybits = yb;
+  const int64_t nx = p->nx, ny = p->ny, batch = p->batch;
+  std::vector<Pass> saved;
+  saved.swap(p->passes);
+  bool ok = true;
+  {
+    UnitShape sh;
+    sh.log2_len = lgx;
+    sh.kron_bits = yb;
+    sh.log2_units = yb ? yb : std::min(lgy, std::max(13 - lgx, unit_log2_elems(lgx) - lgx));
+    int rho[kMaxStages];
+    radix_schedule(yb ? lgx + yb : lgx, rho);
+    sh.tma_load = allow_tma && (lgx - rho[0]) >= 6 && getenv("TFFT_NO_TMA") == nullptr;
+    sh.pipe_stage2 = sh.tma_load && lgx + yb >= 13 && getenv("TFFT_NO_PIPE") == nullptr;
+    const int64_t U = int64_t(1) << sh.log2_units;
+    UnitStrides st;
+    st.in_tstride = yb ? (ny >> yb) * nx : nx;
+    st.in_unit_stride = yb ? nx : U * nx;
+    st.out_tstride = nx;
+    st.out_unit_stride = U * nx;
+    st.units_per_batch = static_cast<uint32_t>(ny / U);
+    st.col_base_stride = 1;   // Kronecker row twiddle: col_base = y_lo
+    st.kron_log2n = yb ? static_cast<uint32_t>(lgy) : 0u;
+    ok = add_pass(p, sh, st, static_cast<uint32_t>(batch * (ny / U)), 0, 1, true, true);
+    if (ok) p->passes.back().kind = 1;
+  }
+  if (ok) {
+    const int lg2 = lgy - yb;
+    UnitShape sh;
+    sh.log2_len = lg2;
+    sh.log2_units = std::max(3, unit_log2_elems(lg2) - lg2);
+    sh.in_mode = kColMode;
+    sh.out_mode = kColMode;
+    const int64_t U = int64_t(1) << sh.log2_units;
+    UnitStrides st;
+    st.in_nstride = nx << yb; st.out_nstride = nx << yb;
+    st.in_unit_stride = U; st.out_unit_stride = U;
+    st.units_per_batch = static_cast<uint32_t>((nx << yb) / U);
+    ok = add_pass(p, sh, st, static_cast<uint32_t>(batch * ((nx << yb) / U)), 1, 1, true, true);
+    if (ok) p->passes.back().kind = 2;
+  }
+  passes->swap(p->passes);
+  if (passes != &p->passes) p->passes.swap(saved);
+  return ok ? TFFT_OK : TFFT_E_UNSUPPORTED;
+}
+
 int launch_pass(const tfft_plan_s* p, const Pass& ps, const __half* src_re, const __half* src_im, __half* dst_re,
                 __half* dst_im, int64_t in_stride, int64_t out_stride, cudaStream_t stream, int tw_log2 = 0,
                 int64_t tw_first_col = 0) {
@@ -359,7 +462,10 @@ int launch_pass(const tfft_plan_s* p, const Pass& ps, const __half* src_re, cons
     st.col_div = 1;
   }
   const int64_t U = int64_t(1) << ps.plan.log2_units;
-  if (ps.plan.in_mode == kRowMode && ps.plan.out_mode == kRowMode) {   // batched 1-D, one pass
+  if (ps.kind != 0) {   // 2-D passes: only the image strides come from the caller
+    st.in_batch_stride = in_stride;
+    st.out_batch_stride = out_stride;
+  } else if (ps.plan.in_mode == kRowMode && ps.plan.out_mode == kRowMode) {   // batched 1-D, one pass
     st.in_tstride = in_stride; st.out_tstride = out_stride;
     st.in_unit_stride = U * in_stride; st.out_unit_stride = U * out_stride;
   } else if (!ps.own_batch_strides) {   // four-step passes: the batch level carries the user's (or workspace) transform stride
@@ -408,9 +514,15 @@ int launch_pass(const tfft_plan_s* p, const Pass& ps, const __half* src_re, cons
     // passes, at src + (t / upb) * batch_stride + (t % upb) * tstride == t * tstride when contiguous
     const int64_t n_tr = static_cast<int64_t>(ps.n_units) << plan.log2_units;
     const bool half_box = kernel2_for(plan) != nullptr;
-    int rc = make_input_tensor_map(plan, src_re, st.in_tstride, plan.n_transforms ? plan.n_transforms : n_tr, &tmap_re, half_box);
-    if (rc == TFFT_OK)
-      rc = make_input_tensor_map(plan, src_im, st.in_tstride, plan.n_transforms ? plan.n_transforms : n_tr, &tmap_im, half_box);
+    int rc;
+    if (plan.kron_bits) {
+      rc = make_kron_tensor_map(plan, src_re, p->ny, p->batch, &tmap_re, half_box);
+      if (rc == TFFT_OK) rc = make_kron_tensor_map(plan, src_im, p->ny, p->batch, &tmap_im, half_box);
+    } else {
+      rc = make_input_tensor_map(plan, src_re, st.in_tstride, plan.n_transforms ? plan.n_transforms : n_tr, &tmap_re, half_box);
+      if (rc == TFFT_OK)
+        rc = make_input_tensor_map(plan, src_im, st.in_tstride, plan.n_transforms ? plan.n_transforms : n_tr, &tmap_im, half_box);
+    }
     if (rc != TFFT_OK) return rc;
   }
   if (Kernel2Fn fn2 = kernel2_for(plan)) {
@@ -475,9 +587,20 @@ int tfft_plan_create(tfft_plan_t* out, int64_t n, int64_t batch, uint32_t flags)
 }
 
 int tfft_plan_create_2d(tfft_plan_t* out, int64_t ny, int64_t nx, int64_t batch, uint32_t flags) {
-  (void)ny; (void)nx; (void)batch; (void)flags;
-  if (out) *out = nullptr;
-  return TFFT_E_UNSUPPORTED;
+  if (!out) return TFFT_E_INVALID_ARG;
+  *out = nullptr;
+  if (ilog2_exact(ny) < 8 || ilog2_exact(nx) < 8 || ny * nx > (int64_t(1) << 30)) return TFFT_E_INVALID_SIZE;
+  if (batch < 1 || batch > (int64_t(1) << 20)) return TFFT_E_INVALID_ARG;
+  tfft_plan_s* p = new (std::nothrow) tfft_plan_s;
+  if (!p) return TFFT_E_NOMEM;
+  p->n = ny * nx; p->ny = ny; p->nx = nx; p->batch = batch; p->flags = flags; p->lg = ilog2_exact(ny * nx);
+  const int rc = build_2d(p, &p->passes, true);
+  if (rc != TFFT_OK) {
+    delete p;
+    return rc;
+  }
+  *out = p;
+  return TFFT_OK;
 }
 
 int tfft_plan_info(tfft_plan_t p, tfft_plan_info_t* info) {
@@ -508,9 +631,16 @@ int tfft_plan_destroy(tfft_plan_t p) {
   if (!p) return TFFT_E_INVALID_ARG;
   if (p->workspace) cudaFree(p->workspace);
   if (p->host_path_buf) cudaFree(p->host_path_buf);
-  for (Pass& ps : p->passes)
-    for (int d = 0; d < 16; ++d)
-      if (ps.d_tables[d]) cudaFree(ps.d_tables[d]);
+  if (p->host_chunk_plan) tfft_plan_destroy(p->host_chunk_plan);
+  if (p->host_tail_plan) tfft_plan_destroy(p->host_tail_plan);
+  for (cudaStream_t s : p->host_streams)
+    if (s) cudaStreamDestroy(s);
+  for (cudaEvent_t ev : p->host_events)
+    if (ev) cudaEventDestroy(ev);
+  for (std::vector<Pass>* v : {&p->passes, &p->passes_strided})
+    for (Pass& ps : *v)
+      for (int d = 0; d < 16; ++d)
+        if (ps.d_tables[d]) cudaFree(ps.d_tables[d]);
   delete p;
   return TFFT_OK;
 }
@@ -530,8 +660,17 @@ int tfft_exec(tfft_plan_t p, const void* in_re, const void* in_im, void* out_re,
   if (g_attr_err) return g_attr_err == static_cast<int>(cudaErrorInvalidDeviceFunction) ? TFFT_E_NO_DEVICE : g_attr_err;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int64_t outer = p->loop_batch ? p->batch : 1;
+  const std::vector<Pass>* passes = &p->passes;
+  if (p->ny && p->batch > 1 && in_stride != p->n && p->passes.front().plan.tma_load) {
+    std::lock_guard<std::mutex> lock(g_upload_mutex);
+    if (p->passes_strided.empty()) {
+      const int rc = build_2d(p, &p->passes_strided, false);
+      if (rc != TFFT_OK) return rc;
+    }
+    passes = &p->passes_strided;
+  }
   for (int64_t ob = 0; ob < outer; ++ob)
-  for (const Pass& ps : p->passes) {
+  for (const Pass& ps : *passes) {
     const __half* ire = static_cast<const __half*>(in_re) + ob * in_stride;
     const __half* iim = static_cast<const __half*>(in_im) + ob * in_stride;
     __half* ore = static_cast<__half*>(out_re) + ob * out_stride;
@@ -583,16 +722,59 @@ int tfft_exec_host(tfft_plan_t p, const void* host_in, void* host_out) {
       cudaGetLastError();
       return e == cudaErrorMemoryAllocation ? TFFT_E_NOMEM : (e == cudaErrorNoDevice ? TFFT_E_NO_DEVICE : static_cast<int>(e));
     }
+    // chunking: about 16 MiB per direction and chunk, at most 32 chunks, whole transforms only
+    const int64_t per_transform = 2 * p->n * static_cast<int64_t>(sizeof(__half));
+    int64_t chunk = std::max<int64_t>(1, (int64_t(16) << 20) / per_transform);
+    chunk = std::max(chunk, (p->batch + 31) / 32);
+    if (chunk >= p->batch || getenv("TFFT_HOST_NO_PIPELINE")) chunk = p->batch;
+    p->host_chunk = chunk;
+    if (chunk < p->batch) {
+      const uint32_t fl = p->flags & ~uint32_t(TFFT_PRESERVE_INPUT);
+      int rc = p->ny ? tfft_plan_create_2d(&p->host_chunk_plan, p->ny, p->nx, chunk, fl)
+                     : tfft_plan_create(&p->host_chunk_plan, p->n, chunk, fl);
+      if (rc == TFFT_OK && p->batch % chunk)
+        rc = p->ny ? tfft_plan_create_2d(&p->host_tail_plan, p->ny, p->nx, p->batch % chunk, fl)
+                   : tfft_plan_create(&p->host_tail_plan, p->n, p->batch % chunk, fl);
+      if (rc != TFFT_OK) return rc;
+      for (cudaStream_t& s : p->host_streams)
+        if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return static_cast<int>(cudaGetLastError());
+      p->host_events.resize(2 * ((p->batch + chunk - 1) / chunk));
+      for (cudaEvent_t& ev : p->host_events)
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return static_cast<int>(cudaGetLastError());
+    }
   }
   __half* din = p->host_path_buf;
   __half* dout = p->host_path_buf + halves;
-  cudaError_t e = cudaMemcpyAsync(din, host_in, halves * sizeof(__half), cudaMemcpyHostToDevice, 0);
-  if (e != cudaSuccess) return static_cast<int>(e);
-  int rc = tfft_exec(p, din, din + p->n, dout, dout + p->n, 2 * p->n, 2 * p->n, nullptr);
-  if (rc != TFFT_OK) return rc;
-  e = cudaMemcpyAsync(host_out, dout, halves * sizeof(__half), cudaMemcpyDeviceToHost, 0);
-  if (e != cudaSuccess) return static_cast<int>(e);
-  e = cudaStreamSynchronize(0);
+  if (p->host_chunk >= p->batch) {
+    cudaError_t e = cudaMemcpyAsync(din, host_in, halves * sizeof(__half), cudaMemcpyHostToDevice, 0);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    int rc = tfft_exec(p, din, din + p->n, dout, dout + p->n, 2 * p->n, 2 * p->n, nullptr);
+    if (rc != TFFT_OK) return rc;
+    e = cudaMemcpyAsync(host_out, dout, halves * sizeof(__half), cudaMemcpyDeviceToHost, 0);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    e = cudaStreamSynchronize(0);
+    return e == cudaSuccess ? TFFT_OK : static_cast<int>(e);
+  }
+  cudaStream_t s_up = p->host_streams[0], s_fft = p->host_streams[1], s_down = p->host_streams[2];
+  const __half* hin = static_cast<const __half*>(host_in);
+  __half* hout = static_cast<__half*>(host_out);
+  int64_t ci = 0;
+  for (int64_t b0 = 0; b0 < p->batch; b0 += p->host_chunk, ++ci) {
+    const int64_t nb = std::min(p->host_chunk, p->batch - b0);
+    const int64_t off = 2 * p->n * b0, cnt = 2 * p->n * nb;
+    cudaError_t e = cudaMemcpyAsync(din + off, hin + off, cnt * sizeof(__half), cudaMemcpyHostToDevice, s_up);
+    if (e == cudaSuccess) e = cudaEventRecord(p->host_events[2 * ci], s_up);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(s_fft, p->host_events[2 * ci], 0);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    tfft_plan_s* cp = nb == p->host_chunk ? p->host_chunk_plan : p->host_tail_plan;
+    int rc = tfft_exec(cp, din + off, din + off + p->n, dout + off, dout + off + p->n, 2 * p->n, 2 * p->n, s_fft);
+    if (rc != TFFT_OK) return rc;
+    e = cudaEventRecord(p->host_events[2 * ci + 1], s_fft);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(s_down, p->host_events[2 * ci + 1], 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hout + off, dout + off, cnt * sizeof(__half), cudaMemcpyDeviceToHost, s_down);
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
+  cudaError_t e = cudaStreamSynchronize(s_down);
   return e == cudaSuccess ? TFFT_OK : static_cast<int>(e);
 }
 

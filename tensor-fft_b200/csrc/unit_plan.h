@@ -47,6 +47,9 @@ struct UnitShape {
   AxisMode in_mode = kRowMode;   // kRowMode: transform elements contiguous; kColMode: 8+ transforms interleaved
   AxisMode out_mode = kRowMode;
   bool tma_load = false;   // stage-1 operand written by a TMA tensor load (SWIZZLE_128B, natural row order)
+  int kron_bits = 0;         // 2-D row pass: the U = 2^kron_bits transforms of a unit are rows y_lo + u*(ny/U) of one image
+                             // and the LAST tensor stage also transforms across them (DFT matrix = F_x (x) F_y), i.e.
+                             // the unit computes a 2-D DFT of size U x L.  Needs kron_bits == log2_units, row modes.
   bool pipe_stage2 = false;  // 3-stage plans: make the top row bit of stages 2 and 3 the same logical bit (k_1's
                              // top bit), so that the epilogue of the first half of stage 2's tiles only writes into
                              // the already consumed first half of the operand planes (MMA / epilogue overlap)
@@ -64,6 +67,7 @@ struct UnitPlan {
   uint32_t plane_bytes;                    // bytes of one operand plane, max over stages and staging
   uint32_t tmem_cols;                      // power of two >= E/64
   uint32_t pipe_stage2;                    // 1: stage 2 may overlap its second-half MMAs with its first-half epilogue
+  uint32_t kron_bits;                      // see UnitShape::kron_bits (0: plain 1-D units)
   uint32_t tma_load;                       // 1: stage-1 operand = SWIZZLE_128B MN-major atoms of 64 rows filled by TMA:
                                            //    element (row, kappa) at (row>>6)*128R + (kappa>>3)*1024 + (kappa&7)*128
                                            //    + ((((row>>3)&7) ^ (kappa&7))<<4) + (row&7)*2   (verified by probe/tma_probe.cu)
@@ -80,6 +84,7 @@ struct UnitPlan {
     uint32_t dst_k[3];           // byte offsets of the chunk-index bits k_t[3], k_t[4], k_t[5]
     uint32_t tw_mode;            // 0: none; 1: x = (aux << tw_shift) * k, unit angle 2*pi/L;
                                  // 2: x = (aux + k*tw_kw) * (col_base + col), unit angle 2*pi/2^tw_log2n
+                                 // 3: x = (k >> tw_shift) * col_base, unit angle 2*pi/2^tw_log2n (Kronecker stage)
     uint32_t tw_shift;
     uint32_t tw_log2n;
     uint32_t tw_kw;
@@ -119,6 +124,9 @@ struct PlanBuildInfo {   // host-only by-products, used by fill_strides and the 
   std::vector<LBit> store_bits;             // store item bit -> logical bit
   LBit store_x[3];
   int rho[kMaxStages] = {0, 0, 0};
+  int rx[kMaxStages] = {0, 0, 0};           // bits of the transform index each stage consumes (== rho except for
+                                            // a Kronecker last stage: rho - kron_bits)
+  int kron_bits = 0;
   int lo_bit[kMaxStages] = {0, 0, 0};       // n_t = n bits [lo_bit, lo_bit + rho)
   std::string error;
 };
@@ -157,9 +165,18 @@ inline bool build_unit_plan(const UnitShape& shape, UnitPlan* plan, PlanBuildInf
   const int ups = shape.log2_units;
   const int eps = lg + ups;
   int* rho = info->rho;
-  const int s = radix_schedule(lg, rho);
+  const int kb = shape.kron_bits;
+  if (kb && (kb != ups || shape.in_mode != kRowMode || shape.out_mode != kRowMode || lg < 8)) {
+    info->error = "Kronecker units need kron_bits == log2_units and row modes"; return false;
+  }
+  const int s = radix_schedule(kb ? eps : lg, rho);
   if (s == 0) { info->error = "length must be 2^8 .. 2^15"; return false; }
   if (eps < 13 || eps > 15) { info->error = "unit must hold 2^13 .. 2^15 elements"; return false; }
+  int* rx = info->rx;
+  for (int t = 0; t < s; ++t) rx[t] = rho[t] - (t == s - 1 ? kb : 0);
+  if (rx[s - 1] < 3) { info->error = "Kronecker stage keeps fewer than 3 transform bits"; return false; }
+  info->kron_bits = kb;
+  plan->kron_bits = static_cast<uint32_t>(kb);
   if ((shape.in_mode == kColMode || shape.out_mode == kColMode) && ups < 3) {
     info->error = "column modes need >= 8 transforms per unit"; return false;
   }
@@ -172,7 +189,7 @@ inline bool build_unit_plan(const UnitShape& shape, UnitPlan* plan, PlanBuildInf
   plan->pipe_stage2 = (shape.pipe_stage2 && s == 3) ? 1u : 0u;
   {
     int lo = lg;
-    for (int t = 0; t < s; ++t) { lo -= rho[t]; info->lo_bit[t] = lo; }
+    for (int t = 0; t < s; ++t) { lo -= rx[t]; info->lo_bit[t] = lo; }
   }
   uint32_t max_plane = 0;
   for (int t = 0; t < s; ++t) {
@@ -190,10 +207,11 @@ inline bool build_unit_plan(const UnitShape& shape, UnitPlan* plan, PlanBuildInf
     plan->tmem_cols = c;
   }
 
-  auto is_kbit_of_stage = [&](const LBit& b, int t, int* p) {  // is b a bit of n_t (t = 1..s)?
+  auto is_kbit_of_stage = [&](const LBit& b, int t, int* p) {  // is b a bit of the K index of stage t (t = 1..s)?
+    if (kb && t == s && b.kind == LBit::U) { *p = rx[s - 1] + b.idx; return true; }
     if (b.kind != LBit::R) return false;
     const int lo = info->lo_bit[t - 1];
-    if (b.idx >= lo && b.idx < lo + rho[t - 1]) { *p = b.idx - lo; return true; }
+    if (b.idx >= lo && b.idx < lo + rx[t - 1]) { *p = b.idx - lo; return true; }
     return false;
   };
   auto row_pos_bytes = [&](int t, int p) { return (1u << (p - 3)) * plan->chunk_stride[t - 1]; };
@@ -228,7 +246,8 @@ inline bool build_unit_plan(const UnitShape& shape, UnitPlan* plan, PlanBuildInf
     for (int i = 0; i < info->lo_bit[t - 1]; ++i) all.push_back({LBit::R, 0, (uint8_t)i});
     for (int tt = 1; tt < t; ++tt)
       for (int i = 0; i < rho[tt - 1]; ++i) all.push_back({LBit::K, (uint8_t)tt, (uint8_t)i});
-    for (int b = 0; b < ups; ++b) all.push_back({LBit::U, 0, (uint8_t)b});
+    if (!(kb && t == s))
+      for (int b = 0; b < ups; ++b) all.push_back({LBit::U, 0, (uint8_t)b});
     std::vector<LBit> rest;
     for (auto& b : all)
       if (find_bit(rb, b) < 0) rest.push_back(b);
@@ -288,9 +307,12 @@ inline bool build_unit_plan(const UnitShape& shape, UnitPlan* plan, PlanBuildInf
   // chunk = 8 consecutive k_s[0..2]; chunk bits = row bits of stage s plus k_s[3..rho_s).
   std::vector<LBit> obits;  // logical bits of the output index o, LSB first
   for (int t = 1; t <= s; ++t)
-    for (int i = 0; i < rho[t - 1]; ++i) obits.push_back({LBit::K, (uint8_t)t, (uint8_t)i});
+    for (int i = 0; i < rx[t - 1]; ++i) obits.push_back({LBit::K, (uint8_t)t, (uint8_t)i});
   std::vector<LBit> addr_bits;  // output address bits, fastest first
-  if (shape.out_mode == kRowMode) {
+  if (kb) {   // output row = the high bits of the Kronecker stage's output digit
+    addr_bits = obits;
+    for (int b = 0; b < kb; ++b) addr_bits.push_back({LBit::K, (uint8_t)s, (uint8_t)(rx[s - 1] + b)});
+  } else if (shape.out_mode == kRowMode) {
     addr_bits = obits;
     for (int b = 0; b < ups; ++b) addr_bits.push_back({LBit::U, 0, (uint8_t)b});
   } else {
@@ -376,10 +398,10 @@ inline bool build_unit_plan(const UnitShape& shape, UnitPlan* plan, PlanBuildInf
     if (t < s) {
       e.tw_mode = 1;
       // N_t = 2^(lo_bit[t-1] + rho_t); unit angle 2*pi/L: x = m_t * (L / N_t) * k
-      e.tw_shift = lg - (info->lo_bit[t - 1] + rho[t - 1]);
+      e.tw_shift = lg - (info->lo_bit[t - 1] + rx[t - 1]);
     } else {
       e.tw_mode = 0;
-      e.tw_kw = 1u << (lg - rho[s - 1]);  // weight of k_s in o
+      e.tw_kw = 1u << (lg - rx[s - 1]);  // weight of k_s in o
     }
   }
 
@@ -414,6 +436,7 @@ struct UnitStrides {
   bool col_from_u = true;    // tw_mode 2 column index includes the unit-local transform index u
   uint32_t n_transforms = 0;
   uint32_t pass1_log2n = 0;  // != 0: multiply outputs by exp(-2*pi*i*o*(col_base+u)/2^pass1_log2n)
+  uint32_t kron_log2n = 0;   // Kronecker units, != 0: multiply output row k_y by exp(-2*pi*i*k_y*col_base/2^kron_log2n)
 };
 
 inline void fill_strides(const UnitStrides& st, const PlanBuildInfo& info, UnitPlan* plan) {
@@ -426,10 +449,12 @@ inline void fill_strides(const UnitStrides& st, const PlanBuildInfo& info, UnitP
   for (size_t i = 0; i < info.load_bits.size(); ++i) plan->load_gofs[i] = in_contrib(info.load_bits[i]);
   auto o_weight = [&](const LBit& b) -> int64_t {
     int w = 0;
-    for (int t = 1; t < b.stage; ++t) w += info.rho[t - 1];
+    for (int t = 1; t < b.stage; ++t) w += info.rx[t - 1];
     return int64_t(1) << (w + b.idx);
   };
   auto out_contrib = [&](const LBit& b) -> uint32_t {
+    if (info.kron_bits && b.kind == LBit::K && b.stage == s && b.idx >= info.rx[s - 1])   // output row bit
+      return static_cast<uint32_t>(st.out_tstride << (b.idx - info.rx[s - 1]));
     if (b.kind == LBit::U) return static_cast<uint32_t>((plan->out_mode == kRowMode ? st.out_tstride : 1) << b.idx);
     return static_cast<uint32_t>(o_weight(b) * (plan->out_mode == kRowMode ? 1 : st.out_nstride));
   };
@@ -445,6 +470,11 @@ inline void fill_strides(const UnitStrides& st, const PlanBuildInfo& info, UnitP
   if (st.pass1_log2n) {
     plan->epi[s - 1].tw_mode = 2;
     plan->epi[s - 1].tw_log2n = st.pass1_log2n;
+  }
+  if (info.kron_bits && st.kron_log2n) {
+    plan->epi[s - 1].tw_mode = 3;
+    plan->epi[s - 1].tw_log2n = st.kron_log2n;
+    plan->epi[s - 1].tw_shift = static_cast<uint32_t>(info.rx[s - 1]);
   }
   if (!st.col_from_u)
     for (int i = 0; i < kMaxRowBits; ++i) plan->epi[s - 1].col[i] = 0;

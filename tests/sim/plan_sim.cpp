@@ -37,10 +37,12 @@ extern "C" {
 // Runs `n_units` units.  in/out are planar double arrays (element offsets as the plan says).
 // Returns the total number of bank conflicts found (negative = plan error).
 // conflicts[0..3] = load stores, epilogue stores, store-phase loads, (unused)
-int plansim_run(int log2_len, int log2_units, int in_mode_flags, int out_mode, const int64_t* strides9,
-                int pass1_log2n, int n_units, const double* in_re, const double* in_im,
-                double* out_re, double* out_im, int emulate_fp16, int* conflicts) {
+// ext3 (may be null): {kron_bits, kron_log2n, col_base_stride} for Kronecker (2-D row pass) units
+int plansim_run_ex(int log2_len, int log2_units, int in_mode_flags, int out_mode, const int64_t* strides9,
+                   int pass1_log2n, int n_units, const double* in_re, const double* in_im,
+                   double* out_re, double* out_im, int emulate_fp16, int* conflicts, const int64_t* ext3) {
   UnitShape shape; shape.log2_len = log2_len; shape.log2_units = log2_units;
+  if (ext3) shape.kron_bits = (int)ext3[0];
   const int in_mode = in_mode_flags & 1;
   shape.in_mode = (AxisMode)in_mode; shape.out_mode = (AxisMode)out_mode; shape.tma_load = (in_mode_flags & 2) != 0;
   shape.pipe_stage2 = (in_mode_flags & 4) != 0;
@@ -52,6 +54,7 @@ int plansim_run(int log2_len, int log2_units, int in_mode_flags, int out_mode, c
   st.out_unit_stride = strides9[7]; st.units_per_batch = (uint32_t)strides9[8]; st.col_base_stride = 1u << log2_units;
   st.n_units = (uint32_t)n_units;
   st.pass1_log2n = pass1_log2n;
+  if (ext3) { st.kron_log2n = (uint32_t)ext3[1]; st.col_base_stride = (uint32_t)ext3[2]; }
   fill_strides(st, info, &P);
   const bool h = emulate_fp16 != 0;
   const int s = P.stages;
@@ -121,6 +124,10 @@ int plansim_run(int log2_len, int log2_units, int in_mode_flags, int out_mode, c
             cd acc = 0;
             for (int kap = 0; kap < R; ++kap) {
               cd f = twd((int64_t)kap * k, R) / (double)R;
+              if (P.kron_bits && t == s) {   // F_x (x) F_y: K index = (kappa_x, kappa_y), column = (k_x, k_y)
+                const int Rx = R >> P.kron_bits, Ry = 1 << P.kron_bits;
+                f = twd((int64_t)(kap % Rx) * (k % Rx), Rx) * twd((int64_t)(kap / Rx) * (k / Rx), Ry) / (double)R;
+              }
               if (h) f = cd(rh(f.real(), true), rh(f.imag(), true));
               acc += a[kap] * f;
             }
@@ -141,6 +148,7 @@ int plansim_run(int log2_len, int log2_units, int in_mode_flags, int out_mode, c
             cd v = y[k];
             if (E.tw_mode == 1) v *= twd(((int64_t)aux << E.tw_shift) * k, L);
             if (E.tw_mode == 2) v *= twd(((int64_t)aux + (int64_t)k * E.tw_kw) * (int64_t)(col_base + col), int64_t(1) << E.tw_log2n);
+            if (E.tw_mode == 3) v *= twd((int64_t)(k >> E.tw_shift) * (int64_t)col_base, int64_t(1) << E.tw_log2n);
             uint32_t o = dst + bitsum((uint32_t)(k >> 3), E.dst_k, 3);
             if (o + 16 > P.plane_bytes) { fprintf(stderr, "dst out of range\n"); return -2; }
             o = o / 2 + (k & 7);
@@ -174,6 +182,13 @@ int plansim_run(int log2_len, int log2_units, int in_mode_flags, int out_mode, c
     }
   }
   return conflicts[0] + conflicts[1] + conflicts[2];
+}
+
+int plansim_run(int log2_len, int log2_units, int in_mode_flags, int out_mode, const int64_t* strides9,
+                int pass1_log2n, int n_units, const double* in_re, const double* in_im,
+                double* out_re, double* out_im, int emulate_fp16, int* conflicts) {
+  return plansim_run_ex(log2_len, log2_units, in_mode_flags, out_mode, strides9, pass1_log2n, n_units, in_re, in_im,
+                        out_re, out_im, emulate_fp16, conflicts, nullptr);
 }
 
 int plansim_plan_bytes() { return (int)sizeof(UnitPlan); }

@@ -80,3 +80,73 @@ def test_four_step_passes(sim, lg1, lg2, u1, u2):
     want = np.fft.fft(re + 1j * im) / N
     assert rc1 == 0 and rc2 == 0 and c1 == [0, 0, 0] and list(conf)[:3] == [0, 0, 0]
     assert np.linalg.norm(o_re + 1j * o_im - want) / np.linalg.norm(want) < 1e-13
+
+
+@pytest.mark.parametrize("lgy,lgx,yb,flags", [(9, 12, 1, 6), (10, 11, 2, 0)])
+def test_two_d_passes(sim, lgy, lgx, yb, flags):
+    """2-D ny x nx: row pass on Kronecker units (U = 2^yb rows y_lo + u*ny/U, last tensor stage = F_x (x) F_y, row
+    twiddle exp(-2 pi i k_y y_lo/ny)) then in-place column pass of length ny/U; equals fft2/(ny*nx)."""
+    sim.plansim_run_ex.argtypes = list(sim.plansim_run.argtypes) + [ctypes.POINTER(ctypes.c_int64)]
+    ny, nx = 1 << lgy, 1 << lgx
+    rng = np.random.default_rng(11)
+    re, im = rng.standard_normal(ny * nx), rng.standard_normal(ny * nx)
+    t_re, t_im = np.zeros(ny * nx), np.zeros(ny * nx)
+    conf = (ctypes.c_int * 4)()
+    if yb:
+        U, ups = 1 << yb, yb
+        st = (ctypes.c_int64 * 9)((ny >> yb) * nx, 1, nx, 1, 0, nx, 0, U * nx, ny // U)
+    else:
+        ups = 14 - lgx
+        U = 1 << ups
+        st = (ctypes.c_int64 * 9)(nx, 1, nx, 1, 0, U * nx, 0, U * nx, ny // U)
+    ext = (ctypes.c_int64 * 3)(yb, lgy if yb else 0, 1)
+    rc1 = sim.plansim_run_ex(lgx, ups, flags, 0, st, 0, ny // U, re.ctypes.data_as(dp), im.ctypes.data_as(dp),
+                             t_re.ctypes.data_as(dp), t_im.ctypes.data_as(dp), 0, conf, ext)
+    c1 = list(conf)[:3]
+    lg2 = lgy - yb
+    u2 = max(3, 14 - lg2)
+    U2 = 1 << u2
+    st = (ctypes.c_int64 * 9)(0, nx << yb, 0, nx << yb, 0, U2, 0, U2, 1 << 30)
+    o_re, o_im = t_re.copy(), t_im.copy()
+    rc2 = sim.plansim_run(lg2, u2, 1, 1, st, 0, (nx << yb) // U2, t_re.ctypes.data_as(dp), t_im.ctypes.data_as(dp),
+                          o_re.ctypes.data_as(dp), o_im.ctypes.data_as(dp), 0, conf)
+    want = np.fft.fft2((re + 1j * im).reshape(ny, nx)) / (ny * nx)
+    got = (o_re + 1j * o_im).reshape(ny, nx)
+    assert rc1 == 0 and rc2 == 0 and c1 == [0, 0, 0] and list(conf)[:3] == [0, 0, 0]
+    assert np.linalg.norm(got - want) / np.linalg.norm(want) < 1e-13
+
+
+@pytest.mark.parametrize("lgy,lgx,yb,flags", [(13, 13, 1, 6), (13, 13, 2, 6), (13, 13, 1, 0), (14, 12, 2, 2), (13, 11, 2, 0)])
+def test_kronecker_units_of_large_images(sim, lgy, lgx, yb, flags):
+    """Two units of the row pass of a big image (C5 is 8192 x 8192) against the direct formula
+    Z[k_y][k_x] = exp(-2 pi i k_y y_lo/ny) / (U nx) * sum_u sum_x in[y_lo + u ny/U][x] exp(-2 pi i (x k_x/nx + u k_y/U))."""
+    sim.plansim_run_ex.argtypes = list(sim.plansim_run.argtypes) + [ctypes.POINTER(ctypes.c_int64)]
+    ny, nx, U = 1 << lgy, 1 << lgx, 1 << yb
+    rng = np.random.default_rng(3)
+    y_los = [5, 6]   # units 5 and 6 of the image
+    rows = {(yl, u): rng.standard_normal(nx) + 1j * rng.standard_normal(nx) for yl in y_los for u in range(U)}
+    span = (ny // U) * nx
+    # sparse image: only the rows the two units touch are materialised, at offset (y - 5) * nx in a compact buffer
+    comp = {}
+    size_in = (U - 1) * span + (y_los[-1] - y_los[0] + 1) * nx
+    re, im = np.zeros(size_in), np.zeros(size_in)
+    for (yl, u), v in rows.items():
+        o = u * span + (yl - y_los[0]) * nx
+        re[o:o + nx], im[o:o + nx] = v.real, v.imag
+    o_re, o_im = np.zeros(2 * U * nx), np.zeros(2 * U * nx)
+    conf = (ctypes.c_int * 4)()
+    st = (ctypes.c_int64 * 9)(span, 1, nx, 1, 0, nx, 0, U * nx, ny // U)
+    ext = (ctypes.c_int64 * 3)(yb, lgy, 1)
+    # the simulator numbers units from 0: shift so that unit index == y_lo by passing pointers moved back by 5 units
+    shift_in, shift_out = y_los[0] * nx, y_los[0] * U * nx
+    full_re, full_im = np.zeros(shift_in + size_in), np.zeros(shift_in + size_in)
+    full_re[shift_in:], full_im[shift_in:] = re, im
+    full_ore, full_oim = np.zeros(shift_out + 2 * U * nx), np.zeros(shift_out + 2 * U * nx)
+    rc = sim.plansim_run_ex(lgx, yb, flags, 0, st, 0, y_los[-1] + 1, full_re.ctypes.data_as(dp), full_im.ctypes.data_as(dp),
+                            full_ore.ctypes.data_as(dp), full_oim.ctypes.data_as(dp), 0, conf, ext)
+    assert rc == 0 and list(conf)[:3] == [0, 0, 0]
+    got = (full_ore + 1j * full_oim)[shift_out:].reshape(2, U, nx)
+    for i, yl in enumerate(y_los):
+        x = np.stack([rows[(yl, u)] for u in range(U)])
+        want = np.fft.fft2(x) / (U * nx) * np.exp(-2j * np.pi * np.arange(U) * yl / ny)[:, None]
+        assert np.linalg.norm(got[i] - want) / np.linalg.norm(want) < 1e-13
