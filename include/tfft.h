@@ -38,7 +38,13 @@ enum {
   /* multi-pass sizes (N > 32768) overwrite the input planes like the reference does
    * (src/base/ComputeFFT.h:89-145 ping-pongs between input and result buffers); set this flag
    * to make the plan own a scratch buffer instead and leave the input intact. */
-  TFFT_PRESERVE_INPUT = 1
+  TFFT_PRESERVE_INPUT = 1,
+  /* SURVEY.md 8f rank 2, the conventions of the other fp16 FFT the reference is compared with (cuFFT,
+   * src/testing/unitTesting/CuFFTTest.h:25-57): inverse transform exp(+2*pi*i*n*k/N) (computed as the forward
+   * transform with the real and imaginary planes exchanged on both sides: bit-identical arithmetic), and no 1/N
+   * scaling (every stage's DFT matrix unscaled; intermediate values must stay inside the fp16 range). */
+  TFFT_INVERSE = 2,
+  TFFT_UNSCALED = 4
 };
 
 typedef struct tfft_plan_info_s {
@@ -92,6 +98,19 @@ int tfft_exec_twiddled(tfft_plan_t plan, const void* in_re, const void* in_im, v
  * per transform, [RE(n) | IM(n)] halves (2*n*batch values each).  Uses plan-owned device
  * buffers; synchronises before returning like the reference's batch overload does. */
 int tfft_exec_host(tfft_plan_t plan, const void* host_in, void* host_out);
+
+/* Device-side harness helpers.
+ * tfft_fixture_sine: the reference's test signal (CreateSineSuperpostionKernel,
+ * src/testing/TestingDataCreation.h:89-117) for `batch` transforms, written as planar fp16 at re/im + b*stride:
+ * x_b[t] = sum_{i<cutoff} w_b[i] * sinf(2*pi*i*t/n); w_re / w_im are HOST arrays of batch*cutoff floats (the
+ * reference draws them with GetRandomWeights, TestingDataCreation.h:15-27).  Synchronises `stream`.
+ * tfft_error_stats: deviation statistics of a planar fp16 device result against planar fp64 device values over
+ * the 2*count real and imaginary parts, as src/testing/AccuracyCalculator.h:86-148 computes them on the host:
+ * out4 (HOST) = {largest deviation, average deviation, sigma of the deviation, relative L2 error}. */
+int tfft_fixture_sine(void* re, void* im, int64_t n, int64_t batch, int64_t stride, const float* w_re,
+                      const float* w_im, int32_t cutoff, void* stream);
+int tfft_error_stats(const void* a_re, const void* a_im, const double* b_re, const double* b_im, int64_t count,
+                     double* out4, void* stream);
 
 const char* tfft_error_string(int code);
 int tfft_version(void);

@@ -265,31 +265,71 @@ __device__ __forceinline__ uint32_t bit_sum_c(const uint32_t* contrib, int first
 // Epilogue of work item (2*II + wgroup) of stage ST: one 128-row tile x 16 output columns.
 //   RHO: log2 radix, LAST: final stage (no inter-stage twiddle), items are numbered
 //   item = tile * G + g (G = R/16 column groups per tile); bit 0 of the item index is the warp group.
-template <int RHO, uint32_t II>
+// Work items of a stage: item = tile * G + g (G = R/16 column groups per 128-row tile).  Warp group w of NG (2 or 4)
+// processes items NG*II + w, II = 0, 1, ...: the low bits of the item index come from the warp group, the rest is
+// compile-time.
+template <int NG, uint32_t G>
+__host__ __device__ constexpr uint32_t item_tile_hi(uint32_t ii) { return (NG * ii) / G; }       // multiple of max(1, NG/G)
+template <int NG, uint32_t G>
+__host__ __device__ constexpr uint32_t item_g_hi(uint32_t ii) { return G > NG ? (NG * ii) % G : 0; }   // multiple of NG
+template <int NG, uint32_t G>
+__device__ __forceinline__ uint32_t item_tile_lo(uint32_t wgroup) { return G >= NG ? 0u : wgroup / G; }
+template <int NG, uint32_t G>
+__device__ __forceinline__ uint32_t item_g_lo(uint32_t wgroup) { return G >= NG ? wgroup : wgroup % G; }
+
+template <int RHO, uint32_t II, int NG = 2>
 __device__ __forceinline__ void epilogue_load(const KernelCtx& c, uint32_t (&are)[16], uint32_t (&aim)[16]) {
   constexpr uint32_t R = 1u << RHO, G = R / 16;
-  constexpr uint32_t kTileHi = (G == 1) ? (2 * II) : (G == 2 ? II : II / 2);
-  constexpr uint32_t kGHi = (G == 4) ? 2 * (II % 2) : 0;
-  const uint32_t tile = kTileHi + (G == 1 ? c.wgroup : 0u);
-  const uint32_t g = kGHi + (G == 1 ? 0u : c.wgroup);
+  const uint32_t tile = item_tile_hi<NG, G>(II) + item_tile_lo<NG, G>(c.wgroup);
+  const uint32_t g = item_g_hi<NG, G>(II) + item_g_lo<NG, G>(c.wgroup);
   const uint32_t tcol = c.taddr + c.lane_base + tile * 2 * R + g * 16;
   ptx::tmem_ld_32x32b_x16(tcol, are);
   ptx::tmem_ld_32x32b_x16(tcol + R, aim);
 }
 
-template <int ST, int RHO, bool LAST, uint32_t II>
+// Per-thread constant part of the bit-linear row maps of stage ST (7 lane-row bits + the warp-group bits), computed once
+// per kernel: (dst >> 4) | (aux << 16).  dst is a multiple of 16 below 2^20, aux (twiddle integer) is below 2^16.
+template <int ST, int RHO, int NG>
+__device__ __forceinline__ uint32_t thread_map(const UnitPlan& P, const KernelCtx& c) {
+  constexpr uint32_t G = (1u << RHO) / 16;
+  const UnitPlan::Epi& E = P.epi[ST];
+  uint32_t dst = bit_sum(c.lane_row, E.dst, 0, 7), aux = bit_sum(c.lane_row, E.aux, 0, 7);
+  // warp-group bits: first the g bits (k_t[4], k_t[5]), then tile bits (row bits 7, 8)
+  constexpr int kGBits = G >= 4 ? 2 : (G == 2 ? 1 : 0), kWBits = NG == 4 ? 2 : 1;
+#pragma unroll
+  for (int b = 0; b < kWBits; ++b) {
+    if (!((c.wgroup >> b) & 1u)) continue;
+    if (b < kGBits) dst += E.dst_k[1 + b];
+    else { dst += E.dst[7 + b - kGBits]; aux += E.aux[7 + b - kGBits]; }
+  }
+  return (dst >> 4) | (aux << 16);
+}
+template <int ST, int RHO, int NG>
+__device__ __forceinline__ uint32_t thread_col(const UnitPlan& P, const KernelCtx& c) {   // last stage, tw_mode 2
+  constexpr uint32_t G = (1u << RHO) / 16;
+  const UnitPlan::Epi& E = P.epi[ST];
+  uint32_t col = bit_sum(c.lane_row, E.col, 0, 7);
+  constexpr int kGBits = G >= 4 ? 2 : (G == 2 ? 1 : 0), kWBits = NG == 4 ? 2 : 1;
+#pragma unroll
+  for (int b = kGBits; b < kWBits; ++b)
+    if ((c.wgroup >> b) & 1u) col += E.col[7 + b - kGBits];
+  return col;
+}
+
+template <int ST, int RHO, bool LAST, uint32_t II, int NG = 2>
 __device__ __forceinline__ void epilogue_item(const UnitPlan& P, const KernelCtx& c, uint32_t dst_thr, uint32_t aux_thr,
                                               uint32_t col_thr, const uint32_t (&are)[16], const uint32_t (&aim)[16]) {
   using namespace ptx;
   constexpr uint32_t R = 1u << RHO, G = R / 16;
   const UnitPlan::Epi& E = P.epi[ST];
-  // item = 2*II + wgroup;  tile = item / G, g = item % G
-  constexpr uint32_t kTileHi = (G == 1) ? (2 * II) : (G == 2 ? II : II / 2);   // compile-time part of the tile index
-  constexpr uint32_t kGHi = (G == 4) ? 2 * (II % 2) : 0;                       // compile-time part of g
-  const uint32_t g = kGHi + (G == 1 ? 0u : c.wgroup);
-  // dst_thr / aux_thr already hold the per-thread part including the warp-group bit
-  uint32_t dst = dst_thr + bit_sum_c<kTileHi, kMaxRowBits - 7>(E.dst, 7);
-  if (G == 4) dst += bit_sum_c<(kGHi >> 1), 1>(E.dst_k, 2);   // k_t[5]
+  // item = NG*II + wgroup;  tile = item / G, g = item % G
+  constexpr uint32_t kTileHi = item_tile_hi<NG, G>(II);   // compile-time part of the tile index
+  constexpr uint32_t kGHi = item_g_hi<NG, G>(II);         // compile-time part of g
+  const uint32_t g = kGHi + item_g_lo<NG, G>(c.wgroup);
+  // dst_thr / aux_thr already hold the per-thread part including the warp-group bits
+  constexpr uint32_t kTileShift = G >= NG ? 0 : (NG / G == 2 ? 1 : 2);   // tile bits below this come from the warp group
+  uint32_t dst = dst_thr + bit_sum_c<(kTileHi >> kTileShift), kMaxRowBits - 7 - kTileShift>(E.dst, 7 + kTileShift);
+  if (G == 4 && NG == 2) dst += bit_sum_c<(kGHi >> 1), 1>(E.dst_k, 2);   // k_t[5]
   uint32_t pre[8], pim[8];
   bool plain = LAST && E.tw_mode == 0;
   if (plain) {
@@ -299,7 +339,7 @@ __device__ __forceinline__ void epilogue_item(const UnitPlan& P, const KernelCtx
       pim[k >> 1] = pack_half2(__uint_as_float(aim[k]), __uint_as_float(aim[k + 1]));
     }
   } else {
-    const uint32_t aux = aux_thr + bit_sum_c<kTileHi, kMaxRowBits - 7>(E.aux, 7);
+    const uint32_t aux = aux_thr + bit_sum_c<(kTileHi >> kTileShift), kMaxRowBits - 7 - kTileShift>(E.aux, 7 + kTileShift);
     Cplx t0, t1, s2;
     if (LAST && E.tw_mode == 3) {
       // Kronecker stage: columns k of this item belong to output row k_y = k >> tw_shift (tw_shift >= 3, so
@@ -331,7 +371,7 @@ __device__ __forceinline__ void epilogue_item(const UnitPlan& P, const KernelCtx
         t1 = cmul(t0, w1);
       }
     } else {
-      const uint64_t col = col_thr + bit_sum_c<kTileHi, kMaxRowBits - 7>(E.col, 7) + c.col_base;
+      const uint64_t col = col_thr + bit_sum_c<(kTileHi >> kTileShift), kMaxRowBits - 7 - kTileShift>(E.col, 7 + kTileShift) + c.col_base;
       const uint64_t mask = (uint64_t(1) << E.tw_log2n) - 1u;
       const Cplx w1 = twiddle64((E.tw_kw * col) & mask, E.tw_log2n);
       t0 = twiddle64(((aux + 16u * g * E.tw_kw) * col) & mask, E.tw_log2n);
@@ -373,15 +413,15 @@ __device__ __forceinline__ void epilogue_item(const UnitPlan& P, const KernelCtx
 // Software-pipelined item loop over items [II, END): the tensor-memory load of item II+1 is in flight
 // while item II is processed (tcgen05.wait::ld waits for ALL outstanding loads, so the next load is
 // issued right after the wait and before the arithmetic).
-template <int ST, int RHO, bool LAST, uint32_t II, uint32_t END>
+template <int ST, int RHO, bool LAST, uint32_t II, uint32_t END, int NG = 2>
 __device__ __forceinline__ void epilogue_range(const UnitPlan& P, const KernelCtx& c, uint32_t dst_thr,
                                                uint32_t aux_thr, uint32_t col_thr, uint32_t (&cre)[16],
                                                uint32_t (&cim)[16], uint32_t (&nre)[16], uint32_t (&nim)[16]) {
   if constexpr (II < END) {
     ptx::tmem_ld_wait();                                            // item II has landed in (cre, cim)
-    if constexpr (II + 1 < END) epilogue_load<RHO, II + 1>(c, nre, nim);
-    epilogue_item<ST, RHO, LAST, II>(P, c, dst_thr, aux_thr, col_thr, cre, cim);
-    epilogue_range<ST, RHO, LAST, II + 1, END>(P, c, dst_thr, aux_thr, col_thr, nre, nim, cre, cim);
+    if constexpr (II + 1 < END) epilogue_load<RHO, II + 1, NG>(c, nre, nim);
+    epilogue_item<ST, RHO, LAST, II, NG>(P, c, dst_thr, aux_thr, col_thr, cre, cim);
+    epilogue_range<ST, RHO, LAST, II + 1, END, NG>(P, c, dst_thr, aux_thr, col_thr, nre, nim, cre, cim);
   }
 }
 
@@ -403,21 +443,21 @@ struct NoHook {
   __device__ __forceinline__ void before_half(int) const {}
   __device__ __forceinline__ void after_half(int) const {}
 };
-template <int RHO, int LOG2E, bool PIPE>
+template <int RHO, int LOG2E, bool PIPE, int NG = 2>
 struct StageShape {
   static constexpr uint32_t R = 1u << RHO, G = R / 16, kSteps = R / 16;
   static constexpr uint32_t S = 16 * R + 16;                       // chunk stride of this stage's operand layout
   static constexpr uint32_t kTiles = (1u << LOG2E) / R / 128;
-  static constexpr uint32_t kItemsPerGroup = (1u << LOG2E) / 2048 / 2;   // E/2048 work items per stage, two warp groups
+  static constexpr uint32_t kItemsPerGroup = (1u << LOG2E) / 2048 / NG;   // E/2048 work items per stage, NG warp groups
   static constexpr bool kPipe = PIPE && kTiles >= 2 && kItemsPerGroup >= 2;
 };
 
 // All UMMAs of one stage, issued by ONE thread (under elect_one()).
-template <int ST, int RHO, int LOG2E, bool SW128, bool PIPE, class Hook>
+template <int ST, int RHO, int LOG2E, bool SW128, bool PIPE, class Hook, int NG = 2>
 __device__ __forceinline__ void stage_issue(const KernelCtx& c, uint32_t b1_saddr, uint64_t* bar, const Hook& hook,
                                             long long* trace, uint32_t trace_unit) {
   using namespace ptx;
-  using SS = StageShape<RHO, LOG2E, PIPE>;
+  using SS = StageShape<RHO, LOG2E, PIPE, NG>;
   constexpr uint32_t R = SS::R, kSteps = SS::kSteps, S = SS::S, kTiles = SS::kTiles;
   constexpr bool kPipe = SS::kPipe;
   constexpr uint32_t idesc = make_idesc_f16(128, 2 * R, /*a_mn=*/1, /*b_mn=*/0);
@@ -425,7 +465,13 @@ __device__ __forceinline__ void stage_issue(const KernelCtx& c, uint32_t b1_sadd
   // A operand: SWIZZLE_NONE padded chunks (written by cp.async / epilogues), or for a TMA-loaded
   // stage 1 SWIZZLE_128B atoms of 64 rows (LBO = atom stride 128R, SBO = K-group stride 1024)
   constexpr uint64_t kSw128 = uint64_t(2) << 61;
-  const uint32_t pa_re = ST == 0 ? c.a_re : c.s_re, pa_im = ST == 0 ? c.a_im : c.s_im;
+  // an opaque zero pins the descriptor arithmetic below to this (single-thread) branch: without it the compiler
+  // hoists ~100 integer instructions per stage into the code every warp executes
+  uint32_t zero;
+  asm volatile("mov.u32 %0, 0;" : "=r"(zero));
+  b1_saddr += zero;
+  const uint32_t pa_re = (ST == 0 ? c.a_re : c.s_re) + zero, pa_im = (ST == 0 ? c.a_im : c.s_im) + zero;
+  const uint32_t taddr = c.taddr + zero;
   const uint64_t da_re = SW128 ? (make_smem_desc(pa_re, 128 * R, 1024) | kSw128) : make_smem_desc(pa_re, kKGroupStride, S);
   const uint64_t da_im = SW128 ? (make_smem_desc(pa_im, 128 * R, 1024) | kSw128) : make_smem_desc(pa_im, kKGroupStride, S);
   constexpr uint32_t kTileStep = SW128 ? (2 * 128 * R) / 16 : S;   // descriptor address units (16 B) per tile
@@ -434,7 +480,7 @@ __device__ __forceinline__ void stage_issue(const KernelCtx& c, uint32_t b1_sadd
   const uint64_t db2 = make_smem_desc(b1_saddr + 4 * R * R, kKGroupStride, 16 * R);
 #pragma unroll
   for (uint32_t tile = 0; tile < kTiles; ++tile) {
-    const uint32_t d = c.taddr + tile * 2 * R;
+    const uint32_t d = taddr + tile * 2 * R;
     if (tile == 0) {
       hook.before_half(0);
       TFFT_TRACE_MARK(16 + 4 * ST);
@@ -476,13 +522,13 @@ __device__ __forceinline__ void stage_observe(uint64_t* bar, uint32_t (&phase)[2
 //         stage-1 UMMAs of a unit ahead of time (during the previous unit's store phase), so stage 1 has
 //         no leading barrier here.
 template <int ST, int RHO, bool LAST, int LOG2E, bool SW128 = false, bool PIPE = false, class Hook = NoHook,
-          int ROLE = 0>
+          int ROLE = 0, int NG = 2>
 __device__ __forceinline__ void run_stage(const UnitPlan& P, const KernelCtx& c, uint32_t b1_saddr, uint64_t* bar,
                                           uint32_t (&phase)[2], int warp, int lane, long long* trace,
-                                          uint32_t trace_unit, Hook hook = Hook()) {
+                                          uint32_t trace_unit, uint32_t tmap, uint32_t col_thr, Hook hook = Hook()) {
   using namespace ptx;
-  using SS = StageShape<RHO, LOG2E, PIPE>;
-  constexpr uint32_t R = SS::R, G = SS::G, kItemsPerGroup = SS::kItemsPerGroup;
+  using SS = StageShape<RHO, LOG2E, PIPE, NG>;
+  constexpr uint32_t kItemsPerGroup = SS::kItemsPerGroup;
   constexpr bool kPipe = SS::kPipe;
   if (ROLE == 0 || ST > 0) {
     fence_proxy_async_smem();   // generic-proxy / cp.async operand writes -> visible to the tensor core
@@ -492,22 +538,10 @@ __device__ __forceinline__ void run_stage(const UnitPlan& P, const KernelCtx& c,
   }
   TFFT_TRACE_MARK(9 + 2 * ST);
   if (ROLE == 0 && warp == 0 && elect_one())
-    stage_issue<ST, RHO, LOG2E, SW128, PIPE, Hook>(c, b1_saddr, bar, hook, trace, trace_unit);
+    stage_issue<ST, RHO, LOG2E, SW128, PIPE, Hook, NG>(c, b1_saddr, bar, hook, trace, trace_unit);
   const bool hook_warp = ROLE == 0 && warp == 0;   // converged at every use below (after warp_wait)
-  // per-thread parts of the bit-linear row maps: 7 lane-row bits + the warp-group bit of the item index
-  const UnitPlan::Epi& E = P.epi[ST];
-  uint32_t dst_thr = bit_sum(c.lane_row, E.dst, 0, 7);
-  uint32_t aux_thr = bit_sum(c.lane_row, E.aux, 0, 7);
-  uint32_t col_thr = LAST ? bit_sum(c.lane_row, E.col, 0, 7) : 0u;
-  if (c.wgroup) {
-    if (G == 1) {          // the warp group selects tile bit 0 = row bit 7
-      dst_thr += E.dst[7];
-      aux_thr += E.aux[7];
-      if (LAST) col_thr += E.col[7];
-    } else {               // the warp group selects g bit 0 = k_t[4]
-      dst_thr += E.dst_k[1];
-    }
-  }
+  // per-thread parts of the bit-linear row maps (thread_map(): 7 lane-row bits + the warp-group bits)
+  const uint32_t dst_thr = (tmap & 0xFFFFu) << 4, aux_thr = tmap >> 16;
   uint32_t ra[16], rb[16], rc[16], rd[16];
 #if defined(TFFT_DEBUG_SKIP) || defined(TFFT_DEBUG_MMA_ONLY)
   if (true) {   // developer experiment: no epilogue work, only the barrier protocol
@@ -521,17 +555,17 @@ __device__ __forceinline__ void run_stage(const UnitPlan& P, const KernelCtx& c,
   }
 #endif
   if constexpr (kPipe) {
-    // items [0, half) only touch tiles of the first half for every radix (item = 2*II + wgroup)
+    // items [0, half) only touch tiles of the first half for every radix (item = NG*II + wgroup)
     constexpr uint32_t kHalf = kItemsPerGroup / 2;
     warp_wait(bar, phase[0] & 1u, lane);
     if (hook_warp && elect_one()) hook.after_half(0);
     TFFT_TRACE_MARK(10 + 2 * ST);
-    epilogue_load<RHO, 0>(c, ra, rb);
-    epilogue_range<ST, RHO, LAST, 0, kHalf>(P, c, dst_thr, aux_thr, col_thr, ra, rb, rc, rd);
+    epilogue_load<RHO, 0, NG>(c, ra, rb);
+    epilogue_range<ST, RHO, LAST, 0, kHalf, NG>(P, c, dst_thr, aux_thr, col_thr, ra, rb, rc, rd);
     warp_wait(bar + 1, phase[1] & 1u, lane);
     if (hook_warp && elect_one()) hook.after_half(1);
-    epilogue_load<RHO, kHalf>(c, ra, rb);
-    epilogue_range<ST, RHO, LAST, kHalf, kItemsPerGroup>(P, c, dst_thr, aux_thr, col_thr, ra, rb, rc, rd);
+    epilogue_load<RHO, kHalf, NG>(c, ra, rb);
+    epilogue_range<ST, RHO, LAST, kHalf, kItemsPerGroup, NG>(P, c, dst_thr, aux_thr, col_thr, ra, rb, rc, rd);
     phase[0]++;
     phase[1]++;
   } else {
@@ -541,24 +575,25 @@ __device__ __forceinline__ void run_stage(const UnitPlan& P, const KernelCtx& c,
       hook.after_half(1);
     }
     TFFT_TRACE_MARK(10 + 2 * ST);
-    epilogue_load<RHO, 0>(c, ra, rb);
-    epilogue_range<ST, RHO, LAST, 0, kItemsPerGroup>(P, c, dst_thr, aux_thr, col_thr, ra, rb, rc, rd);
+    epilogue_load<RHO, 0, NG>(c, ra, rb);
+    epilogue_range<ST, RHO, LAST, 0, kItemsPerGroup, NG>(P, c, dst_thr, aux_thr, col_thr, ra, rb, rc, rd);
     phase[0]++;
   }
 }
 
 // Store phase: 16-byte shared loads of 8 staging chunks, 8x8 in-register transpose, 16-byte global stores.
-template <int LOG2E>
+template <int LOG2E, int NT = kThreads>
 __device__ __forceinline__ void store_phase(const UnitPlan& P, const KernelCtx& c, __half* gre, __half* gim, int tid,
                                             uint32_t st_s_lo, uint32_t st_g_lo, uint32_t st_u_lo, uint32_t u_limit) {
   constexpr uint32_t kStoreBlocks = (1u << LOG2E) / 64;            // 8x8 blocks per plane
-  constexpr uint32_t kStoreItems = kStoreBlocks >= kThreads ? kStoreBlocks / kThreads : 1;
+  constexpr uint32_t kStoreItems = kStoreBlocks >= NT ? kStoreBlocks / NT : 1;
+  constexpr int TB = NT == 512 ? 9 : 8;                            // item q = tid + NT * i
 #pragma unroll
   for (uint32_t i = 0; i < kStoreItems; ++i) {
-    const uint32_t so = st_s_lo + bit_sum(i, P.store_sofs, 8, kMaxItemBits - 8);
-    const uint32_t g = st_g_lo + bit_sum(i, P.store_gofs, 8, kMaxItemBits - 8);
-    if (kStoreBlocks < kThreads && tid >= static_cast<int>(kStoreBlocks)) continue;
-    if (st_u_lo + bit_sum(i, P.store_uval, 8, kMaxItemBits - 8) >= u_limit) continue;
+    const uint32_t so = st_s_lo + bit_sum(i, P.store_sofs, TB, kMaxItemBits - TB);
+    const uint32_t g = st_g_lo + bit_sum(i, P.store_gofs, TB, kMaxItemBits - TB);
+    if (kStoreBlocks < NT && tid >= static_cast<int>(kStoreBlocks)) continue;
+    if (st_u_lo + bit_sum(i, P.store_uval, TB, kMaxItemBits - TB) >= u_limit) continue;
 #pragma unroll
     for (int plane = 0; plane < 2; ++plane) {
       const uint32_t sp = plane ? c.s_im : c.s_re;
@@ -582,8 +617,9 @@ __device__ __forceinline__ void store_phase(const UnitPlan& P, const KernelCtx& 
   }
 }
 
-template <int LOG2E, int RHO0, int RHO1, int RHO2, bool TMA>
-__global__ void __launch_bounds__(kThreads, (LOG2E == 15 ? 1 : 2))
+// NT threads: 256 (two warp groups), or 512 (four warp groups) for the 32K-element units that run one CTA per SM
+template <int LOG2E, int RHO0, int RHO1, int RHO2, bool TMA, int NT = kThreads>
+__global__ void __launch_bounds__(NT, (LOG2E == 15 ? 1 : 2))
 fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ in_re,
                 const __half* __restrict__ in_im, __half* __restrict__ out_re, __half* __restrict__ out_im,
                 const uint4* __restrict__ tables, long long* __restrict__ trace,
@@ -591,6 +627,7 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
   using namespace ptx;
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int kStages = RHO2 ? 3 : 2;
+  constexpr int NG = NT / 128, TB = NT == 512 ? 9 : 8;
   const SmemLayout SL = smem_layout(P);
   const TableLayout TL = table_layout(P);
   KernelCtx c;
@@ -610,7 +647,7 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
   c.a_re = c.s_re;
   c.a_im = c.s_im;
   c.bar_id = 0;
-  c.sync_threads = kThreads;
+  c.sync_threads = NT;
   c.mma_warp = 0;
   c.ytw = reinterpret_cast<const float2*>(smem + SL.ytw_off);
   uint32_t trace_unit = 0;
@@ -627,22 +664,25 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
     mbar_init(load_bar, 1);
     fence_mbar_init();
   }
-  for (uint32_t o = tid * 16; o < TL.total; o += kThreads * 16) sts128(table_base + o, ldg128(tables + (o >> 4)));
+  for (uint32_t o = tid * 16; o < TL.total; o += NT * 16) sts128(table_base + o, ldg128(tables + (o >> 4)));
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   c.taddr = *tmem_slot;
   uint32_t phase[2] = {0, 0}, load_phase = 0;
 
-  // per-thread constant parts of the bit-linear load / store maps (item q = tid + 256*i)
-  constexpr uint32_t kLoadItems = (1u << LOG2E) / 8 / kThreads;    // 16-byte chunks per thread and plane
-  const uint32_t ld_g_lo = bit_sum(tid, P.load_gofs, 0, 8), ld_s_lo = bit_sum(tid, P.load_sofs, 0, 8);
-  const uint32_t ld_u_lo = bit_sum(tid, P.load_uval, 0, 8);
-  const uint32_t st_s_lo = bit_sum(tid, P.store_sofs, 0, 8), st_g_lo = bit_sum(tid, P.store_gofs, 0, 8);
-  const uint32_t st_u_lo = bit_sum(tid, P.store_uval, 0, 8);
+  // per-thread constant parts of the bit-linear load / store maps (item q = tid + NT*i) and of the epilogue row maps
+  constexpr uint32_t kLoadItems = (1u << LOG2E) / 8 / NT;    // 16-byte chunks per thread and plane
+  const uint32_t ld_g_lo = bit_sum(tid, P.load_gofs, 0, TB), ld_s_lo = bit_sum(tid, P.load_sofs, 0, TB);
+  const uint32_t ld_u_lo = bit_sum(tid, P.load_uval, 0, TB);
+  const uint32_t st_s_lo = bit_sum(tid, P.store_sofs, 0, TB), st_g_lo = bit_sum(tid, P.store_gofs, 0, TB);
+  const uint32_t st_u_lo = bit_sum(tid, P.store_uval, 0, TB);
+  const uint32_t tmap0 = thread_map<0, RHO0, NG>(P, c), tmap1 = thread_map<1, RHO1, NG>(P, c);
+  const uint32_t tmap2 = kStages == 3 ? thread_map<2, (RHO2 ? RHO2 : 4), NG>(P, c) : 0u;
+  const uint32_t col_thr = kStages == 3 ? thread_col<2, (RHO2 ? RHO2 : 4), NG>(P, c) : thread_col<1, RHO1, NG>(P, c);
 
   for (uint32_t unit = blockIdx.x; unit < P.n_units; unit += gridDim.x) {
-    const uint32_t ub = unit / P.units_per_batch, uu = unit % P.units_per_batch;
+    const uint32_t ub = unit >> P.upb_shift, uu = unit & ((1u << P.upb_shift) - 1u);
     const int64_t in_base =
         static_cast<int64_t>(ub) * P.in_batch_stride + static_cast<int64_t>(uu) * P.in_unit_stride;
     const int64_t out_base =
@@ -650,7 +690,7 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
     // row/row passes with a ragged batch: transforms past the end are loaded as zeros, never stored
     const uint32_t u_limit =
         P.n_transforms ? P.n_transforms - min(P.n_transforms, unit << P.log2_units) : 0xFFFFFFFFu;
-    c.col_base = (uu / P.col_div) * P.col_base_stride + P.col_first;
+    c.col_base = (uu >> P.col_shift) * P.col_base_stride + P.col_first;
     if (P.kron_bits && tid < 8) {   // row twiddles of this unit (read by the last epilogue, two barriers from here)
       const Cplx w = twiddle((static_cast<uint32_t>(tid) * c.col_base) & ((1u << P.epi[kStages - 1].tw_log2n) - 1u),
                              P.epi[kStages - 1].tw_log2n);
@@ -666,11 +706,12 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
         fence_proxy_async_smem();   // earlier generic-proxy reads of the planes precede the async-proxy writes
         mbar_arrive_expect_tx(load_bar, 4u << LOG2E);
         if (P.kron_bits) {
-          tma_load_5d(c.s_re, &tmap_re, uu, ub << P.log2_units, load_bar);
-          tma_load_5d(c.s_im, &tmap_im, uu, ub << P.log2_units, load_bar);
+          tma_load_5d(c.s_re, &tmap_re, uu, ub * P.tma_batch_step, load_bar);
+          tma_load_5d(c.s_im, &tmap_im, uu, ub * P.tma_batch_step, load_bar);
         } else {
-          tma_load_4d(c.s_re, &tmap_re, 0, unit << P.log2_units, load_bar);
-          tma_load_4d(c.s_im, &tmap_im, 0, unit << P.log2_units, load_bar);
+          const uint32_t c3 = ub * P.tma_batch_step + (uu << P.log2_units);
+          tma_load_4d(c.s_re, &tmap_re, 0, c3, load_bar);
+          tma_load_4d(c.s_im, &tmap_im, 0, c3, load_bar);
         }
       }
       TFFT_TRACE_MARK(1);
@@ -682,17 +723,17 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
       if (u_limit == 0xFFFFFFFFu) {
 #pragma unroll
         for (uint32_t i = 0; i < kLoadItems; ++i) {
-          const uint32_t g = ld_g_lo + bit_sum(i, P.load_gofs, 8, kMaxItemBits - 8);
-          const uint32_t so = ld_s_lo + bit_sum(i, P.load_sofs, 8, kMaxItemBits - 8);
+          const uint32_t g = ld_g_lo + bit_sum(i, P.load_gofs, TB, kMaxItemBits - TB);
+          const uint32_t so = ld_s_lo + bit_sum(i, P.load_sofs, TB, kMaxItemBits - TB);
           cp_async16(c.s_re + so, gre + g, 16u);
           cp_async16(c.s_im + so, gim + g, 16u);
         }
       } else {
 #pragma unroll
         for (uint32_t i = 0; i < kLoadItems; ++i) {
-          const uint32_t g = ld_g_lo + bit_sum(i, P.load_gofs, 8, kMaxItemBits - 8);
-          const uint32_t so = ld_s_lo + bit_sum(i, P.load_sofs, 8, kMaxItemBits - 8);
-          const bool live = ld_u_lo + bit_sum(i, P.load_uval, 8, kMaxItemBits - 8) < u_limit;
+          const uint32_t g = ld_g_lo + bit_sum(i, P.load_gofs, TB, kMaxItemBits - TB);
+          const uint32_t so = ld_s_lo + bit_sum(i, P.load_sofs, TB, kMaxItemBits - TB);
+          const bool live = ld_u_lo + bit_sum(i, P.load_uval, TB, kMaxItemBits - TB) < u_limit;
           cp_async16(c.s_re + so, gre + (live ? g : 0u), live ? 16u : 0u);
           cp_async16(c.s_im + so, gim + (live ? g : 0u), live ? 16u : 0u);
         }
@@ -703,20 +744,21 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
     TFFT_TRACE_MARK(2);
 
     // ---------------------------------------------------------------- tensor-core stages
-    run_stage<0, RHO0, false, LOG2E, TMA>(P, c, table_base + TL.b_off[0], bar, phase, warp, lane, trace, trace_unit);
+    run_stage<0, RHO0, false, LOG2E, TMA, false, NoHook, 0, NG>(P, c, table_base + TL.b_off[0], bar, phase, warp, lane,
+                                                                trace, trace_unit, tmap0, 0u);
     TFFT_TRACE_MARK(3);
-    run_stage<1, RHO1, kStages == 2, LOG2E>(P, c, table_base + TL.b_off[1], bar, phase, warp, lane, trace,
-                                            trace_unit);
+    run_stage<1, RHO1, kStages == 2, LOG2E, false, false, NoHook, 0, NG>(P, c, table_base + TL.b_off[1], bar, phase, warp,
+                                                                         lane, trace, trace_unit, tmap1, col_thr);
     TFFT_TRACE_MARK(4);
     if constexpr (kStages == 3)
-      run_stage<2, (RHO2 ? RHO2 : 4), true, LOG2E>(P, c, table_base + TL.b_off[2], bar, phase, warp, lane, trace,
-                                                   trace_unit);
+      run_stage<2, (RHO2 ? RHO2 : 4), true, LOG2E, false, false, NoHook, 0, NG>(P, c, table_base + TL.b_off[2], bar, phase,
+                                                                                warp, lane, trace, trace_unit, tmap2, col_thr);
     TFFT_TRACE_MARK(5);
     __syncthreads();
     TFFT_TRACE_MARK(6);
 
     // ---------------------------------------------------------------- store phase
-    store_phase<LOG2E>(P, c, out_re + out_base, out_im + out_base, tid, st_s_lo, st_g_lo, st_u_lo, u_limit);
+    store_phase<LOG2E, NT>(P, c, out_re + out_base, out_im + out_base, tid, st_s_lo, st_g_lo, st_u_lo, u_limit);
     TFFT_TRACE_MARK(7);
     __syncthreads();   // staging fully read before the next unit's loads overwrite it
     TFFT_TRACE_MARK(8);
@@ -841,14 +883,16 @@ fft_unit_kernel_2slot(const __grid_constant__ UnitPlan P, __half* __restrict__ o
     uint64_t* full = land_full + 2 * (q & 1u) + h;
     mbar_arrive_expect_tx(full, 2u << LOG2E);
     const uint32_t off = h << LOG2E;   // half a plane: E bytes
+    const uint32_t uq = unit_of(q), qb = uq >> P.upb_shift, qu = uq & ((1u << P.upb_shift) - 1u);
     if (P.kron_bits) {   // unit = (image, y_lo); tile halves split the U rows
-      const uint32_t uq = unit_of(q), c3 = uq % P.units_per_batch, c4 = ((uq / P.units_per_batch) << P.log2_units) + h * half_c3;
-      tma_load_5d(c.a_re + off, &tmap_re, c3, c4, full);
-      tma_load_5d(c.a_im + off, &tmap_im, c3, c4, full);
+      const uint32_t c4 = qb * P.tma_batch_step + h * half_c3;
+      tma_load_5d(c.a_re + off, &tmap_re, qu, c4, full);
+      tma_load_5d(c.a_im + off, &tmap_im, qu, c4, full);
       return;
     }
-    tma_load_4d(c.a_re + off, &tmap_re, h * half_c2, (unit_of(q) << P.log2_units) + h * half_c3, full);
-    tma_load_4d(c.a_im + off, &tmap_im, h * half_c2, (unit_of(q) << P.log2_units) + h * half_c3, full);
+    const uint32_t c3 = qb * P.tma_batch_step + (qu << P.log2_units) + h * half_c3;
+    tma_load_4d(c.a_re + off, &tmap_re, h * half_c2, c3, full);
+    tma_load_4d(c.a_im + off, &tmap_im, h * half_c2, c3, full);
   };
   if (tid_cta == 0) {
     request(0, 0);
@@ -921,14 +965,17 @@ fft_unit_kernel_2slot(const __grid_constant__ UnitPlan P, __half* __restrict__ o
     constexpr int ROLE = kDedicatedMmaWarp ? 1 : 0;
     const uint32_t st_s_lo = bit_sum(tid, P.store_sofs, 0, 8), st_g_lo = bit_sum(tid, P.store_gofs, 0, 8);
     const uint32_t st_u_lo = bit_sum(tid, P.store_uval, 0, 8);
+    const uint32_t tmap0 = thread_map<0, RHO0, 2>(P, c), tmap1 = thread_map<1, RHO1, 2>(P, c);
+    const uint32_t tmap2 = kStages == 3 ? thread_map<2, (RHO2 ? RHO2 : 4), 2>(P, c) : 0u;
+    const uint32_t col_thr = kStages == 3 ? thread_col<2, (RHO2 ? RHO2 : 4), 2>(P, c) : thread_col<1, RHO1, 2>(P, c);
     for (uint32_t q = slot; unit_of(q) < P.n_units; q += 2) {
       const uint32_t unit = unit_of(q);
-      const uint32_t ub = unit / P.units_per_batch, uu = unit % P.units_per_batch;
+      const uint32_t ub = unit >> P.upb_shift, uu = unit & ((1u << P.upb_shift) - 1u);
       const int64_t out_base =
           static_cast<int64_t>(ub) * P.out_batch_stride + static_cast<int64_t>(uu) * P.out_unit_stride;
       const uint32_t u_limit =
           P.n_transforms ? P.n_transforms - min(P.n_transforms, unit << P.log2_units) : 0xFFFFFFFFu;
-      c.col_base = (uu / P.col_div) * P.col_base_stride + P.col_first;
+      c.col_base = (uu >> P.col_shift) * P.col_base_stride + P.col_first;
       if (P.kron_bits && tid < 8) {   // row twiddles of this unit (read by the last epilogue, two barriers from here)
         const Cplx w = twiddle((static_cast<uint32_t>(tid) * c.col_base) & ((1u << P.epi[kStages - 1].tw_log2n) - 1u),
                                P.epi[kStages - 1].tw_log2n);
@@ -939,19 +986,19 @@ fft_unit_kernel_2slot(const __grid_constant__ UnitPlan P, __half* __restrict__ o
       TFFT_TRACE_MARK(2);
       LandingHook hook{land_full + 2 * slot, (q >> 1) & 1u, q, request};
       run_stage<0, RHO0, false, LOG2E, true, true, LandingHook, ROLE>(P, c, b_saddr0, mma_bar, phase, warp, lane, trace,
-                                                                      trace_unit, hook);
+                                                                      trace_unit, tmap0, 0u, hook);
       TFFT_TRACE_MARK(3);
 #if !defined(TFFT_DEBUG_SKIP)
       if (pipe2)
         run_stage<1, RHO1, kStages == 2, LOG2E, false, true, NoHook, ROLE>(P, c, b_saddr1, mma_bar, phase, warp, lane,
-                                                                           trace, trace_unit);
+                                                                           trace, trace_unit, tmap1, col_thr);
       else
         run_stage<1, RHO1, kStages == 2, LOG2E, false, false, NoHook, ROLE>(P, c, b_saddr1, mma_bar, phase, warp, lane,
-                                                                            trace, trace_unit);
+                                                                            trace, trace_unit, tmap1, col_thr);
       TFFT_TRACE_MARK(4);
       if constexpr (kStages == 3)
         run_stage<2, (RHO2 ? RHO2 : 4), true, LOG2E, false, false, NoHook, ROLE>(P, c, b_saddr2, mma_bar, phase, warp,
-                                                                                 lane, trace, trace_unit);
+                                                                                 lane, trace, trace_unit, tmap2, col_thr);
 #endif
       TFFT_TRACE_MARK(5);
       tc_fence_before_sync();

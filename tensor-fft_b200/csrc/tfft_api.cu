@@ -16,6 +16,7 @@
 
 #include "../../include/tfft.h"
 #include "fft_unit_kernel.cuh"
+#include "harness_kernels.cuh"
 
 namespace {
 
@@ -46,7 +47,7 @@ int ilog2_exact(int64_t n) {
 // Host image of the per-plan constant tables the kernel stages into shared memory
 // (layout: fft_unit_kernel.cuh "Device tables"): two-level twiddle table for unit angle 2*pi/L and
 // the fp16 DFT matrices [Fr|Fi]/R, [-Fi|Fr]/R of every radix the plan uses.
-std::vector<uint8_t> make_tables(const UnitPlan& plan) {
+std::vector<uint8_t> make_tables(const UnitPlan& plan, bool unscaled) {
   const TableLayout TL = table_layout(plan);
   std::vector<uint8_t> host(TL.total, 0);
   const double pi = 3.14159265358979323846264338327950288;
@@ -85,7 +86,9 @@ std::vector<uint8_t> make_tables(const UnitPlan& plan) {
         const int k = n % R;
         // phase / R = kap_x*k_x/Rx + kap_y*k_y/Ry
         unit(static_cast<int64_t>(kap % Rx) * (k % Rx) * Ry + static_cast<int64_t>(kap / Rx) * (k / Rx) * Rx, R, &c, &s);
-        const float fr = static_cast<float>(c / R), fi = static_cast<float>(s / R);
+        // 1/R per stage = the reference's "sequential scaling"; TFFT_UNSCALED (cuFFT convention) leaves it out
+        const double sc = unscaled ? 1.0 : 1.0 / R;
+        const float fr = static_cast<float>(c * sc), fi = static_cast<float>(s * sc);
         const uint32_t off = (n >> 3) * (8 * R) + (kap >> 3) * 64 + (n & 7) * 8 + (kap & 7);   // in halves
         b1[off] = __float2half_rn(n < R ? fr : fi);
         b2[off] = __float2half_rn(n < R ? -fi : fr);
@@ -102,26 +105,35 @@ typedef void (*KernelFn)(const UnitPlan, const __half*, const __half*, __half*, 
 struct KernelEntry {
   int log2e, r0, r1, r2;
   KernelFn fn, fn_tma;   // fn_tma: stage-1 operand loaded by TMA (row-mode input, >= 64 rows per K line)
+  int threads;
 };
-#define TFFT_K(E, A, B, C) {E, A, B, C, fft_unit_kernel<E, A, B, C, false>, nullptr}
-#define TFFT_KT(E, A, B, C) {E, A, B, C, fft_unit_kernel<E, A, B, C, false>, fft_unit_kernel<E, A, B, C, true>}
+#define TFFT_K(E, A, B, C) {E, A, B, C, fft_unit_kernel<E, A, B, C, false>, nullptr, kThreads}
+#define TFFT_KT(E, A, B, C) {E, A, B, C, fft_unit_kernel<E, A, B, C, false>, fft_unit_kernel<E, A, B, C, true>, kThreads}
+// 32K-element units (one CTA per SM): 512 threads = four warp groups
+#define TFFT_KW(E, A, B, C) {E, A, B, C, fft_unit_kernel<E, A, B, C, false, 512>, fft_unit_kernel<E, A, B, C, true, 512>, 512}
 const KernelEntry g_kernels[] = {
     TFFT_K(13, 4, 4, 0), TFFT_K(14, 4, 4, 0),                       // L = 2^8
     TFFT_K(13, 4, 5, 0), TFFT_K(14, 4, 5, 0),                       // 2^9
     TFFT_K(13, 5, 5, 0), TFFT_K(14, 5, 5, 0),                       // 2^10
     TFFT_KT(13, 5, 6, 0), TFFT_KT(14, 5, 6, 0),                        // 2^11
-    TFFT_KT(13, 6, 6, 0), TFFT_KT(14, 6, 6, 0), TFFT_KT(15, 6, 6, 0),  // 2^12
+    TFFT_KT(13, 6, 6, 0), TFFT_KT(14, 6, 6, 0), TFFT_KW(15, 6, 6, 0), TFFT_KT(15, 6, 6, 0),  // 2^12
     TFFT_KT(13, 4, 4, 5), TFFT_KT(14, 4, 4, 5),                        // 2^13
     TFFT_KT(14, 4, 5, 5),                                              // 2^14
-    TFFT_KT(15, 5, 5, 5),                                              // 2^15
+    TFFT_KT(14, 5, 5, 4),                                              // 2 rows x 2^13 (2-D row pass, Kronecker last stage)
+    TFFT_KW(15, 5, 5, 5), TFFT_KT(15, 5, 5, 5),                        // 2^15
 };
 #undef TFFT_K
 #undef TFFT_KT
-KernelFn kernel_for(const UnitPlan& p) {
+#undef TFFT_KW
+KernelFn kernel_for(const UnitPlan& p, int* threads) {
+  static const bool narrow = getenv("TFFT_NARROW_32K") != nullptr;   // developer A/B: 256-thread CTAs for 32K-element units
   for (const KernelEntry& k : g_kernels)
     if (k.log2e == static_cast<int>(p.log2_elems) && k.r0 == static_cast<int>(p.log2_radix[0]) &&
-        k.r1 == static_cast<int>(p.log2_radix[1]) && k.r2 == static_cast<int>(p.stages == 3 ? p.log2_radix[2] : 0))
+        k.r1 == static_cast<int>(p.log2_radix[1]) && k.r2 == static_cast<int>(p.stages == 3 ? p.log2_radix[2] : 0) &&
+        !(narrow && k.threads == 512)) {
+      *threads = k.threads;
       return p.tma_load ? k.fn_tma : k.fn;
+    }
   return nullptr;
 }
 
@@ -130,8 +142,10 @@ typedef void (*Kernel2Fn)(const UnitPlan, __half*, __half*, const uint4*, const 
                           long long*);
 Kernel2Fn kernel2_for(const UnitPlan& p) {
   if (!p.tma_load || p.log2_elems != 14 || p.stages != 3 || getenv("TFFT_NO_2SLOT")) return nullptr;
+  if (smem2_layout(p).total > 227 * 1024) return nullptr;   // e.g. three distinct DFT matrices
   if (p.log2_radix[0] == 4 && p.log2_radix[1] == 4 && p.log2_radix[2] == 5) return fft_unit_kernel_2slot<4, 4, 5>;
   if (p.log2_radix[0] == 4 && p.log2_radix[1] == 5 && p.log2_radix[2] == 5) return fft_unit_kernel_2slot<4, 5, 5>;
+  if (p.log2_radix[0] == 5 && p.log2_radix[1] == 5 && p.log2_radix[2] == 4) return fft_unit_kernel_2slot<5, 5, 4>;
   return nullptr;
 }
 
@@ -170,15 +184,17 @@ int make_input_tensor_map(const UnitPlan& plan, const __half* base, int64_t tstr
   return r == CUDA_SUCCESS ? TFFT_OK : TFFT_E_INVALID_ARG;
 }
 
-// Kronecker units (2-D row pass): unit (image b, y_lo) reads rows y_lo + u*(ny/U), u < U, of image b.  Images are
-// contiguous (stride ny*nx), so row = y_lo + (ny/U)*(u + U*b): dims {64, R, M/64, y_lo (stride nx), u + U*b}.
-int make_kron_tensor_map(const UnitPlan& plan, const __half* base, int64_t ny, int64_t batch, CUtensorMap* out,
-                         bool half_box) {
+// Kronecker units (2-D row pass): unit (image b, y_lo) reads rows y_lo + u*(ny/U), u < U, of image b.  The image
+// stride is batch_step * (ny/U) rows (U for contiguous images, 2U for the [RE_b | IM_b] layout), so
+// row = y_lo + (ny/U)*(u + batch_step*b): dims {64, R, M/64, y_lo (stride nx), u + batch_step*b}.
+int make_kron_tensor_map(const UnitPlan& plan, const __half* base, int64_t ny, int64_t batch, int64_t batch_step,
+                         CUtensorMap* out, bool half_box) {
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) return TFFT_E_UNSUPPORTED;
   const uint64_t L = uint64_t(1) << plan.log2_len, R = uint64_t(1) << plan.log2_radix[0], M = L / R;
   const uint64_t U = uint64_t(1) << plan.log2_units;
-  cuuint64_t gdim[5] = {64, R, M / 64, static_cast<cuuint64_t>(ny) / U, U * static_cast<cuuint64_t>(batch)};
+  cuuint64_t gdim[5] = {64, R, M / 64, static_cast<cuuint64_t>(ny) / U,
+                        static_cast<cuuint64_t>(batch_step) * static_cast<cuuint64_t>(batch - 1) + U};
   cuuint64_t gstride[4] = {M * 2, 128, L * 2, (static_cast<cuuint64_t>(ny) / U) * L * 2};
   cuuint32_t box[5] = {64, static_cast<cuuint32_t>(R), static_cast<cuuint32_t>(M / 64), 1,
                        static_cast<cuuint32_t>(half_box ? U / 2 : U)};
@@ -198,7 +214,8 @@ void set_kernel_attrs() {
       cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       if (e != cudaSuccess) g_attr_err = static_cast<int>(e);
     }
-  for (Kernel2Fn fn : {static_cast<Kernel2Fn>(fft_unit_kernel_2slot<4, 4, 5>), static_cast<Kernel2Fn>(fft_unit_kernel_2slot<4, 5, 5>)}) {
+  for (Kernel2Fn fn : {static_cast<Kernel2Fn>(fft_unit_kernel_2slot<4, 4, 5>), static_cast<Kernel2Fn>(fft_unit_kernel_2slot<4, 5, 5>),
+                       static_cast<Kernel2Fn>(fft_unit_kernel_2slot<5, 5, 4>)}) {
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) g_attr_err = static_cast<int>(e);
   }
@@ -256,7 +273,7 @@ bool add_pass(tfft_plan_s* p, const UnitShape& shape, const UnitStrides& st, uin
   ps.strides.n_units = n_units;
   ps.n_units = n_units;
   ps.smem = smem_layout(ps.plan).total;
-  ps.tables = make_tables(ps.plan);
+  ps.tables = make_tables(ps.plan, (p->flags & TFFT_UNSCALED) != 0);
   ps.src = src;
   ps.dst = dst;
   ps.in_stride_is_user = in_user;
@@ -462,9 +479,15 @@ int launch_pass(const tfft_plan_s* p, const Pass& ps, const __half* src_re, cons
     st.col_div = 1;
   }
   const int64_t U = int64_t(1) << ps.plan.log2_units;
+  int64_t tma_extent = 0;   // 2-D row pass: rows (4-D map) the tensor map spans
   if (ps.kind != 0) {   // 2-D passes: only the image strides come from the caller
     st.in_batch_stride = in_stride;
     st.out_batch_stride = out_stride;
+    if (ps.kind == 1 && ps.plan.tma_load) {   // tfft_exec checked tma_ok_2d(): the image stride is a whole number of steps
+      const int64_t step_elems = ps.plan.kron_bits ? (p->ny >> ps.plan.kron_bits) * p->nx : p->nx;
+      st.tma_batch_step = static_cast<uint32_t>(p->batch > 1 ? in_stride / step_elems : 0);
+      tma_extent = static_cast<int64_t>(st.tma_batch_step) * (p->batch - 1) + p->ny;
+    }
   } else if (ps.plan.in_mode == kRowMode && ps.plan.out_mode == kRowMode) {   // batched 1-D, one pass
     st.in_tstride = in_stride; st.out_tstride = out_stride;
     st.in_unit_stride = U * in_stride; st.out_unit_stride = U * out_stride;
@@ -472,10 +495,13 @@ int launch_pass(const tfft_plan_s* p, const Pass& ps, const __half* src_re, cons
     st.in_batch_stride = in_stride;
     st.out_batch_stride = out_stride;
   }
+  if (ps.kind == 0 && ps.plan.tma_load && st.units_per_batch != 0x7FFFFFFFu)   // batches of contiguous transforms
+    st.tma_batch_step = st.units_per_batch << ps.plan.log2_units;
   UnitPlan plan = ps.plan;
   fill_strides(st, ps.info, &plan);
   plan.col_first = static_cast<uint32_t>(tw_first_col);
-  KernelFn fn = kernel_for(plan);
+  int threads = kThreads;
+  KernelFn fn = kernel_for(plan, &threads);
   if (!fn) return TFFT_E_UNSUPPORTED;
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
@@ -490,7 +516,7 @@ int launch_pass(const tfft_plan_s* p, const Pass& ps, const __half* src_re, cons
       e = cudaMemcpy(d, ps.tables.data(), ps.tables.size(), cudaMemcpyHostToDevice);
       if (e != cudaSuccess) { cudaFree(d); return static_cast<int>(e); }
       int per_sm = 0, sms = 0, smem_sm = 0;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, ps.smem);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, ps.smem);
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
       cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
       if (getenv("TFFT_DEBUG")) fprintf(stderr, "tfft: occupancy api=%d smem/sm=%d\n", per_sm, smem_sm);
@@ -512,12 +538,12 @@ int launch_pass(const tfft_plan_s* p, const Pass& ps, const __half* src_re, cons
   if (plan.tma_load) {
     // row-mode input: transform t of the launch starts at src + t * tstride, or, for four-step row
     // passes, at src + (t / upb) * batch_stride + (t % upb) * tstride == t * tstride when contiguous
-    const int64_t n_tr = static_cast<int64_t>(ps.n_units) << plan.log2_units;
+    const int64_t n_tr = tma_extent ? tma_extent : static_cast<int64_t>(ps.n_units) << plan.log2_units;
     const bool half_box = kernel2_for(plan) != nullptr;
     int rc;
     if (plan.kron_bits) {
-      rc = make_kron_tensor_map(plan, src_re, p->ny, p->batch, &tmap_re, half_box);
-      if (rc == TFFT_OK) rc = make_kron_tensor_map(plan, src_im, p->ny, p->batch, &tmap_im, half_box);
+      rc = make_kron_tensor_map(plan, src_re, p->ny, p->batch, plan.tma_batch_step, &tmap_re, half_box);
+      if (rc == TFFT_OK) rc = make_kron_tensor_map(plan, src_im, p->ny, p->batch, plan.tma_batch_step, &tmap_im, half_box);
     } else {
       rc = make_input_tensor_map(plan, src_re, st.in_tstride, plan.n_transforms ? plan.n_transforms : n_tr, &tmap_re, half_box);
       if (rc == TFFT_OK)
@@ -525,22 +551,21 @@ int launch_pass(const tfft_plan_s* p, const Pass& ps, const __half* src_re, cons
     }
     if (rc != TFFT_OK) return rc;
   }
-  if (Kernel2Fn fn2 = kernel2_for(plan)) {
+  if (Kernel2Fn fn2 = kernel2_for(plan)) {   // the tensor maps above hold half-tile boxes: no other kernel may run them
     const Smem2Layout S2 = smem2_layout(plan);
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (S2.total <= 227 * 1024 && sms > 0) {
-      const unsigned grid2 = std::min<unsigned>(ps.n_units, static_cast<unsigned>(sms));
-      void* args2[] = {&plan, &dst_re, &dst_im, &tables, &tmap_re, &tmap_im, &trace};
-      e = cudaLaunchKernel(reinterpret_cast<const void*>(fn2), dim3(grid2), dim3(kCta2Threads), args2, S2.total, stream);
-      return e == cudaSuccess ? TFFT_OK : static_cast<int>(e);
-    }
+    if (sms < 1) return TFFT_E_UNSUPPORTED;
+    const unsigned grid2 = std::min<unsigned>(ps.n_units, static_cast<unsigned>(sms));
+    void* args2[] = {&plan, &dst_re, &dst_im, &tables, &tmap_re, &tmap_im, &trace};
+    e = cudaLaunchKernel(reinterpret_cast<const void*>(fn2), dim3(grid2), dim3(kCta2Threads), args2, S2.total, stream);
+    return e == cudaSuccess ? TFFT_OK : static_cast<int>(e);
   }
   void* args[] = {&plan, &src_re, &src_im, &dst_re, &dst_im, &tables, &trace, &tmap_re, &tmap_im};
   if (getenv("TFFT_DEBUG"))
     fprintf(stderr, "tfft: launch grid=%u units=%u smem=%u tmem=%u resident=%d\n", grid, ps.n_units, ps.smem,
             plan.tmem_cols, ps.resident_ctas[dev]);
-  e = cudaLaunchKernel(reinterpret_cast<const void*>(fn), dim3(grid), dim3(kThreads), args, ps.smem, stream);
+  e = cudaLaunchKernel(reinterpret_cast<const void*>(fn), dim3(grid), dim3(threads), args, ps.smem, stream);
   (void)p;
   return e == cudaSuccess ? TFFT_OK : static_cast<int>(e);
 }
@@ -659,9 +684,20 @@ int tfft_exec(tfft_plan_t p, const void* in_re, const void* in_im, void* out_re,
   std::call_once(g_attr_once, set_kernel_attrs);
   if (g_attr_err) return g_attr_err == static_cast<int>(cudaErrorInvalidDeviceFunction) ? TFFT_E_NO_DEVICE : g_attr_err;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (p->flags & TFFT_INVERSE) {   // F^-1(x) = swap(F(swap(x))), swap = exchange of the real and imaginary planes
+    std::swap(in_re, in_im);
+    std::swap(out_re, out_im);
+  }
   const int64_t outer = p->loop_batch ? p->batch : 1;
   const std::vector<Pass>* passes = &p->passes;
-  if (p->ny && p->batch > 1 && in_stride != p->n && p->passes.front().plan.tma_load) {
+  // 2-D row pass with TMA tiles: the image stride must be a whole number of tensor-map steps (rows, or groups of ny/U
+  // rows for Kronecker units); otherwise the same passes with 16-byte asynchronous copies
+  auto tma_ok_2d = [&]() {
+    const UnitPlan& rp = p->passes.front().plan;
+    const int64_t step = rp.kron_bits ? (p->ny >> rp.kron_bits) * p->nx : p->nx;
+    return in_stride % step == 0 && in_stride / step < (int64_t(1) << 31);
+  };
+  if (p->ny && p->batch > 1 && p->passes.front().plan.tma_load && !tma_ok_2d()) {
     std::lock_guard<std::mutex> lock(g_upload_mutex);
     if (p->passes_strided.empty()) {
       const int rc = build_2d(p, &p->passes_strided, false);
@@ -697,7 +733,7 @@ int tfft_exec(tfft_plan_t p, const void* in_re, const void* in_im, void* out_re,
 int tfft_exec_twiddled(tfft_plan_t p, const void* in_re, const void* in_im, void* out_re, void* out_im,
                        int64_t in_stride, int64_t out_stride, int32_t log2_total, int64_t first_col, void* stream_) {
   if (!p || !in_re || !in_im || !out_re || !out_im) return TFFT_E_INVALID_ARG;
-  if (p->passes.size() != 1 || log2_total < p->lg || log2_total > 30) return TFFT_E_UNSUPPORTED;
+  if (p->passes.size() != 1 || log2_total < p->lg || log2_total > 30 || (p->flags & TFFT_INVERSE)) return TFFT_E_UNSUPPORTED;
   if (first_col < 0 || first_col + p->batch > (int64_t(1) << (log2_total - p->lg))) return TFFT_E_INVALID_ARG;
   if (!aligned16(in_re) || !aligned16(in_im) || !aligned16(out_re) || !aligned16(out_im)) return TFFT_E_INVALID_ARG;
   if ((in_stride & 7) || (out_stride & 7) || in_stride < p->n || out_stride < p->n) return TFFT_E_INVALID_ARG;
@@ -776,6 +812,62 @@ int tfft_exec_host(tfft_plan_t p, const void* host_in, void* host_out) {
   }
   cudaError_t e = cudaStreamSynchronize(s_down);
   return e == cudaSuccess ? TFFT_OK : static_cast<int>(e);
+}
+
+int tfft_fixture_sine(void* re, void* im, int64_t n, int64_t batch, int64_t stride, const float* w_re,
+                      const float* w_im, int32_t cutoff, void* stream_) {
+  if (!re || !im || !w_re || !w_im || n < 1 || batch < 1 || batch > 65535 || cutoff < 1 || stride < n) return TFFT_E_INVALID_ARG;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  float* d_w = nullptr;
+  const size_t wbytes = static_cast<size_t>(batch) * cutoff * sizeof(float);
+  cudaError_t e = cudaMalloc(&d_w, 2 * wbytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? TFFT_E_NO_DEVICE
+           : e == cudaErrorMemoryAllocation                            ? TFFT_E_NOMEM
+                                                                       : static_cast<int>(e);
+  }
+  e = cudaMemcpyAsync(d_w, w_re, wbytes, cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_w + static_cast<size_t>(batch) * cutoff, w_im, wbytes, cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess) {
+    const dim3 grid(static_cast<unsigned>((n + 255) / 256), static_cast<unsigned>(batch));
+    sine_fixture_kernel<<<grid, 256, 0, stream>>>(static_cast<__half*>(re), static_cast<__half*>(im), n, stride, d_w,
+                                                  d_w + static_cast<size_t>(batch) * cutoff, cutoff);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);   // the weights staging buffer is freed below
+  cudaFree(d_w);
+  return e == cudaSuccess ? TFFT_OK : static_cast<int>(e);
+}
+
+int tfft_error_stats(const void* a_re, const void* a_im, const double* b_re, const double* b_im, int64_t count,
+                     double* out4, void* stream_) {
+  if (!a_re || !a_im || !b_re || !b_im || !out4 || count < 1) return TFFT_E_INVALID_ARG;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  double* d_acc = nullptr;
+  cudaError_t e = cudaMalloc(&d_acc, 4 * sizeof(double));
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? TFFT_E_NO_DEVICE : static_cast<int>(e);
+  }
+  e = cudaMemsetAsync(d_acc, 0, 4 * sizeof(double), stream);
+  if (e == cudaSuccess) {
+    const unsigned grid = static_cast<unsigned>(std::min<int64_t>((count + 255) / 256, 148 * 8));
+    deviation_sums_kernel<<<grid, 256, 0, stream>>>(static_cast<const __half*>(a_re), static_cast<const __half*>(a_im), b_re,
+                                                    b_im, count, d_acc, reinterpret_cast<unsigned long long*>(d_acc + 3));
+    e = cudaGetLastError();
+  }
+  double h[4] = {0, 0, 0, 0};
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h, d_acc, sizeof(h), cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  cudaFree(d_acc);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  const double cnt = 2.0 * static_cast<double>(count), avg = h[0] / cnt;
+  out4[0] = h[3];                                                             // largest deviation
+  out4[1] = avg;                                                              // average deviation
+  out4[2] = std::sqrt(std::max(0.0, h[1] - 2.0 * avg * h[0] + cnt * avg * avg) / (cnt - 1.0));   // sigma
+  out4[3] = h[2] > 0.0 ? std::sqrt(h[1] / h[2]) : 0.0;                        // relative L2 error
+  return TFFT_OK;
 }
 
 }  // extern "C"

@@ -99,7 +99,11 @@ struct UnitPlan {
   // ---- global addressing (elements)
   int64_t in_batch_stride, in_unit_stride;     // unit base = (unit / upb) * batch_stride + (unit % upb) * unit_stride
   int64_t out_batch_stride, out_unit_stride;
-  uint32_t units_per_batch;
+  uint32_t units_per_batch;                    // always a power of two (or the sentinel 0x7FFFFFFF = "one batch")
+  uint32_t upb_shift;                          // log2(units_per_batch) (31 for the sentinel): the kernel shifts and masks
+  uint32_t col_shift;                          // log2(col_div)
+  uint32_t tma_batch_step;                     // TMA loads: outermost tile coordinate = (unit >> upb_shift) * tma_batch_step
+                                               //   + ((unit & mask) << log2_units)   (0: the unit index alone, 1-D batches)
   uint32_t n_units;                            // total units of the launch (persistent CTAs loop over them)
   uint32_t n_transforms;                       // != 0 (row/row passes): transforms >= n_transforms are masked
   uint32_t col_base_stride;   // tw_mode 2: col_base = ((unit % upb) / col_div) * col_base_stride
@@ -132,7 +136,11 @@ struct PlanBuildInfo {   // host-only by-products, used by fill_strides and the 
 };
 
 // radix schedule: fewest stages, largest radix last (the last stage has no twiddle)
-inline int radix_schedule(int log2_len, int* rho) {
+inline int radix_schedule(int log2_len, int* rho, int kron_bits = 0) {
+  if (kron_bits == 1 && log2_len == 14) {   // 2 rows x 8192: the Kronecker stage as the small radix, so that stages 1 and
+    rho[0] = 5; rho[1] = 5; rho[2] = 4;     // 2 share one DFT matrix and the two-slot kernel fits in shared memory
+    return 3;
+  }
   switch (log2_len) {
     case 8: rho[0] = 4; rho[1] = 4; return 2;
     case 9: rho[0] = 4; rho[1] = 5; return 2;
@@ -169,7 +177,7 @@ inline bool build_unit_plan(const UnitShape& shape, UnitPlan* plan, PlanBuildInf
   if (kb && (kb != ups || shape.in_mode != kRowMode || shape.out_mode != kRowMode || lg < 8)) {
     info->error = "Kronecker units need kron_bits == log2_units and row modes"; return false;
   }
-  const int s = radix_schedule(kb ? eps : lg, rho);
+  const int s = radix_schedule(kb ? eps : lg, rho, kb);
   if (s == 0) { info->error = "length must be 2^8 .. 2^15"; return false; }
   if (eps < 13 || eps > 15) { info->error = "unit must hold 2^13 .. 2^15 elements"; return false; }
   int* rx = info->rx;
@@ -186,7 +194,10 @@ inline bool build_unit_plan(const UnitShape& shape, UnitPlan* plan, PlanBuildInf
     info->error = "TMA load needs row mode and >= 64 contiguous rows per K line"; return false;
   }
   plan->tma_load = shape.tma_load ? 1u : 0u;
-  plan->pipe_stage2 = (shape.pipe_stage2 && s == 3) ? 1u : 0u;
+  // the first-half epilogue of stage 2 writes the first half of stage 3's layout, which must lie inside the half of
+  // stage 2's layout that its first-half MMAs have consumed: padded plane sizes shrink with the radix, so R_3 >= R_2
+  const bool pipe2 = shape.pipe_stage2 && s == 3 && rho[2] >= rho[1];
+  plan->pipe_stage2 = pipe2 ? 1u : 0u;
   {
     int lo = lg;
     for (int t = 0; t < s; ++t) { lo -= rx[t]; info->lo_bit[t] = lo; }
@@ -279,7 +290,7 @@ inline bool build_unit_plan(const UnitShape& shape, UnitPlan* plan, PlanBuildInf
     }
     for (auto& b : rest) rb.push_back(b);
     if ((int)rb.size() != eps - rho[t - 1]) { info->error = "row bit count mismatch"; return false; }
-    if (shape.pipe_stage2 && s == 3 && t >= 2) {
+    if (pipe2 && t >= 2) {
       const LBit hbit = {LBit::K, 1, (uint8_t)(rho[0] - 1)};
       const int pos = find_bit(rb, hbit);
       if (pos < 6) { info->error = "pipeline bit is not free"; return false; }
@@ -436,6 +447,7 @@ struct UnitStrides {
   bool col_from_u = true;    // tw_mode 2 column index includes the unit-local transform index u
   uint32_t n_transforms = 0;
   uint32_t pass1_log2n = 0;  // != 0: multiply outputs by exp(-2*pi*i*o*(col_base+u)/2^pass1_log2n)
+  uint32_t tma_batch_step = 0;
   uint32_t kron_log2n = 0;   // Kronecker units, != 0: multiply output row k_y by exp(-2*pi*i*k_y*col_base/2^kron_log2n)
 };
 
@@ -463,6 +475,13 @@ inline void fill_strides(const UnitStrides& st, const PlanBuildInfo& info, UnitP
   plan->in_batch_stride = st.in_batch_stride; plan->in_unit_stride = st.in_unit_stride;
   plan->out_batch_stride = st.out_batch_stride; plan->out_unit_stride = st.out_unit_stride;
   plan->units_per_batch = st.units_per_batch;
+  plan->upb_shift = 31;
+  for (uint32_t i = 0; i < 31; ++i)
+    if (st.units_per_batch == (1u << i)) plan->upb_shift = i;
+  plan->col_shift = 0;
+  for (uint32_t i = 0; i < 31; ++i)
+    if (st.col_div == (1u << i)) plan->col_shift = i;
+  plan->tma_batch_step = st.tma_batch_step;
   plan->n_units = st.n_units;
   plan->col_base_stride = st.col_base_stride;
   plan->col_div = st.col_div ? st.col_div : 1;

@@ -29,6 +29,8 @@ MODE_256 = 0      # BaseFFTMode::Mode_256   (Plan.h:14)
 MODE_4096 = 1     # BaseFFTMode::Mode_4096
 
 TFFT_PRESERVE_INPUT = 1
+TFFT_INVERSE = 2      # exp(+2 pi i n k / N)
+TFFT_UNSCALED = 4     # no 1/N (cuFFT convention)
 
 
 class TfftError(RuntimeError):
@@ -46,7 +48,8 @@ class _PlanInfo(ctypes.Structure):
 
 
 EXPORTS = ("tfft_plan_create", "tfft_plan_create_2d", "tfft_plan_info", "tfft_plan_destroy", "tfft_exec",
-           "tfft_exec_twiddled", "tfft_exec_host", "tfft_error_string", "tfft_version")
+           "tfft_exec_twiddled", "tfft_exec_host", "tfft_error_string", "tfft_version", "tfft_fixture_sine",
+           "tfft_error_stats")
 
 
 def lib() -> ctypes.CDLL:
@@ -65,6 +68,9 @@ def lib() -> ctypes.CDLL:
         L.tfft_exec.argtypes = [vp, vp, vp, vp, vp, i64, i64, vp]
         L.tfft_exec_twiddled.argtypes = [vp, vp, vp, vp, vp, i64, i64, ctypes.c_int32, i64, vp]
         L.tfft_exec_host.argtypes = [vp, vp, vp]
+        fp, dp = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)
+        L.tfft_fixture_sine.argtypes = [vp, vp, i64, i64, i64, fp, fp, ctypes.c_int32, vp]
+        L.tfft_error_stats.argtypes = [vp, vp, vp, vp, i64, dp, vp]
         L.tfft_error_string.argtypes = [ctypes.c_int]
         L.tfft_error_string.restype = ctypes.c_char_p
         _lib = L
@@ -74,6 +80,34 @@ def lib() -> ctypes.CDLL:
 def _check(rc: int) -> None:
     if rc != 0:
         raise TfftError(f"tfft error {rc}: {lib().tfft_error_string(rc).decode()}")
+
+
+def fixture_sine(re, im, n: int, weights_re, weights_im, stride: Optional[int] = None) -> None:
+    """tfft_fixture_sine: fill fp16 CUDA tensors with the reference's sine superposition
+    (TestingDataCreation.h:89-117). weights_*: float32 numpy arrays (batch, cutoff)."""
+    import numpy as np
+    import torch
+    wr = np.ascontiguousarray(np.atleast_2d(weights_re), dtype=np.float32)
+    wi = np.ascontiguousarray(np.atleast_2d(weights_im), dtype=np.float32)
+    for t in (re, im):
+        if not (t.is_cuda and t.dtype == torch.float16):
+            raise TfftError("fixture_sine needs CUDA float16 tensors (no CPU fallback)")
+    fp = ctypes.POINTER(ctypes.c_float)
+    _check(lib().tfft_fixture_sine(re.data_ptr(), im.data_ptr(), n, wr.shape[0], stride or n, wr.ctypes.data_as(fp),
+                                   wi.ctypes.data_as(fp), wr.shape[1],
+                                   ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+
+def error_stats(a_re, a_im, b_re, b_im) -> dict:
+    """tfft_error_stats: fp16 CUDA result planes vs float64 CUDA reference planes ->
+    {max, avg, sigma, rel_l2} (AccuracyCalculator.h:86-148 on the device)."""
+    import torch
+    if not (a_re.is_cuda and a_re.dtype == torch.float16 and b_re.is_cuda and b_re.dtype == torch.float64):
+        raise TfftError("error_stats needs CUDA float16 results and CUDA float64 reference values")
+    out = (ctypes.c_double * 4)()
+    _check(lib().tfft_error_stats(a_re.data_ptr(), a_im.data_ptr(), b_re.data_ptr(), b_im.data_ptr(), a_re.numel(),
+                                  out, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    return {"max": out[0], "avg": out[1], "sigma": out[2], "rel_l2": out[3]}
 
 
 class NativePlan:

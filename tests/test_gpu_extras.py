@@ -1,0 +1,85 @@
+"""GPU (-m gpu): the steps either side of the hot path through the C ABI:
+inverse / unscaled transforms (the cuFFT conventions the reference compares itself with,
+src/testing/unitTesting/CuFFTTest.h:25-57) and the device-side fixture + deviation statistics
+(src/testing/TestingDataCreation.h:89-117, src/testing/AccuracyCalculator.h:86-148)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+import tfft
+
+pytestmark = pytest.mark.gpu
+
+
+def _exec(n, b, flags, x):
+    y = torch.empty_like(x)
+    plan = tfft.NativePlan(n, b, flags)
+    plan.exec(x, x[n:], y, y[n:], 2 * n, 2 * n)
+    torch.cuda.synchronize()
+    return y
+
+
+@pytest.mark.parametrize("lg,b", [(8, 9), (12, 3), (14, 2), (15, 1), (18, 1)])
+def test_inverse_flag_is_the_conjugate_transform(lg, b):
+    """F^-1(x) == conj(F(conj(x))) up to fp32 summation order (the planes are exchanged instead of negated), and
+    within the reference's fp16 error level of the fp64 oracle."""
+    n = 1 << lg
+    re, im = O.gauss_fixture(n, b, seed=300 + lg)
+    host = np.ascontiguousarray(np.stack([re, im], axis=1)).reshape(-1)
+    x = torch.from_numpy(host).cuda()
+    inv = _exec(n, b, tfft.TFFT_INVERSE, x.clone()).view(b, 2, n)
+    xc = x.clone().view(b, 2, n)
+    xc[:, 1] = -xc[:, 1]
+    fc = _exec(n, b, 0, xc.view(-1)).view(b, 2, n)
+    d = torch.stack([inv[:, 0].float() - fc[:, 0].float(), inv[:, 1].float() + fc[:, 1].float()])
+    assert float(torch.linalg.vector_norm(d) / torch.linalg.vector_norm(fc.float())) < 2e-4
+    w_re, w_im = O.fft_f64(re.astype(np.float64), -im.astype(np.float64))        # fp64 oracle of the conjugate
+    st = O.error_stats(inv[:, 0].cpu().numpy().astype(np.float64), inv[:, 1].cpu().numpy().astype(np.float64), w_re, -w_im)
+    assert st["rel_l2"] <= 9.0e-4, st
+
+
+@pytest.mark.parametrize("lg,b", [(8, 9), (11, 4), (14, 2), (16, 1)])
+def test_unscaled_flag_matches_cufft_convention(lg, b):
+    n = 1 << lg
+    re, im = O.gauss_fixture(n, b, seed=400 + lg)
+    host = np.ascontiguousarray(np.stack([re, im], axis=1)).reshape(-1)
+    x = torch.from_numpy(host).cuda()
+    y = _exec(n, b, tfft.TFFT_UNSCALED, x.clone()).view(b, 2, n).cpu().numpy().astype(np.float64)
+    w_re, w_im = O.fft_f64(re.astype(np.float64), im.astype(np.float64))
+    st = O.error_stats(y[:, 0], y[:, 1], w_re * n, w_im * n)                       # oracle is 1/N scaled
+    assert st["rel_l2"] <= 9.0e-4, st
+    # round trip: unscaled forward, then scaled inverse gives x back (to fp16 accuracy of two transforms)
+    z = _exec(n, b, tfft.TFFT_INVERSE, torch.from_numpy(np.ascontiguousarray(y.astype(np.float16)).reshape(-1)).cuda())
+    z = z.view(b, 2, n).cpu().numpy().astype(np.float64)
+    assert O.error_stats(z[:, 0], z[:, 1], re.astype(np.float64), im.astype(np.float64))["rel_l2"] <= 2e-3
+
+
+def test_device_sine_fixture_matches_the_oracle_fixture():
+    """Same recipe as the reference's fixture kernel; the host oracle evaluates it with libm's sinf, the device
+    with CUDA's: results may differ by one fp16 ulp on a small fraction of samples."""
+    n, cutoff = 4096, 256
+    w_re, w_im = O.random_weights(cutoff, 42), O.random_weights(cutoff, 42 * 42)
+    re = torch.empty(n, dtype=torch.float16, device="cuda")
+    im = torch.empty(n, dtype=torch.float16, device="cuda")
+    tfft.fixture_sine(re, im, n, w_re, w_im)
+    h_re, h_im = O.sine_fixture(n, cutoff=cutoff, seed_re=42, seed_im=42 * 42)
+    for got, want in ((re, h_re), (im, h_im)):
+        g = got.cpu().numpy().astype(np.float64)
+        w = np.asarray(want).astype(np.float16).astype(np.float64)
+        ulp = np.maximum(np.abs(w), 2.0 ** -14) * 2.0 ** -10
+        assert np.all(np.abs(g - w) <= ulp)
+        assert np.mean(g != w) < 0.02
+
+
+def test_device_error_stats_match_the_oracle_statistics():
+    n, b = 8192, 3
+    re, im = O.gauss_fixture(n, b, seed=77)
+    host = np.ascontiguousarray(np.stack([re, im], axis=1)).reshape(-1)
+    y = _exec(n, b, 0, torch.from_numpy(host).cuda()).view(b, 2, n)
+    w_re, w_im = O.fft_f64(re.astype(np.float64), im.astype(np.float64))
+    a_re, a_im = y[:, 0].contiguous(), y[:, 1].contiguous()
+    got = tfft.error_stats(a_re, a_im, torch.from_numpy(w_re).cuda(), torch.from_numpy(w_im).cuda())
+    want = O.error_stats(a_re.cpu().numpy().astype(np.float64), a_im.cpu().numpy().astype(np.float64), w_re, w_im)
+    for k in ("max", "avg", "sigma", "rel_l2"):
+        assert abs(got[k] - want[k]) <= 1e-9 * max(1.0, abs(want[k])) + 1e-6 * abs(want[k]), (k, got, want)
