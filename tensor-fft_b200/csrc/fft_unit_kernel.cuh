@@ -193,6 +193,15 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
       : "memory");
 }
 
+// column-mode tile {8 columns, R kappa, M rows, 1 batch}: coordinates (first column, 0, 0, batch)
+__device__ __forceinline__ void tma_load_4d_col(uint32_t dst, const CUtensorMap* map, uint32_t c0, uint32_t c3,
+                                                uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %3, %4}], [%5];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(0), "r"(c3), "r"(ptx::smem_u32(bar))
+      : "memory");
+}
+
 // 4-D TMA tile load {64 rows, R kappa, M/64, U transforms} -> SWIZZLE_128B stage-1 operand plane
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t c2, uint32_t c3,
                                             uint64_t* bar) {
@@ -236,6 +245,12 @@ __device__ __forceinline__ Cplx tw_lookup(const float2* tw_table, uint32_t x) {
 #else
 #define TFFT_TRACE_MARK(slot) do {} while (0)
 #endif
+
+// Programmatic dependent launch: every kernel lets its successor's CTAs become resident as soon as SMs free up
+// (launch_dependents at entry) and itself waits for its predecessor's completion and memory flush only after its own
+// prologue (tensor-memory allocation, barrier setup, constant tables), right before it first touches data.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 struct KernelCtx {
   uint32_t sbase, s_re, s_im, taddr, lane_row, wgroup, lane_base;
@@ -453,12 +468,14 @@ struct StageShape {
 };
 
 // All UMMAs of one stage, issued by ONE thread (under elect_one()).
-template <int ST, int RHO, int LOG2E, bool SW128, bool PIPE, class Hook, int NG = 2>
+template <int ST, int RHO, int LOG2E, int LM, bool PIPE, class Hook, int NG = 2>
 __device__ __forceinline__ void stage_issue(const KernelCtx& c, uint32_t b1_saddr, uint64_t* bar, const Hook& hook,
                                             long long* trace, uint32_t trace_unit) {
   using namespace ptx;
   using SS = StageShape<RHO, LOG2E, PIPE, NG>;
-  constexpr uint32_t R = SS::R, kSteps = SS::kSteps, S = SS::S, kTiles = SS::kTiles;
+  constexpr uint32_t R = SS::R, kSteps = SS::kSteps, kTiles = SS::kTiles;
+  constexpr bool SW128 = LM == 1 && ST == 0;
+  constexpr uint32_t S = (LM == 2 && ST == 0) ? 16 * R : SS::S;   // column tiles loaded by TMA are dense: no padding
   constexpr bool kPipe = SS::kPipe;
   constexpr uint32_t idesc = make_idesc_f16(128, 2 * R, /*a_mn=*/1, /*b_mn=*/0);
   // descriptors differ only in the 14-bit start-address field (units of 16 bytes): add offsets there
@@ -521,7 +538,7 @@ __device__ __forceinline__ void stage_observe(uint64_t* bar, uint32_t (&phase)[2
 // ROLE 1: epilogue warp of a slot whose UMMAs are issued by a dedicated warp.  That warp issues the
 //         stage-1 UMMAs of a unit ahead of time (during the previous unit's store phase), so stage 1 has
 //         no leading barrier here.
-template <int ST, int RHO, bool LAST, int LOG2E, bool SW128 = false, bool PIPE = false, class Hook = NoHook,
+template <int ST, int RHO, bool LAST, int LOG2E, int LM = 0, bool PIPE = false, class Hook = NoHook,
           int ROLE = 0, int NG = 2>
 __device__ __forceinline__ void run_stage(const UnitPlan& P, const KernelCtx& c, uint32_t b1_saddr, uint64_t* bar,
                                           uint32_t (&phase)[2], int warp, int lane, long long* trace,
@@ -538,7 +555,7 @@ __device__ __forceinline__ void run_stage(const UnitPlan& P, const KernelCtx& c,
   }
   TFFT_TRACE_MARK(9 + 2 * ST);
   if (ROLE == 0 && warp == 0 && elect_one())
-    stage_issue<ST, RHO, LOG2E, SW128, PIPE, Hook, NG>(c, b1_saddr, bar, hook, trace, trace_unit);
+    stage_issue<ST, RHO, LOG2E, LM, PIPE, Hook, NG>(c, b1_saddr, bar, hook, trace, trace_unit);
   const bool hook_warp = ROLE == 0 && warp == 0;   // converged at every use below (after warp_wait)
   // per-thread parts of the bit-linear row maps (thread_map(): 7 lane-row bits + the warp-group bits)
   const uint32_t dst_thr = (tmap & 0xFFFFu) << 4, aux_thr = tmap >> 16;
@@ -618,7 +635,9 @@ __device__ __forceinline__ void store_phase(const UnitPlan& P, const KernelCtx& 
 }
 
 // NT threads: 256 (two warp groups), or 512 (four warp groups) for the 32K-element units that run one CTA per SM
-template <int LOG2E, int RHO0, int RHO1, int RHO2, bool TMA, int NT = kThreads>
+// LM: how the stage-1 operand is loaded: 0 = 16-byte cp.async (any mode), 1 = one SWIZZLE_128B TMA tile per plane (row
+// mode), 2 = dense TMA tiles of 8 columns (column mode)
+template <int LOG2E, int RHO0, int RHO1, int RHO2, int LM, int NT = kThreads>
 __global__ void __launch_bounds__(NT, (LOG2E == 15 ? 1 : 2))
 fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ in_re,
                 const __half* __restrict__ in_im, __half* __restrict__ out_re, __half* __restrict__ out_im,
@@ -654,6 +673,7 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
   (void)trace_unit;
 
   // ------------------------------------------------------------------ setup (once per CTA)
+  pdl_launch_dependents();
   if (warp == 0) {
     tmem_alloc(tmem_slot, P.tmem_cols);
     tmem_relinquish();
@@ -668,6 +688,7 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
+  pdl_wait();   // the predecessor in the stream may have produced this kernel's input (or still read its output)
   c.taddr = *tmem_slot;
   uint32_t phase[2] = {0, 0}, load_phase = 0;
 
@@ -699,7 +720,21 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
 
     // ---------------------------------------------------------------- load phase
     TFFT_TRACE_MARK(0);
-    if constexpr (TMA) {
+    if constexpr (LM == 2) {
+      // per 8-column group one tile {8 columns, R kappa, M rows, 1 batch} per plane, dense: [group][m][kappa][8]
+      if (tid == 0) {
+        fence_proxy_async_smem();
+        mbar_arrive_expect_tx(load_bar, 4u << LOG2E);
+        const uint32_t group_bytes = 16u << P.log2_len;
+        for (uint32_t ug = 0; ug < (1u << P.log2_units) / 8; ++ug) {
+          tma_load_4d_col(c.s_re + ug * group_bytes, &tmap_re, (uu << P.log2_units) + 8 * ug, ub, load_bar);
+          tma_load_4d_col(c.s_im + ug * group_bytes, &tmap_im, (uu << P.log2_units) + 8 * ug, ub, load_bar);
+        }
+      }
+      TFFT_TRACE_MARK(1);
+      mbar_wait(load_bar, load_phase & 1u);
+      load_phase++;
+    } else if constexpr (LM == 1) {
       // one tensor tile per plane: {64 rows, R kappa, M/64, U transforms}; transforms past the end of
       // the batch are out of bounds of the tensor map and arrive as zeros
       if (tid == 0) {
@@ -744,14 +779,14 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
     TFFT_TRACE_MARK(2);
 
     // ---------------------------------------------------------------- tensor-core stages
-    run_stage<0, RHO0, false, LOG2E, TMA, false, NoHook, 0, NG>(P, c, table_base + TL.b_off[0], bar, phase, warp, lane,
+    run_stage<0, RHO0, false, LOG2E, LM, false, NoHook, 0, NG>(P, c, table_base + TL.b_off[0], bar, phase, warp, lane,
                                                                 trace, trace_unit, tmap0, 0u);
     TFFT_TRACE_MARK(3);
-    run_stage<1, RHO1, kStages == 2, LOG2E, false, false, NoHook, 0, NG>(P, c, table_base + TL.b_off[1], bar, phase, warp,
+    run_stage<1, RHO1, kStages == 2, LOG2E, 0, false, NoHook, 0, NG>(P, c, table_base + TL.b_off[1], bar, phase, warp,
                                                                          lane, trace, trace_unit, tmap1, col_thr);
     TFFT_TRACE_MARK(4);
     if constexpr (kStages == 3)
-      run_stage<2, (RHO2 ? RHO2 : 4), true, LOG2E, false, false, NoHook, 0, NG>(P, c, table_base + TL.b_off[2], bar, phase,
+      run_stage<2, (RHO2 ? RHO2 : 4), true, LOG2E, 0, false, NoHook, 0, NG>(P, c, table_base + TL.b_off[2], bar, phase,
                                                                                 warp, lane, trace, trace_unit, tmap2, col_thr);
     TFFT_TRACE_MARK(5);
     __syncthreads();
@@ -856,19 +891,7 @@ fft_unit_kernel_2slot(const __grid_constant__ UnitPlan P, __half* __restrict__ o
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
-  if (tid_cta == 32) {
-    mbar_init(bars + 0, 1);
-    mbar_init(bars + 1, 1);
-    mbar_init(bars + 2, 1);
-    mbar_init(bars + 3, 1);
-    for (int i = 0; i < 4; ++i) mbar_init(land_full + i, 1);
-    fence_mbar_init();
-  }
-  for (uint32_t o = tid_cta * 16; o < TL.total; o += kCta2Threads * 16) sts128(table_base + o, ldg128(tables + (o >> 4)));
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  c.taddr = *tmem_slot + slot * 256;
+  pdl_launch_dependents();
   uint32_t phase[2] = {0, 0};
 
   // landing use q (q = 0, 1, 2, ...) carries unit blockIdx.x + q * gridDim.x and belongs to slot q & 1.
@@ -894,10 +917,25 @@ fft_unit_kernel_2slot(const __grid_constant__ UnitPlan P, __half* __restrict__ o
     tma_load_4d(c.a_re + off, &tmap_re, h * half_c2, c3, full);
     tma_load_4d(c.a_im + off, &tmap_im, h * half_c2, c3, full);
   };
-  if (tid_cta == 0) {
+  // one thread sets up the barriers, waits for the predecessor kernel and requests the first tile; the constant
+  // tables are staged meanwhile
+  if (tid_cta == 32) {
+    mbar_init(bars + 0, 1);
+    mbar_init(bars + 1, 1);
+    mbar_init(bars + 2, 1);
+    mbar_init(bars + 3, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(land_full + i, 1);
+    fence_mbar_init();
+    pdl_wait();
     request(0, 0);
     request(0, 1);
   }
+  for (uint32_t o = tid_cta * 16; o < TL.total; o += kCta2Threads * 16) sts128(table_base + o, ldg128(tables + (o >> 4)));
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  pdl_wait();
+  c.taddr = *tmem_slot + slot * 256;
   struct LandingHook {
     uint64_t* full;
     uint32_t parity, q;
@@ -922,7 +960,7 @@ fft_unit_kernel_2slot(const __grid_constant__ UnitPlan P, __half* __restrict__ o
         if (unit_of(q) >= P.n_units) return;
         LandingHook hook{land_full + 2 * slot, (q >> 1) & 1u, q, request};
         if (elect_one())
-          stage_issue<0, RHO0, LOG2E, true, true, LandingHook>(c, b_saddr0, mma_bar, hook, trace, trace_unit);
+          stage_issue<0, RHO0, LOG2E, 1, true, LandingHook>(c, b_saddr0, mma_bar, hook, trace, trace_unit);
         __syncwarp();
       };
       issue0(slot);
@@ -934,11 +972,11 @@ fft_unit_kernel_2slot(const __grid_constant__ UnitPlan P, __half* __restrict__ o
         group_sync(c);   // stage-1 epilogue complete: stage-2 operands in place
         tc_fence_after_sync();
         if (pipe2) {
-          if (elect_one()) stage_issue<1, RHO1, LOG2E, false, true, NoHook>(c, b_saddr1, mma_bar, NoHook(), trace, trace_unit);
+          if (elect_one()) stage_issue<1, RHO1, LOG2E, 0, true, NoHook>(c, b_saddr1, mma_bar, NoHook(), trace, trace_unit);
           __syncwarp();
           stage_observe<RHO1, LOG2E, true>(mma_bar, phase, NoHook());
         } else {
-          if (elect_one()) stage_issue<1, RHO1, LOG2E, false, false, NoHook>(c, b_saddr1, mma_bar, NoHook(), trace, trace_unit);
+          if (elect_one()) stage_issue<1, RHO1, LOG2E, 0, false, NoHook>(c, b_saddr1, mma_bar, NoHook(), trace, trace_unit);
           __syncwarp();
           stage_observe<RHO1, LOG2E, false>(mma_bar, phase, NoHook());
         }
@@ -947,7 +985,7 @@ fft_unit_kernel_2slot(const __grid_constant__ UnitPlan P, __half* __restrict__ o
           group_sync(c);
           tc_fence_after_sync();
           if (elect_one())
-            stage_issue<2, (RHO2 ? RHO2 : 4), LOG2E, false, false, NoHook>(c, b_saddr2, mma_bar, NoHook(), trace, trace_unit);
+            stage_issue<2, (RHO2 ? RHO2 : 4), LOG2E, 0, false, NoHook>(c, b_saddr2, mma_bar, NoHook(), trace, trace_unit);
           __syncwarp();
           stage_observe<(RHO2 ? RHO2 : 4), LOG2E, false>(mma_bar, phase, NoHook());
         }
@@ -985,19 +1023,19 @@ fft_unit_kernel_2slot(const __grid_constant__ UnitPlan P, __half* __restrict__ o
       TFFT_TRACE_MARK(1);
       TFFT_TRACE_MARK(2);
       LandingHook hook{land_full + 2 * slot, (q >> 1) & 1u, q, request};
-      run_stage<0, RHO0, false, LOG2E, true, true, LandingHook, ROLE>(P, c, b_saddr0, mma_bar, phase, warp, lane, trace,
+      run_stage<0, RHO0, false, LOG2E, 1, true, LandingHook, ROLE>(P, c, b_saddr0, mma_bar, phase, warp, lane, trace,
                                                                       trace_unit, tmap0, 0u, hook);
       TFFT_TRACE_MARK(3);
 #if !defined(TFFT_DEBUG_SKIP)
       if (pipe2)
-        run_stage<1, RHO1, kStages == 2, LOG2E, false, true, NoHook, ROLE>(P, c, b_saddr1, mma_bar, phase, warp, lane,
+        run_stage<1, RHO1, kStages == 2, LOG2E, 0, true, NoHook, ROLE>(P, c, b_saddr1, mma_bar, phase, warp, lane,
                                                                            trace, trace_unit, tmap1, col_thr);
       else
-        run_stage<1, RHO1, kStages == 2, LOG2E, false, false, NoHook, ROLE>(P, c, b_saddr1, mma_bar, phase, warp, lane,
+        run_stage<1, RHO1, kStages == 2, LOG2E, 0, false, NoHook, ROLE>(P, c, b_saddr1, mma_bar, phase, warp, lane,
                                                                             trace, trace_unit, tmap1, col_thr);
       TFFT_TRACE_MARK(4);
       if constexpr (kStages == 3)
-        run_stage<2, (RHO2 ? RHO2 : 4), true, LOG2E, false, false, NoHook, ROLE>(P, c, b_saddr2, mma_bar, phase, warp,
+        run_stage<2, (RHO2 ? RHO2 : 4), true, LOG2E, 0, false, NoHook, ROLE>(P, c, b_saddr2, mma_bar, phase, warp,
                                                                                  lane, trace, trace_unit, tmap2, col_thr);
 #endif
       TFFT_TRACE_MARK(5);

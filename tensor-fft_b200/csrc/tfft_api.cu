@@ -105,18 +105,23 @@ typedef void (*KernelFn)(const UnitPlan, const __half*, const __half*, __half*, 
 struct KernelEntry {
   int log2e, r0, r1, r2;
   KernelFn fn, fn_tma;   // fn_tma: stage-1 operand loaded by TMA (row-mode input, >= 64 rows per K line)
+  KernelFn fn_tma_col;   // column-mode input loaded by TMA tiles of 8 columns (the 16K/32K-element units of column passes)
   int threads;
 };
-#define TFFT_K(E, A, B, C) {E, A, B, C, fft_unit_kernel<E, A, B, C, false>, nullptr, kThreads}
-#define TFFT_KT(E, A, B, C) {E, A, B, C, fft_unit_kernel<E, A, B, C, false>, fft_unit_kernel<E, A, B, C, true>, kThreads}
+#define TFFT_K(E, A, B, C) {E, A, B, C, fft_unit_kernel<E, A, B, C, 0>, nullptr, nullptr, kThreads}
+#define TFFT_KC(E, A, B, C) {E, A, B, C, fft_unit_kernel<E, A, B, C, 0>, nullptr, fft_unit_kernel<E, A, B, C, 2>, kThreads}
+#define TFFT_KT(E, A, B, C) {E, A, B, C, fft_unit_kernel<E, A, B, C, 0>, fft_unit_kernel<E, A, B, C, 1>, nullptr, kThreads}
+#define TFFT_KTC(E, A, B, C) \
+  {E, A, B, C, fft_unit_kernel<E, A, B, C, 0>, fft_unit_kernel<E, A, B, C, 1>, fft_unit_kernel<E, A, B, C, 2>, kThreads}
 // 32K-element units (one CTA per SM): 512 threads = four warp groups
-#define TFFT_KW(E, A, B, C) {E, A, B, C, fft_unit_kernel<E, A, B, C, false, 512>, fft_unit_kernel<E, A, B, C, true, 512>, 512}
+#define TFFT_KW(E, A, B, C) \
+  {E, A, B, C, fft_unit_kernel<E, A, B, C, 0, 512>, fft_unit_kernel<E, A, B, C, 1, 512>, fft_unit_kernel<E, A, B, C, 2, 512>, 512}
 const KernelEntry g_kernels[] = {
-    TFFT_K(13, 4, 4, 0), TFFT_K(14, 4, 4, 0),                       // L = 2^8
-    TFFT_K(13, 4, 5, 0), TFFT_K(14, 4, 5, 0),                       // 2^9
-    TFFT_K(13, 5, 5, 0), TFFT_K(14, 5, 5, 0),                       // 2^10
-    TFFT_KT(13, 5, 6, 0), TFFT_KT(14, 5, 6, 0),                        // 2^11
-    TFFT_KT(13, 6, 6, 0), TFFT_KT(14, 6, 6, 0), TFFT_KW(15, 6, 6, 0), TFFT_KT(15, 6, 6, 0),  // 2^12
+    TFFT_K(13, 4, 4, 0), TFFT_KC(14, 4, 4, 0),                      // L = 2^8
+    TFFT_K(13, 4, 5, 0), TFFT_KC(14, 4, 5, 0),                      // 2^9
+    TFFT_K(13, 5, 5, 0), TFFT_KC(14, 5, 5, 0),                      // 2^10
+    TFFT_KT(13, 5, 6, 0), TFFT_KTC(14, 5, 6, 0),                       // 2^11
+    TFFT_KT(13, 6, 6, 0), TFFT_KT(14, 6, 6, 0), TFFT_KW(15, 6, 6, 0), TFFT_KTC(15, 6, 6, 0),  // 2^12
     TFFT_KT(13, 4, 4, 5), TFFT_KT(14, 4, 4, 5),                        // 2^13
     TFFT_KT(14, 4, 5, 5),                                              // 2^14
     TFFT_KT(14, 5, 5, 4),                                              // 2 rows x 2^13 (2-D row pass, Kronecker last stage)
@@ -125,6 +130,8 @@ const KernelEntry g_kernels[] = {
 #undef TFFT_K
 #undef TFFT_KT
 #undef TFFT_KW
+#undef TFFT_KC
+#undef TFFT_KTC
 KernelFn kernel_for(const UnitPlan& p, int* threads) {
   static const bool narrow = getenv("TFFT_NARROW_32K") != nullptr;   // developer A/B: 256-thread CTAs for 32K-element units
   for (const KernelEntry& k : g_kernels)
@@ -132,7 +139,7 @@ KernelFn kernel_for(const UnitPlan& p, int* threads) {
         k.r1 == static_cast<int>(p.log2_radix[1]) && k.r2 == static_cast<int>(p.stages == 3 ? p.log2_radix[2] : 0) &&
         !(narrow && k.threads == 512)) {
       *threads = k.threads;
-      return p.tma_load ? k.fn_tma : k.fn;
+      return p.tma_load == 2 ? k.fn_tma_col : (p.tma_load ? k.fn_tma : k.fn);
     }
   return nullptr;
 }
@@ -141,7 +148,7 @@ KernelFn kernel_for(const UnitPlan& p, int* threads) {
 typedef void (*Kernel2Fn)(const UnitPlan, __half*, __half*, const uint4*, const CUtensorMap, const CUtensorMap,
                           long long*);
 Kernel2Fn kernel2_for(const UnitPlan& p) {
-  if (!p.tma_load || p.log2_elems != 14 || p.stages != 3 || getenv("TFFT_NO_2SLOT")) return nullptr;
+  if (p.tma_load != 1 || p.log2_elems != 14 || p.stages != 3 || getenv("TFFT_NO_2SLOT")) return nullptr;
   if (smem2_layout(p).total > 227 * 1024) return nullptr;   // e.g. three distinct DFT matrices
   if (p.log2_radix[0] == 4 && p.log2_radix[1] == 4 && p.log2_radix[2] == 5) return fft_unit_kernel_2slot<4, 4, 5>;
   if (p.log2_radix[0] == 4 && p.log2_radix[1] == 5 && p.log2_radix[2] == 5) return fft_unit_kernel_2slot<4, 5, 5>;
@@ -205,11 +212,50 @@ int make_kron_tensor_map(const UnitPlan& plan, const __half* base, int64_t ny, i
   return r == CUDA_SUCCESS ? TFFT_OK : TFFT_E_INVALID_ARG;
 }
 
+// Column-mode input (four-step column pass, 2-D column pass): element n of column c of batch b at
+// base + b*batch_stride + c + n*nstride, n = kappa*M + m.  Dims {columns, R kappa (stride M*nstride), M rows (stride
+// nstride), batches}; box {8, R, M, 1}, no swizzle: the tile lands as dense 16-byte chunks [m][kappa][8 columns].
+int make_col_tensor_map(const UnitPlan& plan, const __half* base, int64_t nstride, int64_t columns, int64_t batches,
+                        int64_t batch_stride, CUtensorMap* out) {
+  EncodeTiledFn encode = get_encode_fn();
+  if (!encode) return TFFT_E_UNSUPPORTED;
+  const uint64_t L = uint64_t(1) << plan.log2_len, R = uint64_t(1) << plan.log2_radix[0], M = L / R;
+  if (batches <= 1 || batch_stride <= 0) batch_stride = static_cast<int64_t>(L) * nstride;
+  cuuint64_t gdim[4] = {static_cast<cuuint64_t>(columns), R, M, static_cast<cuuint64_t>(batches < 1 ? 1 : batches)};
+  cuuint64_t gstride[3] = {M * static_cast<cuuint64_t>(nstride) * 2, static_cast<cuuint64_t>(nstride) * 2,
+                           static_cast<cuuint64_t>(batch_stride) * 2};
+  cuuint32_t box[4] = {8, static_cast<cuuint32_t>(R), static_cast<cuuint32_t>(M), 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(base), gdim, gstride, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? TFFT_OK : TFFT_E_INVALID_ARG;
+}
+
+// All kernels are launched with programmatic stream serialization: a kernel's CTAs may become resident while its
+// predecessor in the stream drains; the kernels themselves wait (griddepcontrol.wait) before they touch data.
+cudaError_t launch_pdl(const void* fn, unsigned grid, unsigned block, void** args, size_t smem, cudaStream_t stream) {
+  static const bool no_pdl = getenv("TFFT_NO_PDL") != nullptr;
+  if (no_pdl) return cudaLaunchKernel(fn, dim3(grid), dim3(block), args, smem, stream);
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelExC(&cfg, fn, args);
+}
+
 std::once_flag g_attr_once;
 int g_attr_err = 0;
 void set_kernel_attrs() {
   for (const KernelEntry& k : g_kernels)
-    for (KernelFn fn : {k.fn, k.fn_tma}) {
+    for (KernelFn fn : {k.fn, k.fn_tma, k.fn_tma_col}) {
       if (!fn) continue;
       cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       if (e != cudaSuccess) g_attr_err = static_cast<int>(e);
@@ -367,6 +413,7 @@ int build_1d(tfft_plan_s* p) {
     sh.log2_units = std::max(3, unit_log2_elems(lg1) - lg1);
     sh.in_mode = kColMode;
     sh.out_mode = kColMode;
+    sh.tma_load = getenv("TFFT_NO_TMA_COL") == nullptr;   // column tiles {8 columns, R, M} loaded by TMA
     const int64_t U = int64_t(1) << sh.log2_units;
     UnitStrides st;
     st.in_nstride = N2; st.out_nstride = N2;
@@ -456,6 +503,11 @@ int build_2d(tfft_plan_s* p, std::vector<Pass>* passes, bool allow_tma) {
     sh.log2_units = std::max(3, unit_log2_elems(lg2) - lg2);
     sh.in_mode = kColMode;
     sh.out_mode = kColMode;
+    // Column tiles by TMA are measured SLOWER here (C5 on B200: 1.27 ms against 0.77 ms with 16-byte cp.async): with a
+    // row stride of 2*nx elements consecutive 16-byte pieces of a tile lie 32 KiB apart and the tile walks kappa
+    // (2 MiB jumps) before m, while the cp.async units of neighbouring CTAs sweep the rows together.  Four-step column
+    // passes (row stride <= 8 KiB) gain 1-4 % from the tiles and keep them.
+    sh.tma_load = getenv("TFFT_TMA_COL_2D") != nullptr;
     const int64_t U = int64_t(1) << sh.log2_units;
     UnitStrides st;
     st.in_nstride = nx << yb; st.out_nstride = nx << yb;
@@ -495,7 +547,7 @@ int launch_pass(const tfft_plan_s* p, const Pass& ps, const __half* src_re, cons
     st.in_batch_stride = in_stride;
     st.out_batch_stride = out_stride;
   }
-  if (ps.kind == 0 && ps.plan.tma_load && st.units_per_batch != 0x7FFFFFFFu)   // batches of contiguous transforms
+  if (ps.kind == 0 && ps.plan.tma_load == 1 && st.units_per_batch != 0x7FFFFFFFu)   // batches of contiguous transforms
     st.tma_batch_step = st.units_per_batch << ps.plan.log2_units;
   UnitPlan plan = ps.plan;
   fill_strides(st, ps.info, &plan);
@@ -541,7 +593,12 @@ int launch_pass(const tfft_plan_s* p, const Pass& ps, const __half* src_re, cons
     const int64_t n_tr = tma_extent ? tma_extent : static_cast<int64_t>(ps.n_units) << plan.log2_units;
     const bool half_box = kernel2_for(plan) != nullptr;
     int rc;
-    if (plan.kron_bits) {
+    if (plan.tma_load == 2) {
+      const int64_t columns = static_cast<int64_t>(plan.units_per_batch) << plan.log2_units;
+      const int64_t batches = (ps.n_units + plan.units_per_batch - 1) / plan.units_per_batch;
+      rc = make_col_tensor_map(plan, src_re, st.in_nstride, columns, batches, plan.in_batch_stride, &tmap_re);
+      if (rc == TFFT_OK) rc = make_col_tensor_map(plan, src_im, st.in_nstride, columns, batches, plan.in_batch_stride, &tmap_im);
+    } else if (plan.kron_bits) {
       rc = make_kron_tensor_map(plan, src_re, p->ny, p->batch, plan.tma_batch_step, &tmap_re, half_box);
       if (rc == TFFT_OK) rc = make_kron_tensor_map(plan, src_im, p->ny, p->batch, plan.tma_batch_step, &tmap_im, half_box);
     } else {
@@ -558,14 +615,14 @@ int launch_pass(const tfft_plan_s* p, const Pass& ps, const __half* src_re, cons
     if (sms < 1) return TFFT_E_UNSUPPORTED;
     const unsigned grid2 = std::min<unsigned>(ps.n_units, static_cast<unsigned>(sms));
     void* args2[] = {&plan, &dst_re, &dst_im, &tables, &tmap_re, &tmap_im, &trace};
-    e = cudaLaunchKernel(reinterpret_cast<const void*>(fn2), dim3(grid2), dim3(kCta2Threads), args2, S2.total, stream);
+    e = launch_pdl(reinterpret_cast<const void*>(fn2), grid2, kCta2Threads, args2, S2.total, stream);
     return e == cudaSuccess ? TFFT_OK : static_cast<int>(e);
   }
   void* args[] = {&plan, &src_re, &src_im, &dst_re, &dst_im, &tables, &trace, &tmap_re, &tmap_im};
   if (getenv("TFFT_DEBUG"))
     fprintf(stderr, "tfft: launch grid=%u units=%u smem=%u tmem=%u resident=%d\n", grid, ps.n_units, ps.smem,
             plan.tmem_cols, ps.resident_ctas[dev]);
-  e = cudaLaunchKernel(reinterpret_cast<const void*>(fn), dim3(grid), dim3(threads), args, ps.smem, stream);
+  e = launch_pdl(reinterpret_cast<const void*>(fn), grid, static_cast<unsigned>(threads), args, ps.smem, stream);
   (void)p;
   return e == cudaSuccess ? TFFT_OK : static_cast<int>(e);
 }

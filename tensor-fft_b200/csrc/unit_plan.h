@@ -68,7 +68,10 @@ struct UnitPlan {
   uint32_t tmem_cols;                      // power of two >= E/64
   uint32_t pipe_stage2;                    // 1: stage 2 may overlap its second-half MMAs with its first-half epilogue
   uint32_t kron_bits;                      // see UnitShape::kron_bits (0: plain 1-D units)
-  uint32_t tma_load;                       // 1: stage-1 operand = SWIZZLE_128B MN-major atoms of 64 rows filled by TMA:
+  uint32_t tma_load;                       // 2: column-mode input, stage-1 operand filled by TMA tiles {8 columns, R kappa,
+                                           //    M rows} per 8-column group, no swizzle: dense chunks [group][m][kappa][8 cols],
+                                           //    i.e. chunk_stride[0] = 16R without padding and natural row order (u&7, m, u>>3)
+                                           // 1: stage-1 operand = SWIZZLE_128B MN-major atoms of 64 rows filled by TMA:
                                            //    element (row, kappa) at (row>>6)*128R + (kappa>>3)*1024 + (kappa&7)*128
                                            //    + ((((row>>3)&7) ^ (kappa&7))<<4) + (row&7)*2   (verified by probe/tma_probe.cu)
   // ---- load phase: chunk q (bit-linear) -> offsets
@@ -190,10 +193,13 @@ inline bool build_unit_plan(const UnitShape& shape, UnitPlan* plan, PlanBuildInf
   }
   plan->log2_len = lg; plan->log2_units = ups; plan->stages = s;
   plan->log2_elems = eps; plan->in_mode = shape.in_mode; plan->out_mode = shape.out_mode;
-  if (shape.tma_load && (shape.in_mode != kRowMode || (lg - rho[0]) < 6)) {
-    info->error = "TMA load needs row mode and >= 64 contiguous rows per K line"; return false;
+  if (shape.tma_load && shape.in_mode == kRowMode && (lg - rho[0]) < 6) {
+    info->error = "TMA load needs >= 64 contiguous rows per K line"; return false;
   }
-  plan->tma_load = shape.tma_load ? 1u : 0u;
+  if (shape.tma_load && shape.in_mode == kColMode && (lg - rho[0]) > 8) {
+    info->error = "column-mode TMA load: more than 256 rows per K line"; return false;
+  }
+  plan->tma_load = shape.tma_load ? (shape.in_mode == kColMode ? 2u : 1u) : 0u;
   // the first-half epilogue of stage 2 writes the first half of stage 3's layout, which must lie inside the half of
   // stage 2's layout that its first-half MMAs have consumed: padded plane sizes shrink with the radix, so R_3 >= R_2
   const bool pipe2 = shape.pipe_stage2 && s == 3 && rho[2] >= rho[1];
@@ -208,7 +214,7 @@ inline bool build_unit_plan(const UnitShape& shape, UnitPlan* plan, PlanBuildInf
     const uint32_t rows = 1u << (eps - rho[t]);
     if (rows < 128) { info->error = "unit too small for a 128-row tile"; return false; }
     plan->n_tiles[t] = rows / 128;
-    plan->chunk_stride[t] = (16u << rho[t]) + 16u;
+    plan->chunk_stride[t] = (16u << rho[t]) + ((t == 0 && plan->tma_load == 2) ? 0u : 16u);
     const uint32_t pb = (rows / 8) * plan->chunk_stride[t];
     if (pb > max_plane) max_plane = pb;
   }

@@ -67,7 +67,18 @@ int plansim_run_ex(int log2_len, int log2_units, int in_mode_flags, int out_mode
     const uint32_t col_base = ((unit % P.units_per_batch) / P.col_div) * P.col_base_stride;
     std::vector<double> sre(smem_halves, NAN), sim(smem_halves, NAN);
     // ---------------- load: TMA tensor tile {64 rows, R kappa, M/64, U} with 128-byte swizzle ...
-    if (P.tma_load) {
+    if (P.tma_load == 2) {   // column mode: tiles {8 columns, R kappa, M rows} per 8-column group, dense, no swizzle
+      const int R = 1 << P.log2_radix[0];
+      const int64_t M = L / R, U = int64_t(1) << P.log2_units;
+      for (int64_t ug = 0; ug < U / 8; ++ug)
+        for (int64_t m = 0; m < M; ++m)
+          for (int kap = 0; kap < R; ++kap)
+            for (int cc = 0; cc < 8; ++cc) {
+              const uint32_t off = (uint32_t)((((ug * M + m) * R + kap) * 8 + cc) * 2);
+              const int64_t a = ibase + ug * 8 + cc + (kap * M + m) * strides9[1];
+              sre[off / 2] = rh(in_re[a], h); sim[off / 2] = rh(in_im[a], h);
+            }
+    } else if (P.tma_load) {
       const int R = 1 << P.log2_radix[0];
       const int64_t M = L / R, U = int64_t(1) << P.log2_units;
       for (int64_t u = 0; u < U; ++u)
@@ -115,7 +126,7 @@ int plansim_run_ex(int log2_len, int log2_units, int in_mode_flags, int out_mode
           std::vector<cd> a(R), y(R);
           for (int kap = 0; kap < R; ++kap) {
             uint32_t off = (row >> 3) * S + (kap >> 3) * kKGroupStride + (kap & 7) * 16 + (row & 7) * 2;
-            if (t == 1 && P.tma_load)
+            if (t == 1 && P.tma_load == 1)
               off = (row >> 6) * 128 * R + (kap >> 3) * 1024 + (kap & 7) * 128 + ((((row >> 3) & 7) ^ (kap & 7)) << 4) + (row & 7) * 2;
             a[kap] = cd(sre[off / 2], sim[off / 2]);
             if (std::isnan(sre[off / 2])) { fprintf(stderr, "stage %d reads an unwritten operand slot\n", t); return -6; }

@@ -59,9 +59,10 @@ def test_predicted_fp16_error_below_reference(sim, lg, ups, ref_level):
     assert rc == 0 and err < ref_level
 
 
-@pytest.mark.parametrize("lg1,lg2,u1,u2", [(8, 8, 5, 5), (8, 8, 6, 6), (10, 10, 4, 4), (11, 11, 3, 3),
-                                           (12, 12, 3, 3), (9, 8, 5, 6), (12, 9, 3, 5)])
-def test_four_step_passes(sim, lg1, lg2, u1, u2):
+@pytest.mark.parametrize("lg1,lg2,u1,u2,tma", [(8, 8, 5, 5, 0), (8, 8, 6, 6, 2), (10, 10, 4, 4, 0), (11, 11, 3, 3, 0),
+                                               (12, 11, 3, 3, 0), (9, 8, 5, 6, 2), (12, 9, 3, 5, 2), (11, 9, 3, 5, 2),
+                                               (10, 8, 4, 6, 2)])
+def test_four_step_passes(sim, lg1, lg2, u1, u2, tma):
     """N = N1*N2: column pass (+ exp(-2 pi i k1 n2/N)) then row pass with transposed store."""
     N1, N2 = 1 << lg1, 1 << lg2
     N = N1 * N2
@@ -71,14 +72,14 @@ def test_four_step_passes(sim, lg1, lg2, u1, u2):
     U1, U2 = 1 << u1, 1 << u2
     conf = (ctypes.c_int * 4)()
     st = (ctypes.c_int64 * 9)(0, N2, 0, N2, 0, U1, 0, U1, 1 << 30)
-    rc1 = sim.plansim_run(lg1, u1, 1, 1, st, lg1 + lg2, N2 // U1, re.ctypes.data_as(dp), im.ctypes.data_as(dp),
+    rc1 = sim.plansim_run(lg1, u1, 1 | tma, 1, st, lg1 + lg2, N2 // U1, re.ctypes.data_as(dp), im.ctypes.data_as(dp),
                           t_re.ctypes.data_as(dp), t_im.ctypes.data_as(dp), 0, conf)
     c1 = list(conf)[:3]
     st = (ctypes.c_int64 * 9)(N2, 1, 0, N1, 0, U2 * N2, 0, U2, 1 << 30)
     rc2 = sim.plansim_run(lg2, u2, 0, 1, st, 0, N1 // U2, t_re.ctypes.data_as(dp), t_im.ctypes.data_as(dp),
                           o_re.ctypes.data_as(dp), o_im.ctypes.data_as(dp), 0, conf)
     want = np.fft.fft(re + 1j * im) / N
-    assert rc1 == 0 and rc2 == 0 and c1 == [0, 0, 0] and list(conf)[:3] == [0, 0, 0]
+    assert rc1 == 0 and rc2 == 0 and c1 == [0, 0, 0] and list(conf)[:3] == [0, 0, 0]   # tma: column tiles loaded by TMA
     assert np.linalg.norm(o_re + 1j * o_im - want) / np.linalg.norm(want) < 1e-13
 
 
