@@ -120,10 +120,23 @@ __device__ __forceinline__ uint4 ldg128(const void* p) {
                : "l"(p));
   return r;
 }
+// The transform streams: every byte is read once and written once, so loads and stores are marked evict-first in L2
+// (C2 on B200: 121.1 -> 119.2 us; -DTFFT_NO_L2_HINTS builds without).
+__device__ __forceinline__ uint64_t l2_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
 __device__ __forceinline__ void stg128(__half* p, uint4 v) {
+#ifndef TFFT_NO_L2_HINTS
+  asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w), "l"(l2_evict_first())
+               : "memory");
+#else
   asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
                "r"(v.w)
                : "memory");
+#endif
 }
 __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
   uint4 r;
@@ -193,6 +206,27 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
       : "memory");
 }
 
+// L2 prefetches of the NEXT unit's input (no shared memory needed), enabled per plan (UnitPlan::prefetch_next).
+// Measured on B200: helps where nothing else overlaps the load phase (32K-element units, one CTA per SM: four-step
+// sizes 2^22..2^24 -5 %; N = 2048 -9 %), hurts where loads already overlap compute (two-slot kernel at C2: 118.6 ->
+// 124.6 us; 16K-element column passes), so the planner switches it on only for the former.
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, uint32_t c0, uint32_t c2, uint32_t c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(c0), "r"(0),
+               "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_5d(const CUtensorMap* map, uint32_t c3, uint32_t c4) {
+  asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %1, %1, %2, %3}];" ::"l"(map), "r"(0), "r"(c3),
+               "r"(c4)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_4d_col(const CUtensorMap* map, uint32_t c0, uint32_t c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %2, %3}];" ::"l"(map), "r"(c0), "r"(0),
+               "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // column-mode tile {8 columns, R kappa, M rows, 1 batch}: coordinates (first column, 0, 0, batch)
 __device__ __forceinline__ void tma_load_4d_col(uint32_t dst, const CUtensorMap* map, uint32_t c0, uint32_t c3,
                                                 uint64_t* bar) {
@@ -205,10 +239,17 @@ __device__ __forceinline__ void tma_load_4d_col(uint32_t dst, const CUtensorMap*
 // 4-D TMA tile load {64 rows, R kappa, M/64, U transforms} -> SWIZZLE_128B stage-1 operand plane
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t c2, uint32_t c3,
                                             uint64_t* bar) {
+#ifndef TFFT_NO_L2_HINTS
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %2, %3, %4}], [%5], %6;"
+      ::"r"(dst), "l"(map), "r"(0), "r"(c2), "r"(c3), "r"(ptx::smem_u32(bar)), "l"(l2_evict_first())
+      : "memory");
+#else
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %2, %3, %4}], [%5];"
       ::"r"(dst), "l"(map), "r"(0), "r"(c2), "r"(c3), "r"(ptx::smem_u32(bar))
       : "memory");
+#endif
 }
 
 __device__ __forceinline__ void cp_async16(uint32_t saddr, const void* gptr, uint32_t src_bytes) {
@@ -777,6 +818,39 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
       cp_async_wait_all();
     }
     TFFT_TRACE_MARK(2);
+    // pull the next unit's input into L2 while this one is transformed and stored
+    const bool pf = P.prefetch_next && unit + gridDim.x < P.n_units;
+    if (pf) {
+      const uint32_t un = unit + gridDim.x, nb = un >> P.upb_shift, nu = un & ((1u << P.upb_shift) - 1u);
+      if constexpr (LM == 2) {
+        if (tid == 0)
+          for (uint32_t ug = 0; ug < (1u << P.log2_units) / 8; ++ug) {
+            tma_prefetch_4d_col(&tmap_re, (nu << P.log2_units) + 8 * ug, nb);
+            tma_prefetch_4d_col(&tmap_im, (nu << P.log2_units) + 8 * ug, nb);
+          }
+      } else if constexpr (LM == 1) {
+        if (tid == 0) {
+          if (P.kron_bits) {
+            tma_prefetch_5d(&tmap_re, nu, nb * P.tma_batch_step);
+            tma_prefetch_5d(&tmap_im, nu, nb * P.tma_batch_step);
+          } else {
+            tma_prefetch_4d(&tmap_re, 0, 0, nb * P.tma_batch_step + (nu << P.log2_units));
+            tma_prefetch_4d(&tmap_im, 0, 0, nb * P.tma_batch_step + (nu << P.log2_units));
+          }
+        }
+      } else {
+        const int64_t nbase = static_cast<int64_t>(nb) * P.in_batch_stride + static_cast<int64_t>(nu) * P.in_unit_stride;
+        // row mode: 8 consecutive items share a 128-byte line; column mode: every 16-byte piece is its own line
+        if (P.in_mode == kColMode || (tid & 7) == 0) {
+#pragma unroll
+          for (uint32_t i = 0; i < kLoadItems; ++i) {
+            const uint32_t g = ld_g_lo + bit_sum(i, P.load_gofs, TB, kMaxItemBits - TB);
+            prefetch_l2(in_re + nbase + g);
+            prefetch_l2(in_im + nbase + g);
+          }
+        }
+      }
+    }
 
     // ---------------------------------------------------------------- tensor-core stages
     run_stage<0, RHO0, false, LOG2E, LM, false, NoHook, 0, NG>(P, c, table_base + TL.b_off[0], bar, phase, warp, lane,
@@ -907,15 +981,27 @@ fft_unit_kernel_2slot(const __grid_constant__ UnitPlan P, __half* __restrict__ o
     mbar_arrive_expect_tx(full, 2u << LOG2E);
     const uint32_t off = h << LOG2E;   // half a plane: E bytes
     const uint32_t uq = unit_of(q), qb = uq >> P.upb_shift, qu = uq & ((1u << P.upb_shift) - 1u);
+    // the same half of the NEXT use is pulled into L2 now
+    const uint32_t un = unit_of(q + 1), nb = un >> P.upb_shift, nu = un & ((1u << P.upb_shift) - 1u);
+    const bool pf = P.prefetch_next && un < P.n_units;
     if (P.kron_bits) {   // unit = (image, y_lo); tile halves split the U rows
       const uint32_t c4 = qb * P.tma_batch_step + h * half_c3;
       tma_load_5d(c.a_re + off, &tmap_re, qu, c4, full);
       tma_load_5d(c.a_im + off, &tmap_im, qu, c4, full);
+      if (pf) {
+        tma_prefetch_5d(&tmap_re, nu, nb * P.tma_batch_step + h * half_c3);
+        tma_prefetch_5d(&tmap_im, nu, nb * P.tma_batch_step + h * half_c3);
+      }
       return;
     }
     const uint32_t c3 = qb * P.tma_batch_step + (qu << P.log2_units) + h * half_c3;
     tma_load_4d(c.a_re + off, &tmap_re, h * half_c2, c3, full);
     tma_load_4d(c.a_im + off, &tmap_im, h * half_c2, c3, full);
+    if (pf) {
+      const uint32_t n3 = nb * P.tma_batch_step + (nu << P.log2_units) + h * half_c3;
+      tma_prefetch_4d(&tmap_re, 0, h * half_c2, n3);
+      tma_prefetch_4d(&tmap_im, 0, h * half_c2, n3);
+    }
   };
   // one thread sets up the barriers, waits for the predecessor kernel and requests the first tile; the constant
   // tables are staged meanwhile

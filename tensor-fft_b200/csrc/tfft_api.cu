@@ -551,6 +551,11 @@ int launch_pass(const tfft_plan_s* p, const Pass& ps, const __half* src_re, cons
     st.tma_batch_step = st.units_per_batch << ps.plan.log2_units;
   UnitPlan plan = ps.plan;
   fill_strides(st, ps.info, &plan);
+  {
+    static const char* pf_env = getenv("TFFT_PREFETCH");   // developer override: 0 / 1
+    plan.prefetch_next = pf_env ? static_cast<uint32_t>(atoi(pf_env))
+                                : ((plan.log2_elems == 15 || (plan.log2_len == 11 && plan.tma_load == 1)) ? 1u : 0u);
+  }
   plan.col_first = static_cast<uint32_t>(tw_first_col);
   int threads = kThreads;
   KernelFn fn = kernel_for(plan, &threads);
