@@ -554,7 +554,7 @@ int launch_pass(const tfft_plan_s* p, const Pass& ps, const __half* src_re, cons
   {
     static const char* pf_env = getenv("TFFT_PREFETCH");   // developer override: 0 / 1
     plan.prefetch_next = pf_env ? static_cast<uint32_t>(atoi(pf_env))
-                                : ((plan.log2_elems == 15 || (plan.log2_len == 11 && plan.tma_load == 1)) ? 1u : 0u);
+                                : (((plan.log2_elems == 15 && ps.kind == 0) || (plan.log2_len == 11 && plan.tma_load == 1)) ? 1u : 0u);
   }
   plan.col_first = static_cast<uint32_t>(tw_first_col);
   int threads = kThreads;
@@ -820,10 +820,12 @@ int tfft_exec_host(tfft_plan_t p, const void* host_in, void* host_out) {
       cudaGetLastError();
       return e == cudaErrorMemoryAllocation ? TFFT_E_NOMEM : (e == cudaErrorNoDevice ? TFFT_E_NO_DEVICE : static_cast<int>(e));
     }
-    // chunking: about 16 MiB per direction and chunk, at most 32 chunks, whole transforms only
+    // chunking: about 16 MiB per direction and chunk, at most 64 chunks, whole transforms only
     const int64_t per_transform = 2 * p->n * static_cast<int64_t>(sizeof(__half));
-    int64_t chunk = std::max<int64_t>(1, (int64_t(16) << 20) / per_transform);
-    chunk = std::max(chunk, (p->batch + 31) / 32);
+    int64_t chunk_mb = 16;
+    if (const char* e = getenv("TFFT_HOST_CHUNK_MB")) chunk_mb = std::max(1, atoi(e));   // developer tuning knob
+    int64_t chunk = std::max<int64_t>(1, (chunk_mb << 20) / per_transform);
+    chunk = std::max(chunk, (p->batch + 63) / 64);
     if (chunk >= p->batch || getenv("TFFT_HOST_NO_PIPELINE")) chunk = p->batch;
     p->host_chunk = chunk;
     if (chunk < p->batch) {
