@@ -403,8 +403,17 @@ int build_1d(tfft_plan_s* p) {
   // four-step: n = N1 * N2, element n1*N2 + n2.  Pass 1: N2 strided length-N1 transforms (column
   // mode, in place on the source), times exp(-2*pi*i*k1*n2/n).  Pass 2: N1 contiguous length-N2
   // transforms stored transposed: X[k1 + N1*k2].   
-  const int lg1 = (lg + 1) / 2, lg2 = lg - lg1;
-  if (lg1 > 12 || lg2 < 8) return TFFT_E_INVALID_SIZE;
+  // column-pass length 2^lg1, measured per size on B200 (tools/tune_fourstep.py): the balanced split except where it
+  // would produce 2048-point units (40 KiB of DFT matrices -> one 16K-element CTA per SM): 2^19 = 512 x 1024 (-9 %),
+  // 2^21 = 4096 x 512 (-3 %), 2^22 = 4096 x 1024 (-26 %)
+  static const int kLg1[9] = {8, 9, 9, 9, 10, 12, 12, 12, 12};   // lg = 16 .. 24
+  int lg1 = kLg1[lg - 16];
+  if (const char* e = getenv("TFFT_FOURSTEP_LG1")) {   // developer knob: length 2^lg1 of the column pass
+    const int v = atoi(e);
+    if (v >= 8 && v <= 12 && lg - v >= 8 && lg - v <= 12) lg1 = v;
+  }
+  const int lg2 = lg - lg1;
+  if (lg1 > 12 || lg2 < 8 || lg2 > 12) return TFFT_E_INVALID_SIZE;
   const int64_t N1 = int64_t(1) << lg1, N2 = int64_t(1) << lg2;
   const bool preserve = (p->flags & TFFT_PRESERVE_INPUT) != 0;
   {
