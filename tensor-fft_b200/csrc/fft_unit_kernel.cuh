@@ -495,9 +495,11 @@ __device__ __forceinline__ void warp_wait(uint64_t* bar, uint32_t parity, int la
 // built with pipe_stage2 (checked on the CPU by tests/sim/plan_sim.cpp).
 // Hooks of the MMA-issuing thread (warp 0, lane 0): before it issues the UMMAs of tile half h, and once it
 // has observed their completion.  The two-slot kernel uses them for its landing-buffer ring.
+// mid(): called by EVERY thread of a pipelined stage between the epilogues of its two tile halves.
 struct NoHook {
   __device__ __forceinline__ void before_half(int) const {}
   __device__ __forceinline__ void after_half(int) const {}
+  __device__ __forceinline__ void mid(int, int) const {}
 };
 template <int RHO, int LOG2E, bool PIPE, int NG = 2>
 struct StageShape {
@@ -509,7 +511,9 @@ struct StageShape {
 };
 
 // All UMMAs of one stage, issued by ONE thread (under elect_one()).
-template <int ST, int RHO, int LOG2E, int LM, bool PIPE, class Hook, int NG = 2>
+// PART: 0 = all tiles; 1 = only the first half of the tiles, committed to bar[0]; 2 = only the second half, committed
+// to bar[1] (split issue of the last stage, see run_stage EARLY)
+template <int ST, int RHO, int LOG2E, int LM, bool PIPE, class Hook, int NG = 2, int PART = 0>
 __device__ __forceinline__ void stage_issue(const KernelCtx& c, uint32_t b1_saddr, uint64_t* bar, const Hook& hook,
                                             long long* trace, uint32_t trace_unit) {
   using namespace ptx;
@@ -536,8 +540,9 @@ __device__ __forceinline__ void stage_issue(const KernelCtx& c, uint32_t b1_sadd
   constexpr uint32_t kKStep = SW128 ? 2048 / 16 : 16;              // ... per 16-wide K step
   const uint64_t db1 = make_smem_desc(b1_saddr, kKGroupStride, 16 * R);
   const uint64_t db2 = make_smem_desc(b1_saddr + 4 * R * R, kKGroupStride, 16 * R);
+  constexpr uint32_t kTileBegin = PART == 2 ? kTiles / 2 : 0, kTileEnd = PART == 1 ? kTiles / 2 : kTiles;
 #pragma unroll
-  for (uint32_t tile = 0; tile < kTiles; ++tile) {
+  for (uint32_t tile = kTileBegin; tile < kTileEnd; ++tile) {
     const uint32_t d = taddr + tile * 2 * R;
     if (tile == 0) {
       hook.before_half(0);
@@ -554,9 +559,10 @@ __device__ __forceinline__ void stage_issue(const KernelCtx& c, uint32_t b1_sadd
 #pragma unroll
     for (uint32_t j = 0; j < kSteps; ++j)
       umma_f16_ss(d, da_im + (tile * kTileStep + j * kKStep), db2 + j * 16, idesc, 1u);
-    if (kPipe && tile + 1 == kTiles / 2) umma_commit(bar);     // first half of the tiles
+    if (PART == 0 && kPipe && tile + 1 == kTiles / 2) umma_commit(bar);     // first half of the tiles
   }
-  umma_commit(kPipe ? bar + 1 : bar);   // separate barriers: a parity wait must never fall two phases behind
+  if (PART == 1) umma_commit(bar);
+  else umma_commit((kPipe || PART == 2) ? bar + 1 : bar);   // separate barriers: a parity wait must never fall two phases behind
   TFFT_TRACE_MARK(18 + 4 * ST);
 }
 
@@ -579,8 +585,10 @@ __device__ __forceinline__ void stage_observe(uint64_t* bar, uint32_t (&phase)[2
 // ROLE 1: epilogue warp of a slot whose UMMAs are issued by a dedicated warp.  That warp issues the
 //         stage-1 UMMAs of a unit ahead of time (during the previous unit's store phase), so stage 1 has
 //         no leading barrier here.
+// EARLY2: the first half of this stage's UMMAs was already issued (and committed to bar[0]) by the previous stage's
+// mid() hook; only the second half is issued here (bar[1]) and the epilogue starts when both have completed.
 template <int ST, int RHO, bool LAST, int LOG2E, int LM = 0, bool PIPE = false, class Hook = NoHook,
-          int ROLE = 0, int NG = 2>
+          int ROLE = 0, int NG = 2, bool EARLY2 = false>
 __device__ __forceinline__ void run_stage(const UnitPlan& P, const KernelCtx& c, uint32_t b1_saddr, uint64_t* bar,
                                           uint32_t (&phase)[2], int warp, int lane, long long* trace,
                                           uint32_t trace_unit, uint32_t tmap, uint32_t col_thr, Hook hook = Hook()) {
@@ -596,7 +604,7 @@ __device__ __forceinline__ void run_stage(const UnitPlan& P, const KernelCtx& c,
   }
   TFFT_TRACE_MARK(9 + 2 * ST);
   if (ROLE == 0 && warp == 0 && elect_one())
-    stage_issue<ST, RHO, LOG2E, LM, PIPE, Hook, NG>(c, b1_saddr, bar, hook, trace, trace_unit);
+    stage_issue<ST, RHO, LOG2E, LM, PIPE, Hook, NG, (EARLY2 ? 2 : 0)>(c, b1_saddr, bar, hook, trace, trace_unit);
   const bool hook_warp = ROLE == 0 && warp == 0;   // converged at every use below (after warp_wait)
   // per-thread parts of the bit-linear row maps (thread_map(): 7 lane-row bits + the warp-group bits)
   const uint32_t dst_thr = (tmap & 0xFFFFu) << 4, aux_thr = tmap >> 16;
@@ -620,6 +628,7 @@ __device__ __forceinline__ void run_stage(const UnitPlan& P, const KernelCtx& c,
     TFFT_TRACE_MARK(10 + 2 * ST);
     epilogue_load<RHO, 0, NG>(c, ra, rb);
     epilogue_range<ST, RHO, LAST, 0, kHalf, NG>(P, c, dst_thr, aux_thr, col_thr, ra, rb, rc, rd);
+    hook.mid(warp, lane);
     warp_wait(bar + 1, phase[1] & 1u, lane);
     if (hook_warp && elect_one()) hook.after_half(1);
     epilogue_load<RHO, kHalf, NG>(c, ra, rb);
@@ -628,6 +637,7 @@ __device__ __forceinline__ void run_stage(const UnitPlan& P, const KernelCtx& c,
     phase[1]++;
   } else {
     warp_wait(bar, phase[0] & 1u, lane);
+    if (EARLY2) warp_wait(bar + 1, phase[1] & 1u, lane);
     if (hook_warp && elect_one()) {
       hook.after_half(0);
       hook.after_half(1);
@@ -636,6 +646,7 @@ __device__ __forceinline__ void run_stage(const UnitPlan& P, const KernelCtx& c,
     epilogue_load<RHO, 0, NG>(c, ra, rb);
     epilogue_range<ST, RHO, LAST, 0, kItemsPerGroup, NG>(P, c, dst_thr, aux_thr, col_thr, ra, rb, rc, rd);
     phase[0]++;
+    if (EARLY2) phase[1]++;
   }
 }
 
@@ -894,6 +905,14 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
 // moving its registers to the epilogue warps, and the stage-1 UMMAs of the next unit issued during the
 // store phase).  Measured at C2 on B200: 127-130 us either way -- the slots are not latency-bound on the
 // issuing warp -- so the simpler program is the default.
+// -DTFFT_EARLY3 issues stage 3's first-half UMMAs from stage 2's mid() hook (Early3Hook below).  Correct (the GPU
+// parity suite passes) but measured SLOWER at C2 on B200: 121.9 us against 117.1 us without -- the extra barrier stalls
+// the issuing warp in the middle of its epilogue and the early UMMAs compete with the other slot's -- so it is off.
+#ifdef TFFT_EARLY3
+constexpr bool kNoEarly3 = false;
+#else
+constexpr bool kNoEarly3 = true;
+#endif
 #ifdef TFFT_DEDICATED_MMA_WARP
 constexpr bool kDedicatedMmaWarp = true;
 #else
@@ -1011,6 +1030,8 @@ fft_unit_kernel_2slot(const __grid_constant__ UnitPlan P, __half* __restrict__ o
     mbar_init(bars + 2, 1);
     mbar_init(bars + 3, 1);
     for (int i = 0; i < 4; ++i) mbar_init(land_full + i, 1);
+    mbar_init(bars + 10, 8);   // half_done of slot 0 / 1: one arrival per epilogue warp
+    mbar_init(bars + 11, 8);
     fence_mbar_init();
     pdl_wait();
     request(0, 0);
@@ -1028,6 +1049,35 @@ fft_unit_kernel_2slot(const __grid_constant__ UnitPlan P, __half* __restrict__ o
     decltype(request)& req;
     __device__ __forceinline__ void before_half(int h) const { mbar_wait(full + h, parity); }   // tile half landed
     __device__ __forceinline__ void after_half(int h) const { req(q + 1, static_cast<uint32_t>(h)); }
+    __device__ __forceinline__ void mid(int, int) const {}
+  };
+  // Stage 2 of a pipe_stage2 plan: once EVERY warp has finished the epilogue of the first tile half, the operand
+  // rows of stage 3's first tile half are complete (both stages keep k_1's top bit as the top row bit) and the
+  // accumulators of those tiles are drained, so stage 3's first-half UMMAs are issued right away and run under
+  // the second-half epilogue of stage 2.
+  uint64_t* half_done = bars + 10 + slot;
+  struct Early3Hook {
+    const KernelCtx& c;
+    uint64_t *half_done, *mma_bar;
+    uint32_t parity, b_saddr2;
+    long long* trace;
+    uint32_t trace_unit;
+    __device__ __forceinline__ void before_half(int) const {}
+    __device__ __forceinline__ void after_half(int) const {}
+    __device__ __forceinline__ void mid(int warp, int lane) const {
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(half_done);
+      if (warp == 0) {
+        if (elect_one()) {
+          mbar_wait(half_done, parity);
+          tc_fence_after_sync();
+          stage_issue<2, (RHO2 ? RHO2 : 4), LOG2E, 0, false, NoHook, 2, 1>(c, b_saddr2, mma_bar, NoHook(), trace, trace_unit);
+        }
+        __syncwarp();
+      }
+    }
   };
   const uint32_t b_saddr0 = table_base + TL.b_off[0], b_saddr1 = table_base + TL.b_off[1],
                  b_saddr2 = table_base + TL.b_off[2];
@@ -1092,6 +1142,7 @@ fft_unit_kernel_2slot(const __grid_constant__ UnitPlan P, __half* __restrict__ o
     const uint32_t tmap0 = thread_map<0, RHO0, 2>(P, c), tmap1 = thread_map<1, RHO1, 2>(P, c);
     const uint32_t tmap2 = kStages == 3 ? thread_map<2, (RHO2 ? RHO2 : 4), 2>(P, c) : 0u;
     const uint32_t col_thr = kStages == 3 ? thread_col<2, (RHO2 ? RHO2 : 4), 2>(P, c) : thread_col<1, RHO1, 2>(P, c);
+    uint32_t units_done = 0;   // parity of this slot's half_done barrier
     for (uint32_t q = slot; unit_of(q) < P.n_units; q += 2) {
       const uint32_t unit = unit_of(q);
       const uint32_t ub = unit >> P.upb_shift, uu = unit & ((1u << P.upb_shift) - 1u);
@@ -1113,16 +1164,27 @@ fft_unit_kernel_2slot(const __grid_constant__ UnitPlan P, __half* __restrict__ o
                                                                       trace_unit, tmap0, 0u, hook);
       TFFT_TRACE_MARK(3);
 #if !defined(TFFT_DEBUG_SKIP)
-      if (pipe2)
+      constexpr bool kEarly3 = kStages == 3 && !kDedicatedMmaWarp && !kNoEarly3;
+      if (pipe2 && kEarly3)
+        run_stage<1, RHO1, kStages == 2, LOG2E, 0, true, Early3Hook, ROLE>(
+            P, c, b_saddr1, mma_bar, phase, warp, lane, trace, trace_unit, tmap1, col_thr,
+            Early3Hook{c, half_done, mma_bar, units_done & 1u, b_saddr2, trace, trace_unit});
+      else if (pipe2)
         run_stage<1, RHO1, kStages == 2, LOG2E, 0, true, NoHook, ROLE>(P, c, b_saddr1, mma_bar, phase, warp, lane,
                                                                            trace, trace_unit, tmap1, col_thr);
       else
         run_stage<1, RHO1, kStages == 2, LOG2E, 0, false, NoHook, ROLE>(P, c, b_saddr1, mma_bar, phase, warp, lane,
                                                                             trace, trace_unit, tmap1, col_thr);
       TFFT_TRACE_MARK(4);
-      if constexpr (kStages == 3)
-        run_stage<2, (RHO2 ? RHO2 : 4), true, LOG2E, 0, false, NoHook, ROLE>(P, c, b_saddr2, mma_bar, phase, warp,
-                                                                                 lane, trace, trace_unit, tmap2, col_thr);
+      if constexpr (kStages == 3) {
+        if (pipe2 && kEarly3)
+          run_stage<2, (RHO2 ? RHO2 : 4), true, LOG2E, 0, false, NoHook, ROLE, 2, true>(
+              P, c, b_saddr2, mma_bar, phase, warp, lane, trace, trace_unit, tmap2, col_thr);
+        else
+          run_stage<2, (RHO2 ? RHO2 : 4), true, LOG2E, 0, false, NoHook, ROLE>(P, c, b_saddr2, mma_bar, phase, warp,
+                                                                                   lane, trace, trace_unit, tmap2, col_thr);
+      }
+      units_done++;
 #endif
       TFFT_TRACE_MARK(5);
       tc_fence_before_sync();
