@@ -99,6 +99,17 @@ int tfft_exec_twiddled(tfft_plan_t plan, const void* in_re, const void* in_im, v
  * buffers; synchronises before returning like the reference's batch overload does. */
 int tfft_exec_host(tfft_plan_t plan, const void* host_in, void* host_out);
 
+/* Pack / unpack kernels of the all-to-all exchanges of the multi-GPU 1-D transform (nothing in the
+ * reference).  tfft_transpose_blocks: dst[b][c][r] = src[b][r][c] for nb0*nb1 fp16 matrices of rows x cols (multiples
+ * of 64); matrix (b0, b1) starts at src + b0*src_b0 + b1*src_b1 / dst + b0*dst_b0 + b1*dst_b1, row strides in
+ * elements (multiples of 8).  tfft_copy_runs: copies n0*n1*n2 contiguous runs of `run` elements between two
+ * three-level strided layouts.  Asynchronous on `stream`. */
+int tfft_transpose_blocks(const void* src, void* dst, int64_t rows, int64_t cols, int64_t src_row_stride,
+                          int64_t dst_row_stride, int64_t nb0, int64_t nb1, int64_t src_b0, int64_t src_b1,
+                          int64_t dst_b0, int64_t dst_b1, void* stream);
+int tfft_copy_runs(const void* src, void* dst, int64_t run, int64_t n0, int64_t n1, int64_t n2, int64_t s0, int64_t s1,
+                   int64_t s2, int64_t d0, int64_t d1, int64_t d2, void* stream);
+
 /* Device-side harness helpers.
  * tfft_fixture_sine: the reference's test signal (CreateSineSuperpostionKernel,
  * src/testing/TestingDataCreation.h:89-117) for `batch` transforms, written as planar fp16 at re/im + b*stride:

@@ -17,6 +17,7 @@
 #include "../../include/tfft.h"
 #include "fft_unit_kernel.cuh"
 #include "harness_kernels.cuh"
+#include "exchange_kernels.cuh"
 
 namespace {
 
@@ -884,6 +885,47 @@ int tfft_exec_host(tfft_plan_t p, const void* host_in, void* host_out) {
     if (e != cudaSuccess) return static_cast<int>(e);
   }
   cudaError_t e = cudaStreamSynchronize(s_down);
+  return e == cudaSuccess ? TFFT_OK : static_cast<int>(e);
+}
+
+int tfft_transpose_blocks(const void* src, void* dst, int64_t rows, int64_t cols, int64_t src_row_stride,
+                          int64_t dst_row_stride, int64_t nb0, int64_t nb1, int64_t src_b0, int64_t src_b1, int64_t dst_b0,
+                          int64_t dst_b1, void* stream_) {
+  if (!src || !dst || rows < 64 || cols < 64 || (rows & 63) || (cols & 63) || nb0 < 1 || nb1 < 1 || nb0 * nb1 > 65535)
+    return TFFT_E_INVALID_ARG;
+  if (((src_row_stride | dst_row_stride | src_b0 | src_b1 | dst_b0 | dst_b1) & 7) || !aligned16(src) || !aligned16(dst))
+    return TFFT_E_INVALID_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return TFFT_E_NO_DEVICE;
+  }
+  const dim3 grid(static_cast<unsigned>(cols / 64), static_cast<unsigned>(rows / 64), static_cast<unsigned>(nb0 * nb1));
+  if (grid.y > 65535) return TFFT_E_INVALID_ARG;
+  transpose64_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const __half*>(src), static_cast<__half*>(dst), src_row_stride, dst_row_stride, static_cast<int>(nb0),
+      src_b0, src_b1, dst_b0, dst_b1);
+  const cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? TFFT_OK : static_cast<int>(e);
+}
+
+int tfft_copy_runs(const void* src, void* dst, int64_t run, int64_t n0, int64_t n1, int64_t n2, int64_t s0, int64_t s1,
+                   int64_t s2, int64_t d0, int64_t d1, int64_t d2, void* stream_) {
+  if (!src || !dst || run < 8 || (run & 7) || n0 < 1 || n1 < 1 || n2 < 1 || n0 * n1 * n2 > (int64_t(1) << 30))
+    return TFFT_E_INVALID_ARG;
+  if (((s0 | s1 | s2 | d0 | d1 | d2) & 7) || !aligned16(src) || !aligned16(dst)) return TFFT_E_INVALID_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return TFFT_E_NO_DEVICE;
+  }
+  const int64_t vec = run / 8;
+  const unsigned gy = static_cast<unsigned>(std::min<int64_t>(std::max<int64_t>(1, vec / 1024), 64));
+  const dim3 grid(static_cast<unsigned>(n0 * n1 * n2), gy);
+  copy_runs_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const __half*>(src), static_cast<__half*>(dst), run, static_cast<int>(n0), static_cast<int>(n1), s0, s1, s2,
+      d0, d1, d2);
+  const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? TFFT_OK : static_cast<int>(e);
 }
 

@@ -49,7 +49,7 @@ class _PlanInfo(ctypes.Structure):
 
 EXPORTS = ("tfft_plan_create", "tfft_plan_create_2d", "tfft_plan_info", "tfft_plan_destroy", "tfft_exec",
            "tfft_exec_twiddled", "tfft_exec_host", "tfft_error_string", "tfft_version", "tfft_fixture_sine",
-           "tfft_error_stats")
+           "tfft_error_stats", "tfft_transpose_blocks", "tfft_copy_runs")
 
 
 def lib() -> ctypes.CDLL:
@@ -71,6 +71,8 @@ def lib() -> ctypes.CDLL:
         fp, dp = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)
         L.tfft_fixture_sine.argtypes = [vp, vp, i64, i64, i64, fp, fp, ctypes.c_int32, vp]
         L.tfft_error_stats.argtypes = [vp, vp, vp, vp, i64, dp, vp]
+        L.tfft_transpose_blocks.argtypes = [vp, vp] + [i64] * 10 + [vp]
+        L.tfft_copy_runs.argtypes = [vp, vp] + [i64] * 10 + [vp]
         L.tfft_error_string.argtypes = [ctypes.c_int]
         L.tfft_error_string.restype = ctypes.c_char_p
         _lib = L

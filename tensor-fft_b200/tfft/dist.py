@@ -39,25 +39,61 @@ def max_over_ranks(value: float, device: torch.device) -> float:
     return float(t.item())
 
 
-def _a2a_transpose(x: torch.Tensor, world: int, group=None) -> torch.Tensor:
-    """x: (rows_local, cols) on every rank, rows block-distributed.  Returns (cols_local, rows) with the
-    columns block-distributed: the distributed transpose, one all_to_all_single."""
-    rows_local, cols = x.shape
+def _gpu_pack(z: torch.Tensor, world: int) -> torch.Tensor:
+    """send[p][plane][c][r] = z[plane][r][p*cols_local + c] with the library's 64x64-tile transpose kernel."""
+    import ctypes
+    from . import lib, _check
+    _, rows_local, cols = z.shape
+    cl = cols // world
+    send = torch.empty((world, 2, cl, rows_local), dtype=z.dtype, device=z.device)
+    s = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    # matrices indexed (b0 = plane, b1 = peer): source block z[plane][:, p*cl:(p+1)*cl], destination send[p][plane]
+    _check(lib().tfft_transpose_blocks(z.data_ptr(), send.data_ptr(), rows_local, cl, cols, rows_local, 2, world,
+                                       rows_local * cols, cl, cl * rows_local, 2 * cl * rows_local, s))
+    return send
+
+
+def _gpu_unpack(recv: torch.Tensor, world: int) -> torch.Tensor:
+    """out[plane][c][p*rows_local + r] = recv[p][plane][c][r]: runs of rows_local elements."""
+    import ctypes
+    from . import lib, _check
+    _, _, cl, rows_local = recv.shape
+    out = torch.empty((2, cl, world * rows_local), dtype=recv.dtype, device=recv.device)
+    s = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    # levels (i0 = c, i1 = plane, i2 = peer)
+    _check(lib().tfft_copy_runs(recv.data_ptr(), out.data_ptr(), rows_local, cl, 2, world,
+                                rows_local, cl * rows_local, 2 * cl * rows_local,
+                                world * rows_local, cl * world * rows_local, rows_local, s))
+    return out
+
+
+def _a2a_transpose(z: torch.Tensor, world: int, group=None) -> torch.Tensor:
+    """z: (2, rows_local, cols) on every rank -- the real and the imaginary plane, rows block-distributed.
+    Returns (2, cols_local, rows) with the columns block-distributed: the distributed transpose of both planes
+    in ONE all_to_all_single."""
+    _, rows_local, cols = z.shape
     cols_local = cols // world
-    # block for peer p = my rows x p's columns, sent transposed so the receiver only concatenates
-    send = x.reshape(rows_local, world, cols_local).permute(1, 2, 0).contiguous()   # (peer, cols_local, rows_local)
+    # block for peer p = my rows x p's columns of both planes, sent transposed so the receiver only concatenates
+    fast = (z.is_cuda and z.dtype == torch.float16 and z.is_contiguous() and rows_local % 64 == 0
+            and cols_local % 64 == 0 and world * 2 <= 65535)
+    if fast:
+        send = _gpu_pack(z, world)
+    else:   # CPU ranks (gloo tests) and odd shapes
+        send = z.reshape(2, rows_local, world, cols_local).permute(2, 0, 3, 1).contiguous()   # (peer, plane, cols_local, rows_local)
     recv = torch.empty_like(send)
     dist.all_to_all_single(recv, send, group=group)
-    # recv[p] = (my cols_local, p's rows_local)  ->  (cols_local, world * rows_local)
-    return recv.permute(1, 0, 2).reshape(cols_local, world * rows_local).contiguous()
+    # recv[p] = (plane, my cols_local, p's rows_local)  ->  (plane, cols_local, world * rows_local)
+    if fast:
+        return _gpu_unpack(recv, world)
+    return recv.permute(1, 2, 0, 3).reshape(2, cols_local, world * rows_local).contiguous()
 
 
 class SixStepPlan:
     """Distributed 1-D FFT of length n1*n2 over `world` ranks, natural order in and out, scale 1/N.
 
-    local_fft(re, im, n, batch, log2_total, first_col) -> (re, im): `batch` contiguous transforms of
-    length n on 2-D tensors (batch, n); when log2_total > 0 output k of transform b is also multiplied
-    by exp(-2 pi i k (first_col + b) / 2^log2_total).
+    local_fft(z, n, batch, log2_total, first_col) -> z': `batch` contiguous transforms of length n on the
+    stacked planes z = (2, batch, n) (z[0] real, z[1] imaginary); when log2_total > 0 output k of transform b
+    is also multiplied by exp(-2 pi i k (first_col + b) / 2^log2_total).
     """
 
     def __init__(self, n1: int, n2: int, rank: int, world: int,
@@ -72,17 +108,17 @@ class SixStepPlan:
         """re/im: this rank's slab, n1/world rows of n2 (1-D of length N/world or 2-D). Returns the rank's
         contiguous N/world slice of the spectrum as 1-D tensors."""
         n1, n2, w = self.n1, self.n2, self.world
-        re, im = re.reshape(n1 // w, n2), im.reshape(n1 // w, n2)
+        z = torch.stack([re.reshape(n1 // w, n2), im.reshape(n1 // w, n2)])             # (2, n1/w, n2)
         # A2A #1: columns of the N1 x N2 matrix become local rows
-        re, im = _a2a_transpose(re, w, self.group), _a2a_transpose(im, w, self.group)     # (n2/w, n1)
+        z = _a2a_transpose(z, w, self.group)                                             # (2, n2/w, n1)
         first_col = self.rank * (n2 // w)
-        re, im = self.local_fft(re, im, n1, n2 // w, self.log2_total, first_col)           # Y[i2][k1] * w^(k1 i2)
+        z = self.local_fft(z, n1, n2 // w, self.log2_total, first_col)                   # Y[i2][k1] * w^(k1 i2)
         # A2A #2
-        re, im = _a2a_transpose(re, w, self.group), _a2a_transpose(im, w, self.group)     # (n1/w, n2)
-        re, im = self.local_fft(re, im, n2, n1 // w, 0, 0)                                 # Z[k1][k2]
+        z = _a2a_transpose(z, w, self.group)                                             # (2, n1/w, n2)
+        z = self.local_fft(z, n2, n1 // w, 0, 0)                                         # Z[k1][k2]
         # A2A #3: natural order k = k1 + n1*k2  ->  rank r owns k2 in block r
-        re, im = _a2a_transpose(re, w, self.group), _a2a_transpose(im, w, self.group)     # (n2/w, n1)
-        return re.reshape(-1), im.reshape(-1)
+        z = _a2a_transpose(z, w, self.group)                                             # (2, n2/w, n1)
+        return z[0].reshape(-1), z[1].reshape(-1)
 
     def nvlink_bytes_per_rank(self) -> int:
         """fp16 planar bytes this rank sends per transform: A * (G-1)/G * 4N/G."""
@@ -95,15 +131,15 @@ def tfft_local_fft():
     from . import NativePlan
     cache = {}
 
-    def run(re, im, n, batch, log2_total, first_col):
+    def run(z, n, batch, log2_total, first_col):
         plan = cache.get((n, batch))
         if plan is None:
             plan = cache[(n, batch)] = NativePlan(n, batch)
-        o_re, o_im = torch.empty_like(re), torch.empty_like(im)
+        o = torch.empty_like(z)
         if log2_total:
-            plan.exec_twiddled(re, im, o_re, o_im, n, n, log2_total, first_col)
+            plan.exec_twiddled(z[0], z[1], o[0], o[1], n, n, log2_total, first_col)
         else:
-            plan.exec(re, im, o_re, o_im, n, n)
-        return o_re, o_im
+            plan.exec(z[0], z[1], o[0], o[1], n, n)
+        return o
 
     return run

@@ -14,14 +14,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tensor-fft_b200"))
 
 
-def _numpy_local_fft(re, im, n, batch, log2_total, first_col):
-    x = re.double().numpy() + 1j * im.double().numpy()
+def _numpy_local_fft(z, n, batch, log2_total, first_col):
+    x = z[0].double().numpy() + 1j * z[1].double().numpy()
     y = np.fft.fft(x.reshape(batch, n), axis=1) / n
     if log2_total:
         k = np.arange(n)[None, :]
         col = (first_col + np.arange(batch))[:, None]
         y = y * np.exp(-2j * np.pi * ((k * col) % (1 << log2_total)) / (1 << log2_total))
-    return torch.from_numpy(y.real.copy()), torch.from_numpy(y.imag.copy())
+    return torch.stack([torch.from_numpy(y.real.copy()), torch.from_numpy(y.imag.copy())])
 
 
 def _worker(rank, world, port, n1, n2, q):

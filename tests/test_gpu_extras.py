@@ -83,3 +83,19 @@ def test_device_error_stats_match_the_oracle_statistics():
     want = O.error_stats(a_re.cpu().numpy().astype(np.float64), a_im.cpu().numpy().astype(np.float64), w_re, w_im)
     for k in ("max", "avg", "sigma", "rel_l2"):
         assert abs(got[k] - want[k]) <= 1e-9 * max(1.0, abs(want[k])) + 1e-6 * abs(want[k]), (k, got, want)
+
+
+def test_exchange_pack_unpack_kernels_match_torch():
+    """tfft_transpose_blocks / tfft_copy_runs (the pack / unpack of the six-step's all-to-all) against the torch
+    permute they replace: bit-exact data movement."""
+    from tfft import dist as tdist
+    for world, rows_local, cols in ((2, 128, 512), (4, 64, 1024), (8, 256, 512)):
+        z = torch.randn(2, rows_local, cols, device="cuda").to(torch.float16)
+        cl = cols // world
+        want_send = z.reshape(2, rows_local, world, cl).permute(2, 0, 3, 1).contiguous()
+        got_send = tdist._gpu_pack(z, world)
+        assert bool(torch.equal(got_send, want_send))
+        want_out = want_send.permute(1, 2, 0, 3).reshape(2, cl, world * rows_local).contiguous()
+        got_out = tdist._gpu_unpack(got_send, world)
+        torch.cuda.synchronize()
+        assert bool(torch.equal(got_out, want_out))
