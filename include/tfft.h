@@ -44,7 +44,12 @@ enum {
    * transform with the real and imaginary planes exchanged on both sides: bit-identical arithmetic), and no 1/N
    * scaling (every stage's DFT matrix unscaled; intermediate values must stay inside the fp16 range). */
   TFFT_INVERSE = 2,
-  TFFT_UNSCALED = 4
+  TFFT_UNSCALED = 4,
+  /* interleaved layout (cuFFT's half2 / the reference's CuFFTTest.h:25-57 buffers): in_re and out_re point to arrays of
+   * (re, im) fp16 pairs, in_im / out_im are ignored, strides count complex elements.  1-D, N <= 2^24; these plans load
+   * with 16-byte vector loads instead of TMA tiles (the split into planes happens in registers) and multi-pass sizes own
+   * a planar scratch buffer. */
+  TFFT_INTERLEAVED = 8
 };
 
 typedef struct tfft_plan_info_s {

@@ -663,6 +663,34 @@ __device__ __forceinline__ void store_phase(const UnitPlan& P, const KernelCtx& 
     const uint32_t g = st_g_lo + bit_sum(i, P.store_gofs, TB, kMaxItemBits - TB);
     if (kStoreBlocks < NT && tid >= static_cast<int>(kStoreBlocks)) continue;
     if (st_u_lo + bit_sum(i, P.store_uval, TB, kMaxItemBits - TB) >= u_limit) continue;
+    if (P.il_out) {
+      // interleaved output (TFFT_INTERLEAVED): element k of the result is the half2 (re, im) at gre + 2*k
+      uint4 ar[8], ai[8];
+#pragma unroll
+      for (int x = 0; x < 8; ++x) {   // il_swap (inverse transform): the planes hold (im, re)
+        const uint32_t o = so + bit_sum(static_cast<uint32_t>(x), P.store_xs, 0, 3);
+        ar[x] = lds128((P.il_swap ? c.s_im : c.s_re) + o);
+        ai[x] = lds128((P.il_swap ? c.s_re : c.s_im) + o);
+      }
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) {
+        const uint32_t sel = (cc & 1) ? 0x7632u : 0x5410u;
+        uint32_t wr[4], wi[4];
+#pragma unroll
+        for (int i2 = 0; i2 < 4; ++i2) {
+          wr[i2] = __byte_perm(reinterpret_cast<const uint32_t*>(&ar[2 * i2])[cc >> 1],
+                               reinterpret_cast<const uint32_t*>(&ar[2 * i2 + 1])[cc >> 1], sel);
+          wi[i2] = __byte_perm(reinterpret_cast<const uint32_t*>(&ai[2 * i2])[cc >> 1],
+                               reinterpret_cast<const uint32_t*>(&ai[2 * i2 + 1])[cc >> 1], sel);
+        }
+        __half* gp = gre + 2 * (static_cast<size_t>(g) + bit_sum(static_cast<uint32_t>(cc), P.store_cg, 0, 3));
+        stg128(gp, make_uint4(__byte_perm(wr[0], wi[0], 0x5410u), __byte_perm(wr[0], wi[0], 0x7632u),
+                              __byte_perm(wr[1], wi[1], 0x5410u), __byte_perm(wr[1], wi[1], 0x7632u)));
+        stg128(gp + 8, make_uint4(__byte_perm(wr[2], wi[2], 0x5410u), __byte_perm(wr[2], wi[2], 0x7632u),
+                                  __byte_perm(wr[3], wi[3], 0x5410u), __byte_perm(wr[3], wi[3], 0x7632u)));
+      }
+      continue;
+    }
 #pragma unroll
     for (int plane = 0; plane < 2; ++plane) {
       const uint32_t sp = plane ? c.s_im : c.s_re;
@@ -807,7 +835,27 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
     } else {
       const __half* gre = in_re + in_base;
       const __half* gim = in_im + in_base;
-      if (u_limit == 0xFFFFFFFFu) {
+      if (P.il_in) {
+        // interleaved input (TFFT_INTERLEAVED): 8 consecutive elements are 32 bytes of (re, im) pairs at in_re + 2*k;
+        // split into one chunk of real and one of imaginary parts in registers
+        const __half* gil = in_re + 2 * in_base;
+        const uint32_t sel_re = P.il_swap ? 0x7632u : 0x5410u, sel_im = P.il_swap ? 0x5410u : 0x7632u;
+#pragma unroll
+        for (uint32_t i = 0; i < kLoadItems; ++i) {
+          const uint32_t g = ld_g_lo + bit_sum(i, P.load_gofs, TB, kMaxItemBits - TB);
+          const uint32_t so = ld_s_lo + bit_sum(i, P.load_sofs, TB, kMaxItemBits - TB);
+          const bool live = ld_u_lo + bit_sum(i, P.load_uval, TB, kMaxItemBits - TB) < u_limit;
+          uint4 a = make_uint4(0, 0, 0, 0), b = a;
+          if (live) {
+            a = ldg128(gil + 2 * static_cast<size_t>(g));
+            b = ldg128(gil + 2 * static_cast<size_t>(g) + 8);
+          }
+          sts128(c.s_re + so, make_uint4(__byte_perm(a.x, a.y, sel_re), __byte_perm(a.z, a.w, sel_re),
+                                         __byte_perm(b.x, b.y, sel_re), __byte_perm(b.z, b.w, sel_re)));
+          sts128(c.s_im + so, make_uint4(__byte_perm(a.x, a.y, sel_im), __byte_perm(a.z, a.w, sel_im),
+                                         __byte_perm(b.x, b.y, sel_im), __byte_perm(b.z, b.w, sel_im)));
+        }
+      } else if (u_limit == 0xFFFFFFFFu) {
 #pragma unroll
         for (uint32_t i = 0; i < kLoadItems; ++i) {
           const uint32_t g = ld_g_lo + bit_sum(i, P.load_gofs, TB, kMaxItemBits - TB);
@@ -878,7 +926,8 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
     TFFT_TRACE_MARK(6);
 
     // ---------------------------------------------------------------- store phase
-    store_phase<LOG2E, NT>(P, c, out_re + out_base, out_im + out_base, tid, st_s_lo, st_g_lo, st_u_lo, u_limit);
+    store_phase<LOG2E, NT>(P, c, out_re + (P.il_out ? 2 * out_base : out_base), out_im + out_base, tid, st_s_lo, st_g_lo,
+                           st_u_lo, u_limit);
     TFFT_TRACE_MARK(7);
     __syncthreads();   // staging fully read before the next unit's loads overwrite it
     TFFT_TRACE_MARK(8);

@@ -35,6 +35,7 @@ struct Pass {
   int src = 0, dst = 0;    // 0 = user input planes, 1 = user output planes, 2 = plan workspace
   bool in_stride_is_user = false, out_stride_is_user = false;
   bool own_batch_strides = false;   // three-pass plans: the batch level of the unit addressing is internal
+  bool il_in = false, il_out = false;   // TFFT_INTERLEAVED: the pass reads / writes half2 elements
   int kind = 0;                     // 0: 1-D passes; 1: 2-D row pass (row mode, unit = U rows of one image); 2: 2-D column pass
 };
 
@@ -339,15 +340,19 @@ int build_1d(tfft_plan_s* p) {
     {
       int rho[kMaxStages];
       radix_schedule(lg, rho);
-      sh.tma_load = (lg - rho[0]) >= 6 && getenv("TFFT_NO_TMA") == nullptr;
+      sh.tma_load = (lg - rho[0]) >= 6 && getenv("TFFT_NO_TMA") == nullptr && !(p->flags & TFFT_INTERLEAVED);
       sh.pipe_stage2 = sh.tma_load && lg >= 13 && getenv("TFFT_NO_PIPE") == nullptr;
     }
     UnitStrides st;
     st.n_transforms = static_cast<uint32_t>(batch);
     st.units_per_batch = 0x7FFFFFFFu;   // unit base = unit * unit_stride
     const int64_t U = int64_t(1) << sh.log2_units;
-    return add_pass(p, sh, st, static_cast<uint32_t>((batch + U - 1) / U), 0, 1, true, true) ? TFFT_OK
-                                                                                             : TFFT_E_UNSUPPORTED;
+    if (!add_pass(p, sh, st, static_cast<uint32_t>((batch + U - 1) / U), 0, 1, true, true)) return TFFT_E_UNSUPPORTED;
+    p->passes.back().il_in = p->passes.back().il_out = (p->flags & TFFT_INTERLEAVED) != 0;
+    return TFFT_OK;
+  }
+  if (p->flags & TFFT_INTERLEAVED) {
+    if (lg > 24) return TFFT_E_UNSUPPORTED;   // three-pass sizes: planar only
   }
   if (lg > 24) {
     // three passes: n = N1 * Na * Nb (each 2^8 .. 2^12), one transform at a time (exec loops over the batch).
@@ -416,14 +421,16 @@ int build_1d(tfft_plan_s* p) {
   const int lg2 = lg - lg1;
   if (lg1 > 12 || lg2 < 8 || lg2 > 12) return TFFT_E_INVALID_SIZE;
   const int64_t N1 = int64_t(1) << lg1, N2 = int64_t(1) << lg2;
-  const bool preserve = (p->flags & TFFT_PRESERVE_INPUT) != 0;
+  // interleaved transforms go through a planar scratch between the passes (pass 1 reads half2, pass 2 writes half2)
+  const bool interleaved = (p->flags & TFFT_INTERLEAVED) != 0;
+  const bool preserve = (p->flags & TFFT_PRESERVE_INPUT) != 0 || interleaved;
   {
     UnitShape sh;
     sh.log2_len = lg1;
     sh.log2_units = std::max(3, unit_log2_elems(lg1) - lg1);
     sh.in_mode = kColMode;
     sh.out_mode = kColMode;
-    sh.tma_load = getenv("TFFT_NO_TMA_COL") == nullptr;   // column tiles {8 columns, R, M} loaded by TMA
+    sh.tma_load = getenv("TFFT_NO_TMA_COL") == nullptr && !interleaved;   // column tiles {8 columns, R, M} loaded by TMA
     const int64_t U = int64_t(1) << sh.log2_units;
     UnitStrides st;
     st.in_nstride = N2; st.out_nstride = N2;
@@ -434,6 +441,7 @@ int build_1d(tfft_plan_s* p) {
     // batch stride: user's input stride (source) ; destination = source (in place) or workspace
     if (!add_pass(p, sh, st, static_cast<uint32_t>(batch * (N2 / U)), 0, preserve ? 2 : 0, true, !preserve))
       return TFFT_E_UNSUPPORTED;
+    p->passes.back().il_in = interleaved;
   }
   {
     UnitShape sh;
@@ -448,6 +456,7 @@ int build_1d(tfft_plan_s* p) {
     st.units_per_batch = static_cast<uint32_t>(N1 / U);
     if (!add_pass(p, sh, st, static_cast<uint32_t>(batch * (N1 / U)), preserve ? 2 : 0, 1, !preserve, true))
       return TFFT_E_UNSUPPORTED;
+    p->passes.back().il_out = interleaved;
   }
   if (preserve) {
     p->workspace_bytes = 2 * n * batch * static_cast<int64_t>(sizeof(__half));
@@ -563,7 +572,10 @@ int launch_pass(const tfft_plan_s* p, const Pass& ps, const __half* src_re, cons
   fill_strides(st, ps.info, &plan);
   {
     static const char* pf_env = getenv("TFFT_PREFETCH");   // developer override: 0 / 1
-    plan.prefetch_next = pf_env ? static_cast<uint32_t>(atoi(pf_env))
+    plan.il_in = ps.il_in ? 1u : 0u;
+    plan.il_out = ps.il_out ? 1u : 0u;
+    plan.il_swap = (p->flags & TFFT_INVERSE) ? 1u : 0u;
+    plan.prefetch_next = ps.il_in ? 0u : pf_env ? static_cast<uint32_t>(atoi(pf_env))
                                 : (((plan.log2_elems == 15 && ps.kind == 0) || (plan.log2_len == 11 && plan.tma_load == 1)) ? 1u : 0u);
   }
   plan.col_first = static_cast<uint32_t>(tw_first_col);
@@ -687,6 +699,7 @@ int tfft_plan_create_2d(tfft_plan_t* out, int64_t ny, int64_t nx, int64_t batch,
   if (!out) return TFFT_E_INVALID_ARG;
   *out = nullptr;
   if (ilog2_exact(ny) < 8 || ilog2_exact(nx) < 8 || ny * nx > (int64_t(1) << 30)) return TFFT_E_INVALID_SIZE;
+  if (flags & TFFT_INTERLEAVED) return TFFT_E_UNSUPPORTED;   // 2-D: planar only
   if (batch < 1 || batch > (int64_t(1) << 20)) return TFFT_E_INVALID_ARG;
   tfft_plan_s* p = new (std::nothrow) tfft_plan_s;
   if (!p) return TFFT_E_NOMEM;
@@ -744,7 +757,12 @@ int tfft_plan_destroy(tfft_plan_t p) {
 
 int tfft_exec(tfft_plan_t p, const void* in_re, const void* in_im, void* out_re, void* out_im, int64_t in_stride,
               int64_t out_stride, void* stream_) {
-  if (!p || !in_re || !in_im || !out_re || !out_im) return TFFT_E_INVALID_ARG;
+  if (!p || !in_re || !out_re) return TFFT_E_INVALID_ARG;
+  if (p->flags & TFFT_INTERLEAVED) {   // one half2 array each way; the imaginary-plane arguments are ignored
+    in_im = in_re;
+    out_im = out_re;
+  }
+  if (!in_im || !out_im) return TFFT_E_INVALID_ARG;
   if (!aligned16(in_re) || !aligned16(in_im) || !aligned16(out_re) || !aligned16(out_im)) return TFFT_E_INVALID_ARG;
   if (in_stride < 0 || out_stride < 0 || (in_stride & 7) || (out_stride & 7)) return TFFT_E_INVALID_ARG;
   if (p->batch > 1 && (in_stride < p->n || out_stride < p->n)) return TFFT_E_INVALID_ARG;
@@ -756,7 +774,8 @@ int tfft_exec(tfft_plan_t p, const void* in_re, const void* in_im, void* out_re,
   std::call_once(g_attr_once, set_kernel_attrs);
   if (g_attr_err) return g_attr_err == static_cast<int>(cudaErrorInvalidDeviceFunction) ? TFFT_E_NO_DEVICE : g_attr_err;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (p->flags & TFFT_INVERSE) {   // F^-1(x) = swap(F(swap(x))), swap = exchange of the real and imaginary planes
+  if ((p->flags & TFFT_INVERSE) && !(p->flags & TFFT_INTERLEAVED)) {   // F^-1(x) = swap(F(swap(x))), swap = exchange of the
+    // real and imaginary planes (interleaved plans exchange the halves of every pair inside the kernel instead)
     std::swap(in_re, in_im);
     std::swap(out_re, out_im);
   }
@@ -805,7 +824,8 @@ int tfft_exec(tfft_plan_t p, const void* in_re, const void* in_im, void* out_re,
 int tfft_exec_twiddled(tfft_plan_t p, const void* in_re, const void* in_im, void* out_re, void* out_im,
                        int64_t in_stride, int64_t out_stride, int32_t log2_total, int64_t first_col, void* stream_) {
   if (!p || !in_re || !in_im || !out_re || !out_im) return TFFT_E_INVALID_ARG;
-  if (p->passes.size() != 1 || log2_total < p->lg || log2_total > 30 || (p->flags & TFFT_INVERSE)) return TFFT_E_UNSUPPORTED;
+  if (p->passes.size() != 1 || log2_total < p->lg || log2_total > 30 || (p->flags & (TFFT_INVERSE | TFFT_INTERLEAVED)))
+    return TFFT_E_UNSUPPORTED;
   if (first_col < 0 || first_col + p->batch > (int64_t(1) << (log2_total - p->lg))) return TFFT_E_INVALID_ARG;
   if (!aligned16(in_re) || !aligned16(in_im) || !aligned16(out_re) || !aligned16(out_im)) return TFFT_E_INVALID_ARG;
   if ((in_stride & 7) || (out_stride & 7) || in_stride < p->n || out_stride < p->n) return TFFT_E_INVALID_ARG;
@@ -858,7 +878,8 @@ int tfft_exec_host(tfft_plan_t p, const void* host_in, void* host_out) {
   if (p->host_chunk >= p->batch) {
     cudaError_t e = cudaMemcpyAsync(din, host_in, halves * sizeof(__half), cudaMemcpyHostToDevice, 0);
     if (e != cudaSuccess) return static_cast<int>(e);
-    int rc = tfft_exec(p, din, din + p->n, dout, dout + p->n, 2 * p->n, 2 * p->n, nullptr);
+    const int64_t tstride = (p->flags & TFFT_INTERLEAVED) ? p->n : 2 * p->n;   // complex elements / plane elements
+    int rc = tfft_exec(p, din, din + p->n, dout, dout + p->n, tstride, tstride, nullptr);
     if (rc != TFFT_OK) return rc;
     e = cudaMemcpyAsync(host_out, dout, halves * sizeof(__half), cudaMemcpyDeviceToHost, 0);
     if (e != cudaSuccess) return static_cast<int>(e);
@@ -877,7 +898,8 @@ int tfft_exec_host(tfft_plan_t p, const void* host_in, void* host_out) {
     if (e == cudaSuccess) e = cudaStreamWaitEvent(s_fft, p->host_events[2 * ci], 0);
     if (e != cudaSuccess) return static_cast<int>(e);
     tfft_plan_s* cp = nb == p->host_chunk ? p->host_chunk_plan : p->host_tail_plan;
-    int rc = tfft_exec(cp, din + off, din + off + p->n, dout + off, dout + off + p->n, 2 * p->n, 2 * p->n, s_fft);
+    const int64_t tstride = (p->flags & TFFT_INTERLEAVED) ? p->n : 2 * p->n;
+    int rc = tfft_exec(cp, din + off, din + off + p->n, dout + off, dout + off + p->n, tstride, tstride, s_fft);
     if (rc != TFFT_OK) return rc;
     e = cudaEventRecord(p->host_events[2 * ci + 1], s_fft);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(s_down, p->host_events[2 * ci + 1], 0);

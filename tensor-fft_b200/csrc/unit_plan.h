@@ -68,6 +68,9 @@ struct UnitPlan {
   uint32_t tmem_cols;                      // power of two >= E/64
   uint32_t pipe_stage2;                    // 1: stage 2 may overlap its second-half MMAs with its first-half epilogue
   uint32_t kron_bits;                      // see UnitShape::kron_bits (0: plain 1-D units)
+  uint32_t il_swap;                        // interleaved + inverse: the pairs are read / written as (im, re)
+  uint32_t il_in, il_out;                  // TFFT_INTERLEAVED: this pass reads / writes half2 (re, im) elements (cp.async
+                                           // load path only); the element offsets of the plan are doubled on the fly
   uint32_t prefetch_next;                  // 1: pull the next unit's input into L2 during this unit's stages
   uint32_t tma_load;                       // 2: column-mode input, stage-1 operand filled by TMA tiles {8 columns, R kappa,
                                            //    M rows} per 8-column group, no swizzle: dense chunks [group][m][kappa][8 cols],

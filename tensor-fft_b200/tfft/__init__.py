@@ -31,6 +31,7 @@ MODE_4096 = 1     # BaseFFTMode::Mode_4096
 TFFT_PRESERVE_INPUT = 1
 TFFT_INVERSE = 2      # exp(+2 pi i n k / N)
 TFFT_UNSCALED = 4     # no 1/N (cuFFT convention)
+TFFT_INTERLEAVED = 8  # half2 (re, im) arrays instead of planes
 
 
 class TfftError(RuntimeError):

@@ -99,3 +99,36 @@ def test_exchange_pack_unpack_kernels_match_torch():
         got_out = tdist._gpu_unpack(got_send, world)
         torch.cuda.synchronize()
         assert bool(torch.equal(got_out, want_out))
+
+
+@pytest.mark.parametrize("lg,b,flags", [(8, 13, 0), (10, 5, 0), (12, 3, 0), (13, 2, 0), (14, 2, tfft.TFFT_INVERSE),
+                                        (15, 1, 0), (16, 2, 0), (20, 1, tfft.TFFT_INVERSE), (22, 1, 0)])
+def test_interleaved_layout_equals_planar_bit_for_bit(lg, b, flags):
+    """TFFT_INTERLEAVED (cuFFT's half2 layout, CuFFTTest.h:25-57): same arithmetic as the planar transform, so the
+    results agree bit for bit (the planar run uses the cp.async load path too: TFFT_NO_TMA is not needed because the
+    tensor-core stages do not depend on how the operand was loaded)."""
+    n = 1 << lg
+    re, im = O.gauss_fixture(n, b, seed=500 + lg)
+    planar = torch.from_numpy(np.ascontiguousarray(np.stack([re, im], axis=1)).reshape(-1)).cuda()
+    want = _exec(n, b, flags, planar.clone()).view(b, 2, n)
+    inter = torch.from_numpy(np.ascontiguousarray(np.stack([re, im], axis=2)).reshape(-1)).cuda()   # (b, n, 2)
+    keep = inter.clone()
+    out = torch.full_like(inter, float("nan"))
+    plan = tfft.NativePlan(n, b, flags | tfft.TFFT_INTERLEAVED)
+    plan.exec(inter, inter, out, out, n, n)
+    torch.cuda.synchronize()
+    got = out.view(b, n, 2)
+    assert bool(torch.equal(got[:, :, 0], want[:, 0])) and bool(torch.equal(got[:, :, 1], want[:, 1]))
+    assert bool(torch.equal(inter, keep))                     # interleaved plans never overwrite their input
+    # host path with interleaved buffers
+    if lg <= 14:
+        h_out = np.empty(2 * n * b, dtype=np.float16)
+        plan.exec_host(keep.cpu().numpy(), h_out)
+        assert np.array_equal(h_out.view(np.uint16), out.cpu().numpy().view(np.uint16))
+
+
+def test_interleaved_unsupported_combinations_fail_loudly():
+    with pytest.raises(tfft.TfftError):
+        tfft.NativePlan(1 << 25, 1, tfft.TFFT_INTERLEAVED)
+    with pytest.raises(tfft.TfftError):
+        tfft.NativePlan(256 * 256, 1, tfft.TFFT_INTERLEAVED, shape2d=(256, 256))
