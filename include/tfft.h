@@ -29,7 +29,8 @@ enum {
   TFFT_E_INVALID_ARG = -2,    /* null pointer, misaligned pointer or stride */
   TFFT_E_NO_DEVICE = -3,      /* no sm_100 device: the product has no CPU path */
   TFFT_E_UNSUPPORTED = -4,
-  TFFT_E_NOMEM = -5
+  TFFT_E_NOMEM = -5,
+  TFFT_E_NOT_IN_FILE = -6     /* tuner file has no line for this length (Plan.h:238-254 prints + nullopt) */
 };
 
 /* flags for tfft_plan_create */
@@ -74,6 +75,14 @@ typedef struct tfft_plan_info_s {
  * (src/base/DataHandler.h:88-89).  The plan is immutable afterwards; exec calls on one plan
  * may be issued from several host threads / streams (except with workspace-owning plans). */
 int tfft_plan_create(tfft_plan_t* plan, int64_t n, int64_t batch, uint32_t flags);
+
+/* Replaces CreatePlan(fft_length, tuner_results_file) (src/base/Plan.h:197-255): the plan for length n is configured
+ * from the line of `path` that starts with n.  Line format: the reference's `N mode base_warps r16_warps r2_block`
+ * (written by src/testing/FileWriter.h:250-269; those four columns are accepted and ignored) optionally followed by
+ * `key=value` knobs of the B200 kernels: tma, pipe, two_slot, prefetch (0/1), lg1 (log2 of the four-step column-pass
+ * length), tma_col (0/1).  tools/tune.py measures and writes such a file.  TFFT_E_NOT_IN_FILE when no line matches.
+ * The environment variable TFFT_TUNER_FILE makes tfft_plan_create consult a file the same way. */
+int tfft_plan_create_from_file(tfft_plan_t* plan, int64_t n, int64_t batch, uint32_t flags, const char* path);
 
 /* Plan for `batch` 2-D transforms of ny rows x nx columns (row-major planar images), scale
  * 1/(ny*nx).  The reference has no 2-D path. */

@@ -35,7 +35,9 @@ inline tfft_plan_t cached_plan(long long n, long long batch, int* rc) {
   auto it = cache.find({n, batch});
   if (it != cache.end()) { *rc = TFFT_OK; return it->second; }
   tfft_plan_t p = nullptr;
-  *rc = tfft_plan_create(&p, n, batch, TFFT_DEFAULT);
+  *rc = TFFT_E_NOT_IN_FILE;
+  if (!tuner_file().empty()) *rc = tfft_plan_create_from_file(&p, n, batch, TFFT_DEFAULT, tuner_file().c_str());
+  if (*rc == TFFT_E_NOT_IN_FILE) *rc = tfft_plan_create(&p, n, batch, TFFT_DEFAULT);
   if (*rc == TFFT_OK) cache[{n, batch}] = p;
   return p;
 }

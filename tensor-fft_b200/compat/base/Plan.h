@@ -109,6 +109,12 @@ std::optional<Plan<Integer>> CreatePlan(const Integer fft_length, const BaseFFTM
   return p;
 }
 
+namespace tfft_compat {
+// the file the last successful CreatePlan(N, tuner_file) was given: ComputeFFT builds its library plans from it
+// (tfft_plan_create_from_file reads the optional key=value knobs of the B200 kernels from the same lines)
+inline std::string& tuner_file() { static std::string s; return s; }
+}  // namespace tfft_compat
+
 // Tuner-file overload, reference: Plan.h:197-255; line format `N mode base_warps r16_warps r2_block`
 // (written by src/testing/FileWriter.h:250-269).
 template <typename Integer>
@@ -124,8 +130,10 @@ std::optional<Plan<Integer>> CreatePlan(const Integer fft_length, const std::str
     double n = 0;
     int mode = 0, bw = 0, rw = 0, r2 = 0;
     if (!(ss >> n >> mode >> bw >> rw >> r2)) continue;
-    if (static_cast<Integer>(n) == fft_length)
+    if (static_cast<Integer>(n) == fft_length) {
+      tfft_compat::tuner_file() = tuner_results_file;
       return CreatePlan(fft_length, mode == 256 ? Mode_256 : Mode_4096, bw, rw, r2);
+    }
   }
   std::cout << "Error! Tuner file didnt contain requested fft length." << std::endl;
   return std::nullopt;

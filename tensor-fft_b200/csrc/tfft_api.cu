@@ -149,8 +149,8 @@ KernelFn kernel_for(const UnitPlan& p, int* threads) {
 // Two-slot variant (one CTA per SM, two units in flight, shared landing buffer) for 16K-element units
 typedef void (*Kernel2Fn)(const UnitPlan, __half*, __half*, const uint4*, const CUtensorMap, const CUtensorMap,
                           long long*);
-Kernel2Fn kernel2_for(const UnitPlan& p) {
-  if (p.tma_load != 1 || p.log2_elems != 14 || p.stages != 3 || getenv("TFFT_NO_2SLOT")) return nullptr;
+Kernel2Fn kernel2_for(const UnitPlan& p, bool allowed = true) {
+  if (!allowed || p.tma_load != 1 || p.log2_elems != 14 || p.stages != 3) return nullptr;
   if (smem2_layout(p).total > 227 * 1024) return nullptr;   // e.g. three distinct DFT matrices
   if (p.log2_radix[0] == 4 && p.log2_radix[1] == 4 && p.log2_radix[2] == 5) return fft_unit_kernel_2slot<4, 4, 5>;
   if (p.log2_radix[0] == 4 && p.log2_radix[1] == 5 && p.log2_radix[2] == 5) return fft_unit_kernel_2slot<4, 5, 5>;
@@ -271,7 +271,24 @@ void set_kernel_attrs() {
 
 }  // namespace
 
+// Per-plan tuning knobs (tfft_plan_create_tuned / a tuner file); -1 = default (the environment variable of the same
+// purpose, then the built-in choice).
+struct Tuning {
+  int tma = -1;            // TMA tile loads for row-mode units            (TFFT_NO_TMA)
+  int pipe = -1;           // MMA / epilogue overlap of stage 2            (TFFT_NO_PIPE)
+  int two_slot = -1;       // two-slot kernel for 16K-element TMA units    (TFFT_NO_2SLOT)
+  int prefetch = -1;       // L2 prefetch of the next unit                 (TFFT_PREFETCH)
+  int fourstep_lg1 = -1;   // log2 of the column-pass length, N > 2^15     (TFFT_FOURSTEP_LG1)
+  int tma_col = -1;        // TMA column tiles in four-step column passes  (TFFT_NO_TMA_COL)
+};
+int knob(int tuned, const char* env_off, int dflt) {   // env_off: variable whose presence switches the feature off
+  if (tuned >= 0) return tuned;
+  if (env_off && getenv(env_off)) return 0;
+  return dflt;
+}
+
 struct tfft_plan_s {
+  Tuning tune;
   int64_t n = 0, batch = 0, ny = 0, nx = 0;
   uint32_t flags = 0;
   int lg = 0;
@@ -340,8 +357,8 @@ int build_1d(tfft_plan_s* p) {
     {
       int rho[kMaxStages];
       radix_schedule(lg, rho);
-      sh.tma_load = (lg - rho[0]) >= 6 && getenv("TFFT_NO_TMA") == nullptr && !(p->flags & TFFT_INTERLEAVED);
-      sh.pipe_stage2 = sh.tma_load && lg >= 13 && getenv("TFFT_NO_PIPE") == nullptr;
+      sh.tma_load = (lg - rho[0]) >= 6 && knob(p->tune.tma, "TFFT_NO_TMA", 1) && !(p->flags & TFFT_INTERLEAVED);
+      sh.pipe_stage2 = sh.tma_load && lg >= 13 && knob(p->tune.pipe, "TFFT_NO_PIPE", 1);
     }
     UnitStrides st;
     st.n_transforms = static_cast<uint32_t>(batch);
@@ -414,8 +431,9 @@ int build_1d(tfft_plan_s* p) {
   // 2^21 = 4096 x 512 (-3 %), 2^22 = 4096 x 1024 (-26 %)
   static const int kLg1[9] = {8, 9, 9, 9, 10, 12, 12, 12, 12};   // lg = 16 .. 24
   int lg1 = kLg1[lg - 16];
-  if (const char* e = getenv("TFFT_FOURSTEP_LG1")) {   // developer knob: length 2^lg1 of the column pass
-    const int v = atoi(e);
+  {   // tuner file / developer knob: length 2^lg1 of the column pass
+    const char* e = getenv("TFFT_FOURSTEP_LG1");
+    const int v = p->tune.fourstep_lg1 >= 0 ? p->tune.fourstep_lg1 : (e ? atoi(e) : -1);
     if (v >= 8 && v <= 12 && lg - v >= 8 && lg - v <= 12) lg1 = v;
   }
   const int lg2 = lg - lg1;
@@ -430,7 +448,7 @@ int build_1d(tfft_plan_s* p) {
     sh.log2_units = std::max(3, unit_log2_elems(lg1) - lg1);
     sh.in_mode = kColMode;
     sh.out_mode = kColMode;
-    sh.tma_load = getenv("TFFT_NO_TMA_COL") == nullptr && !interleaved;   // column tiles {8 columns, R, M} loaded by TMA
+    sh.tma_load = knob(p->tune.tma_col, "TFFT_NO_TMA_COL", 1) && !interleaved;   // column tiles {8 columns, R, M} by TMA
     const int64_t U = int64_t(1) << sh.log2_units;
     UnitStrides st;
     st.in_nstride = N2; st.out_nstride = N2;
@@ -501,8 +519,8 @@ int build_2d(tfft_plan_s* p, std::vector<Pass>* passes, bool allow_tma) {
     sh.log2_units = yb ? yb : std::min(lgy, std::max(13 - lgx, unit_log2_elems(lgx) - lgx));
     int rho[kMaxStages];
     radix_schedule(yb ? lgx + yb : lgx, rho);
-    sh.tma_load = allow_tma && (lgx - rho[0]) >= 6 && getenv("TFFT_NO_TMA") == nullptr;
-    sh.pipe_stage2 = sh.tma_load && lgx + yb >= 13 && getenv("TFFT_NO_PIPE") == nullptr;
+    sh.tma_load = allow_tma && (lgx - rho[0]) >= 6 && knob(p->tune.tma, "TFFT_NO_TMA", 1);
+    sh.pipe_stage2 = sh.tma_load && lgx + yb >= 13 && knob(p->tune.pipe, "TFFT_NO_PIPE", 1);
     const int64_t U = int64_t(1) << sh.log2_units;
     UnitStrides st;
     st.in_tstride = yb ? (ny >> yb) * nx : nx;
@@ -575,10 +593,12 @@ int launch_pass(const tfft_plan_s* p, const Pass& ps, const __half* src_re, cons
     plan.il_in = ps.il_in ? 1u : 0u;
     plan.il_out = ps.il_out ? 1u : 0u;
     plan.il_swap = (p->flags & TFFT_INVERSE) ? 1u : 0u;
-    plan.prefetch_next = ps.il_in ? 0u : pf_env ? static_cast<uint32_t>(atoi(pf_env))
+    plan.prefetch_next = ps.il_in ? 0u : p->tune.prefetch >= 0 ? static_cast<uint32_t>(p->tune.prefetch)
+                         : pf_env ? static_cast<uint32_t>(atoi(pf_env))
                                 : (((plan.log2_elems == 15 && ps.kind == 0) || (plan.log2_len == 11 && plan.tma_load == 1)) ? 1u : 0u);
   }
   plan.col_first = static_cast<uint32_t>(tw_first_col);
+  const bool allow2 = knob(p->tune.two_slot, "TFFT_NO_2SLOT", 1) != 0;
   int threads = kThreads;
   KernelFn fn = kernel_for(plan, &threads);
   if (!fn) return TFFT_E_UNSUPPORTED;
@@ -618,7 +638,7 @@ int launch_pass(const tfft_plan_s* p, const Pass& ps, const __half* src_re, cons
     // row-mode input: transform t of the launch starts at src + t * tstride, or, for four-step row
     // passes, at src + (t / upb) * batch_stride + (t % upb) * tstride == t * tstride when contiguous
     const int64_t n_tr = tma_extent ? tma_extent : static_cast<int64_t>(ps.n_units) << plan.log2_units;
-    const bool half_box = kernel2_for(plan) != nullptr;
+    const bool half_box = kernel2_for(plan, allow2) != nullptr;
     int rc;
     if (plan.tma_load == 2) {
       const int64_t columns = static_cast<int64_t>(plan.units_per_batch) << plan.log2_units;
@@ -635,7 +655,7 @@ int launch_pass(const tfft_plan_s* p, const Pass& ps, const __half* src_re, cons
     }
     if (rc != TFFT_OK) return rc;
   }
-  if (Kernel2Fn fn2 = kernel2_for(plan)) {   // the tensor maps above hold half-tile boxes: no other kernel may run them
+  if (Kernel2Fn fn2 = kernel2_for(plan, allow2)) {   // the tensor maps above hold half-tile boxes: no other kernel may run them
     const Smem2Layout S2 = smem2_layout(plan);
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -673,11 +693,58 @@ const char* tfft_error_string(int code) {
     case TFFT_E_NO_DEVICE: return "no sm_100 CUDA device (this library has no CPU path)";
     case TFFT_E_UNSUPPORTED: return "unsupported configuration";
     case TFFT_E_NOMEM: return "device memory allocation failed";
+    case TFFT_E_NOT_IN_FILE: return "tuner file holds no line for this transform length";
     default: return code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "unknown tfft error";
   }
 }
 
+static int plan_create_tuned(tfft_plan_t* out, int64_t n, int64_t batch, uint32_t flags, const Tuning& tune);
+
 int tfft_plan_create(tfft_plan_t* out, int64_t n, int64_t batch, uint32_t flags) {
+  // TFFT_TUNER_FILE: every plan looks its length up in that file first (see tfft_plan_create_from_file)
+  if (const char* f = getenv("TFFT_TUNER_FILE")) {
+    const int rc = tfft_plan_create_from_file(out, n, batch, flags, f);
+    if (rc != TFFT_E_NOT_IN_FILE) return rc;
+  }
+  return plan_create_tuned(out, n, batch, flags, Tuning());
+}
+
+// Tuner file: one line per length, the reference's format `N mode base_warps r16_warps r2_block`
+// (src/base/Plan.h:211-236, written by src/testing/FileWriter.h:250-269) optionally followed by the knobs of the new
+// kernels as `key=value` words (tma, pipe, two_slot, prefetch, lg1, tma_col); tools/tune.py writes such files.  The five
+// reference columns are accepted and ignored: they describe launch shapes of kernels that no longer exist.
+int tfft_plan_create_from_file(tfft_plan_t* out, int64_t n, int64_t batch, uint32_t flags, const char* path) {
+  if (!out || !path) return TFFT_E_INVALID_ARG;
+  *out = nullptr;
+  FILE* f = fopen(path, "r");
+  if (!f) return TFFT_E_INVALID_ARG;
+  char line[512];
+  int rc = TFFT_E_NOT_IN_FILE;
+  while (fgets(line, sizeof(line), f)) {
+    char* save = nullptr;
+    char* tok = strtok_r(line, " \t\r\n", &save);
+    if (!tok || static_cast<int64_t>(atof(tok)) != n) continue;
+    Tuning t;
+    while ((tok = strtok_r(nullptr, " \t\r\n", &save)) != nullptr) {
+      const char* eq = strchr(tok, '=');
+      if (!eq) continue;   // one of the reference's four launch-shape columns
+      const int v = atoi(eq + 1);
+      const size_t kl = static_cast<size_t>(eq - tok);
+      if (kl == 3 && !strncmp(tok, "tma", 3)) t.tma = v;
+      else if (kl == 4 && !strncmp(tok, "pipe", 4)) t.pipe = v;
+      else if (kl == 8 && !strncmp(tok, "two_slot", 8)) t.two_slot = v;
+      else if (kl == 8 && !strncmp(tok, "prefetch", 8)) t.prefetch = v;
+      else if (kl == 3 && !strncmp(tok, "lg1", 3)) t.fourstep_lg1 = v;
+      else if (kl == 7 && !strncmp(tok, "tma_col", 7)) t.tma_col = v;
+    }
+    rc = plan_create_tuned(out, n, batch, flags, t);
+    break;
+  }
+  fclose(f);
+  return rc;
+}
+
+static int plan_create_tuned(tfft_plan_t* out, int64_t n, int64_t batch, uint32_t flags, const Tuning& tune) {
   if (!out) return TFFT_E_INVALID_ARG;
   *out = nullptr;
   const int lg = ilog2_exact(n);
@@ -685,6 +752,7 @@ int tfft_plan_create(tfft_plan_t* out, int64_t n, int64_t batch, uint32_t flags)
   if (batch < 1 || batch > (int64_t(1) << 30)) return TFFT_E_INVALID_ARG;
   tfft_plan_s* p = new (std::nothrow) tfft_plan_s;
   if (!p) return TFFT_E_NOMEM;
+  p->tune = tune;
   p->n = n; p->batch = batch; p->flags = flags; p->lg = lg;
   int rc = build_1d(p);
   if (rc != TFFT_OK) {

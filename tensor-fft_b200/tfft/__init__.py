@@ -50,7 +50,7 @@ class _PlanInfo(ctypes.Structure):
 
 EXPORTS = ("tfft_plan_create", "tfft_plan_create_2d", "tfft_plan_info", "tfft_plan_destroy", "tfft_exec",
            "tfft_exec_twiddled", "tfft_exec_host", "tfft_error_string", "tfft_version", "tfft_fixture_sine",
-           "tfft_error_stats", "tfft_transpose_blocks", "tfft_copy_runs")
+           "tfft_error_stats", "tfft_transpose_blocks", "tfft_copy_runs", "tfft_plan_create_from_file")
 
 
 def lib() -> ctypes.CDLL:
@@ -64,6 +64,7 @@ def lib() -> ctypes.CDLL:
         vp, i64, u32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint32
         L.tfft_plan_create.argtypes = [ctypes.POINTER(vp), i64, i64, u32]
         L.tfft_plan_create_2d.argtypes = [ctypes.POINTER(vp), i64, i64, i64, u32]
+        L.tfft_plan_create_from_file.argtypes = [ctypes.POINTER(vp), i64, i64, u32, ctypes.c_char_p]
         L.tfft_plan_info.argtypes = [vp, ctypes.POINTER(_PlanInfo)]
         L.tfft_plan_destroy.argtypes = [vp]
         L.tfft_exec.argtypes = [vp, vp, vp, vp, vp, i64, i64, vp]
@@ -116,9 +117,12 @@ def error_stats(a_re, a_im, b_re, b_im) -> dict:
 class NativePlan:
     """Owner of a tfft_plan_t."""
 
-    def __init__(self, n: int, batch: int = 1, flags: int = 0, shape2d: Optional[tuple] = None):
+    def __init__(self, n: int, batch: int = 1, flags: int = 0, shape2d: Optional[tuple] = None,
+                 tuner_file: Optional[str] = None):
         self._h = ctypes.c_void_p()
-        if shape2d is None:
+        if tuner_file is not None:
+            _check(lib().tfft_plan_create_from_file(ctypes.byref(self._h), n, batch, flags, tuner_file.encode()))
+        elif shape2d is None:
             _check(lib().tfft_plan_create(ctypes.byref(self._h), n, batch, flags))
         else:
             _check(lib().tfft_plan_create_2d(ctypes.byref(self._h), shape2d[0], shape2d[1], batch, flags))

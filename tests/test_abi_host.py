@@ -92,3 +92,19 @@ def test_misaligned_arguments_rejected():
     rc = L.tfft_exec(p._h, 2, 32, 48, 64, 8192, 8192, None)      # misaligned pointer
     assert rc == -2
     assert b"invalid argument" in L.tfft_error_string(-2)
+
+
+def test_tuner_file_plan_creation(tmp_path):
+    """tfft_plan_create_from_file (CreatePlan(N, tuner_file), Plan.h:197-255): the reference's 5-column lines are
+    accepted, the key=value knobs of the new kernels are applied, a missing length is TFFT_E_NOT_IN_FILE (-6)."""
+    import ctypes
+    f = tmp_path / "TunerResults.dat"
+    f.write_text("4096 256 8 8 256\n1048576 4096 16 16 512 lg1=8 tma_col=0 prefetch=1\n16384 256 8 8 256 two_slot=0 pipe=0\n")
+    L = tfft.lib()
+    for n, passes in ((4096, 1), (1048576, 2), (16384, 1)):
+        p = tfft.NativePlan(n, 4, tuner_file=str(f))
+        assert p.info["passes"] == passes and p.info["n"] == n
+    h = ctypes.c_void_p()
+    assert L.tfft_plan_create_from_file(ctypes.byref(h), 8192, 1, 0, str(f).encode()) == -6
+    assert L.tfft_plan_create_from_file(ctypes.byref(h), 8192, 1, 0, b"/nonexistent/file") == -2
+    assert b"tuner file" in L.tfft_error_string(-6)
