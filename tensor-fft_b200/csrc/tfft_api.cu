@@ -558,6 +558,15 @@ int build_2d(tfft_plan_s* p, std::vector<Pass>* passes, bool allow_tma) {
   return ok ? TFFT_OK : TFFT_E_UNSUPPORTED;
 }
 
+// L2 prefetch of the next unit, measured per size with tools/tune.py on B200 (profiles/r01_TunerResults.dat): it pays
+// for single-pass N = 2048 / 4096 (-9 % / -4 %) and for the 32K-element units of N = 32768 and N >= 2^23, and costs up to
+// 8 % everywhere else (16K-element units whose loads already overlap compute; 2-D column passes; N = 2^21, 2^22)
+bool prefetch_default(const tfft_plan_s* p, const Pass& ps, const UnitPlan& plan) {
+  if (ps.kind != 0) return false;
+  if (p->lg <= 15) return plan.tma_load == 1 && (p->lg == 11 || p->lg == 12 || p->lg == 15);
+  return plan.log2_elems == 15 && p->lg >= 23;
+}
+
 int launch_pass(const tfft_plan_s* p, const Pass& ps, const __half* src_re, const __half* src_im, __half* dst_re,
                 __half* dst_im, int64_t in_stride, int64_t out_stride, cudaStream_t stream, int tw_log2 = 0,
                 int64_t tw_first_col = 0) {
@@ -595,7 +604,7 @@ int launch_pass(const tfft_plan_s* p, const Pass& ps, const __half* src_re, cons
     plan.il_swap = (p->flags & TFFT_INVERSE) ? 1u : 0u;
     plan.prefetch_next = ps.il_in ? 0u : p->tune.prefetch >= 0 ? static_cast<uint32_t>(p->tune.prefetch)
                          : pf_env ? static_cast<uint32_t>(atoi(pf_env))
-                                : (((plan.log2_elems == 15 && ps.kind == 0) || (plan.log2_len == 11 && plan.tma_load == 1)) ? 1u : 0u);
+                                : (prefetch_default(p, ps, plan) ? 1u : 0u);
   }
   plan.col_first = static_cast<uint32_t>(tw_first_col);
   const bool allow2 = knob(p->tune.two_slot, "TFFT_NO_2SLOT", 1) != 0;
