@@ -520,6 +520,7 @@ __device__ __forceinline__ void stage_issue(const KernelCtx& c, uint32_t b1_sadd
   using SS = StageShape<RHO, LOG2E, PIPE, NG>;
   constexpr uint32_t R = SS::R, kSteps = SS::kSteps, kTiles = SS::kTiles;
   constexpr bool SW128 = LM == 1 && ST == 0;
+  constexpr bool SW32 = LM == 3 && ST == 0;   // 16-row atoms: LBO = atom stride 32R, SBO = K-group stride 256
   constexpr uint32_t S = (LM == 2 && ST == 0) ? 16 * R : SS::S;   // column tiles loaded by TMA are dense: no padding
   constexpr bool kPipe = SS::kPipe;
   constexpr uint32_t idesc = make_idesc_f16(128, 2 * R, /*a_mn=*/1, /*b_mn=*/0);
@@ -534,10 +535,13 @@ __device__ __forceinline__ void stage_issue(const KernelCtx& c, uint32_t b1_sadd
   b1_saddr += zero;
   const uint32_t pa_re = (ST == 0 ? c.a_re : c.s_re) + zero, pa_im = (ST == 0 ? c.a_im : c.s_im) + zero;
   const uint32_t taddr = c.taddr + zero;
-  const uint64_t da_re = SW128 ? (make_smem_desc(pa_re, 128 * R, 1024) | kSw128) : make_smem_desc(pa_re, kKGroupStride, S);
-  const uint64_t da_im = SW128 ? (make_smem_desc(pa_im, 128 * R, 1024) | kSw128) : make_smem_desc(pa_im, kKGroupStride, S);
-  constexpr uint32_t kTileStep = SW128 ? (2 * 128 * R) / 16 : S;   // descriptor address units (16 B) per tile
-  constexpr uint32_t kKStep = SW128 ? 2048 / 16 : 16;              // ... per 16-wide K step
+  constexpr uint64_t kSw32 = uint64_t(6) << 61;
+  const uint64_t da_re = SW128 ? (make_smem_desc(pa_re, 128 * R, 1024) | kSw128)
+                         : SW32 ? (make_smem_desc(pa_re, 32 * R, 256) | kSw32) : make_smem_desc(pa_re, kKGroupStride, S);
+  const uint64_t da_im = SW128 ? (make_smem_desc(pa_im, 128 * R, 1024) | kSw128)
+                         : SW32 ? (make_smem_desc(pa_im, 32 * R, 256) | kSw32) : make_smem_desc(pa_im, kKGroupStride, S);
+  constexpr uint32_t kTileStep = (SW128 || SW32) ? (2 * 128 * R) / 16 : S;   // descriptor address units (16 B) per tile
+  constexpr uint32_t kKStep = SW128 ? 2048 / 16 : SW32 ? 512 / 16 : 16;      // ... per 16-wide K step
   const uint64_t db1 = make_smem_desc(b1_saddr, kKGroupStride, 16 * R);
   const uint64_t db2 = make_smem_desc(b1_saddr + 4 * R * R, kKGroupStride, 16 * R);
   constexpr uint32_t kTileBegin = PART == 2 ? kTiles / 2 : 0, kTileEnd = PART == 1 ? kTiles / 2 : kTiles;
@@ -814,7 +818,7 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
       TFFT_TRACE_MARK(1);
       mbar_wait(load_bar, load_phase & 1u);
       load_phase++;
-    } else if constexpr (LM == 1) {
+    } else if constexpr (LM == 1 || LM == 3) {
       // one tensor tile per plane: {64 rows, R kappa, M/64, U transforms}; transforms past the end of
       // the batch are out of bounds of the tensor map and arrive as zeros
       if (tid == 0) {
@@ -887,7 +891,7 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
             tma_prefetch_4d_col(&tmap_re, (nu << P.log2_units) + 8 * ug, nb);
             tma_prefetch_4d_col(&tmap_im, (nu << P.log2_units) + 8 * ug, nb);
           }
-      } else if constexpr (LM == 1) {
+      } else if constexpr (LM == 1 || LM == 3) {
         if (tid == 0) {
           if (P.kron_bits) {
             tma_prefetch_5d(&tmap_re, nu, nb * P.tma_batch_step);

@@ -113,15 +113,19 @@ struct KernelEntry {
 #define TFFT_K(E, A, B, C) {E, A, B, C, fft_unit_kernel<E, A, B, C, 0>, nullptr, nullptr, kThreads}
 #define TFFT_KC(E, A, B, C) {E, A, B, C, fft_unit_kernel<E, A, B, C, 0>, nullptr, fft_unit_kernel<E, A, B, C, 2>, kThreads}
 #define TFFT_KT(E, A, B, C) {E, A, B, C, fft_unit_kernel<E, A, B, C, 0>, fft_unit_kernel<E, A, B, C, 1>, nullptr, kThreads}
+// N <= 1024: the row tile uses SWIZZLE_32B atoms (load mode 3)
+#define TFFT_KS(E, A, B, C) {E, A, B, C, fft_unit_kernel<E, A, B, C, 0>, fft_unit_kernel<E, A, B, C, 3>, nullptr, kThreads}
+#define TFFT_KSC(E, A, B, C) \
+  {E, A, B, C, fft_unit_kernel<E, A, B, C, 0>, fft_unit_kernel<E, A, B, C, 3>, fft_unit_kernel<E, A, B, C, 2>, kThreads}
 #define TFFT_KTC(E, A, B, C) \
   {E, A, B, C, fft_unit_kernel<E, A, B, C, 0>, fft_unit_kernel<E, A, B, C, 1>, fft_unit_kernel<E, A, B, C, 2>, kThreads}
 // 32K-element units (one CTA per SM): 512 threads = four warp groups
 #define TFFT_KW(E, A, B, C) \
   {E, A, B, C, fft_unit_kernel<E, A, B, C, 0, 512>, fft_unit_kernel<E, A, B, C, 1, 512>, fft_unit_kernel<E, A, B, C, 2, 512>, 512}
 const KernelEntry g_kernels[] = {
-    TFFT_K(13, 4, 4, 0), TFFT_KC(14, 4, 4, 0),                      // L = 2^8
-    TFFT_K(13, 4, 5, 0), TFFT_KC(14, 4, 5, 0),                      // 2^9
-    TFFT_K(13, 5, 5, 0), TFFT_KC(14, 5, 5, 0),                      // 2^10
+    TFFT_KS(13, 4, 4, 0), TFFT_KSC(14, 4, 4, 0),                    // L = 2^8
+    TFFT_KS(13, 4, 5, 0), TFFT_KSC(14, 4, 5, 0),                    // 2^9
+    TFFT_KS(13, 5, 5, 0), TFFT_KSC(14, 5, 5, 0),                    // 2^10
     TFFT_KT(13, 5, 6, 0), TFFT_KTC(14, 5, 6, 0),                       // 2^11
     TFFT_KT(13, 6, 6, 0), TFFT_KT(14, 6, 6, 0), TFFT_KW(15, 6, 6, 0), TFFT_KTC(15, 6, 6, 0),  // 2^12
     TFFT_KT(13, 4, 4, 5), TFFT_KT(14, 4, 4, 5),                        // 2^13
@@ -132,6 +136,8 @@ const KernelEntry g_kernels[] = {
 #undef TFFT_K
 #undef TFFT_KT
 #undef TFFT_KW
+#undef TFFT_KS
+#undef TFFT_KSC
 #undef TFFT_KC
 #undef TFFT_KTC
 KernelFn kernel_for(const UnitPlan& p, int* threads) {
@@ -141,7 +147,7 @@ KernelFn kernel_for(const UnitPlan& p, int* threads) {
         k.r1 == static_cast<int>(p.log2_radix[1]) && k.r2 == static_cast<int>(p.stages == 3 ? p.log2_radix[2] : 0) &&
         !(narrow && k.threads == 512)) {
       *threads = k.threads;
-      return p.tma_load == 2 ? k.fn_tma_col : (p.tma_load ? k.fn_tma : k.fn);
+      return p.tma_load == 2 ? k.fn_tma_col : (p.tma_load ? k.fn_tma : k.fn);   // tma_load 1 / 3: the entry's row-tile kernel
     }
   return nullptr;
 }
@@ -182,13 +188,20 @@ int make_input_tensor_map(const UnitPlan& plan, const __half* base, int64_t tstr
   cuuint64_t gdim[4] = {64, R, M / 64, static_cast<cuuint64_t>(n_transforms)};
   cuuint64_t gstride[3] = {M * 2, 128, static_cast<cuuint64_t>(tstride) * 2};
   cuuint32_t box[4] = {64, static_cast<cuuint32_t>(R), static_cast<cuuint32_t>(M / 64), static_cast<cuuint32_t>(U)};
+  CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B;
+  if (plan.tma_load == 3) {   // M = 16 / 32 rows per K line: atoms of 16 rows, 32-byte swizzle
+    gdim[0] = 16; gdim[2] = M / 16;
+    gstride[1] = 32;
+    box[0] = 16; box[2] = static_cast<cuuint32_t>(M / 16);
+    swz = CU_TENSOR_MAP_SWIZZLE_32B;
+  }
   if (half_box) {   // two-slot kernel: one box = half of a unit's stage-1 tiles
     if (U >= 2) box[3] = static_cast<cuuint32_t>(U / 2);
     else box[2] = static_cast<cuuint32_t>(M / 128);
   }
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(base), gdim, gstride, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? TFFT_OK : TFFT_E_INVALID_ARG;
 }
@@ -357,7 +370,9 @@ int build_1d(tfft_plan_s* p) {
     {
       int rho[kMaxStages];
       radix_schedule(lg, rho);
-      sh.tma_load = (lg - rho[0]) >= 6 && knob(p->tune.tma, "TFFT_NO_TMA", 1) && !(p->flags & TFFT_INTERLEAVED);
+      // 16 or 32 rows per K line (N <= 1024): SWIZZLE_32B atoms (TFFT_NO_TMA_SMALL switches back to cp.async)
+      const bool small_ok = (lg - rho[0]) >= 4 && getenv("TFFT_NO_TMA_SMALL") == nullptr;
+      sh.tma_load = ((lg - rho[0]) >= 6 || small_ok) && knob(p->tune.tma, "TFFT_NO_TMA", 1) && !(p->flags & TFFT_INTERLEAVED);
       sh.pipe_stage2 = sh.tma_load && lg >= 13 && knob(p->tune.pipe, "TFFT_NO_PIPE", 1);
     }
     UnitStrides st;

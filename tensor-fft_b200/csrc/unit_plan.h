@@ -72,7 +72,10 @@ struct UnitPlan {
   uint32_t il_in, il_out;                  // TFFT_INTERLEAVED: this pass reads / writes half2 (re, im) elements (cp.async
                                            // load path only); the element offsets of the plan are doubled on the fly
   uint32_t prefetch_next;                  // 1: pull the next unit's input into L2 during this unit's stages
-  uint32_t tma_load;                       // 2: column-mode input, stage-1 operand filled by TMA tiles {8 columns, R kappa,
+  uint32_t tma_load;                       // 3: row-mode input with 16 or 32 rows per K line: SWIZZLE_32B MN-major atoms of
+                                           //    16 rows filled by TMA: element (row, kappa) at (row>>4)*32R + kappa*32 +
+                                           //    (row&15)*2, byte-address bit 4 ^= bit 7
+                                           // 2: column-mode input, stage-1 operand filled by TMA tiles {8 columns, R kappa,
                                            //    M rows} per 8-column group, no swizzle: dense chunks [group][m][kappa][8 cols],
                                            //    i.e. chunk_stride[0] = 16R without padding and natural row order (u&7, m, u>>3)
                                            // 1: stage-1 operand = SWIZZLE_128B MN-major atoms of 64 rows filled by TMA:
@@ -197,13 +200,16 @@ inline bool build_unit_plan(const UnitShape& shape, UnitPlan* plan, PlanBuildInf
   }
   plan->log2_len = lg; plan->log2_units = ups; plan->stages = s;
   plan->log2_elems = eps; plan->in_mode = shape.in_mode; plan->out_mode = shape.out_mode;
-  if (shape.tma_load && shape.in_mode == kRowMode && (lg - rho[0]) < 6) {
-    info->error = "TMA load needs >= 64 contiguous rows per K line"; return false;
+  // row-mode TMA tiles: SWIZZLE_128B atoms of 64 consecutive rows when a K line has M = L/R_1 >= 64 contiguous rows
+  // (tma_load 1), SWIZZLE_32B atoms of 16 rows for M = 16 / 32 (tma_load 3; a 32-byte inner box under SWIZZLE_128B is
+  // padded to 128-byte lines by the hardware, probe/tma_small_probe.cu)
+  if (shape.tma_load && shape.in_mode == kRowMode && (lg - rho[0]) < 4) {
+    info->error = "TMA load needs >= 16 contiguous rows per K line"; return false;
   }
   if (shape.tma_load && shape.in_mode == kColMode && (lg - rho[0]) > 8) {
     info->error = "column-mode TMA load: more than 256 rows per K line"; return false;
   }
-  plan->tma_load = shape.tma_load ? (shape.in_mode == kColMode ? 2u : 1u) : 0u;
+  plan->tma_load = shape.tma_load ? (shape.in_mode == kColMode ? 2u : ((lg - rho[0]) < 6 ? 3u : 1u)) : 0u;
   // the first-half epilogue of stage 2 writes the first half of stage 3's layout, which must lie inside the half of
   // stage 2's layout that its first-half MMAs have consumed: padded plane sizes shrink with the radix, so R_3 >= R_2
   const bool pipe2 = shape.pipe_stage2 && s == 3 && rho[2] >= rho[1];

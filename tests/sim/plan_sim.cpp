@@ -78,6 +78,18 @@ int plansim_run_ex(int log2_len, int log2_units, int in_mode_flags, int out_mode
               const int64_t a = ibase + ug * 8 + cc + (kap * M + m) * strides9[1];
               sre[off / 2] = rh(in_re[a], h); sim[off / 2] = rh(in_im[a], h);
             }
+    } else if (P.tma_load == 3) {   // SWIZZLE_32B atoms of 16 rows: dense [atom][kappa][16 rows], byte bit 4 ^= bit 7
+      const int R = 1 << P.log2_radix[0];
+      const int64_t M = L / R, U = int64_t(1) << P.log2_units;
+      for (int64_t u = 0; u < U; ++u)
+        for (int64_t m = 0; m < M; ++m)
+          for (int kap = 0; kap < R; ++kap) {
+            const int64_t row = u * M + m;
+            uint32_t off = (uint32_t)((row >> 4) * 32 * R + kap * 32 + (row & 15) * 2);
+            off ^= ((off >> 7) & 1u) << 4;
+            const int64_t a = ibase + u * strides9[0] + kap * M + m;
+            sre[off / 2] = rh(in_re[a], h); sim[off / 2] = rh(in_im[a], h);
+          }
     } else if (P.tma_load) {
       const int R = 1 << P.log2_radix[0];
       const int64_t M = L / R, U = int64_t(1) << P.log2_units;
@@ -126,6 +138,10 @@ int plansim_run_ex(int log2_len, int log2_units, int in_mode_flags, int out_mode
           std::vector<cd> a(R), y(R);
           for (int kap = 0; kap < R; ++kap) {
             uint32_t off = (row >> 3) * S + (kap >> 3) * kKGroupStride + (kap & 7) * 16 + (row & 7) * 2;
+            if (t == 1 && P.tma_load == 3) {
+              off = (row >> 4) * 32 * R + kap * 32 + (row & 15) * 2;
+              off ^= ((off >> 7) & 1u) << 4;
+            }
             if (t == 1 && P.tma_load == 1)
               off = (row >> 6) * 128 * R + (kap >> 3) * 1024 + (kap & 7) * 128 + ((((row >> 3) & 7) ^ (kap & 7)) << 4) + (row & 7) * 2;
             a[kap] = cd(sre[off / 2], sim[off / 2]);

@@ -19,7 +19,7 @@ def sim():
     return L
 
 
-def _rows(sim, lg, ups, n_units=2, h=0, tstride=None):
+def _rows(sim, lg, ups, n_units=2, h=0, tstride=None, flags=0):
     n, U = 1 << lg, 1 << ups
     tstride = tstride or n
     tot = n_units * U * tstride
@@ -28,7 +28,7 @@ def _rows(sim, lg, ups, n_units=2, h=0, tstride=None):
     ore, oim = np.zeros(tot), np.zeros(tot)
     st = (ctypes.c_int64 * 9)(tstride, 1, tstride, 1, 0, U * tstride, 0, U * tstride, 1 << 30)
     conf = (ctypes.c_int * 4)()
-    rc = sim.plansim_run(lg, ups, 0, 0, st, 0, n_units, re.ctypes.data_as(dp), im.ctypes.data_as(dp),
+    rc = sim.plansim_run(lg, ups, flags, 0, st, 0, n_units, re.ctypes.data_as(dp), im.ctypes.data_as(dp),
                          ore.ctypes.data_as(dp), oim.ctypes.data_as(dp), h, conf)
     x = (re + 1j * im).reshape(n_units * U, tstride)[:, :n]
     if h:
@@ -44,6 +44,15 @@ SHAPES = [(lg, ups) for lg in range(8, 16) for ups in range(0, 8) if 13 <= lg + 
 @pytest.mark.parametrize("lg,ups", SHAPES)
 def test_row_pass_is_the_dft_and_conflict_free(sim, lg, ups):
     rc, conf, err = _rows(sim, lg, ups)
+    assert rc == 0 and conf == [0, 0, 0]
+    assert err < 1e-13
+
+
+@pytest.mark.parametrize("lg,ups", [(8, 6), (8, 5), (9, 5), (10, 4), (10, 3), (11, 2), (12, 2), (13, 1), (14, 0), (15, 0)])
+def test_row_pass_with_tma_tiles(sim, lg, ups):
+    """Stage-1 operand filled by a SWIZZLE_128B TMA tile (natural row order); for N <= 1024 an atom of 64 rows is
+    64/M consecutive transforms.  flags: 2 = TMA, 4 = stage-2 pipelining."""
+    rc, conf, err = _rows(sim, lg, ups, flags=6 if lg >= 13 else 2)
     assert rc == 0 and conf == [0, 0, 0]
     assert err < 1e-13
 
