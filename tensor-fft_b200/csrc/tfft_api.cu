@@ -487,6 +487,21 @@ int build_1d(tfft_plan_s* p) {
     st.in_tstride = N2; st.in_unit_stride = U * N2;
     st.out_nstride = N1; st.out_unit_stride = U;
     st.units_per_batch = static_cast<uint32_t>(N1 / U);
+    // the contiguous rows are loaded as TMA tiles (transform t of batch b at b*stride + t*N2: the batch stride must be
+    // a whole number of rows; otherwise tfft_exec takes the cp.async twin of this pass from passes_strided)
+    // Measured on B200 (C3 sizes): -8 .. -13 % for row lengths up to 1024 (2^16 .. 2^22), +10 .. +22 % for 2048 / 4096
+    // (2^23, 2^24), so only the former use tiles.
+    const bool row_tma = lg2 <= 10 && knob(p->tune.tma, "TFFT_NO_TMA", 1) && getenv("TFFT_NO_TMA_PASS2") == nullptr;
+    if (row_tma) {
+      const Pass first = p->passes.back();
+      if (!add_pass(p, sh, st, static_cast<uint32_t>(batch * (N1 / U)), preserve ? 2 : 0, 1, !preserve, true))
+        return TFFT_E_UNSUPPORTED;
+      p->passes.back().il_out = interleaved;
+      p->passes_strided.push_back(first);
+      p->passes_strided.push_back(p->passes.back());
+      p->passes.pop_back();
+      sh.tma_load = true;
+    }
     if (!add_pass(p, sh, st, static_cast<uint32_t>(batch * (N1 / U)), preserve ? 2 : 0, 1, !preserve, true))
       return TFFT_E_UNSUPPORTED;
     p->passes.back().il_out = interleaved;
@@ -608,8 +623,13 @@ int launch_pass(const tfft_plan_s* p, const Pass& ps, const __half* src_re, cons
     st.in_batch_stride = in_stride;
     st.out_batch_stride = out_stride;
   }
-  if (ps.kind == 0 && ps.plan.tma_load == 1 && st.units_per_batch != 0x7FFFFFFFu)   // batches of contiguous transforms
-    st.tma_batch_step = st.units_per_batch << ps.plan.log2_units;
+  if (ps.kind == 0 && (ps.plan.tma_load == 1 || ps.plan.tma_load == 3) && st.units_per_batch != 0x7FFFFFFFu) {
+    // four-step row pass: transform t of batch b at b*batch_stride + t*tstride (tfft_exec checked divisibility)
+    const int64_t batches = (ps.n_units + st.units_per_batch - 1) / st.units_per_batch;
+    st.tma_batch_step = static_cast<uint32_t>(batches > 1 ? st.in_batch_stride / st.in_tstride : 0);
+    tma_extent = static_cast<int64_t>(st.tma_batch_step) * (batches - 1) +
+                 (static_cast<int64_t>(st.units_per_batch) << ps.plan.log2_units);
+  }
   UnitPlan plan = ps.plan;
   fill_strides(st, ps.info, &plan);
   {
@@ -880,6 +900,9 @@ int tfft_exec(tfft_plan_t p, const void* in_re, const void* in_im, void* out_re,
     const int64_t step = rp.kron_bits ? (p->ny >> rp.kron_bits) * p->nx : p->nx;
     return in_stride % step == 0 && in_stride / step < (int64_t(1) << 31);
   };
+  if (!p->ny && p->passes.size() == 2 && !p->passes_strided.empty() && p->batch > 1 && p->passes[1].src == 0 &&
+      in_stride % p->passes[1].strides.in_tstride != 0)
+    passes = &p->passes_strided;   // four-step row pass: the batch stride is not a whole number of rows
   if (p->ny && p->batch > 1 && p->passes.front().plan.tma_load && !tma_ok_2d()) {
     std::lock_guard<std::mutex> lock(g_upload_mutex);
     if (p->passes_strided.empty()) {

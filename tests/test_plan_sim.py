@@ -85,7 +85,8 @@ def test_four_step_passes(sim, lg1, lg2, u1, u2, tma):
                           t_re.ctypes.data_as(dp), t_im.ctypes.data_as(dp), 0, conf)
     c1 = list(conf)[:3]
     st = (ctypes.c_int64 * 9)(N2, 1, 0, N1, 0, U2 * N2, 0, U2, 1 << 30)
-    rc2 = sim.plansim_run(lg2, u2, 0, 1, st, 0, N1 // U2, t_re.ctypes.data_as(dp), t_im.ctypes.data_as(dp),
+    # pass 2 (contiguous rows in, transposed out): cp.async chunks or, with tma, row tiles (SWIZZLE_32B / 128B atoms)
+    rc2 = sim.plansim_run(lg2, u2, tma, 1, st, 0, N1 // U2, t_re.ctypes.data_as(dp), t_im.ctypes.data_as(dp),
                           o_re.ctypes.data_as(dp), o_im.ctypes.data_as(dp), 0, conf)
     want = np.fft.fft(re + 1j * im) / N
     assert rc1 == 0 and rc2 == 0 and c1 == [0, 0, 0] and list(conf)[:3] == [0, 0, 0]   # tma: column tiles loaded by TMA
