@@ -520,7 +520,7 @@ __device__ __forceinline__ void stage_issue(const KernelCtx& c, uint32_t b1_sadd
   using SS = StageShape<RHO, LOG2E, PIPE, NG>;
   constexpr uint32_t R = SS::R, kSteps = SS::kSteps, kTiles = SS::kTiles;
   constexpr bool SW128 = LM == 1 && ST == 0;
-  constexpr bool SW32 = LM == 3 && ST == 0;   // 16-row atoms: LBO = atom stride 32R, SBO = K-group stride 256
+  constexpr bool SW32 = (LM == 3 || LM == 4) && ST == 0;   // 16-row atoms: LBO = atom stride 32R, SBO = K-group stride 256
   constexpr uint32_t S = (LM == 2 && ST == 0) ? 16 * R : SS::S;   // column tiles loaded by TMA are dense: no padding
   constexpr bool kPipe = SS::kPipe;
   constexpr uint32_t idesc = make_idesc_f16(128, 2 * R, /*a_mn=*/1, /*b_mn=*/0);
@@ -804,15 +804,16 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
 
     // ---------------------------------------------------------------- load phase
     TFFT_TRACE_MARK(0);
-    if constexpr (LM == 2) {
-      // per 8-column group one tile {8 columns, R kappa, M rows, 1 batch} per plane, dense: [group][m][kappa][8]
+    if constexpr (LM == 2 || LM == 4) {
+      // per group of W = 8 (16) columns one tile {W columns, R kappa, M rows, 1 batch} per plane, dense: [group][m][kappa][W]
       if (tid == 0) {
+        constexpr uint32_t W = LM == 4 ? 16 : 8;
         fence_proxy_async_smem();
         mbar_arrive_expect_tx(load_bar, 4u << LOG2E);
-        const uint32_t group_bytes = 16u << P.log2_len;
-        for (uint32_t ug = 0; ug < (1u << P.log2_units) / 8; ++ug) {
-          tma_load_4d_col(c.s_re + ug * group_bytes, &tmap_re, (uu << P.log2_units) + 8 * ug, ub, load_bar);
-          tma_load_4d_col(c.s_im + ug * group_bytes, &tmap_im, (uu << P.log2_units) + 8 * ug, ub, load_bar);
+        const uint32_t group_bytes = (2 * W) << P.log2_len;
+        for (uint32_t ug = 0; ug < (1u << P.log2_units) / W; ++ug) {
+          tma_load_4d_col(c.s_re + ug * group_bytes, &tmap_re, (uu << P.log2_units) + W * ug, ub, load_bar);
+          tma_load_4d_col(c.s_im + ug * group_bytes, &tmap_im, (uu << P.log2_units) + W * ug, ub, load_bar);
         }
       }
       TFFT_TRACE_MARK(1);
@@ -885,11 +886,12 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
     const bool pf = P.prefetch_next && unit + gridDim.x < P.n_units;
     if (pf) {
       const uint32_t un = unit + gridDim.x, nb = un >> P.upb_shift, nu = un & ((1u << P.upb_shift) - 1u);
-      if constexpr (LM == 2) {
+      if constexpr (LM == 2 || LM == 4) {
+        constexpr uint32_t W = LM == 4 ? 16 : 8;
         if (tid == 0)
-          for (uint32_t ug = 0; ug < (1u << P.log2_units) / 8; ++ug) {
-            tma_prefetch_4d_col(&tmap_re, (nu << P.log2_units) + 8 * ug, nb);
-            tma_prefetch_4d_col(&tmap_im, (nu << P.log2_units) + 8 * ug, nb);
+          for (uint32_t ug = 0; ug < (1u << P.log2_units) / W; ++ug) {
+            tma_prefetch_4d_col(&tmap_re, (nu << P.log2_units) + W * ug, nb);
+            tma_prefetch_4d_col(&tmap_im, (nu << P.log2_units) + W * ug, nb);
           }
       } else if constexpr (LM == 1 || LM == 3) {
         if (tid == 0) {

@@ -115,8 +115,8 @@ struct KernelEntry {
 #define TFFT_KT(E, A, B, C) {E, A, B, C, fft_unit_kernel<E, A, B, C, 0>, fft_unit_kernel<E, A, B, C, 1>, nullptr, kThreads}
 // N <= 1024: the row tile uses SWIZZLE_32B atoms (load mode 3)
 #define TFFT_KS(E, A, B, C) {E, A, B, C, fft_unit_kernel<E, A, B, C, 0>, fft_unit_kernel<E, A, B, C, 3>, nullptr, kThreads}
-#define TFFT_KSC(E, A, B, C) \
-  {E, A, B, C, fft_unit_kernel<E, A, B, C, 0>, fft_unit_kernel<E, A, B, C, 3>, fft_unit_kernel<E, A, B, C, 2>, kThreads}
+#define TFFT_KSC(E, A, B, C) /* column passes of these lengths have >= 16 columns per unit: 16-column tiles (mode 4) */ \
+  {E, A, B, C, fft_unit_kernel<E, A, B, C, 0>, fft_unit_kernel<E, A, B, C, 3>, fft_unit_kernel<E, A, B, C, 4>, kThreads}
 #define TFFT_KTC(E, A, B, C) \
   {E, A, B, C, fft_unit_kernel<E, A, B, C, 0>, fft_unit_kernel<E, A, B, C, 1>, fft_unit_kernel<E, A, B, C, 2>, kThreads}
 // 32K-element units (one CTA per SM): 512 threads = four warp groups
@@ -147,7 +147,8 @@ KernelFn kernel_for(const UnitPlan& p, int* threads) {
         k.r1 == static_cast<int>(p.log2_radix[1]) && k.r2 == static_cast<int>(p.stages == 3 ? p.log2_radix[2] : 0) &&
         !(narrow && k.threads == 512)) {
       *threads = k.threads;
-      return p.tma_load == 2 ? k.fn_tma_col : (p.tma_load ? k.fn_tma : k.fn);   // tma_load 1 / 3: the entry's row-tile kernel
+      // tma_load 2 / 4: the entry's column-tile kernel; 1 / 3: its row-tile kernel
+      return (p.tma_load == 2 || p.tma_load == 4) ? k.fn_tma_col : (p.tma_load ? k.fn_tma : k.fn);
     }
   return nullptr;
 }
@@ -239,11 +240,13 @@ int make_col_tensor_map(const UnitPlan& plan, const __half* base, int64_t nstrid
   cuuint64_t gdim[4] = {static_cast<cuuint64_t>(columns), R, M, static_cast<cuuint64_t>(batches < 1 ? 1 : batches)};
   cuuint64_t gstride[3] = {M * static_cast<cuuint64_t>(nstride) * 2, static_cast<cuuint64_t>(nstride) * 2,
                            static_cast<cuuint64_t>(batch_stride) * 2};
-  cuuint32_t box[4] = {8, static_cast<cuuint32_t>(R), static_cast<cuuint32_t>(M), 1};
+  // mode 2: 8-column tiles, dense; mode 4: 16-column tiles (whole 32-byte sectors) as SWIZZLE_32B atoms
+  cuuint32_t box[4] = {plan.tma_load == 4 ? 16u : 8u, static_cast<cuuint32_t>(R), static_cast<cuuint32_t>(M), 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(base), gdim, gstride, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                      CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      plan.tma_load == 4 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? TFFT_OK : TFFT_E_INVALID_ARG;
 }
 
@@ -684,7 +687,7 @@ int launch_pass(const tfft_plan_s* p, const Pass& ps, const __half* src_re, cons
     const int64_t n_tr = tma_extent ? tma_extent : static_cast<int64_t>(ps.n_units) << plan.log2_units;
     const bool half_box = kernel2_for(plan, allow2) != nullptr;
     int rc;
-    if (plan.tma_load == 2) {
+    if (plan.tma_load == 2 || plan.tma_load == 4) {
       const int64_t columns = static_cast<int64_t>(plan.units_per_batch) << plan.log2_units;
       const int64_t batches = (ps.n_units + plan.units_per_batch - 1) / plan.units_per_batch;
       rc = make_col_tensor_map(plan, src_re, st.in_nstride, columns, batches, plan.in_batch_stride, &tmap_re);

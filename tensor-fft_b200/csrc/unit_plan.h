@@ -72,7 +72,10 @@ struct UnitPlan {
   uint32_t il_in, il_out;                  // TFFT_INTERLEAVED: this pass reads / writes half2 (re, im) elements (cp.async
                                            // load path only); the element offsets of the plan are doubled on the fly
   uint32_t prefetch_next;                  // 1: pull the next unit's input into L2 during this unit's stages
-  uint32_t tma_load;                       // 3: row-mode input with 16 or 32 rows per K line: SWIZZLE_32B MN-major atoms of
+  uint32_t tma_load;                       // 4: column-mode input, >= 16 columns per unit: tiles {16 columns, R kappa, M rows} per
+                                           //    16-column group as SWIZZLE_32B atoms: row = (u&15) + 16*(m + M*(u>>4)), element
+                                           //    (row, kappa) as in mode 3
+                                           // 3: row-mode input with 16 or 32 rows per K line: SWIZZLE_32B MN-major atoms of
                                            //    16 rows filled by TMA: element (row, kappa) at (row>>4)*32R + kappa*32 +
                                            //    (row&15)*2, byte-address bit 4 ^= bit 7
                                            // 2: column-mode input, stage-1 operand filled by TMA tiles {8 columns, R kappa,
@@ -209,7 +212,8 @@ inline bool build_unit_plan(const UnitShape& shape, UnitPlan* plan, PlanBuildInf
   if (shape.tma_load && shape.in_mode == kColMode && (lg - rho[0]) > 8) {
     info->error = "column-mode TMA load: more than 256 rows per K line"; return false;
   }
-  plan->tma_load = shape.tma_load ? (shape.in_mode == kColMode ? 2u : ((lg - rho[0]) < 6 ? 3u : 1u)) : 0u;
+  // column mode: tiles of 16 columns (full 32-byte sectors, SWIZZLE_32B atoms) when the unit has >= 16 columns
+  plan->tma_load = shape.tma_load ? (shape.in_mode == kColMode ? (ups >= 4 ? 4u : 2u) : ((lg - rho[0]) < 6 ? 3u : 1u)) : 0u;
   // the first-half epilogue of stage 2 writes the first half of stage 3's layout, which must lie inside the half of
   // stage 2's layout that its first-half MMAs have consumed: padded plane sizes shrink with the radix, so R_3 >= R_2
   const bool pipe2 = shape.pipe_stage2 && s == 3 && rho[2] >= rho[1];
@@ -266,6 +270,7 @@ inline bool build_unit_plan(const UnitShape& shape, UnitPlan* plan, PlanBuildInf
     if (t == 1) {
       for (int i = 0; i < 3; ++i)
         rb.push_back(shape.in_mode == kRowMode ? LBit{LBit::R, 0, (uint8_t)i} : LBit{LBit::U, 0, (uint8_t)i});
+      if (plan->tma_load == 4) rb.push_back({LBit::U, 0, 3});   // 16 columns = one atom of 16 rows
     } else {
       for (int i = 0; i < 3; ++i) rb.push_back({LBit::K, (uint8_t)(t - 1), (uint8_t)i});
     }

@@ -67,7 +67,19 @@ int plansim_run_ex(int log2_len, int log2_units, int in_mode_flags, int out_mode
     const uint32_t col_base = ((unit % P.units_per_batch) / P.col_div) * P.col_base_stride;
     std::vector<double> sre(smem_halves, NAN), sim(smem_halves, NAN);
     // ---------------- load: TMA tensor tile {64 rows, R kappa, M/64, U} with 128-byte swizzle ...
-    if (P.tma_load == 2) {   // column mode: tiles {8 columns, R kappa, M rows} per 8-column group, dense, no swizzle
+    if (P.tma_load == 4) {   // column mode, 16-column tiles as SWIZZLE_32B atoms: row = (u&15) + 16*(m + M*(u>>4))
+      const int R = 1 << P.log2_radix[0];
+      const int64_t M = L / R, U = int64_t(1) << P.log2_units;
+      for (int64_t u = 0; u < U; ++u)
+        for (int64_t m = 0; m < M; ++m)
+          for (int kap = 0; kap < R; ++kap) {
+            const int64_t row = (u & 15) + 16 * (m + M * (u >> 4));
+            uint32_t off = (uint32_t)((row >> 4) * 32 * R + kap * 32 + (row & 15) * 2);
+            off ^= ((off >> 7) & 1u) << 4;
+            const int64_t a = ibase + u + (kap * M + m) * strides9[1];
+            sre[off / 2] = rh(in_re[a], h); sim[off / 2] = rh(in_im[a], h);
+          }
+    } else if (P.tma_load == 2) {   // column mode: tiles {8 columns, R kappa, M rows} per 8-column group, dense, no swizzle
       const int R = 1 << P.log2_radix[0];
       const int64_t M = L / R, U = int64_t(1) << P.log2_units;
       for (int64_t ug = 0; ug < U / 8; ++ug)
@@ -138,7 +150,7 @@ int plansim_run_ex(int log2_len, int log2_units, int in_mode_flags, int out_mode
           std::vector<cd> a(R), y(R);
           for (int kap = 0; kap < R; ++kap) {
             uint32_t off = (row >> 3) * S + (kap >> 3) * kKGroupStride + (kap & 7) * 16 + (row & 7) * 2;
-            if (t == 1 && P.tma_load == 3) {
+            if (t == 1 && (P.tma_load == 3 || P.tma_load == 4)) {
               off = (row >> 4) * 32 * R + kap * 32 + (row & 15) * 2;
               off ^= ((off >> 7) & 1u) << 4;
             }
