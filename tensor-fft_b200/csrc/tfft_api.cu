@@ -128,6 +128,7 @@ const KernelEntry g_kernels[] = {
     TFFT_KS(13, 5, 5, 0), TFFT_KSC(14, 5, 5, 0),                    // 2^10
     TFFT_KT(13, 5, 6, 0), TFFT_KTC(14, 5, 6, 0),                       // 2^11
     TFFT_KT(13, 6, 6, 0), TFFT_KT(14, 6, 6, 0), TFFT_KW(15, 6, 6, 0), TFFT_KTC(15, 6, 6, 0),  // 2^12
+    {15, 5, 6, 0, fft_unit_kernel<15, 5, 6, 0, 0, 512>, nullptr, fft_unit_kernel<15, 5, 6, 0, 4, 512>, 512},   // 16 columns x 2^11
     TFFT_KT(13, 4, 4, 5), TFFT_KT(14, 4, 4, 5),                        // 2^13
     TFFT_KT(14, 4, 5, 5),                                              // 2^14
     TFFT_KT(14, 5, 5, 4),                                              // 2 rows x 2^13 (2-D row pass, Kronecker last stage)
@@ -389,7 +390,9 @@ int build_1d(tfft_plan_s* p) {
   if (p->flags & TFFT_INTERLEAVED) {
     if (lg > 24) return TFFT_E_UNSUPPORTED;   // three-pass sizes: planar only
   }
-  if (lg > 24) {
+  int three_from = 25;   // developer knob: three passes from this log2 length on (>= 24: all factors >= 256)
+  if (const char* e = getenv("TFFT_THREEPASS_LG")) three_from = std::max(24, atoi(e));
+  if (lg >= three_from && !(p->flags & (TFFT_INTERLEAVED | TFFT_PRESERVE_INPUT))) {
     // three passes: n = N1 * Na * Nb (each 2^8 .. 2^12), one transform at a time (exec loops over the batch).
     //   A: N2 = Na*Nb strided length-N1 transforms, times exp(-2*pi*i*k1*n2/n)            (column mode, in place)
     //   B: for every k1, Nb strided length-Na transforms of row k1, times exp(-2*pi*i*ka*b/N2)   (column mode, in place)
@@ -446,8 +449,8 @@ int build_1d(tfft_plan_s* p) {
   // transforms stored transposed: X[k1 + N1*k2].   
   // column-pass length 2^lg1, measured per size on B200 (tools/tune_fourstep.py): the balanced split except where it
   // would produce 2048-point units (40 KiB of DFT matrices -> one 16K-element CTA per SM): 2^19 = 512 x 1024 (-9 %),
-  // 2^21 = 4096 x 512 (-3 %), 2^22 = 4096 x 1024 (-26 %)
-  static const int kLg1[9] = {8, 9, 9, 9, 10, 12, 12, 12, 12};   // lg = 16 .. 24
+  // 2^21 = 4096 x 512 (-3 %), 2^22 = 4096 x 1024 (-26 %); 2^23 = 2048 x 4096 with 16-column units (-16 %)
+  static const int kLg1[9] = {8, 9, 9, 9, 10, 12, 12, 11, 12};   // lg = 16 .. 24
   int lg1 = kLg1[lg - 16];
   {   // tuner file / developer knob: length 2^lg1 of the column pass
     const char* e = getenv("TFFT_FOURSTEP_LG1");
@@ -464,6 +467,9 @@ int build_1d(tfft_plan_s* p) {
     UnitShape sh;
     sh.log2_len = lg1;
     sh.log2_units = std::max(3, unit_log2_elems(lg1) - lg1);
+    // 2048-point columns: 16 columns per unit (32K elements, 16-column tiles) instead of 8 (measured at 2^23 = 2048 x 4096:
+    // 2.23 -> 1.87 ms)
+    if (lg1 == 11 && getenv("TFFT_COL2048_U8") == nullptr) sh.log2_units = 4;
     sh.in_mode = kColMode;
     sh.out_mode = kColMode;
     sh.tma_load = knob(p->tune.tma_col, "TFFT_NO_TMA_COL", 1) && !interleaved;   // column tiles {8 columns, R, M} by TMA
