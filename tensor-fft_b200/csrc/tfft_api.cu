@@ -558,7 +558,7 @@ int build_2d(tfft_plan_s* p, std::vector<Pass>* passes, bool allow_tma) {
     sh.log2_units = yb ? yb : std::min(lgy, std::max(13 - lgx, unit_log2_elems(lgx) - lgx));
     int rho[kMaxStages];
     radix_schedule(yb ? lgx + yb : lgx, rho);
-    sh.tma_load = allow_tma && (lgx - rho[0]) >= 6 && knob(p->tune.tma, "TFFT_NO_TMA", 1);
+    sh.tma_load = allow_tma && (lgx - rho[0]) >= 4 && knob(p->tune.tma, "TFFT_NO_TMA", 1);   // 128-byte or 32-byte atoms
     sh.pipe_stage2 = sh.tma_load && lgx + yb >= 13 && knob(p->tune.pipe, "TFFT_NO_PIPE", 1);
     const int64_t U = int64_t(1) << sh.log2_units;
     UnitStrides st;
