@@ -584,6 +584,7 @@ int build_2d(tfft_plan_s* p, std::vector<Pass>* passes, bool allow_tma) {
     // (2 MiB jumps) before m, while the cp.async units of neighbouring CTAs sweep the rows together.  Four-step column
     // passes (row stride <= 8 KiB) gain 1-4 % from the tiles and keep them.
     sh.tma_load = getenv("TFFT_TMA_COL_2D") != nullptr;
+    if (lg2 == 11 && getenv("TFFT_2D_COL_U16")) sh.log2_units = 4;   // developer knob: 16 columns x 2048 (32-byte pieces)
     const int64_t U = int64_t(1) << sh.log2_units;
     UnitStrides st;
     st.in_nstride = nx << yb; st.out_nstride = nx << yb;
