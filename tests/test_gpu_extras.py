@@ -132,3 +132,55 @@ def test_interleaved_unsupported_combinations_fail_loudly():
         tfft.NativePlan(1 << 25, 1, tfft.TFFT_INTERLEAVED)
     with pytest.raises(tfft.TfftError):
         tfft.NativePlan(256 * 256, 1, tfft.TFFT_INTERLEAVED, shape2d=(256, 256))
+
+
+def test_dependent_launches_back_to_back_are_ordered():
+    """Every kernel is launched with programmatic stream serialization (the next kernel's prologue may start while the
+    previous one drains) and waits with griddepcontrol.wait before touching data.  A chain forward -> inverse ->
+    forward ... on ONE stream without host synchronisation must behave like serialized launches: after 2k launches
+    the data is back (up to fp16 rounding), and the result equals the same chain run with a sync after every launch."""
+    n, b = 16384, 1024
+    g = torch.Generator(device="cuda"); g.manual_seed(3)
+    x0 = (torch.randn(b * 2 * n, generator=g, device="cuda") * 0.5).to(torch.float16)
+    fwd = tfft.NativePlan(n, b, tfft.TFFT_UNSCALED)
+    inv = tfft.NativePlan(n, b, tfft.TFFT_INVERSE)
+
+    def chain(sync):
+        a, c = x0.clone(), torch.empty_like(x0)
+        for _ in range(4):
+            fwd.exec(a, a[n:], c, c[n:], 2 * n, 2 * n)
+            if sync:
+                torch.cuda.synchronize()
+            inv.exec(c, c[n:], a, a[n:], 2 * n, 2 * n)
+            if sync:
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        return a
+
+    a_async, a_sync = chain(False), chain(True)
+    assert bool(torch.equal(a_async, a_sync))
+    rel = float(torch.linalg.vector_norm(a_async.float() - x0.float()) / torch.linalg.vector_norm(x0.float()))
+    assert rel < 5e-3, rel
+
+
+def test_two_plans_on_two_streams_concurrently():
+    """Plans are immutable after creation: execs of different plans on different streams may overlap on the device
+    (CTAs of both kernels share SMs, shared memory and tensor memory) and must give the serial results."""
+    n1, b1, n2, b2 = 4096, 2048, 1 << 18, 8
+    g = torch.Generator(device="cuda"); g.manual_seed(4)
+    x1 = torch.randn(b1 * 2 * n1, generator=g, device="cuda").to(torch.float16)
+    x2 = torch.randn(b2 * 2 * n2, generator=g, device="cuda").to(torch.float16)
+    p1, p2 = tfft.NativePlan(n1, b1), tfft.NativePlan(n2, b2, tfft.TFFT_PRESERVE_INPUT)
+    w1, w2 = torch.empty_like(x1), torch.empty_like(x2)
+    p1.exec(x1, x1[n1:], w1, w1[n1:], 2 * n1, 2 * n1)
+    p2.exec(x2, x2[n2:], w2, w2[n2:], 2 * n2, 2 * n2)
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    y1, y2 = torch.empty_like(x1), torch.empty_like(x2)
+    for _ in range(5):
+        with torch.cuda.stream(s1):
+            p1.exec(x1, x1[n1:], y1, y1[n1:], 2 * n1, 2 * n1)
+        with torch.cuda.stream(s2):
+            p2.exec(x2, x2[n2:], y2, y2[n2:], 2 * n2, 2 * n2)
+    torch.cuda.synchronize()
+    assert bool(torch.equal(y1, w1)) and bool(torch.equal(y2, w2))
