@@ -407,6 +407,9 @@ int build_1d(tfft_plan_s* p) {
       UnitShape sh;
       sh.log2_len = lg1; sh.log2_units = std::max(3, unit_log2_elems(lg1) - lg1);
       sh.in_mode = kColMode; sh.out_mode = kColMode;
+      // column tiles by TMA as in the four-step pass: -5 % up to 2^27, +12 % at 2^28 / 2^29 (row strides of 1 MiB and
+      // more), measured with tools/bench_large.py
+      sh.tma_load = lg <= 27 && knob(p->tune.tma_col, "TFFT_NO_TMA_COL", 1) != 0;
       const int64_t U = int64_t(1) << sh.log2_units;
       UnitStrides st;
       st.in_nstride = N2; st.out_nstride = N2; st.in_unit_stride = U; st.out_unit_stride = U;
@@ -420,6 +423,7 @@ int build_1d(tfft_plan_s* p) {
       UnitShape sh;
       sh.log2_len = la; sh.log2_units = std::max(3, unit_log2_elems(la) - la);
       sh.in_mode = kColMode; sh.out_mode = kColMode;
+      sh.tma_load = lg <= 27 && knob(p->tune.tma_col, "TFFT_NO_TMA_COL", 1) != 0;
       const int64_t U = int64_t(1) << sh.log2_units;
       UnitStrides st;
       st.in_nstride = Nb; st.out_nstride = Nb; st.in_unit_stride = U; st.out_unit_stride = U;
