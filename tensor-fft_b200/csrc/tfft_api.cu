@@ -552,6 +552,14 @@ int build_2d(tfft_plan_s* p, std::vector<Pass>* passes, bool allow_tma) {
   if (yb < 0 || yb > 3 || !yb_ok(yb)) return TFFT_E_UNSUPPORTED;
   p->ybits = yb;
   const int64_t nx = p->nx, ny = p->ny, batch = p->batch;
+  // Tiled intermediate (TFFT_2D_TILED=1, experiment kept for the record): the row pass writes, into a plan-owned
+  // scratch, the operand order of the 8-column column units -- [k_y][x/8][y][x%8], one contiguous chunk per unit -- so
+  // that the column pass loads contiguous 128-byte lines instead of 16-byte pieces 2*nx elements apart, and writes the
+  // natural layout.  Correct (GPU suite passes) but measured SLOWER at C5 on B200: 1.33 ms against 0.78 ms -- the row
+  // pass's stores become 16-byte pieces 64 KiB apart, which costs more than the column pass's loads gain.
+  const int lg2c = lgy - yb;
+  const bool tiled = getenv("TFFT_2D_TILED") != nullptr && std::max(3, unit_log2_elems(lg2c) - lg2c) == 3;
+  const int64_t rows2 = ny >> yb;
   std::vector<Pass> saved;
   saved.swap(p->passes);
   bool ok = true;
@@ -573,7 +581,13 @@ int build_2d(tfft_plan_s* p, std::vector<Pass>* passes, bool allow_tma) {
     st.units_per_batch = static_cast<uint32_t>(ny / U);
     st.col_base_stride = 1;   // Kronecker row twiddle: col_base = y_lo
     st.kron_log2n = yb ? static_cast<uint32_t>(lgy) : 0u;
-    ok = add_pass(p, sh, st, static_cast<uint32_t>(batch * (ny / U)), 0, 1, true, true);
+    if (tiled) {
+      st.out_tstride = yb ? rows2 * nx : 8;      // output row k_y: next block of chunks / next row inside a chunk
+      st.out_unit_stride = yb ? 8 : U * 8;       // unit = y_lo (Kronecker) or U consecutive rows
+      st.out_hi_from = 3;
+      st.out_hi_stride = rows2 * 8;              // x / 8 selects the chunk
+    }
+    ok = add_pass(p, sh, st, static_cast<uint32_t>(batch * (ny / U)), 0, tiled ? 2 : 1, true, true);
     if (ok) p->passes.back().kind = 1;
   }
   if (ok) {
@@ -593,12 +607,23 @@ int build_2d(tfft_plan_s* p, std::vector<Pass>* passes, bool allow_tma) {
     UnitStrides st;
     st.in_nstride = nx << yb; st.out_nstride = nx << yb;
     st.in_unit_stride = U; st.out_unit_stride = U;
+    if (tiled) {   // unit uu = k_y * (nx/8) + x/8 is the uu-th contiguous chunk of rows2 x 8 elements
+      st.in_nstride = 8;
+      st.in_unit_stride = rows2 * 8;
+    }
     st.units_per_batch = static_cast<uint32_t>((nx << yb) / U);
-    ok = add_pass(p, sh, st, static_cast<uint32_t>(batch * ((nx << yb) / U)), 1, 1, true, true);
+    ok = add_pass(p, sh, st, static_cast<uint32_t>(batch * ((nx << yb) / U)), tiled ? 2 : 1, 1, true, true);
     if (ok) p->passes.back().kind = 2;
   }
   passes->swap(p->passes);
   if (passes != &p->passes) p->passes.swap(saved);
+  if (ok && tiled && !p->workspace) {
+    p->workspace_bytes = 2 * p->n * batch * static_cast<int64_t>(sizeof(__half));
+    if (cudaMalloc(&p->workspace, p->workspace_bytes) != cudaSuccess) {
+      cudaGetLastError();
+      return TFFT_E_NOMEM;
+    }
+  }
   return ok ? TFFT_OK : TFFT_E_UNSUPPORTED;
 }
 

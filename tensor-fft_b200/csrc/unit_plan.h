@@ -469,6 +469,8 @@ struct UnitStrides {
   uint32_t n_transforms = 0;
   uint32_t pass1_log2n = 0;  // != 0: multiply outputs by exp(-2*pi*i*o*(col_base+u)/2^pass1_log2n)
   uint32_t tma_batch_step = 0;
+  int64_t out_hi_stride = 0;   // tiled row-mode output (2-D row pass writing the column units' operand order):
+  int out_hi_from = 0;         //   output-index bit i >= out_hi_from has stride out_hi_stride << (i - out_hi_from)
   uint32_t kron_log2n = 0;   // Kronecker units, != 0: multiply output row k_y by exp(-2*pi*i*k_y*col_base/2^kron_log2n)
 };
 
@@ -489,7 +491,11 @@ inline void fill_strides(const UnitStrides& st, const PlanBuildInfo& info, UnitP
     if (info.kron_bits && b.kind == LBit::K && b.stage == s && b.idx >= info.rx[s - 1])   // output row bit
       return static_cast<uint32_t>(st.out_tstride << (b.idx - info.rx[s - 1]));
     if (b.kind == LBit::U) return static_cast<uint32_t>((plan->out_mode == kRowMode ? st.out_tstride : 1) << b.idx);
-    return static_cast<uint32_t>(o_weight(b) * (plan->out_mode == kRowMode ? 1 : st.out_nstride));
+    const int64_t w = o_weight(b);
+    // row-mode output into a tiled layout: output-index bits >= out_hi_from advance by out_hi_stride per unit step
+    if (plan->out_mode == kRowMode && st.out_hi_stride && w >= (int64_t(1) << st.out_hi_from))
+      return static_cast<uint32_t>((w >> st.out_hi_from) * st.out_hi_stride);
+    return static_cast<uint32_t>(w * (plan->out_mode == kRowMode ? 1 : st.out_nstride));
   };
   for (size_t i = 0; i < info.store_bits.size(); ++i) plan->store_gofs[i] = out_contrib(info.store_bits[i]);
   for (int i = 0; i < 3; ++i) plan->store_cg[i] = out_contrib({LBit::K, (uint8_t)s, (uint8_t)i});

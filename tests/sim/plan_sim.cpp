@@ -37,7 +37,8 @@ extern "C" {
 // Runs `n_units` units.  in/out are planar double arrays (element offsets as the plan says).
 // Returns the total number of bank conflicts found (negative = plan error).
 // conflicts[0..3] = load stores, epilogue stores, store-phase loads, (unused)
-// ext3 (may be null): {kron_bits, kron_log2n, col_base_stride} for Kronecker (2-D row pass) units
+// ext3 (may be null): {kron_bits, kron_log2n, col_base_stride, out_hi_from, out_hi_stride} for Kronecker (2-D row pass)
+// units; the last two (0 = off) describe a tiled row-mode output
 int plansim_run_ex(int log2_len, int log2_units, int in_mode_flags, int out_mode, const int64_t* strides9,
                    int pass1_log2n, int n_units, const double* in_re, const double* in_im,
                    double* out_re, double* out_im, int emulate_fp16, int* conflicts, const int64_t* ext3) {
@@ -54,7 +55,7 @@ int plansim_run_ex(int log2_len, int log2_units, int in_mode_flags, int out_mode
   st.out_unit_stride = strides9[7]; st.units_per_batch = (uint32_t)strides9[8]; st.col_base_stride = 1u << log2_units;
   st.n_units = (uint32_t)n_units;
   st.pass1_log2n = pass1_log2n;
-  if (ext3) { st.kron_log2n = (uint32_t)ext3[1]; st.col_base_stride = (uint32_t)ext3[2]; }
+  if (ext3) { st.kron_log2n = (uint32_t)ext3[1]; st.col_base_stride = (uint32_t)ext3[2]; st.out_hi_from = (int)ext3[3]; st.out_hi_stride = ext3[4]; }
   fill_strides(st, info, &P);
   const bool h = emulate_fp16 != 0;
   const int s = P.stages;

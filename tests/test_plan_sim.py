@@ -110,7 +110,7 @@ def test_two_d_passes(sim, lgy, lgx, yb, flags):
         ups = 14 - lgx
         U = 1 << ups
         st = (ctypes.c_int64 * 9)(nx, 1, nx, 1, 0, U * nx, 0, U * nx, ny // U)
-    ext = (ctypes.c_int64 * 3)(yb, lgy if yb else 0, 1)
+    ext = (ctypes.c_int64 * 5)(yb, lgy if yb else 0, 1, 0, 0)
     rc1 = sim.plansim_run_ex(lgx, ups, flags, 0, st, 0, ny // U, re.ctypes.data_as(dp), im.ctypes.data_as(dp),
                              t_re.ctypes.data_as(dp), t_im.ctypes.data_as(dp), 0, conf, ext)
     c1 = list(conf)[:3]
@@ -147,7 +147,7 @@ def test_kronecker_units_of_large_images(sim, lgy, lgx, yb, flags):
     o_re, o_im = np.zeros(2 * U * nx), np.zeros(2 * U * nx)
     conf = (ctypes.c_int * 4)()
     st = (ctypes.c_int64 * 9)(span, 1, nx, 1, 0, nx, 0, U * nx, ny // U)
-    ext = (ctypes.c_int64 * 3)(yb, lgy, 1)
+    ext = (ctypes.c_int64 * 5)(yb, lgy, 1, 0, 0)
     # the simulator numbers units from 0: shift so that unit index == y_lo by passing pointers moved back by 5 units
     shift_in, shift_out = y_los[0] * nx, y_los[0] * U * nx
     full_re, full_im = np.zeros(shift_in + size_in), np.zeros(shift_in + size_in)
@@ -161,3 +161,32 @@ def test_kronecker_units_of_large_images(sim, lgy, lgx, yb, flags):
         x = np.stack([rows[(yl, u)] for u in range(U)])
         want = np.fft.fft2(x) / (U * nx) * np.exp(-2j * np.pi * np.arange(U) * yl / ny)[:, None]
         assert np.linalg.norm(got[i] - want) / np.linalg.norm(want) < 1e-13
+
+
+@pytest.mark.parametrize("lgy,lgx,yb,flags", [(11, 12, 1, 6)])
+def test_two_d_passes_with_tiled_intermediate(sim, lgy, lgx, yb, flags):
+    """Same 2-D transform, but the row pass writes the intermediate in the column units' operand order
+    [k_y][x/8][y_lo][x%8] (one contiguous chunk per column unit) and the column pass reads it with a 16-byte row
+    stride and writes the natural layout."""
+    sim.plansim_run_ex.argtypes = list(sim.plansim_run.argtypes) + [ctypes.POINTER(ctypes.c_int64)]
+    ny, nx, U = 1 << lgy, 1 << lgx, 1 << yb
+    n = ny * nx
+    rng = np.random.default_rng(12)
+    re, im = rng.standard_normal(n), rng.standard_normal(n)
+    t_re, t_im, o_re, o_im = np.zeros(n), np.zeros(n), np.zeros(n), np.zeros(n)
+    conf = (ctypes.c_int * 4)()
+    rows2 = ny >> yb                                            # column-pass length
+    st = (ctypes.c_int64 * 9)(rows2 * nx, 1, rows2 * nx, 1, 0, nx, 0, 8, ny // U)   # out: k_y stride, unit (y_lo) stride 8
+    ext = (ctypes.c_int64 * 5)(yb, lgy, 1, 3, rows2 * 8)
+    rc1 = sim.plansim_run_ex(lgx, yb, flags, 0, st, 0, ny // U, re.ctypes.data_as(dp), im.ctypes.data_as(dp),
+                             t_re.ctypes.data_as(dp), t_im.ctypes.data_as(dp), 0, conf, ext)
+    c1 = list(conf)[:3]
+    lg2, u2 = lgy - yb, 3
+    # column units: 8 columns, input row stride 8 (contiguous chunk of rows2*8 elements per unit), natural output
+    st = (ctypes.c_int64 * 9)(0, 8, 0, nx << yb, 0, rows2 * 8, 0, 8, 1 << 30)
+    rc2 = sim.plansim_run(lg2, u2, 1, 1, st, 0, (nx << yb) // 8, t_re.ctypes.data_as(dp), t_im.ctypes.data_as(dp),
+                          o_re.ctypes.data_as(dp), o_im.ctypes.data_as(dp), 0, conf)
+    want = np.fft.fft2((re + 1j * im).reshape(ny, nx)) / n
+    got = (o_re + 1j * o_im).reshape(ny, nx)
+    assert rc1 == 0 and rc2 == 0 and c1 == [0, 0, 0] and list(conf)[:3] == [0, 0, 0]
+    assert np.linalg.norm(got - want) / np.linalg.norm(want) < 1e-13
