@@ -921,8 +921,13 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
     run_stage<0, RHO0, false, LOG2E, LM, false, NoHook, 0, NG>(P, c, table_base + TL.b_off[0], bar, phase, warp, lane,
                                                                 trace, trace_unit, tmap0, 0u);
     TFFT_TRACE_MARK(3);
-    run_stage<1, RHO1, kStages == 2, LOG2E, 0, false, NoHook, 0, NG>(P, c, table_base + TL.b_off[1], bar, phase, warp,
-                                                                         lane, trace, trace_unit, tmap1, col_thr);
+    // 3-stage plans built with pipe_stage2: the epilogue of stage 2's first tile half overlaps the UMMAs of its second
+    if (kStages == 3 && P.pipe_stage2)
+      run_stage<1, RHO1, kStages == 2, LOG2E, 0, true, NoHook, 0, NG>(P, c, table_base + TL.b_off[1], bar, phase, warp,
+                                                                          lane, trace, trace_unit, tmap1, col_thr);
+    else
+      run_stage<1, RHO1, kStages == 2, LOG2E, 0, false, NoHook, 0, NG>(P, c, table_base + TL.b_off[1], bar, phase, warp,
+                                                                           lane, trace, trace_unit, tmap1, col_thr);
     TFFT_TRACE_MARK(4);
     if constexpr (kStages == 3)
       run_stage<2, (RHO2 ? RHO2 : 4), true, LOG2E, 0, false, NoHook, 0, NG>(P, c, table_base + TL.b_off[2], bar, phase,
