@@ -184,3 +184,26 @@ def test_two_plans_on_two_streams_concurrently():
             p2.exec(x2, x2[n2:], y2, y2[n2:], 2 * n2, 2 * n2)
     torch.cuda.synchronize()
     assert bool(torch.equal(y1, w1)) and bool(torch.equal(y2, w2))
+
+
+def test_four_step_odd_batch_stride_takes_the_cp_async_twin():
+    """The four-step row pass loads TMA row tiles when the batch stride is a whole number of rows; any other stride
+    (multiple of 8 elements) must still work, through the cp.async twin of that pass, with identical bits."""
+    n, b = 1 << 16, 3
+    re, im = O.gauss_fixture(n, b, seed=91)
+    want = None
+    for stride in (2 * n, 2 * n + 8, 2 * n + 264):
+        buf = np.zeros((b, stride), dtype=np.float16)
+        buf[:, :n], buf[:, n:2 * n] = re, im
+        x = torch.from_numpy(buf).cuda().reshape(-1)
+        y = torch.empty(b * 2 * n, dtype=torch.float16, device="cuda")
+        plan = tfft.NativePlan(n, b)
+        plan.exec(x, x[n:], y, y[n:], stride, 2 * n)
+        torch.cuda.synchronize()
+        if want is None:
+            want = y.clone()
+            w_re, w_im = O.fft_f64(re.astype(np.float64), im.astype(np.float64))
+            got = y.view(b, 2, n).cpu().numpy().astype(np.float64)
+            assert O.error_stats(got[:, 0], got[:, 1], w_re, w_im)["rel_l2"] <= 9.0e-4
+        else:
+            assert bool(torch.equal(y, want)), stride
