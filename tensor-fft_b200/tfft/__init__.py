@@ -257,6 +257,8 @@ def create_plan_from_file(fft_length: int, tuner_results_file: str) -> Optional[
                 parts = line.split()
                 if parts and int(float(parts[0])) == fft_length:
                     mode = MODE_256 if int(parts[1]) == 256 else MODE_4096
+                    global _tuner_file
+                    _tuner_file = tuner_results_file   # compute_fft builds its native plans from this file
                     return create_plan(fft_length, mode, int(parts[2]), int(parts[3]), int(parts[4]))
     except OSError:
         print("Error! Failed to open tuner file.")
@@ -334,6 +336,7 @@ class DataBatchHandler(DataHandler):
 
 
 _plan_cache: dict = {}
+_tuner_file: Optional[str] = None   # set by create_plan_from_file (the key=value knobs of the same lines steer the kernels)
 
 
 def compute_fft(fft_plan: Plan, data: DataHandler, max_no_optin_shared_mem: int = 32768) -> Optional[str]:
@@ -345,10 +348,16 @@ def compute_fft(fft_plan: Plan, data: DataHandler, max_no_optin_shared_mem: int 
     if n != data.fft_length_:
         return "plan / data handler length mismatch"
     try:
-        key = (n, b, data.dptr_data_.device.index)
+        key = (n, b, data.dptr_data_.device.index, _tuner_file)
         native = _plan_cache.get(key)
         if native is None:
-            native = _plan_cache[key] = NativePlan(n, b)
+            try:
+                native = NativePlan(n, b, tuner_file=_tuner_file)
+            except TfftError:
+                if _tuner_file is None:
+                    raise
+                native = NativePlan(n, b)           # length not in the file: default knobs
+            _plan_cache[key] = native
         buf = data.dptr_data_
         half = 2 * n * b
         native.exec(buf[0:], buf[n:], buf[half:], buf[half + n:], 2 * n, 2 * n)
