@@ -120,15 +120,16 @@ __device__ __forceinline__ uint4 ldg128(const void* p) {
                : "l"(p));
   return r;
 }
-// The transform streams: every byte is read once and written once, so loads and stores are marked evict-first in L2
-// (C2 on B200: 121.1 -> 119.2 us; -DTFFT_NO_L2_HINTS builds without).
+// The transform streams: every byte is read once and written once.  The TMA loads carry an L2 evict-first policy
+// (C2 on B200: -1.6 %; -DTFFT_NO_L2_HINTS builds without).  The same policy on the global stores was measured to cost
+// 1.7 % (123.2 -> 121.3 us without it on the same box), so stores carry no hint (-DTFFT_L2_HINT_STORE adds it).
 __device__ __forceinline__ uint64_t l2_evict_first() {
   uint64_t p;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
 __device__ __forceinline__ void stg128(__half* p, uint4 v) {
-#ifndef TFFT_NO_L2_HINTS
+#if defined(TFFT_L2_HINT_STORE)
   asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y),
                "r"(v.z), "r"(v.w), "l"(l2_evict_first())
                : "memory");
