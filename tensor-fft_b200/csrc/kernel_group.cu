@@ -1,0 +1,60 @@
+// One group of instantiations of the fused FFT kernel (fft_unit_kernel.cuh); see kernel_table.h.
+#include "fft_unit_kernel.cuh"
+#include "kernel_table.h"
+
+#ifndef TFFT_GROUP
+#error "build with -DTFFT_GROUP=0..4"
+#endif
+
+namespace tfft {
+
+#define TFFT_KT(E, A, B, C) {E, A, B, C, fft_unit_kernel<E, A, B, C, 0>, fft_unit_kernel<E, A, B, C, 1>, nullptr, kThreads}
+// N <= 1024: the row tile uses SWIZZLE_32B atoms (load mode 3)
+#define TFFT_KS(E, A, B, C) {E, A, B, C, fft_unit_kernel<E, A, B, C, 0>, fft_unit_kernel<E, A, B, C, 3>, nullptr, kThreads}
+#define TFFT_KSC(E, A, B, C) /* column passes of these lengths have >= 16 columns per unit: 16-column tiles (mode 4) */ \
+  {E, A, B, C, fft_unit_kernel<E, A, B, C, 0>, fft_unit_kernel<E, A, B, C, 3>, fft_unit_kernel<E, A, B, C, 4>, kThreads}
+#define TFFT_KTC(E, A, B, C) \
+  {E, A, B, C, fft_unit_kernel<E, A, B, C, 0>, fft_unit_kernel<E, A, B, C, 1>, fft_unit_kernel<E, A, B, C, 2>, kThreads}
+// 32K-element units (one CTA per SM): 512 threads = four warp groups
+#define TFFT_KW(E, A, B, C) \
+  {E, A, B, C, fft_unit_kernel<E, A, B, C, 0, 512>, fft_unit_kernel<E, A, B, C, 1, 512>, fft_unit_kernel<E, A, B, C, 2, 512>, 512}
+
+static const KernelEntry g_entries[] = {
+#if TFFT_GROUP == 0
+    TFFT_KS(13, 4, 4, 0), TFFT_KSC(14, 4, 4, 0),                    // L = 2^8
+    TFFT_KS(13, 4, 5, 0), TFFT_KSC(14, 4, 5, 0),                    // 2^9
+#elif TFFT_GROUP == 1
+    TFFT_KS(13, 5, 5, 0), TFFT_KSC(14, 5, 5, 0),                    // 2^10
+    TFFT_KT(13, 5, 6, 0), TFFT_KTC(14, 5, 6, 0),                    // 2^11
+#elif TFFT_GROUP == 2
+    TFFT_KT(13, 6, 6, 0), TFFT_KT(14, 6, 6, 0), TFFT_KW(15, 6, 6, 0), TFFT_KTC(15, 6, 6, 0),  // 2^12
+    {15, 5, 6, 0, fft_unit_kernel<15, 5, 6, 0, 0, 512>, nullptr, fft_unit_kernel<15, 5, 6, 0, 4, 512>, 512},   // 16 columns x 2^11
+#elif TFFT_GROUP == 3
+    TFFT_KT(13, 4, 4, 5), TFFT_KT(14, 4, 4, 5),                     // 2^13
+    TFFT_KT(14, 4, 5, 5),                                           // 2^14
+    TFFT_KT(14, 5, 5, 4),                                           // 2 rows x 2^13 (2-D row pass, Kronecker last stage)
+#else
+    TFFT_KW(15, 5, 5, 5), TFFT_KT(15, 5, 5, 5),                     // 2^15
+#endif
+};
+
+#define TFFT_CAT2(a, b) a##b
+#define TFFT_CAT(a, b) TFFT_CAT2(a, b)
+const KernelEntry* TFFT_CAT(kernel_group_, TFFT_GROUP)(int* count) {
+  *count = static_cast<int>(sizeof(g_entries) / sizeof(g_entries[0]));
+  return g_entries;
+}
+
+#if TFFT_GROUP == 4
+static const Kernel2Entry g_entries2[] = {
+    {4, 4, 5, fft_unit_kernel_2slot<4, 4, 5>},
+    {4, 5, 5, fft_unit_kernel_2slot<4, 5, 5>},
+    {5, 5, 4, fft_unit_kernel_2slot<5, 5, 4>},
+};
+const Kernel2Entry* kernel2_group(int* count) {
+  *count = static_cast<int>(sizeof(g_entries2) / sizeof(g_entries2[0]));
+  return g_entries2;
+}
+#endif
+
+}  // namespace tfft

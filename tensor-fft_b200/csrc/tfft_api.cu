@@ -16,12 +16,32 @@
 
 #include "../../include/tfft.h"
 #include "fft_unit_kernel.cuh"
+#include "kernel_table.h"
 #include "harness_kernels.cuh"
 #include "exchange_kernels.cuh"
 
 namespace {
 
 using namespace tfft;
+
+// Everything a launch needs besides the destination pointers.  Building it costs two cuTensorMapEncodeTiled calls, the
+// stride fill and an occupancy query; it only depends on (device, source pointers, strides, fused-twiddle arguments),
+// so each pass keeps the last few in a small cache (a plan that is executed again on the same buffers -- the
+// reference's DataHandler usage, src/base/DataHandler.h:22-82 -- pays for it once).
+struct Prepared {
+  int dev = -1;
+  const void *sre = nullptr, *sim = nullptr;
+  int64_t in_stride = 0, out_stride = 0, tw_first_col = 0;
+  int tw_log2 = 0;
+  UnitPlan plan;
+  alignas(64) CUtensorMap tmap_re, tmap_im;
+  const void* fn = nullptr;
+  const uint4* tables = nullptr;
+  unsigned grid = 0, block = 0;
+  uint32_t smem = 0;
+  bool two_slot = false;
+};
+constexpr size_t kPreparedSlots = 4;
 
 struct Pass {
   UnitPlan plan;           // layout decisions (strides filled per exec)
@@ -37,6 +57,8 @@ struct Pass {
   bool own_batch_strides = false;   // three-pass plans: the batch level of the unit addressing is internal
   bool il_in = false, il_out = false;   // TFFT_INTERLEAVED: the pass reads / writes half2 elements
   int kind = 0;                     // 0: 1-D passes; 1: 2-D row pass (row mode, unit = U rows of one image); 2: 2-D column pass
+  mutable std::vector<Prepared> prepared;   // launch cache (see prepare_launch), guarded by g_upload_mutex
+  mutable size_t prepared_next = 0;
 };
 
 int ilog2_exact(int64_t n) {
@@ -101,68 +123,46 @@ std::vector<uint8_t> make_tables(const UnitPlan& plan, bool unscaled) {
 
 long long* g_trace = nullptr;   // developer phase trace buffer (tfft_debug_set_trace)
 std::mutex g_upload_mutex;
-// Kernel instantiations: one per (unit size, radix schedule) the planner can produce.
-typedef void (*KernelFn)(const UnitPlan, const __half*, const __half*, __half*, __half*, const uint4*, long long*,
-                         const CUtensorMap, const CUtensorMap);
-struct KernelEntry {
-  int log2e, r0, r1, r2;
-  KernelFn fn, fn_tma;   // fn_tma: stage-1 operand loaded by TMA (row-mode input, >= 64 rows per K line)
-  KernelFn fn_tma_col;   // column-mode input loaded by TMA tiles of 8 columns (the 16K/32K-element units of column passes)
-  int threads;
-};
-#define TFFT_K(E, A, B, C) {E, A, B, C, fft_unit_kernel<E, A, B, C, 0>, nullptr, nullptr, kThreads}
-#define TFFT_KC(E, A, B, C) {E, A, B, C, fft_unit_kernel<E, A, B, C, 0>, nullptr, fft_unit_kernel<E, A, B, C, 2>, kThreads}
-#define TFFT_KT(E, A, B, C) {E, A, B, C, fft_unit_kernel<E, A, B, C, 0>, fft_unit_kernel<E, A, B, C, 1>, nullptr, kThreads}
-// N <= 1024: the row tile uses SWIZZLE_32B atoms (load mode 3)
-#define TFFT_KS(E, A, B, C) {E, A, B, C, fft_unit_kernel<E, A, B, C, 0>, fft_unit_kernel<E, A, B, C, 3>, nullptr, kThreads}
-#define TFFT_KSC(E, A, B, C) /* column passes of these lengths have >= 16 columns per unit: 16-column tiles (mode 4) */ \
-  {E, A, B, C, fft_unit_kernel<E, A, B, C, 0>, fft_unit_kernel<E, A, B, C, 3>, fft_unit_kernel<E, A, B, C, 4>, kThreads}
-#define TFFT_KTC(E, A, B, C) \
-  {E, A, B, C, fft_unit_kernel<E, A, B, C, 0>, fft_unit_kernel<E, A, B, C, 1>, fft_unit_kernel<E, A, B, C, 2>, kThreads}
-// 32K-element units (one CTA per SM): 512 threads = four warp groups
-#define TFFT_KW(E, A, B, C) \
-  {E, A, B, C, fft_unit_kernel<E, A, B, C, 0, 512>, fft_unit_kernel<E, A, B, C, 1, 512>, fft_unit_kernel<E, A, B, C, 2, 512>, 512}
-const KernelEntry g_kernels[] = {
-    TFFT_KS(13, 4, 4, 0), TFFT_KSC(14, 4, 4, 0),                    // L = 2^8
-    TFFT_KS(13, 4, 5, 0), TFFT_KSC(14, 4, 5, 0),                    // 2^9
-    TFFT_KS(13, 5, 5, 0), TFFT_KSC(14, 5, 5, 0),                    // 2^10
-    TFFT_KT(13, 5, 6, 0), TFFT_KTC(14, 5, 6, 0),                       // 2^11
-    TFFT_KT(13, 6, 6, 0), TFFT_KT(14, 6, 6, 0), TFFT_KW(15, 6, 6, 0), TFFT_KTC(15, 6, 6, 0),  // 2^12
-    {15, 5, 6, 0, fft_unit_kernel<15, 5, 6, 0, 0, 512>, nullptr, fft_unit_kernel<15, 5, 6, 0, 4, 512>, 512},   // 16 columns x 2^11
-    TFFT_KT(13, 4, 4, 5), TFFT_KT(14, 4, 4, 5),                        // 2^13
-    TFFT_KT(14, 4, 5, 5),                                              // 2^14
-    TFFT_KT(14, 5, 5, 4),                                              // 2 rows x 2^13 (2-D row pass, Kronecker last stage)
-    TFFT_KW(15, 5, 5, 5), TFFT_KT(15, 5, 5, 5),                        // 2^15
-};
-#undef TFFT_K
-#undef TFFT_KT
-#undef TFFT_KW
-#undef TFFT_KS
-#undef TFFT_KSC
-#undef TFFT_KC
-#undef TFFT_KTC
+
+// Developer knobs (A/B switches used by tools/ and a few tests) are environment variables that are honoured ONLY when
+// TFFT_DEVELOPER is set: a production process cannot be steered by a stray TFFT_* variable.  The supported ways to
+// configure a plan are the flags of tfft_plan_create and the tuner file (tfft_plan_create_from_file / TFFT_TUNER_FILE).
+const char* dev_env(const char* name) {
+  static const bool on = getenv("TFFT_DEVELOPER") != nullptr;
+  return on ? getenv(name) : nullptr;
+}
+// Kernel instantiations: one per (unit size, radix schedule) the planner can produce (kernel_table.h / kernel_group.cu).
 KernelFn kernel_for(const UnitPlan& p, int* threads) {
-  static const bool narrow = getenv("TFFT_NARROW_32K") != nullptr;   // developer A/B: 256-thread CTAs for 32K-element units
-  for (const KernelEntry& k : g_kernels)
-    if (k.log2e == static_cast<int>(p.log2_elems) && k.r0 == static_cast<int>(p.log2_radix[0]) &&
-        k.r1 == static_cast<int>(p.log2_radix[1]) && k.r2 == static_cast<int>(p.stages == 3 ? p.log2_radix[2] : 0) &&
-        !(narrow && k.threads == 512)) {
-      *threads = k.threads;
-      // tma_load 2 / 4: the entry's column-tile kernel; 1 / 3: its row-tile kernel
-      return (p.tma_load == 2 || p.tma_load == 4) ? k.fn_tma_col : (p.tma_load ? k.fn_tma : k.fn);
+  static const bool narrow = dev_env("TFFT_NARROW_32K") != nullptr;   // developer A/B: 256-thread CTAs for 32K-element units
+  typedef const KernelEntry* (*GroupFn)(int*);
+  static const GroupFn groups[kKernelGroups] = {kernel_group_0, kernel_group_1, kernel_group_2, kernel_group_3, kernel_group_4};
+  for (GroupFn g : groups) {
+    int count = 0;
+    const KernelEntry* e = g(&count);
+    for (int i = 0; i < count; ++i) {
+      const KernelEntry& k = e[i];
+      if (k.log2e == static_cast<int>(p.log2_elems) && k.r0 == static_cast<int>(p.log2_radix[0]) &&
+          k.r1 == static_cast<int>(p.log2_radix[1]) && k.r2 == static_cast<int>(p.stages == 3 ? p.log2_radix[2] : 0) &&
+          !(narrow && k.threads == 512)) {
+        *threads = k.threads;
+        // tma_load 2 / 4: the entry's column-tile kernel; 1 / 3: its row-tile kernel
+        return (p.tma_load == 2 || p.tma_load == 4) ? k.fn_tma_col : (p.tma_load ? k.fn_tma : k.fn);
+      }
     }
+  }
   return nullptr;
 }
 
 // Two-slot variant (one CTA per SM, two units in flight, shared landing buffer) for 16K-element units
-typedef void (*Kernel2Fn)(const UnitPlan, __half*, __half*, const uint4*, const CUtensorMap, const CUtensorMap,
-                          long long*);
 Kernel2Fn kernel2_for(const UnitPlan& p, bool allowed = true) {
   if (!allowed || p.tma_load != 1 || p.log2_elems != 14 || p.stages != 3) return nullptr;
   if (smem2_layout(p).total > 227 * 1024) return nullptr;   // e.g. three distinct DFT matrices
-  if (p.log2_radix[0] == 4 && p.log2_radix[1] == 4 && p.log2_radix[2] == 5) return fft_unit_kernel_2slot<4, 4, 5>;
-  if (p.log2_radix[0] == 4 && p.log2_radix[1] == 5 && p.log2_radix[2] == 5) return fft_unit_kernel_2slot<4, 5, 5>;
-  if (p.log2_radix[0] == 5 && p.log2_radix[1] == 5 && p.log2_radix[2] == 4) return fft_unit_kernel_2slot<5, 5, 4>;
+  int count = 0;
+  const Kernel2Entry* e = kernel2_group(&count);
+  for (int i = 0; i < count; ++i)
+    if (e[i].r0 == static_cast<int>(p.log2_radix[0]) && e[i].r1 == static_cast<int>(p.log2_radix[1]) &&
+        e[i].r2 == static_cast<int>(p.log2_radix[2]))
+      return e[i].fn;
   return nullptr;
 }
 
@@ -254,7 +254,7 @@ int make_col_tensor_map(const UnitPlan& plan, const __half* base, int64_t nstrid
 // All kernels are launched with programmatic stream serialization: a kernel's CTAs may become resident while its
 // predecessor in the stream drains; the kernels themselves wait (griddepcontrol.wait) before they touch data.
 cudaError_t launch_pdl(const void* fn, unsigned grid, unsigned block, void** args, size_t smem, cudaStream_t stream) {
-  static const bool no_pdl = getenv("TFFT_NO_PDL") != nullptr;
+  static const bool no_pdl = dev_env("TFFT_NO_PDL") != nullptr;
   if (no_pdl) return cudaLaunchKernel(fn, dim3(grid), dim3(block), args, smem, stream);
   cudaLaunchConfig_t cfg;
   std::memset(&cfg, 0, sizeof(cfg));
@@ -268,22 +268,6 @@ cudaError_t launch_pdl(const void* fn, unsigned grid, unsigned block, void** arg
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return cudaLaunchKernelExC(&cfg, fn, args);
-}
-
-std::once_flag g_attr_once;
-int g_attr_err = 0;
-void set_kernel_attrs() {
-  for (const KernelEntry& k : g_kernels)
-    for (KernelFn fn : {k.fn, k.fn_tma, k.fn_tma_col}) {
-      if (!fn) continue;
-      cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      if (e != cudaSuccess) g_attr_err = static_cast<int>(e);
-    }
-  for (Kernel2Fn fn : {static_cast<Kernel2Fn>(fft_unit_kernel_2slot<4, 4, 5>), static_cast<Kernel2Fn>(fft_unit_kernel_2slot<4, 5, 5>),
-                       static_cast<Kernel2Fn>(fft_unit_kernel_2slot<5, 5, 4>)}) {
-    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) g_attr_err = static_cast<int>(e);
-  }
 }
 
 }  // namespace
@@ -300,7 +284,7 @@ struct Tuning {
 };
 int knob(int tuned, const char* env_off, int dflt) {   // env_off: variable whose presence switches the feature off
   if (tuned >= 0) return tuned;
-  if (env_off && getenv(env_off)) return 0;
+  if (env_off && dev_env(env_off)) return 0;
   return dflt;
 }
 
@@ -316,16 +300,31 @@ struct tfft_plan_s {
   __half* workspace = nullptr;   // 2 * n * batch halves when TFFT_PRESERVE_INPUT on multi-pass sizes
   int64_t workspace_bytes = 0;
   bool loop_batch = false;           // three-pass plans run one transform at a time
-  __half* host_path_buf = nullptr;   // lazily allocated [in | out] for tfft_exec_host
-  // tfft_exec_host pipeline: the batch is cut into chunks; chunk i+1 uploads while chunk i transforms and
-  // chunk i-1 downloads (PCIe is full duplex), on three plan-owned streams
-  tfft_plan_s* host_chunk_plan = nullptr;   // plan for `host_chunk` transforms
-  tfft_plan_s* host_tail_plan = nullptr;    // plan for the ragged last chunk
-  int64_t host_chunk = 0;
-  cudaStream_t host_streams[3] = {nullptr, nullptr, nullptr};
-  std::vector<cudaEvent_t> host_events;     // 2 per chunk: uploaded, transformed
+  struct HostPath* host = nullptr;   // tfft_exec_host state, built at the first call
+  std::mutex host_mutex;             // tfft_exec_host calls on one plan are serialised
   int device = 0;
 };
+constexpr int kHostRing = 4;   // device slots per direction of the tfft_exec_host pipeline
+struct HostPath {
+  __half* buf = nullptr;             // [slots input chunks | slots output chunks]
+  tfft_plan_s* chunk_plan = nullptr;   // plan for `chunk` transforms (null: the whole batch is one chunk, the plan itself runs)
+  tfft_plan_s* tail_plan = nullptr;    // plan for the ragged last chunk
+  int64_t chunk = 0;
+  int slots = 1;
+  cudaStream_t streams[3] = {nullptr, nullptr, nullptr};   // upload, transform, download
+  cudaEvent_t events[3 * kHostRing] = {};                  // per slot: uploaded, transformed, downloaded
+};
+static void destroy_host_path(HostPath* h) {
+  if (!h) return;
+  if (h->buf) cudaFree(h->buf);
+  if (h->chunk_plan) tfft_plan_destroy(h->chunk_plan);
+  if (h->tail_plan) tfft_plan_destroy(h->tail_plan);
+  for (cudaStream_t st : h->streams)
+    if (st) cudaStreamDestroy(st);
+  for (cudaEvent_t ev : h->events)
+    if (ev) cudaEventDestroy(ev);
+  delete h;
+}
 
 namespace {
 
@@ -344,8 +343,8 @@ int pick_log2_units(int lg, int64_t batch) {
   return ups;
 }
 
-bool add_pass(tfft_plan_s* p, const UnitShape& shape, const UnitStrides& st, uint32_t n_units, int src, int dst,
-              bool in_user, bool out_user) {
+bool add_pass(tfft_plan_s* p, std::vector<Pass>* out, const UnitShape& shape, const UnitStrides& st, uint32_t n_units,
+              int src, int dst, bool in_user, bool out_user) {
   Pass ps;
   if (!build_unit_plan(shape, &ps.plan, &ps.info)) {
     fprintf(stderr, "tfft: plan error: %s\n", ps.info.error.c_str());
@@ -360,8 +359,12 @@ bool add_pass(tfft_plan_s* p, const UnitShape& shape, const UnitStrides& st, uin
   ps.dst = dst;
   ps.in_stride_is_user = in_user;
   ps.out_stride_is_user = out_user;
-  p->passes.push_back(ps);
+  out->push_back(ps);
   return true;
+}
+bool add_pass(tfft_plan_s* p, const UnitShape& shape, const UnitStrides& st, uint32_t n_units, int src, int dst,
+              bool in_user, bool out_user) {
+  return add_pass(p, &p->passes, shape, st, n_units, src, dst, in_user, out_user);
 }
 
 int build_1d(tfft_plan_s* p) {
@@ -375,7 +378,7 @@ int build_1d(tfft_plan_s* p) {
       int rho[kMaxStages];
       radix_schedule(lg, rho);
       // 16 or 32 rows per K line (N <= 1024): SWIZZLE_32B atoms (TFFT_NO_TMA_SMALL switches back to cp.async)
-      const bool small_ok = (lg - rho[0]) >= 4 && getenv("TFFT_NO_TMA_SMALL") == nullptr;
+      const bool small_ok = (lg - rho[0]) >= 4 && dev_env("TFFT_NO_TMA_SMALL") == nullptr;
       sh.tma_load = ((lg - rho[0]) >= 6 || small_ok) && knob(p->tune.tma, "TFFT_NO_TMA", 1) && !(p->flags & TFFT_INTERLEAVED);
       sh.pipe_stage2 = sh.tma_load && lg >= 13 && knob(p->tune.pipe, "TFFT_NO_PIPE", 1);
     }
@@ -391,8 +394,12 @@ int build_1d(tfft_plan_s* p) {
     if (lg > 24) return TFFT_E_UNSUPPORTED;   // three-pass sizes: planar only
   }
   int three_from = 25;   // developer knob: three passes from this log2 length on (>= 24: all factors >= 256)
-  if (const char* e = getenv("TFFT_THREEPASS_LG")) three_from = std::max(24, atoi(e));
-  if (lg >= three_from && !(p->flags & (TFFT_INTERLEAVED | TFFT_PRESERVE_INPUT))) {
+  if (const char* e = dev_env("TFFT_THREEPASS_LG")) three_from = std::min(25, std::max(24, atoi(e)));   // four-step covers <= 2^24 only
+  if (lg >= three_from && !(p->flags & TFFT_INTERLEAVED)) {
+    // TFFT_PRESERVE_INPUT: pass A writes into a plan-owned scratch of ONE transform (the batch is looped), passes B
+    // and C work from there; without the flag passes A and B run in place on the input planes
+    const bool preserve3 = (p->flags & TFFT_PRESERVE_INPUT) != 0;
+    const int mid = preserve3 ? 2 : 0;
     // three passes: n = N1 * Na * Nb (each 2^8 .. 2^12), one transform at a time (exec loops over the batch).
     //   A: N2 = Na*Nb strided length-N1 transforms, times exp(-2*pi*i*k1*n2/n)            (column mode, in place)
     //   B: for every k1, Nb strided length-Na transforms of row k1, times exp(-2*pi*i*ka*b/N2)   (column mode, in place)
@@ -416,7 +423,7 @@ int build_1d(tfft_plan_s* p) {
       st.units_per_batch = static_cast<uint32_t>(N2 / U);
       st.col_base_stride = static_cast<uint32_t>(U);
       st.pass1_log2n = lg;
-      if (!add_pass(p, sh, st, static_cast<uint32_t>(N2 / U), 0, 0, true, true)) return TFFT_E_UNSUPPORTED;
+      if (!add_pass(p, sh, st, static_cast<uint32_t>(N2 / U), 0, mid, true, true)) return TFFT_E_UNSUPPORTED;
       p->passes.back().own_batch_strides = true;
     }
     {
@@ -431,7 +438,7 @@ int build_1d(tfft_plan_s* p) {
       st.units_per_batch = static_cast<uint32_t>(Nb / U);
       st.col_base_stride = static_cast<uint32_t>(U);
       st.pass1_log2n = lg2;
-      if (!add_pass(p, sh, st, static_cast<uint32_t>(N1 * (Nb / U)), 0, 0, true, true)) return TFFT_E_UNSUPPORTED;
+      if (!add_pass(p, sh, st, static_cast<uint32_t>(N1 * (Nb / U)), mid, mid, true, true)) return TFFT_E_UNSUPPORTED;
       p->passes.back().own_batch_strides = true;
     }
     {
@@ -443,8 +450,15 @@ int build_1d(tfft_plan_s* p) {
       st.in_tstride = N2; st.in_unit_stride = Nb; st.in_batch_stride = U * N2;
       st.out_nstride = N1 * Na; st.out_unit_stride = N1; st.out_batch_stride = U;
       st.units_per_batch = static_cast<uint32_t>(Na);
-      if (!add_pass(p, sh, st, static_cast<uint32_t>((N1 / U) * Na), 0, 1, true, true)) return TFFT_E_UNSUPPORTED;
+      if (!add_pass(p, sh, st, static_cast<uint32_t>((N1 / U) * Na), mid, 1, true, true)) return TFFT_E_UNSUPPORTED;
       p->passes.back().own_batch_strides = true;
+    }
+    if (preserve3) {
+      p->workspace_bytes = 2 * n * static_cast<int64_t>(sizeof(__half));   // one transform: exec loops over the batch
+      if (cudaMalloc(&p->workspace, p->workspace_bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return TFFT_E_NOMEM;
+      }
     }
     return TFFT_OK;
   }
@@ -455,9 +469,10 @@ int build_1d(tfft_plan_s* p) {
   // would produce 2048-point units (40 KiB of DFT matrices -> one 16K-element CTA per SM): 2^19 = 512 x 1024 (-9 %),
   // 2^21 = 4096 x 512 (-3 %), 2^22 = 4096 x 1024 (-26 %); 2^23 = 2048 x 4096 with 16-column units (-16 %)
   static const int kLg1[9] = {8, 9, 9, 9, 10, 12, 12, 11, 12};   // lg = 16 .. 24
+  if (lg < 16 || lg > 24) return TFFT_E_INVALID_SIZE;
   int lg1 = kLg1[lg - 16];
   {   // tuner file / developer knob: length 2^lg1 of the column pass
-    const char* e = getenv("TFFT_FOURSTEP_LG1");
+    const char* e = dev_env("TFFT_FOURSTEP_LG1");
     const int v = p->tune.fourstep_lg1 >= 0 ? p->tune.fourstep_lg1 : (e ? atoi(e) : -1);
     if (v >= 8 && v <= 12 && lg - v >= 8 && lg - v <= 12) lg1 = v;
   }
@@ -473,7 +488,7 @@ int build_1d(tfft_plan_s* p) {
     sh.log2_units = std::max(3, unit_log2_elems(lg1) - lg1);
     // 2048-point columns: 16 columns per unit (32K elements, 16-column tiles) instead of 8 (measured at 2^23 = 2048 x 4096:
     // 2.23 -> 1.87 ms)
-    if (lg1 == 11 && getenv("TFFT_COL2048_U8") == nullptr) sh.log2_units = 4;
+    if (lg1 == 11 && dev_env("TFFT_COL2048_U8") == nullptr) sh.log2_units = 4;
     sh.in_mode = kColMode;
     sh.out_mode = kColMode;
     sh.tma_load = knob(p->tune.tma_col, "TFFT_NO_TMA_COL", 1) && !interleaved;   // column tiles {8 columns, R, M} by TMA
@@ -504,7 +519,7 @@ int build_1d(tfft_plan_s* p) {
     // a whole number of rows; otherwise tfft_exec takes the cp.async twin of this pass from passes_strided)
     // Measured on B200 (C3 sizes): -8 .. -13 % for row lengths up to 1024 (2^16 .. 2^22), +10 .. +22 % for 2048 / 4096
     // (2^23, 2^24), so only the former use tiles.
-    const bool row_tma = lg2 <= 10 && knob(p->tune.tma, "TFFT_NO_TMA", 1) && getenv("TFFT_NO_TMA_PASS2") == nullptr;
+    const bool row_tma = lg2 <= 10 && knob(p->tune.tma, "TFFT_NO_TMA", 1) && dev_env("TFFT_NO_TMA_PASS2") == nullptr;
     if (row_tma) {
       const Pass first = p->passes.back();
       if (!add_pass(p, sh, st, static_cast<uint32_t>(batch * (N1 / U)), preserve ? 2 : 0, 1, !preserve, true))
@@ -548,7 +563,7 @@ int build_2d(tfft_plan_s* p, std::vector<Pass>* passes, bool allow_tma) {
   };
   int yb = lgy > 12 ? lgy - 12 : 0;
   while (yb <= 3 && !yb_ok(yb)) ++yb;
-  if (const char* e = getenv("TFFT_2D_YBITS")) yb = atoi(e);   // developer override (e.g. 2 rows vs 4 rows per unit)
+  if (const char* e = dev_env("TFFT_2D_YBITS")) yb = atoi(e);   // developer override (e.g. 2 rows vs 4 rows per unit)
   if (yb < 0 || yb > 3 || !yb_ok(yb)) return TFFT_E_UNSUPPORTED;
   p->ybits = yb;
   const int64_t nx = p->nx, ny = p->ny, batch = p->batch;
@@ -558,10 +573,9 @@ int build_2d(tfft_plan_s* p, std::vector<Pass>* passes, bool allow_tma) {
   // natural layout.  Correct (GPU suite passes) but measured SLOWER at C5 on B200: 1.33 ms against 0.78 ms -- the row
   // pass's stores become 16-byte pieces 64 KiB apart, which costs more than the column pass's loads gain.
   const int lg2c = lgy - yb;
-  const bool tiled = getenv("TFFT_2D_TILED") != nullptr && std::max(3, unit_log2_elems(lg2c) - lg2c) == 3;
+  const bool tiled = dev_env("TFFT_2D_TILED") != nullptr && std::max(3, unit_log2_elems(lg2c) - lg2c) == 3;
   const int64_t rows2 = ny >> yb;
-  std::vector<Pass> saved;
-  saved.swap(p->passes);
+  passes->clear();
   bool ok = true;
   {
     UnitShape sh;
@@ -587,8 +601,8 @@ int build_2d(tfft_plan_s* p, std::vector<Pass>* passes, bool allow_tma) {
       st.out_hi_from = 3;
       st.out_hi_stride = rows2 * 8;              // x / 8 selects the chunk
     }
-    ok = add_pass(p, sh, st, static_cast<uint32_t>(batch * (ny / U)), 0, tiled ? 2 : 1, true, true);
-    if (ok) p->passes.back().kind = 1;
+    ok = add_pass(p, passes, sh, st, static_cast<uint32_t>(batch * (ny / U)), 0, tiled ? 2 : 1, true, true);
+    if (ok) passes->back().kind = 1;
   }
   if (ok) {
     const int lg2 = lgy - yb;
@@ -601,8 +615,8 @@ int build_2d(tfft_plan_s* p, std::vector<Pass>* passes, bool allow_tma) {
     // row stride of 2*nx elements consecutive 16-byte pieces of a tile lie 32 KiB apart and the tile walks kappa
     // (2 MiB jumps) before m, while the cp.async units of neighbouring CTAs sweep the rows together.  Four-step column
     // passes (row stride <= 8 KiB) gain 1-4 % from the tiles and keep them.
-    sh.tma_load = getenv("TFFT_TMA_COL_2D") != nullptr;
-    if (lg2 == 11 && getenv("TFFT_2D_COL_U16")) sh.log2_units = 4;   // developer knob: 16 columns x 2048 (32-byte pieces)
+    sh.tma_load = dev_env("TFFT_TMA_COL_2D") != nullptr;
+    if (lg2 == 11 && dev_env("TFFT_2D_COL_U16")) sh.log2_units = 4;   // developer knob: 16 columns x 2048 (32-byte pieces)
     const int64_t U = int64_t(1) << sh.log2_units;
     UnitStrides st;
     st.in_nstride = nx << yb; st.out_nstride = nx << yb;
@@ -612,11 +626,9 @@ int build_2d(tfft_plan_s* p, std::vector<Pass>* passes, bool allow_tma) {
       st.in_unit_stride = rows2 * 8;
     }
     st.units_per_batch = static_cast<uint32_t>((nx << yb) / U);
-    ok = add_pass(p, sh, st, static_cast<uint32_t>(batch * ((nx << yb) / U)), tiled ? 2 : 1, 1, true, true);
-    if (ok) p->passes.back().kind = 2;
+    ok = add_pass(p, passes, sh, st, static_cast<uint32_t>(batch * ((nx << yb) / U)), tiled ? 2 : 1, 1, true, true);
+    if (ok) passes->back().kind = 2;
   }
-  passes->swap(p->passes);
-  if (passes != &p->passes) p->passes.swap(saved);
   if (ok && tiled && !p->workspace) {
     p->workspace_bytes = 2 * p->n * batch * static_cast<int64_t>(sizeof(__half));
     if (cudaMalloc(&p->workspace, p->workspace_bytes) != cudaSuccess) {
@@ -636,9 +648,8 @@ bool prefetch_default(const tfft_plan_s* p, const Pass& ps, const UnitPlan& plan
   return plan.log2_elems == 15 && p->lg >= 23;
 }
 
-int launch_pass(const tfft_plan_s* p, const Pass& ps, const __half* src_re, const __half* src_im, __half* dst_re,
-                __half* dst_im, int64_t in_stride, int64_t out_stride, cudaStream_t stream, int tw_log2 = 0,
-                int64_t tw_first_col = 0) {
+int prepare_launch(const tfft_plan_s* p, const Pass& ps, const __half* src_re, const __half* src_im, int64_t in_stride,
+                   int64_t out_stride, int tw_log2, int64_t tw_first_col, int dev, Prepared* out) {
   UnitStrides st = ps.strides;
   if (tw_log2) {   // fused output twiddle: column index of transform b = first_col + b
     st.pass1_log2n = static_cast<uint32_t>(tw_log2);
@@ -669,10 +680,11 @@ int launch_pass(const tfft_plan_s* p, const Pass& ps, const __half* src_re, cons
     tma_extent = static_cast<int64_t>(st.tma_batch_step) * (batches - 1) +
                  (static_cast<int64_t>(st.units_per_batch) << ps.plan.log2_units);
   }
-  UnitPlan plan = ps.plan;
+  UnitPlan& plan = out->plan;
+  plan = ps.plan;
   fill_strides(st, ps.info, &plan);
   {
-    static const char* pf_env = getenv("TFFT_PREFETCH");   // developer override: 0 / 1
+    static const char* pf_env = dev_env("TFFT_PREFETCH");   // developer override: 0 / 1
     plan.il_in = ps.il_in ? 1u : 0u;
     plan.il_out = ps.il_out ? 1u : 0u;
     plan.il_swap = (p->flags & TFFT_INVERSE) ? 1u : 0u;
@@ -685,75 +697,111 @@ int launch_pass(const tfft_plan_s* p, const Pass& ps, const __half* src_re, cons
   int threads = kThreads;
   KernelFn fn = kernel_for(plan, &threads);
   if (!fn) return TFFT_E_UNSUPPORTED;
-  int dev = 0;
-  cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess) return static_cast<int>(e);
-  if (dev < 0 || dev >= 16) return TFFT_E_UNSUPPORTED;
-  {
-    std::lock_guard<std::mutex> lock(g_upload_mutex);
-    if (!ps.d_tables[dev]) {
-      uint4* d = nullptr;
-      e = cudaMalloc(&d, ps.tables.size());
-      if (e != cudaSuccess) { cudaGetLastError(); return e == cudaErrorMemoryAllocation ? TFFT_E_NOMEM : static_cast<int>(e); }
-      e = cudaMemcpy(d, ps.tables.data(), ps.tables.size(), cudaMemcpyHostToDevice);
-      if (e != cudaSuccess) { cudaFree(d); return static_cast<int>(e); }
-      int per_sm = 0, sms = 0, smem_sm = 0;
+  Kernel2Fn fn2 = kernel2_for(plan, allow2);
+  const uint32_t smem = fn2 ? smem2_layout(plan).total : ps.smem;
+  const void* entry = fn2 ? reinterpret_cast<const void*>(fn2) : reinterpret_cast<const void*>(fn);
+  static const bool debug = dev_env("TFFT_DEBUG") != nullptr;
+  cudaError_t e;
+  if (!ps.d_tables[dev]) {   // first use of this pass on this device (caller holds g_upload_mutex)
+    // opt in to > 48 KiB of dynamic shared memory: a per-device attribute of the function (a process-wide
+    // call_once left every device but the first without it)
+    e = cudaFuncSetAttribute(entry, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return e == cudaErrorInvalidDeviceFunction || e == cudaErrorNoKernelImageForDevice ? TFFT_E_NO_DEVICE : static_cast<int>(e);
+    }
+    uint4* d = nullptr;
+    e = cudaMalloc(&d, ps.tables.size());
+    if (e != cudaSuccess) { cudaGetLastError(); return e == cudaErrorMemoryAllocation ? TFFT_E_NOMEM : static_cast<int>(e); }
+    e = cudaMemcpy(d, ps.tables.data(), ps.tables.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(d); return static_cast<int>(e); }
+    int per_sm = 0, sms = 0, smem_sm = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+    if (fn2) {
+      per_sm = 1;   // two units in flight inside one CTA
+    } else {
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, ps.smem);
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
-      if (getenv("TFFT_DEBUG")) fprintf(stderr, "tfft: occupancy api=%d smem/sm=%d\n", per_sm, smem_sm);
+      if (debug) fprintf(stderr, "tfft: occupancy api=%d smem/sm=%d\n", per_sm, smem_sm);
       const int by_smem = smem_sm / static_cast<int>(ps.smem + 1024);
       if (per_sm < by_smem) per_sm = std::min(by_smem, 2);   // the API can under-report before the carve-out is set
       const int tmem_limit = 512 / static_cast<int>(plan.tmem_cols);   // tensor memory: 512 columns per SM
       if (per_sm > tmem_limit) per_sm = tmem_limit;
-      if (per_sm < 1 || sms < 1) { cudaFree(d); return TFFT_E_UNSUPPORTED; }
-      ps.resident_ctas[dev] = per_sm * sms;
-      ps.d_tables[dev] = d;
     }
+    if (per_sm < 1 || sms < 1) { cudaFree(d); return TFFT_E_UNSUPPORTED; }
+    ps.resident_ctas[dev] = per_sm * sms;
+    ps.d_tables[dev] = d;
   }
-  const uint4* tables = ps.d_tables[dev];
-  const unsigned grid = std::min<unsigned>(ps.n_units, static_cast<unsigned>(ps.resident_ctas[dev]));
-  long long* trace = g_trace;
-  alignas(64) CUtensorMap tmap_re, tmap_im;
-  std::memset(&tmap_re, 0, sizeof(tmap_re));
-  std::memset(&tmap_im, 0, sizeof(tmap_im));
+  out->tables = ps.d_tables[dev];
+  out->grid = std::min<unsigned>(ps.n_units, static_cast<unsigned>(ps.resident_ctas[dev]));
+  out->block = fn2 ? static_cast<unsigned>(kCta2Threads) : static_cast<unsigned>(threads);
+  out->smem = smem;
+  out->fn = entry;
+  out->two_slot = fn2 != nullptr;
+  std::memset(&out->tmap_re, 0, sizeof(CUtensorMap));
+  std::memset(&out->tmap_im, 0, sizeof(CUtensorMap));
   if (plan.tma_load) {
     // row-mode input: transform t of the launch starts at src + t * tstride, or, for four-step row
     // passes, at src + (t / upb) * batch_stride + (t % upb) * tstride == t * tstride when contiguous
     const int64_t n_tr = tma_extent ? tma_extent : static_cast<int64_t>(ps.n_units) << plan.log2_units;
-    const bool half_box = kernel2_for(plan, allow2) != nullptr;
+    const bool half_box = fn2 != nullptr;   // half-tile boxes: no other kernel may run these maps
     int rc;
     if (plan.tma_load == 2 || plan.tma_load == 4) {
       const int64_t columns = static_cast<int64_t>(plan.units_per_batch) << plan.log2_units;
       const int64_t batches = (ps.n_units + plan.units_per_batch - 1) / plan.units_per_batch;
-      rc = make_col_tensor_map(plan, src_re, st.in_nstride, columns, batches, plan.in_batch_stride, &tmap_re);
-      if (rc == TFFT_OK) rc = make_col_tensor_map(plan, src_im, st.in_nstride, columns, batches, plan.in_batch_stride, &tmap_im);
+      rc = make_col_tensor_map(plan, src_re, st.in_nstride, columns, batches, plan.in_batch_stride, &out->tmap_re);
+      if (rc == TFFT_OK) rc = make_col_tensor_map(plan, src_im, st.in_nstride, columns, batches, plan.in_batch_stride, &out->tmap_im);
     } else if (plan.kron_bits) {
-      rc = make_kron_tensor_map(plan, src_re, p->ny, p->batch, plan.tma_batch_step, &tmap_re, half_box);
-      if (rc == TFFT_OK) rc = make_kron_tensor_map(plan, src_im, p->ny, p->batch, plan.tma_batch_step, &tmap_im, half_box);
+      rc = make_kron_tensor_map(plan, src_re, p->ny, p->batch, plan.tma_batch_step, &out->tmap_re, half_box);
+      if (rc == TFFT_OK) rc = make_kron_tensor_map(plan, src_im, p->ny, p->batch, plan.tma_batch_step, &out->tmap_im, half_box);
     } else {
-      rc = make_input_tensor_map(plan, src_re, st.in_tstride, plan.n_transforms ? plan.n_transforms : n_tr, &tmap_re, half_box);
+      rc = make_input_tensor_map(plan, src_re, st.in_tstride, plan.n_transforms ? plan.n_transforms : n_tr, &out->tmap_re, half_box);
       if (rc == TFFT_OK)
-        rc = make_input_tensor_map(plan, src_im, st.in_tstride, plan.n_transforms ? plan.n_transforms : n_tr, &tmap_im, half_box);
+        rc = make_input_tensor_map(plan, src_im, st.in_tstride, plan.n_transforms ? plan.n_transforms : n_tr, &out->tmap_im, half_box);
     }
     if (rc != TFFT_OK) return rc;
   }
-  if (Kernel2Fn fn2 = kernel2_for(plan, allow2)) {   // the tensor maps above hold half-tile boxes: no other kernel may run them
-    const Smem2Layout S2 = smem2_layout(plan);
-    int sms = 0;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms < 1) return TFFT_E_UNSUPPORTED;
-    const unsigned grid2 = std::min<unsigned>(ps.n_units, static_cast<unsigned>(sms));
-    void* args2[] = {&plan, &dst_re, &dst_im, &tables, &tmap_re, &tmap_im, &trace};
-    e = launch_pdl(reinterpret_cast<const void*>(fn2), grid2, kCta2Threads, args2, S2.total, stream);
-    return e == cudaSuccess ? TFFT_OK : static_cast<int>(e);
+  if (debug)
+    fprintf(stderr, "tfft: launch grid=%u units=%u smem=%u tmem=%u resident=%d two_slot=%d\n", out->grid, ps.n_units, smem,
+            plan.tmem_cols, ps.resident_ctas[dev], out->two_slot ? 1 : 0);
+  out->dev = dev;
+  out->sre = src_re; out->sim = src_im;
+  out->in_stride = in_stride; out->out_stride = out_stride;
+  out->tw_log2 = tw_log2; out->tw_first_col = tw_first_col;
+  return TFFT_OK;
+}
+
+int launch_pass(const tfft_plan_s* p, const Pass& ps, const __half* src_re, const __half* src_im, __half* dst_re,
+                __half* dst_im, int64_t in_stride, int64_t out_stride, cudaStream_t stream, int tw_log2 = 0,
+                int64_t tw_first_col = 0) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) { cudaGetLastError(); return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? TFFT_E_NO_DEVICE : static_cast<int>(e); }
+  if (dev < 0 || dev >= 16) return TFFT_E_UNSUPPORTED;
+  Prepared L;
+  {
+    std::lock_guard<std::mutex> lock(g_upload_mutex);
+    const Prepared* hit = nullptr;
+    for (const Prepared& c : ps.prepared)
+      if (c.dev == dev && c.sre == src_re && c.sim == src_im && c.in_stride == in_stride && c.out_stride == out_stride &&
+          c.tw_log2 == tw_log2 && c.tw_first_col == tw_first_col) { hit = &c; break; }
+    if (hit) {
+      L = *hit;
+    } else {
+      const int rc = prepare_launch(p, ps, src_re, src_im, in_stride, out_stride, tw_log2, tw_first_col, dev, &L);
+      if (rc != TFFT_OK) return rc;
+      if (ps.prepared.size() < kPreparedSlots) ps.prepared.push_back(L);
+      else ps.prepared[ps.prepared_next++ % kPreparedSlots] = L;
+    }
   }
-  void* args[] = {&plan, &src_re, &src_im, &dst_re, &dst_im, &tables, &trace, &tmap_re, &tmap_im};
-  if (getenv("TFFT_DEBUG"))
-    fprintf(stderr, "tfft: launch grid=%u units=%u smem=%u tmem=%u resident=%d\n", grid, ps.n_units, ps.smem,
-            plan.tmem_cols, ps.resident_ctas[dev]);
-  e = launch_pdl(reinterpret_cast<const void*>(fn), grid, static_cast<unsigned>(threads), args, ps.smem, stream);
-  (void)p;
+  long long* trace = g_trace;
+  if (L.two_slot) {
+    void* args2[] = {&L.plan, &dst_re, &dst_im, &L.tables, &L.tmap_re, &L.tmap_im, &trace};
+    e = launch_pdl(L.fn, L.grid, L.block, args2, L.smem, stream);
+  } else {
+    void* args[] = {&L.plan, &src_re, &src_im, &dst_re, &dst_im, &L.tables, &trace, &L.tmap_re, &L.tmap_im};
+    e = launch_pdl(L.fn, L.grid, L.block, args, L.smem, stream);
+  }
   return e == cudaSuccess ? TFFT_OK : static_cast<int>(e);
 }
 
@@ -855,9 +903,12 @@ int tfft_plan_create_2d(tfft_plan_t* out, int64_t ny, int64_t nx, int64_t batch,
   tfft_plan_s* p = new (std::nothrow) tfft_plan_s;
   if (!p) return TFFT_E_NOMEM;
   p->n = ny * nx; p->ny = ny; p->nx = nx; p->batch = batch; p->flags = flags; p->lg = ilog2_exact(ny * nx);
-  const int rc = build_2d(p, &p->passes, true);
+  int rc = build_2d(p, &p->passes, true);
+  // the twin without TMA loads (image strides that are not a whole number of tensor-map steps) is built now, so that
+  // a plan is immutable after creation and concurrent tfft_exec calls never see a half-built pass list
+  if (rc == TFFT_OK && p->passes.front().plan.tma_load) rc = build_2d(p, &p->passes_strided, false);
   if (rc != TFFT_OK) {
-    delete p;
+    tfft_plan_destroy(p);
     return rc;
   }
   *out = p;
@@ -891,13 +942,7 @@ int tfft_plan_info(tfft_plan_t p, tfft_plan_info_t* info) {
 int tfft_plan_destroy(tfft_plan_t p) {
   if (!p) return TFFT_E_INVALID_ARG;
   if (p->workspace) cudaFree(p->workspace);
-  if (p->host_path_buf) cudaFree(p->host_path_buf);
-  if (p->host_chunk_plan) tfft_plan_destroy(p->host_chunk_plan);
-  if (p->host_tail_plan) tfft_plan_destroy(p->host_tail_plan);
-  for (cudaStream_t s : p->host_streams)
-    if (s) cudaStreamDestroy(s);
-  for (cudaEvent_t ev : p->host_events)
-    if (ev) cudaEventDestroy(ev);
+  destroy_host_path(p->host);
   for (std::vector<Pass>* v : {&p->passes, &p->passes_strided})
     for (Pass& ps : *v)
       for (int d = 0; d < 16; ++d)
@@ -922,8 +967,6 @@ int tfft_exec(tfft_plan_t p, const void* in_re, const void* in_im, void* out_re,
     cudaGetLastError();
     return TFFT_E_NO_DEVICE;
   }
-  std::call_once(g_attr_once, set_kernel_attrs);
-  if (g_attr_err) return g_attr_err == static_cast<int>(cudaErrorInvalidDeviceFunction) ? TFFT_E_NO_DEVICE : g_attr_err;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if ((p->flags & TFFT_INVERSE) && !(p->flags & TFFT_INTERLEAVED)) {   // F^-1(x) = swap(F(swap(x))), swap = exchange of the
     // real and imaginary planes (interleaved plans exchange the halves of every pair inside the kernel instead)
@@ -943,11 +986,7 @@ int tfft_exec(tfft_plan_t p, const void* in_re, const void* in_im, void* out_re,
       in_stride % p->passes[1].strides.in_tstride != 0)
     passes = &p->passes_strided;   // four-step row pass: the batch stride is not a whole number of rows
   if (p->ny && p->batch > 1 && p->passes.front().plan.tma_load && !tma_ok_2d()) {
-    std::lock_guard<std::mutex> lock(g_upload_mutex);
-    if (p->passes_strided.empty()) {
-      const int rc = build_2d(p, &p->passes_strided, false);
-      if (rc != TFFT_OK) return rc;
-    }
+    if (p->passes_strided.empty()) return TFFT_E_UNSUPPORTED;
     passes = &p->passes_strided;
   }
   for (int64_t ob = 0; ob < outer; ++ob)
@@ -988,76 +1027,85 @@ int tfft_exec_twiddled(tfft_plan_t p, const void* in_re, const void* in_im, void
     cudaGetLastError();
     return TFFT_E_NO_DEVICE;
   }
-  std::call_once(g_attr_once, set_kernel_attrs);
-  if (g_attr_err) return g_attr_err;
   return launch_pass(p, p->passes[0], static_cast<const __half*>(in_re), static_cast<const __half*>(in_im),
                      static_cast<__half*>(out_re), static_cast<__half*>(out_im), in_stride, out_stride,
                      static_cast<cudaStream_t>(stream_), log2_total, first_col);
 }
 
+// Host-buffer path.  The batch is cut into chunks of whole transforms; upload, transform and download of consecutive
+// chunks run on three plan-owned streams (PCIe is full duplex) through a ring of kHostRing device slots per direction,
+// so the device footprint is a few chunks, not the batch.  All state is built locally and published only when complete
+// (a failed first call used to leave a half-initialised path behind); calls on one plan are serialised.
 int tfft_exec_host(tfft_plan_t p, const void* host_in, void* host_out) {
   if (!p || !host_in || !host_out) return TFFT_E_INVALID_ARG;
-  const int64_t halves = 2 * p->n * p->batch;
-  if (!p->host_path_buf) {
-    cudaError_t e = cudaMalloc(&p->host_path_buf, 2 * halves * sizeof(__half));
-    if (e != cudaSuccess) {
-      cudaGetLastError();
-      return e == cudaErrorMemoryAllocation ? TFFT_E_NOMEM : (e == cudaErrorNoDevice ? TFFT_E_NO_DEVICE : static_cast<int>(e));
-    }
-    // chunking: about 16 MiB per direction and chunk, at most 64 chunks, whole transforms only
+  std::lock_guard<std::mutex> serial(p->host_mutex);
+  if (!p->host) {
+    HostPath* h = new (std::nothrow) HostPath;
+    if (!h) return TFFT_E_NOMEM;
+    int rc = TFFT_OK;
+    // chunking: about 8 MiB per direction and chunk, whole transforms only
     const int64_t per_transform = 2 * p->n * static_cast<int64_t>(sizeof(__half));
-    int64_t chunk_mb = 16;
-    if (const char* e = getenv("TFFT_HOST_CHUNK_MB")) chunk_mb = std::max(1, atoi(e));   // developer tuning knob
+    int64_t chunk_mb = 8;
+    if (const char* e = dev_env("TFFT_HOST_CHUNK_MB")) chunk_mb = std::max(1, atoi(e));   // developer tuning knob
     int64_t chunk = std::max<int64_t>(1, (chunk_mb << 20) / per_transform);
-    chunk = std::max(chunk, (p->batch + 63) / 64);
-    if (chunk >= p->batch || getenv("TFFT_HOST_NO_PIPELINE")) chunk = p->batch;
-    p->host_chunk = chunk;
+    if (chunk >= p->batch || dev_env("TFFT_HOST_NO_PIPELINE")) chunk = p->batch;
+    h->chunk = chunk;
+    h->slots = chunk < p->batch ? static_cast<int>(std::min<int64_t>(kHostRing, (p->batch + chunk - 1) / chunk)) : 1;
+    const uint32_t fl = p->flags & ~uint32_t(TFFT_PRESERVE_INPUT);
     if (chunk < p->batch) {
-      const uint32_t fl = p->flags & ~uint32_t(TFFT_PRESERVE_INPUT);
-      int rc = p->ny ? tfft_plan_create_2d(&p->host_chunk_plan, p->ny, p->nx, chunk, fl)
-                     : tfft_plan_create(&p->host_chunk_plan, p->n, chunk, fl);
+      rc = p->ny ? tfft_plan_create_2d(&h->chunk_plan, p->ny, p->nx, chunk, fl) : tfft_plan_create(&h->chunk_plan, p->n, chunk, fl);
       if (rc == TFFT_OK && p->batch % chunk)
-        rc = p->ny ? tfft_plan_create_2d(&p->host_tail_plan, p->ny, p->nx, p->batch % chunk, fl)
-                   : tfft_plan_create(&p->host_tail_plan, p->n, p->batch % chunk, fl);
-      if (rc != TFFT_OK) return rc;
-      for (cudaStream_t& s : p->host_streams)
-        if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return static_cast<int>(cudaGetLastError());
-      p->host_events.resize(2 * ((p->batch + chunk - 1) / chunk));
-      for (cudaEvent_t& ev : p->host_events)
-        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return static_cast<int>(cudaGetLastError());
+        rc = p->ny ? tfft_plan_create_2d(&h->tail_plan, p->ny, p->nx, p->batch % chunk, fl)
+                   : tfft_plan_create(&h->tail_plan, p->n, p->batch % chunk, fl);
     }
+    cudaError_t e = cudaSuccess;
+    if (rc == TFFT_OK) {
+      e = cudaMalloc(&h->buf, 2 * static_cast<size_t>(h->slots) * 2 * p->n * chunk * sizeof(__half));
+      for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking);
+      for (int i = 0; i < 3 * kHostRing && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&h->events[i], cudaEventDisableTiming);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        rc = e == cudaErrorMemoryAllocation ? TFFT_E_NOMEM
+             : (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? TFFT_E_NO_DEVICE : static_cast<int>(e);
+      }
+    }
+    if (rc != TFFT_OK) {
+      destroy_host_path(h);
+      return rc;
+    }
+    p->host = h;
   }
-  __half* din = p->host_path_buf;
-  __half* dout = p->host_path_buf + halves;
-  if (p->host_chunk >= p->batch) {
-    cudaError_t e = cudaMemcpyAsync(din, host_in, halves * sizeof(__half), cudaMemcpyHostToDevice, 0);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    const int64_t tstride = (p->flags & TFFT_INTERLEAVED) ? p->n : 2 * p->n;   // complex elements / plane elements
-    int rc = tfft_exec(p, din, din + p->n, dout, dout + p->n, tstride, tstride, nullptr);
-    if (rc != TFFT_OK) return rc;
-    e = cudaMemcpyAsync(host_out, dout, halves * sizeof(__half), cudaMemcpyDeviceToHost, 0);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    e = cudaStreamSynchronize(0);
-    return e == cudaSuccess ? TFFT_OK : static_cast<int>(e);
-  }
-  cudaStream_t s_up = p->host_streams[0], s_fft = p->host_streams[1], s_down = p->host_streams[2];
+  HostPath* h = p->host;
+  const int64_t chunk_halves = 2 * p->n * h->chunk;
+  __half* din = h->buf;
+  __half* dout = h->buf + static_cast<int64_t>(h->slots) * chunk_halves;
+  cudaStream_t s_up = h->streams[0], s_fft = h->streams[1], s_down = h->streams[2];
   const __half* hin = static_cast<const __half*>(host_in);
   __half* hout = static_cast<__half*>(host_out);
+  const int64_t tstride = (p->flags & TFFT_INTERLEAVED) ? p->n : 2 * p->n;   // complex elements / plane elements
   int64_t ci = 0;
-  for (int64_t b0 = 0; b0 < p->batch; b0 += p->host_chunk, ++ci) {
-    const int64_t nb = std::min(p->host_chunk, p->batch - b0);
+  for (int64_t b0 = 0; b0 < p->batch; b0 += h->chunk, ++ci) {
+    const int64_t nb = std::min(h->chunk, p->batch - b0);
     const int64_t off = 2 * p->n * b0, cnt = 2 * p->n * nb;
-    cudaError_t e = cudaMemcpyAsync(din + off, hin + off, cnt * sizeof(__half), cudaMemcpyHostToDevice, s_up);
-    if (e == cudaSuccess) e = cudaEventRecord(p->host_events[2 * ci], s_up);
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(s_fft, p->host_events[2 * ci], 0);
+    const int slot = static_cast<int>(ci % h->slots);
+    __half* si = din + slot * chunk_halves;
+    __half* so = dout + slot * chunk_halves;
+    cudaEvent_t ev_up = h->events[3 * slot], ev_fft = h->events[3 * slot + 1], ev_down = h->events[3 * slot + 2];
+    cudaError_t e = cudaSuccess;
+    // slot reuse: the previous transform out of this input slot / download out of this output slot must be done
+    if (ci >= h->slots) e = cudaStreamWaitEvent(s_up, ev_fft, 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(si, hin + off, cnt * sizeof(__half), cudaMemcpyHostToDevice, s_up);
+    if (e == cudaSuccess) e = cudaEventRecord(ev_up, s_up);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(s_fft, ev_up, 0);
+    if (e == cudaSuccess && ci >= h->slots) e = cudaStreamWaitEvent(s_fft, ev_down, 0);
     if (e != cudaSuccess) return static_cast<int>(e);
-    tfft_plan_s* cp = nb == p->host_chunk ? p->host_chunk_plan : p->host_tail_plan;
-    const int64_t tstride = (p->flags & TFFT_INTERLEAVED) ? p->n : 2 * p->n;
-    int rc = tfft_exec(cp, din + off, din + off + p->n, dout + off, dout + off + p->n, tstride, tstride, s_fft);
+    tfft_plan_s* cp = h->chunk >= p->batch ? p : (nb == h->chunk ? h->chunk_plan : h->tail_plan);
+    const int rc = tfft_exec(cp, si, si + p->n, so, so + p->n, tstride, tstride, s_fft);
     if (rc != TFFT_OK) return rc;
-    e = cudaEventRecord(p->host_events[2 * ci + 1], s_fft);
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(s_down, p->host_events[2 * ci + 1], 0);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(hout + off, dout + off, cnt * sizeof(__half), cudaMemcpyDeviceToHost, s_down);
+    e = cudaEventRecord(ev_fft, s_fft);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(s_down, ev_fft, 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hout + off, so, cnt * sizeof(__half), cudaMemcpyDeviceToHost, s_down);
+    if (e == cudaSuccess) e = cudaEventRecord(ev_down, s_down);
     if (e != cudaSuccess) return static_cast<int>(e);
   }
   cudaError_t e = cudaStreamSynchronize(s_down);
