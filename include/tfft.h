@@ -30,7 +30,8 @@ enum {
   TFFT_E_NO_DEVICE = -3,      /* no sm_100 device: the product has no CPU path */
   TFFT_E_UNSUPPORTED = -4,
   TFFT_E_NOMEM = -5,
-  TFFT_E_NOT_IN_FILE = -6     /* tuner file has no line for this length (Plan.h:238-254 prints + nullopt) */
+  TFFT_E_NOT_IN_FILE = -6,    /* tuner file has no line for this length (Plan.h:238-254 prints + nullopt) */
+  TFFT_E_TIMEOUT = -7         /* multi-GPU plans: a rank did not reach a phase barrier in time (tfft_mg_status) */
 };
 
 /* flags for tfft_plan_create */
@@ -107,6 +108,11 @@ int tfft_exec(tfft_plan_t plan, const void* in_re, const void* in_im, void* out_
 int tfft_exec_twiddled(tfft_plan_t plan, const void* in_re, const void* in_im, void* out_re, void* out_im,
                        int64_t in_stride, int64_t out_stride, int32_t log2_total, int64_t first_col, void* stream);
 
+/* In-place execution: for single-pass sizes (n <= 32768) out_re == in_re and out_im == in_im (same strides) is legal --
+ * every CTA reads its transforms completely before it writes them.  Multi-pass sizes run in place on the INPUT planes
+ * by design (see TFFT_PRESERVE_INPUT) but their final pass is a transposition: out must not alias in.  2-D plans: out
+ * must not alias in. */
+
 /* Whole reference call sequence with HOST buffers: CopyDataHostToDevice -> ComputeFFT ->
  * CopyResultsDeviceToHost (src/base/DataHandler.h:45-70,124-153).  host_in / host_out hold,
  * per transform, [RE(n) | IM(n)] halves (2*n*batch values each).  Uses plan-owned device
@@ -123,6 +129,47 @@ int tfft_transpose_blocks(const void* src, void* dst, int64_t rows, int64_t cols
                           int64_t dst_b0, int64_t dst_b1, void* stream);
 int tfft_copy_runs(const void* src, void* dst, int64_t run, int64_t n0, int64_t n1, int64_t n2, int64_t s0, int64_t s1,
                    int64_t s2, int64_t d0, int64_t d1, int64_t d2, void* stream);
+
+/* ---- one transform sharded over the GPUs of a node (BASELINE config C4) ------------------------
+ * The reference's multi-GPU entry points are commented-out replica code (src/base/ComputeFFT.h:295-557,
+ * DataHandler.h:168-403); these are new.  One process (or host thread) per GPU, `world` a power of two <= 16, n = 2^16
+ * ... 2^30 with n1/world and n2/world >= 64 (n = n1*n2, n1 = 2^ceil(lg/2)).  Rank r holds elements
+ * [r*n/world, (r+1)*n/world) of the planar input and receives the same slice of the spectrum (natural order, 1/n).
+ *
+ *   tfft_mg_plan_create   allocates this rank's exchange buffers on the current device
+ *   tfft_mg_plan_handle   fills TFFT_MG_HANDLE_BYTES that identify them (a CUDA IPC handle inside); the caller moves
+ *                         the handles between the ranks with whatever transport it has (all-gather)
+ *   tfft_mg_plan_connect  maps the peers' buffers; `handles` = world * TFFT_MG_HANDLE_BYTES in rank order
+ *   tfft_mg_exec          transpose -> n2/world transforms of length n1 (twiddle fused) -> transpose -> n1/world
+ *                         transforms of length n2 -> transpose.  Each transpose is ONE kernel that stores 64x64 tiles
+ *                         straight into the owning peer's buffer over NVLink, followed by a flag barrier between the
+ *                         ranks; there is no NCCL call and no pack/unpack pass.  Asynchronous on `stream`.  The result
+ *                         stays in plan-owned planes (tfft_mg_plan_info: result_re / result_im, valid until the next
+ *                         exec); pass out_re / out_im to have it copied out, or NULL for zero-copy use.
+ *   tfft_mg_status        TFFT_E_TIMEOUT if some barrier gave up waiting for a peer (default 10 s; results invalid)
+ * All ranks must call tfft_mg_exec the same number of times. */
+#define TFFT_MG_HANDLE_BYTES 128
+typedef struct tfft_mg_plan_s* tfft_mg_plan_t;
+typedef struct tfft_mg_info_s {
+  int64_t n, n1, n2;             /* n = n1 * n2                                                              */
+  int64_t local_elems;           /* n / world complex elements per rank                                      */
+  int32_t rank, world;
+  int32_t exchanges;             /* 3                                                                        */
+  int32_t reserved;
+  int64_t exchange_bytes_per_rank; /* fp16 planar bytes this rank sends over NVLink per exec:
+                                      exchanges * (world-1)/world * 4*n/world            */
+  int64_t device_bytes;          /* plan-owned device memory on this rank                                    */
+  void* result_re;               /* plan-owned result planes (local_elems halves each)                       */
+  void* result_im;
+} tfft_mg_info_t;
+int tfft_mg_plan_create(tfft_mg_plan_t* plan, int64_t n, int32_t rank, int32_t world, uint32_t flags);
+int tfft_mg_plan_handle(tfft_mg_plan_t plan, void* handle);
+int tfft_mg_plan_connect(tfft_mg_plan_t plan, const void* handles);
+int tfft_mg_plan_info(tfft_mg_plan_t plan, tfft_mg_info_t* info);
+int tfft_mg_exec(tfft_mg_plan_t plan, const void* in_re, const void* in_im, void* out_re, void* out_im, void* stream);
+int tfft_mg_status(tfft_mg_plan_t plan);
+int tfft_mg_set_timeout_ms(tfft_mg_plan_t plan, int64_t milliseconds);
+int tfft_mg_plan_destroy(tfft_mg_plan_t plan);
 
 /* Device-side harness helpers.
  * tfft_fixture_sine: the reference's test signal (CreateSineSuperpostionKernel,

@@ -28,7 +28,14 @@
 namespace tfft {
 
 constexpr int kThreads = 256;
+// -DTFFT_TW_TABLE: the round-1 inter-stage twiddle seeds (two-level shared-memory table, two divergent LDS.64 per seed).
+// Default: per-thread seeds in registers times per-tile factors from kernel-parameter space -- no shared-memory loads
+// in the epilogue (profiles/r02_*: the table lookups were the only instructions with excess shared wavefronts).
+#ifdef TFFT_TW_TABLE
 constexpr uint32_t kTwTableBytes = 512 + 4096;   // [TWlo: 64 float2 | TWhi: 512 float2]
+#else
+constexpr uint32_t kTwTableBytes = 0;
+#endif
 
 // ---------------------------------------------------------------- packed fp32 pairs (FFMA2)
 // Blackwell issues two fp32 FMAs per lane per instruction on 64-bit register pairs
@@ -361,6 +368,20 @@ __device__ __forceinline__ uint32_t thread_map(const UnitPlan& P, const KernelCt
   }
   return (dst >> 4) | (aux << 16);
 }
+// Per-thread twiddle seeds of a non-last stage: w = exp(-2*pi*i*x/L), w16 = w^16 for x = (per-thread part of the
+// twiddle integer) << tw_shift.  sincospif on exact binary fractions, once per kernel.
+struct TwSeed {
+  Cplx w, w16;
+};
+__device__ __forceinline__ TwSeed thread_seed(const UnitPlan& P, int st, uint32_t tmap) {
+  const uint32_t mask = (1u << P.log2_len) - 1u;
+  const uint32_t x = ((tmap >> 16) << P.epi[st].tw_shift) & mask;
+  TwSeed s;
+  s.w = twiddle(x, P.log2_len);
+  s.w16 = twiddle((x * 16u) & mask, P.log2_len);
+  return s;
+}
+
 template <int ST, int RHO, int NG>
 __device__ __forceinline__ uint32_t thread_col(const UnitPlan& P, const KernelCtx& c) {   // last stage, tw_mode 2
   constexpr uint32_t G = (1u << RHO) / 16;
@@ -375,7 +396,8 @@ __device__ __forceinline__ uint32_t thread_col(const UnitPlan& P, const KernelCt
 
 template <int ST, int RHO, bool LAST, uint32_t II, int NG = 2>
 __device__ __forceinline__ void epilogue_item(const UnitPlan& P, const KernelCtx& c, uint32_t dst_thr, uint32_t aux_thr,
-                                              uint32_t col_thr, const uint32_t (&are)[16], const uint32_t (&aim)[16]) {
+                                              uint32_t col_thr, const TwSeed& seed, const uint32_t (&are)[16],
+                                              const uint32_t (&aim)[16]) {
   using namespace ptx;
   constexpr uint32_t R = 1u << RHO, G = R / 16;
   const UnitPlan::Epi& E = P.epi[ST];
@@ -417,6 +439,7 @@ __device__ __forceinline__ void epilogue_item(const UnitPlan& P, const KernelCtx
       return;
     }
     if (!LAST) {
+#ifdef TFFT_TW_TABLE
       const uint32_t idx = aux << E.tw_shift;                       // unit angle 2*pi/L
       const Cplx w1 = tw_lookup(c.tw_table, idx);
       s2 = cmul(w1, w1);
@@ -427,6 +450,24 @@ __device__ __forceinline__ void epilogue_item(const UnitPlan& P, const KernelCtx
         t0 = tw_lookup(c.tw_table, (idx * 16u * g) & ((1u << P.log2_len) - 1u));
         t1 = cmul(t0, w1);
       }
+#else
+      // w1 = exp(-2*pi*i*m/N_t) of this row = (per-thread seed) * (factor of the tile, warp-uniform, parameter space)
+      (void)aux;
+      const Cplx w1 = cmul(seed.w, {E.tile_tw[kTileHi][0], E.tile_tw[kTileHi][1]});
+      s2 = cmul(w1, w1);
+      if (G == 1) {
+        t0 = {1.f, 0.f};
+        t1 = w1;
+      } else {
+        // t0 = w1^(16 g), g < G <= 4: bit 0 of g selects w1^16, bit 1 another factor w1^32
+        const Cplx w16 = cmul(seed.w16, {E.tile_tw16[kTileHi][0], E.tile_tw16[kTileHi][1]});
+        const bool g1 = (g & 1u) != 0;
+        const bool g2 = G == 4 && (NG == 2 ? (kGHi & 2u) != 0 : (g & 2u) != 0);
+        t0 = {g1 ? w16.re : 1.f, g1 ? w16.im : 0.f};
+        if (g2) t0 = cmul(t0, cmul(w16, w16));
+        t1 = cmul(t0, w1);
+      }
+#endif
     } else {
       const uint64_t col = col_thr + bit_sum_c<(kTileHi >> kTileShift), kMaxRowBits - 7 - kTileShift>(E.col, 7 + kTileShift) + c.col_base;
       const uint64_t mask = (uint64_t(1) << E.tw_log2n) - 1u;
@@ -472,13 +513,14 @@ __device__ __forceinline__ void epilogue_item(const UnitPlan& P, const KernelCtx
 // issued right after the wait and before the arithmetic).
 template <int ST, int RHO, bool LAST, uint32_t II, uint32_t END, int NG = 2>
 __device__ __forceinline__ void epilogue_range(const UnitPlan& P, const KernelCtx& c, uint32_t dst_thr,
-                                               uint32_t aux_thr, uint32_t col_thr, uint32_t (&cre)[16],
-                                               uint32_t (&cim)[16], uint32_t (&nre)[16], uint32_t (&nim)[16]) {
+                                               uint32_t aux_thr, uint32_t col_thr, const TwSeed& seed,
+                                               uint32_t (&cre)[16], uint32_t (&cim)[16], uint32_t (&nre)[16],
+                                               uint32_t (&nim)[16]) {
   if constexpr (II < END) {
     ptx::tmem_ld_wait();                                            // item II has landed in (cre, cim)
     if constexpr (II + 1 < END) epilogue_load<RHO, II + 1, NG>(c, nre, nim);
-    epilogue_item<ST, RHO, LAST, II, NG>(P, c, dst_thr, aux_thr, col_thr, cre, cim);
-    epilogue_range<ST, RHO, LAST, II + 1, END, NG>(P, c, dst_thr, aux_thr, col_thr, nre, nim, cre, cim);
+    epilogue_item<ST, RHO, LAST, II, NG>(P, c, dst_thr, aux_thr, col_thr, seed, cre, cim);
+    epilogue_range<ST, RHO, LAST, II + 1, END, NG>(P, c, dst_thr, aux_thr, col_thr, seed, nre, nim, cre, cim);
   }
 }
 
@@ -596,7 +638,8 @@ template <int ST, int RHO, bool LAST, int LOG2E, int LM = 0, bool PIPE = false, 
           int ROLE = 0, int NG = 2, bool EARLY2 = false>
 __device__ __forceinline__ void run_stage(const UnitPlan& P, const KernelCtx& c, uint32_t b1_saddr, uint64_t* bar,
                                           uint32_t (&phase)[2], int warp, int lane, long long* trace,
-                                          uint32_t trace_unit, uint32_t tmap, uint32_t col_thr, Hook hook = Hook()) {
+                                          uint32_t trace_unit, uint32_t tmap, uint32_t col_thr,
+                                          const TwSeed& seed = TwSeed(), Hook hook = Hook()) {
   using namespace ptx;
   using SS = StageShape<RHO, LOG2E, PIPE, NG>;
   constexpr uint32_t kItemsPerGroup = SS::kItemsPerGroup;
@@ -632,12 +675,12 @@ __device__ __forceinline__ void run_stage(const UnitPlan& P, const KernelCtx& c,
     if (hook_warp && elect_one()) hook.after_half(0);
     TFFT_TRACE_MARK(10 + 2 * ST);
     epilogue_load<RHO, 0, NG>(c, ra, rb);
-    epilogue_range<ST, RHO, LAST, 0, kHalf, NG>(P, c, dst_thr, aux_thr, col_thr, ra, rb, rc, rd);
+    epilogue_range<ST, RHO, LAST, 0, kHalf, NG>(P, c, dst_thr, aux_thr, col_thr, seed, ra, rb, rc, rd);
     hook.mid(warp, lane);
     warp_wait(bar + 1, phase[1] & 1u, lane);
     if (hook_warp && elect_one()) hook.after_half(1);
     epilogue_load<RHO, kHalf, NG>(c, ra, rb);
-    epilogue_range<ST, RHO, LAST, kHalf, kItemsPerGroup, NG>(P, c, dst_thr, aux_thr, col_thr, ra, rb, rc, rd);
+    epilogue_range<ST, RHO, LAST, kHalf, kItemsPerGroup, NG>(P, c, dst_thr, aux_thr, col_thr, seed, ra, rb, rc, rd);
     phase[0]++;
     phase[1]++;
   } else {
@@ -649,7 +692,7 @@ __device__ __forceinline__ void run_stage(const UnitPlan& P, const KernelCtx& c,
     }
     TFFT_TRACE_MARK(10 + 2 * ST);
     epilogue_load<RHO, 0, NG>(c, ra, rb);
-    epilogue_range<ST, RHO, LAST, 0, kItemsPerGroup, NG>(P, c, dst_thr, aux_thr, col_thr, ra, rb, rc, rd);
+    epilogue_range<ST, RHO, LAST, 0, kItemsPerGroup, NG>(P, c, dst_thr, aux_thr, col_thr, seed, ra, rb, rc, rd);
     phase[0]++;
     if (EARLY2) phase[1]++;
   }
@@ -786,6 +829,8 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
   const uint32_t tmap0 = thread_map<0, RHO0, NG>(P, c), tmap1 = thread_map<1, RHO1, NG>(P, c);
   const uint32_t tmap2 = kStages == 3 ? thread_map<2, (RHO2 ? RHO2 : 4), NG>(P, c) : 0u;
   const uint32_t col_thr = kStages == 3 ? thread_col<2, (RHO2 ? RHO2 : 4), NG>(P, c) : thread_col<1, RHO1, NG>(P, c);
+  const TwSeed seed0 = thread_seed(P, 0, tmap0);
+  const TwSeed seed1 = kStages == 3 ? thread_seed(P, 1, tmap1) : TwSeed();
 
   for (uint32_t unit = blockIdx.x; unit < P.n_units; unit += gridDim.x) {
     const uint32_t ub = unit >> P.upb_shift, uu = unit & ((1u << P.upb_shift) - 1u);
@@ -920,15 +965,15 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
 
     // ---------------------------------------------------------------- tensor-core stages
     run_stage<0, RHO0, false, LOG2E, LM, false, NoHook, 0, NG>(P, c, table_base + TL.b_off[0], bar, phase, warp, lane,
-                                                                trace, trace_unit, tmap0, 0u);
+                                                                trace, trace_unit, tmap0, 0u, seed0);
     TFFT_TRACE_MARK(3);
     // 3-stage plans built with pipe_stage2: the epilogue of stage 2's first tile half overlaps the UMMAs of its second
     if (kStages == 3 && P.pipe_stage2)
       run_stage<1, RHO1, kStages == 2, LOG2E, 0, true, NoHook, 0, NG>(P, c, table_base + TL.b_off[1], bar, phase, warp,
-                                                                          lane, trace, trace_unit, tmap1, col_thr);
+                                                                          lane, trace, trace_unit, tmap1, col_thr, seed1);
     else
       run_stage<1, RHO1, kStages == 2, LOG2E, 0, false, NoHook, 0, NG>(P, c, table_base + TL.b_off[1], bar, phase, warp,
-                                                                           lane, trace, trace_unit, tmap1, col_thr);
+                                                                           lane, trace, trace_unit, tmap1, col_thr, seed1);
     TFFT_TRACE_MARK(4);
     if constexpr (kStages == 3)
       run_stage<2, (RHO2 ? RHO2 : 4), true, LOG2E, 0, false, NoHook, 0, NG>(P, c, table_base + TL.b_off[2], bar, phase,
@@ -1203,6 +1248,8 @@ fft_unit_kernel_2slot(const __grid_constant__ UnitPlan P, __half* __restrict__ o
     const uint32_t tmap0 = thread_map<0, RHO0, 2>(P, c), tmap1 = thread_map<1, RHO1, 2>(P, c);
     const uint32_t tmap2 = kStages == 3 ? thread_map<2, (RHO2 ? RHO2 : 4), 2>(P, c) : 0u;
     const uint32_t col_thr = kStages == 3 ? thread_col<2, (RHO2 ? RHO2 : 4), 2>(P, c) : thread_col<1, RHO1, 2>(P, c);
+    const TwSeed seed0 = thread_seed(P, 0, tmap0);
+    const TwSeed seed1 = kStages == 3 ? thread_seed(P, 1, tmap1) : TwSeed();
     uint32_t units_done = 0;   // parity of this slot's half_done barrier
     for (uint32_t q = slot; unit_of(q) < P.n_units; q += 2) {
       const uint32_t unit = unit_of(q);
@@ -1222,20 +1269,20 @@ fft_unit_kernel_2slot(const __grid_constant__ UnitPlan P, __half* __restrict__ o
       TFFT_TRACE_MARK(2);
       LandingHook hook{land_full + 2 * slot, (q >> 1) & 1u, q, request};
       run_stage<0, RHO0, false, LOG2E, 1, true, LandingHook, ROLE>(P, c, b_saddr0, mma_bar, phase, warp, lane, trace,
-                                                                      trace_unit, tmap0, 0u, hook);
+                                                                      trace_unit, tmap0, 0u, seed0, hook);
       TFFT_TRACE_MARK(3);
 #if !defined(TFFT_DEBUG_SKIP)
       constexpr bool kEarly3 = kStages == 3 && !kDedicatedMmaWarp && !kNoEarly3;
       if (pipe2 && kEarly3)
         run_stage<1, RHO1, kStages == 2, LOG2E, 0, true, Early3Hook, ROLE>(
-            P, c, b_saddr1, mma_bar, phase, warp, lane, trace, trace_unit, tmap1, col_thr,
+            P, c, b_saddr1, mma_bar, phase, warp, lane, trace, trace_unit, tmap1, col_thr, seed1,
             Early3Hook{c, half_done, mma_bar, units_done & 1u, b_saddr2, trace, trace_unit});
       else if (pipe2)
         run_stage<1, RHO1, kStages == 2, LOG2E, 0, true, NoHook, ROLE>(P, c, b_saddr1, mma_bar, phase, warp, lane,
-                                                                           trace, trace_unit, tmap1, col_thr);
+                                                                           trace, trace_unit, tmap1, col_thr, seed1);
       else
         run_stage<1, RHO1, kStages == 2, LOG2E, 0, false, NoHook, ROLE>(P, c, b_saddr1, mma_bar, phase, warp, lane,
-                                                                            trace, trace_unit, tmap1, col_thr);
+                                                                            trace, trace_unit, tmap1, col_thr, seed1);
       TFFT_TRACE_MARK(4);
       if constexpr (kStages == 3) {
         if (pipe2 && kEarly3)

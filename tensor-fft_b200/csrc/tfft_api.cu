@@ -86,12 +86,12 @@ std::vector<uint8_t> make_tables(const UnitPlan& plan, bool unscaled) {
     *c = std::cos(a); *s = std::sin(a);
   };
   float2* tw = reinterpret_cast<float2*>(host.data());
-  for (int j = 0; j < 64; ++j) {
+  for (int j = 0; j < 64 && kTwTableBytes; ++j) {
     double c, s;
     unit(j, L, &c, &s);
     tw[j] = make_float2(static_cast<float>(c), static_cast<float>(s));
   }
-  for (int64_t j = 0; j < 512; ++j) {
+  for (int64_t j = 0; j < 512 && kTwTableBytes; ++j) {
     double c, s;
     unit((64 * j) % L, L, &c, &s);
     tw[64 + j] = make_float2(static_cast<float>(c), static_cast<float>(s));
@@ -825,6 +825,7 @@ const char* tfft_error_string(int code) {
     case TFFT_E_UNSUPPORTED: return "unsupported configuration";
     case TFFT_E_NOMEM: return "device memory allocation failed";
     case TFFT_E_NOT_IN_FILE: return "tuner file holds no line for this transform length";
+    case TFFT_E_TIMEOUT: return "multi-GPU plan: a peer rank did not reach a phase barrier in time";
     default: return code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "unknown tfft error";
   }
 }

@@ -1,0 +1,224 @@
+// Multi-GPU entry points of the C ABI (include/tfft.h, tfft_mg_*): ONE 1-D transform of length n = N1 * N2 slab-distributed
+// over `world` GPUs of one node, one process (or thread) per GPU.  Six-step: transpose, N2/G transforms of length N1 fused
+// with the twiddle exp(-2*pi*i*k1*i2/n), transpose, N1/G transforms of length N2, transpose (natural order out).
+// The three exchanges are single kernels that store straight into the peers' buffers over NVLink (mg_kernels.cuh); the
+// buffers are cudaMalloc'ed by the plan and shared through CUDA IPC handles that the caller passes between the ranks
+// (any transport: torch.distributed, MPI, a file).  No NCCL on the data path.  The reference has no multi-GPU path
+// (src/base/ComputeFFT.h:295-557 is commented out); SURVEY.md 8e / 8b name these entry points.
+#include <cuda_runtime.h>
+#include <unistd.h>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "../../include/tfft.h"
+#include "mg_kernels.cuh"
+
+using namespace tfft;
+
+namespace {
+
+constexpr uint64_t kBlobMagic = 0x74666674'6d673031ull;   // "tfftmg01"
+struct Blob {   // what a rank publishes (<= TFFT_MG_HANDLE_BYTES)
+  uint64_t magic;
+  int64_t n;
+  int32_t rank, world, pid, device;
+  uint64_t base;    // device pointer in the exporting process (used directly by ranks living in the same process)
+  uint64_t bytes;
+  cudaIpcMemHandle_t ipc;
+};
+static_assert(sizeof(Blob) <= TFFT_MG_HANDLE_BYTES, "handle blob too large");
+
+int cuda_rc(cudaError_t e) {
+  if (e == cudaSuccess) return TFFT_OK;
+  cudaGetLastError();
+  if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return TFFT_E_NO_DEVICE;
+  if (e == cudaErrorMemoryAllocation) return TFFT_E_NOMEM;
+  return static_cast<int>(e);
+}
+
+}  // namespace
+
+struct tfft_mg_plan_s {
+  int64_t n = 0, n1 = 0, n2 = 0, local = 0;   // local = n / world elements per rank and plane
+  int lg = 0, rank = 0, world = 1, device = 0;
+  tfft_plan_t fft1 = nullptr, fft2 = nullptr;
+  char* base = nullptr;                        // [A_re | A_im | B_re | B_im | C_re | C_im | flags]
+  size_t bytes = 0, flags_off = 0;
+  char* peer[kMgMaxRanks] = {};
+  bool opened[kMgMaxRanks] = {};
+  bool connected = false;
+  uint32_t epoch = 0;
+  int* status_host = nullptr;
+  int* status_dev = nullptr;
+  unsigned long long timeout_ns = 10ull * 1000 * 1000 * 1000;
+  __half* plane(int r, int which) const {      // which: 0..5 as in the layout above, on rank r
+    return reinterpret_cast<__half*>(peer[r] + static_cast<size_t>(which) * local * sizeof(__half));
+  }
+};
+
+extern "C" {
+
+int tfft_mg_plan_create(tfft_mg_plan_t* out, int64_t n, int32_t rank, int32_t world, uint32_t flags) {
+  if (!out) return TFFT_E_INVALID_ARG;
+  *out = nullptr;
+  if (world < 1 || world > kMgMaxRanks || (world & (world - 1)) || rank < 0 || rank >= world || flags != 0) return TFFT_E_INVALID_ARG;
+  int lg = 0;
+  while ((int64_t(1) << lg) < n) ++lg;
+  if (n <= 0 || (int64_t(1) << lg) != n || lg < 16 || lg > 30) return TFFT_E_INVALID_SIZE;
+  const int lg1 = (lg + 1) / 2, lg2 = lg - lg1;
+  const int64_t n1 = int64_t(1) << lg1, n2 = int64_t(1) << lg2;
+  // every exchange moves 64 x 64 tiles between slabs: both factors must split into whole tiles per rank
+  if (n1 / world < 64 || n2 / world < 64) return TFFT_E_INVALID_SIZE;
+  tfft_mg_plan_s* p = new (std::nothrow) tfft_mg_plan_s;
+  if (!p) return TFFT_E_NOMEM;
+  p->n = n; p->n1 = n1; p->n2 = n2; p->lg = lg; p->rank = rank; p->world = world; p->local = n / world;
+  int rc = cuda_rc(cudaGetDevice(&p->device));
+  if (rc == TFFT_OK) rc = tfft_plan_create(&p->fft1, n1, n2 / world, 0);
+  if (rc == TFFT_OK) rc = tfft_plan_create(&p->fft2, n2, n1 / world, 0);
+  if (rc == TFFT_OK) {
+    p->flags_off = 6 * static_cast<size_t>(p->local) * sizeof(__half);
+    p->bytes = p->flags_off + 4096;
+    rc = cuda_rc(cudaMalloc(&p->base, p->bytes));
+  }
+  if (rc == TFFT_OK) rc = cuda_rc(cudaMemset(p->base + p->flags_off, 0, 4096));
+  if (rc == TFFT_OK) rc = cuda_rc(cudaHostAlloc(&p->status_host, sizeof(int), cudaHostAllocMapped));
+  if (rc == TFFT_OK) {
+    *p->status_host = 0;
+    rc = cuda_rc(cudaHostGetDevicePointer(&p->status_dev, p->status_host, 0));
+  }
+  if (rc == TFFT_OK) rc = cuda_rc(cudaDeviceSynchronize());
+  if (rc != TFFT_OK) {
+    tfft_mg_plan_destroy(p);
+    return rc;
+  }
+  p->peer[rank] = p->base;
+  if (world == 1) p->connected = true;
+  *out = p;
+  return TFFT_OK;
+}
+
+int tfft_mg_plan_handle(tfft_mg_plan_t p, void* handle) {
+  if (!p || !handle) return TFFT_E_INVALID_ARG;
+  Blob b;
+  std::memset(&b, 0, sizeof(b));
+  b.magic = kBlobMagic; b.n = p->n; b.rank = p->rank; b.world = p->world; b.pid = static_cast<int32_t>(getpid());
+  b.device = p->device; b.base = reinterpret_cast<uint64_t>(p->base); b.bytes = p->bytes;
+  const int rc = cuda_rc(cudaIpcGetMemHandle(&b.ipc, p->base));
+  if (rc != TFFT_OK) return rc;
+  std::memset(handle, 0, TFFT_MG_HANDLE_BYTES);
+  std::memcpy(handle, &b, sizeof(b));
+  return TFFT_OK;
+}
+
+int tfft_mg_plan_connect(tfft_mg_plan_t p, const void* handles) {
+  if (!p || !handles) return TFFT_E_INVALID_ARG;
+  if (p->connected) return TFFT_OK;
+  const char* h = static_cast<const char*>(handles);
+  for (int r = 0; r < p->world; ++r) {
+    Blob b;
+    std::memcpy(&b, h + static_cast<size_t>(r) * TFFT_MG_HANDLE_BYTES, sizeof(b));
+    if (b.magic != kBlobMagic || b.rank != r || b.world != p->world || b.n != p->n || b.bytes != p->bytes) return TFFT_E_INVALID_ARG;
+    if (r == p->rank) continue;
+    if (b.pid == static_cast<int32_t>(getpid())) {
+      // ranks that live in this process (one host thread per GPU, or several ranks on one GPU in the tests)
+      if (b.device != p->device) {
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, p->device, b.device);
+        if (!can) return TFFT_E_UNSUPPORTED;
+        const cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_rc(e);
+        cudaGetLastError();
+      }
+      p->peer[r] = reinterpret_cast<char*>(b.base);
+    } else {
+      void* ptr = nullptr;
+      const int rc = cuda_rc(cudaIpcOpenMemHandle(&ptr, b.ipc, cudaIpcMemLazyEnablePeerAccess));
+      if (rc != TFFT_OK) return rc;
+      p->peer[r] = static_cast<char*>(ptr);
+      p->opened[r] = true;
+    }
+  }
+  p->connected = true;
+  return TFFT_OK;
+}
+
+int tfft_mg_plan_info(tfft_mg_plan_t p, tfft_mg_info_t* info) {
+  if (!p || !info) return TFFT_E_INVALID_ARG;
+  std::memset(info, 0, sizeof(*info));
+  info->n = p->n; info->n1 = p->n1; info->n2 = p->n2; info->local_elems = p->local;
+  info->rank = p->rank; info->world = p->world; info->exchanges = 3;
+  info->exchange_bytes_per_rank = 3 * static_cast<int64_t>(p->world - 1) * 4 * p->local / p->world;
+  info->device_bytes = static_cast<int64_t>(p->bytes);
+  info->result_re = p->base + 4 * static_cast<size_t>(p->local) * sizeof(__half);
+  info->result_im = p->base + 5 * static_cast<size_t>(p->local) * sizeof(__half);
+  return TFFT_OK;
+}
+
+static int mg_exchange(tfft_mg_plan_t p, const __half* src_re, const __half* src_im, int which, int64_t rows_local,
+                       int64_t cols, cudaStream_t s) {
+  MgPeers peers;
+  for (int r = 0; r < p->world; ++r) { peers.re[r] = p->plane(r, which); peers.im[r] = p->plane(r, which + 1); }
+  const dim3 grid(static_cast<unsigned>(cols / 64), static_cast<unsigned>(rows_local / 64), 2);
+  if (grid.y > 65535) return TFFT_E_UNSUPPORTED;
+  mg_transpose_send<<<grid, 256, 0, s>>>(src_re, src_im, peers, static_cast<int>(rows_local), static_cast<int>(cols),
+                                         p->rank, p->world, cols);
+  int rc = cuda_rc(cudaGetLastError());
+  if (rc != TFFT_OK) return rc;
+  MgFlags f;
+  for (int r = 0; r < p->world; ++r) f.flags[r] = reinterpret_cast<uint32_t*>(p->peer[r] + p->flags_off);
+  mg_barrier<<<1, 32, 0, s>>>(f, p->rank, p->world, ++p->epoch, p->timeout_ns, p->status_dev);
+  return cuda_rc(cudaGetLastError());
+}
+
+int tfft_mg_exec(tfft_mg_plan_t p, const void* in_re, const void* in_im, void* out_re, void* out_im, void* stream_) {
+  if (!p || !in_re || !in_im) return TFFT_E_INVALID_ARG;
+  if (!p->connected) return TFFT_E_INVALID_ARG;
+  if ((out_re == nullptr) != (out_im == nullptr)) return TFFT_E_INVALID_ARG;
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  const int64_t g = p->world, r1 = p->n1 / g, r2 = p->n2 / g;
+  __half *a_re = p->plane(p->rank, 0), *a_im = p->plane(p->rank, 1);
+  __half *b_re = p->plane(p->rank, 2), *b_im = p->plane(p->rank, 3);
+  __half *c_re = p->plane(p->rank, 4), *c_im = p->plane(p->rank, 5);
+  // exchange 1: my n1/g rows of n2 -> every rank gets its n2/g columns, transposed: A[i2_local][i1]
+  int rc = mg_exchange(p, static_cast<const __half*>(in_re), static_cast<const __half*>(in_im), 0, r1, p->n2, s);
+  // n2/g transforms over i1, times exp(-2*pi*i*k1*i2/n), in place
+  if (rc == TFFT_OK) rc = tfft_exec_twiddled(p->fft1, a_re, a_im, a_re, a_im, p->n1, p->n1, p->lg, p->rank * r2, s);
+  // exchange 2: A[i2_local][k1] -> B[k1_local][i2]
+  if (rc == TFFT_OK) rc = mg_exchange(p, a_re, a_im, 2, r2, p->n1, s);
+  // n1/g transforms over i2, in place
+  if (rc == TFFT_OK) rc = tfft_exec(p->fft2, b_re, b_im, b_re, b_im, p->n2, p->n2, s);
+  // exchange 3: B[k1_local][k2] -> C[k2_local][k1] = X[k1 + n1*k2], this rank's contiguous n/g slice
+  if (rc == TFFT_OK) rc = mg_exchange(p, b_re, b_im, 4, r1, p->n2, s);
+  if (rc == TFFT_OK && out_re && out_re != c_re)
+    rc = cuda_rc(cudaMemcpyAsync(out_re, c_re, p->local * sizeof(__half), cudaMemcpyDeviceToDevice, s));
+  if (rc == TFFT_OK && out_im && out_im != c_im)
+    rc = cuda_rc(cudaMemcpyAsync(out_im, c_im, p->local * sizeof(__half), cudaMemcpyDeviceToDevice, s));
+  return rc;
+}
+
+int tfft_mg_status(tfft_mg_plan_t p) {
+  if (!p) return TFFT_E_INVALID_ARG;
+  return *static_cast<volatile int*>(p->status_host) ? TFFT_E_TIMEOUT : TFFT_OK;
+}
+
+int tfft_mg_set_timeout_ms(tfft_mg_plan_t p, int64_t ms) {
+  if (!p || ms < 1) return TFFT_E_INVALID_ARG;
+  p->timeout_ns = static_cast<unsigned long long>(ms) * 1000000ull;
+  return TFFT_OK;
+}
+
+int tfft_mg_plan_destroy(tfft_mg_plan_t p) {
+  if (!p) return TFFT_E_INVALID_ARG;
+  for (int r = 0; r < p->world; ++r)
+    if (p->opened[r]) cudaIpcCloseMemHandle(p->peer[r]);
+  if (p->fft1) tfft_plan_destroy(p->fft1);
+  if (p->fft2) tfft_plan_destroy(p->fft2);
+  if (p->base) cudaFree(p->base);
+  if (p->status_host) cudaFreeHost(p->status_host);
+  cudaGetLastError();
+  delete p;
+  return TFFT_OK;
+}
+
+}  // extern "C"

@@ -26,6 +26,7 @@
 //   S_t = 16*R_t + 16: R_t/8 core matrices plus 16 bytes of padding, which makes every 16-byte
 //   store pattern below bank-conflict free (consecutive row chunks land 16 bytes apart mod 128).
 #pragma once
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -36,6 +37,7 @@ namespace tfft {
 constexpr int kMaxRowBits = 12;    // rows per unit = E/16 <= 4096 (bit-linear maps of an MMA row)
 constexpr int kMaxItemBits = 12;   // 16-byte chunks per unit and plane = E/8 <= 4096
 constexpr int kMaxStages = 3;
+constexpr int kMaxTiles = 32;     // 128-row tiles per stage = E / R / 128 <= 16 for the shapes built here
 constexpr uint32_t kKGroupStride = 128;    // bytes between consecutive 8-wide K groups (LBO)
 constexpr int kTwLoBits = 6;               // two-level twiddle table: phase = hi * 64 + lo
 
@@ -101,6 +103,12 @@ struct UnitPlan {
     uint32_t tw_shift;
     uint32_t tw_log2n;
     uint32_t tw_kw;
+    // tw_mode 1: the twiddle integer of a row splits into a per-thread part (lane and warp-group bits, turned into a
+    // complex seed once per kernel) and the part of the 128-row tile, which is the same for the whole warp and comes from
+    // here (kernel-parameter space): tile_tw[t] = exp(-2*pi*i * x_t / L), tile_tw16[t] = exp(-2*pi*i * 16*x_t / L),
+    // x_t = (sum of aux[] over the tile bits of t) << tw_shift
+    float tile_tw[kMaxTiles][2];
+    float tile_tw16[kMaxTiles][2];
   } epi[kMaxStages];
   // ---- store phase: item q (bit-linear) -> offsets
   uint32_t store_item_bits;
@@ -431,6 +439,28 @@ inline bool build_unit_plan(const UnitShape& shape, UnitPlan* plan, PlanBuildInf
       e.tw_mode = 1;
       // N_t = 2^(lo_bit[t-1] + rho_t); unit angle 2*pi/L: x = m_t * (L / N_t) * k
       e.tw_shift = lg - (info->lo_bit[t - 1] + rx[t - 1]);
+      const int tile_bits = static_cast<int>(rb.size()) - 7;
+      if (tile_bits > 5) { info->error = "too many tiles per stage"; return false; }
+      const double two_pi = 6.283185307179586476925286766559;
+      const int64_t L = int64_t(1) << lg;
+      for (int tile = 0; tile < (1 << tile_bits); ++tile) {
+        int64_t x = 0;
+        for (int j = 0; j < tile_bits; ++j)
+          if ((tile >> j) & 1) x += e.aux[7 + j];
+        x = (x << e.tw_shift) % L;
+        auto unit = [&](int64_t ph, float* out) {   // exact on the axes
+          ph %= L;
+          double c = std::cos(-two_pi * static_cast<double>(ph) / static_cast<double>(L));
+          double sn = std::sin(-two_pi * static_cast<double>(ph) / static_cast<double>(L));
+          if (ph == 0) { c = 1; sn = 0; }
+          else if (4 * ph == L) { c = 0; sn = -1; }
+          else if (2 * ph == L) { c = -1; sn = 0; }
+          else if (4 * ph == 3 * L) { c = 0; sn = 1; }
+          out[0] = static_cast<float>(c); out[1] = static_cast<float>(sn);
+        };
+        unit(x, e.tile_tw[tile]);
+        unit(16 * x, e.tile_tw16[tile]);
+      }
     } else {
       e.tw_mode = 0;
       e.tw_kw = 1u << (lg - rx[s - 1]);  // weight of k_s in o

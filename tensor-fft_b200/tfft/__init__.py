@@ -50,7 +50,18 @@ class _PlanInfo(ctypes.Structure):
 
 EXPORTS = ("tfft_plan_create", "tfft_plan_create_2d", "tfft_plan_info", "tfft_plan_destroy", "tfft_exec",
            "tfft_exec_twiddled", "tfft_exec_host", "tfft_error_string", "tfft_version", "tfft_fixture_sine",
-           "tfft_error_stats", "tfft_transpose_blocks", "tfft_copy_runs", "tfft_plan_create_from_file")
+           "tfft_error_stats", "tfft_transpose_blocks", "tfft_copy_runs", "tfft_plan_create_from_file",
+           "tfft_mg_plan_create", "tfft_mg_plan_handle", "tfft_mg_plan_connect", "tfft_mg_plan_info", "tfft_mg_exec",
+           "tfft_mg_status", "tfft_mg_set_timeout_ms", "tfft_mg_plan_destroy")
+
+TFFT_MG_HANDLE_BYTES = 128
+
+
+class _MgInfo(ctypes.Structure):
+    _fields_ = [("n", ctypes.c_int64), ("n1", ctypes.c_int64), ("n2", ctypes.c_int64), ("local_elems", ctypes.c_int64),
+                ("rank", ctypes.c_int32), ("world", ctypes.c_int32), ("exchanges", ctypes.c_int32),
+                ("reserved", ctypes.c_int32), ("exchange_bytes_per_rank", ctypes.c_int64),
+                ("device_bytes", ctypes.c_int64), ("result_re", ctypes.c_void_p), ("result_im", ctypes.c_void_p)]
 
 
 def lib() -> ctypes.CDLL:
@@ -75,6 +86,14 @@ def lib() -> ctypes.CDLL:
         L.tfft_error_stats.argtypes = [vp, vp, vp, vp, i64, dp, vp]
         L.tfft_transpose_blocks.argtypes = [vp, vp] + [i64] * 10 + [vp]
         L.tfft_copy_runs.argtypes = [vp, vp] + [i64] * 10 + [vp]
+        L.tfft_mg_plan_create.argtypes = [ctypes.POINTER(vp), i64, ctypes.c_int32, ctypes.c_int32, u32]
+        L.tfft_mg_plan_handle.argtypes = [vp, vp]
+        L.tfft_mg_plan_connect.argtypes = [vp, vp]
+        L.tfft_mg_plan_info.argtypes = [vp, ctypes.POINTER(_MgInfo)]
+        L.tfft_mg_exec.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.tfft_mg_status.argtypes = [vp]
+        L.tfft_mg_set_timeout_ms.argtypes = [vp, i64]
+        L.tfft_mg_plan_destroy.argtypes = [vp]
         L.tfft_error_string.argtypes = [ctypes.c_int]
         L.tfft_error_string.restype = ctypes.c_char_p
         _lib = L
@@ -161,6 +180,83 @@ class NativePlan:
     def close(self) -> None:
         if self._h:
             lib().tfft_plan_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _DevPlane:
+    """Zero-copy view of a plan-owned device plane for torch.as_tensor (CUDA array interface)."""
+
+    def __init__(self, ptr: int, count: int):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f2", "data": (ptr, False), "version": 3}
+
+
+class MgPlan:
+    """Owner of a tfft_mg_plan_t: ONE transform of length n sharded over `world` GPUs (include/tfft.h, tfft_mg_*).
+
+    The exchange of the IPC handles is the caller's plumbing: `connect_with(gather)` takes a function
+    bytes -> list[bytes] (an all-gather over the ranks, e.g. torch.distributed.all_gather_object);
+    `connect_local(plans)` links ranks that live in one process (tests: several ranks on one GPU)."""
+
+    def __init__(self, n: int, rank: int, world: int):
+        self._h = ctypes.c_void_p()
+        _check(lib().tfft_mg_plan_create(ctypes.byref(self._h), n, rank, world, 0))
+        info = _MgInfo()
+        _check(lib().tfft_mg_plan_info(self._h, ctypes.byref(info)))
+        self.info = {k: getattr(info, k) for k, _ in _MgInfo._fields_}
+        self.n, self.rank, self.world = n, rank, world
+
+    def handle(self) -> bytes:
+        buf = ctypes.create_string_buffer(TFFT_MG_HANDLE_BYTES)
+        _check(lib().tfft_mg_plan_handle(self._h, buf))
+        return buf.raw
+
+    def connect(self, handles) -> None:
+        blob = b"".join(handles)
+        if len(blob) != self.world * TFFT_MG_HANDLE_BYTES:
+            raise TfftError("connect needs one handle per rank")
+        _check(lib().tfft_mg_plan_connect(self._h, ctypes.c_char_p(blob)))
+
+    def connect_with(self, gather) -> None:
+        self.connect(gather(self.handle()))
+
+    @staticmethod
+    def connect_local(plans) -> None:
+        hs = [p.handle() for p in plans]
+        for p in plans:
+            p.connect(hs)
+
+    def exec(self, in_re, in_im, out_re=None, out_im=None, stream=None) -> None:
+        import torch
+        for t in (in_re, in_im) + ((out_re, out_im) if out_re is not None else ()):
+            if not (t.is_cuda and t.dtype == torch.float16 and t.numel() >= self.info["local_elems"]):
+                raise TfftError("tfft mg exec needs CUDA float16 tensors of n/world elements (no CPU fallback)")
+        s = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        _check(lib().tfft_mg_exec(self._h, in_re.data_ptr(), in_im.data_ptr(),
+                                  out_re.data_ptr() if out_re is not None else None,
+                                  out_im.data_ptr() if out_im is not None else None, ctypes.c_void_p(s)))
+
+    def result(self):
+        """Zero-copy torch views of the plan-owned result planes (valid until the next exec)."""
+        import torch
+        m = self.info["local_elems"]
+        return (torch.as_tensor(_DevPlane(self.info["result_re"], m), device="cuda"),
+                torch.as_tensor(_DevPlane(self.info["result_im"], m), device="cuda"))
+
+    def status(self) -> None:
+        _check(lib().tfft_mg_status(self._h))
+
+    def set_timeout_ms(self, ms: int) -> None:
+        _check(lib().tfft_mg_set_timeout_ms(self._h, ms))
+
+    def close(self) -> None:
+        if self._h:
+            lib().tfft_mg_plan_destroy(self._h)
             self._h = ctypes.c_void_p()
 
     def __del__(self):

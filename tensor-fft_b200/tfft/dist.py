@@ -143,3 +143,20 @@ def tfft_local_fft():
         return o
 
     return run
+
+
+def make_mg_plan(n: int, group=None):
+    """tfft.MgPlan for this rank of `group` (default: the world): the IPC handles of the plan-owned exchange buffers are
+    all-gathered over torch.distributed -- plumbing only; the data path of MgPlan.exec is the library's own kernels
+    storing into peer memory over NVLink (include/tfft.h, tfft_mg_*)."""
+    from . import MgPlan
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    plan = MgPlan(n, rank, world)
+
+    def gather(h):
+        out = [None] * world
+        dist.all_gather_object(out, h, group=group)
+        return out
+
+    plan.connect_with(gather)
+    return plan

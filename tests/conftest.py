@@ -3,6 +3,9 @@ import sys
 
 import pytest
 
+# a few tests A/B developer knobs (environment variables the library only honours in developer mode)
+os.environ.setdefault("TFFT_DEVELOPER", "1")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "tensor-fft_b200"), os.path.join(ROOT, "oracle")):
     if p not in sys.path:

@@ -27,11 +27,15 @@ def _tree(tmp_path):
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference sources not present (GPU box)")
-@pytest.mark.parametrize("example", ["ExampleSingleFFT.cu", "ExampleBatchFFT.cu"])
+@pytest.mark.parametrize("example", ["ExampleSingleFFT.cu", "ExampleBatchFFT.cu", "benchmarks/AccuracyTest.cu",
+                                     "benchmarks/FFTBenchSinlge.cu"])
 def test_reference_example_compiles_against_shim(tmp_path, example):
+    """the four acceptance programs -- the two examples, the accuracy sweep
+    (benchmarks/AccuracyTest.cu:17-86 through unitTesting/FFTTest.cu:24-88) and the single-transform benchmark that
+    builds its plans from a tuner file (benchmarks/FFTBenchSinlge.cu:10-44 -> Bench.h:153-228)."""
     src = _tree(tmp_path)
     os.makedirs(OUT, exist_ok=True)
-    exe = os.path.join(OUT, "shim_" + example.replace(".cu", ""))
+    exe = os.path.join(OUT, "shim_" + os.path.basename(example).replace(".cu", ""))
     cmd = ["nvcc", "-std=c++17", "-O2", "-gencode", "arch=compute_100a,code=sm_100a", "-o", exe,
            str(src / "testing" / example), "-L" + os.path.join(ROOT, "tensor-fft_b200", "tfft"), "-ltfft",
            "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../../tensor-fft_b200/tfft", "-lcufft"]

@@ -1,0 +1,95 @@
+"""GPU: ONE 1-D transform sharded over several ranks (BASELINE config C4) through the C ABI tfft_mg_*.
+
+* `test_ranks_on_one_gpu`: `world` ranks live in this process on ONE GPU, each with its own plan, buffers and stream;
+  the peers' buffers are plain device pointers.  Everything that runs on a multi-GPU box runs here too -- the tile
+  transposes that store into the owner's buffer, the flag barriers between the ranks, the twiddled and plain local
+  transforms -- so the driver's single-GPU test box covers the six-step end to end.
+* `test_two_gpus_*`: two processes, one per GPU (torch.distributed.run, NCCL for the plumbing and for the NCCL
+  all-to-all version SixStepPlan); skipped on a single-GPU box.
+Checked against the fp64 FFT of the fp16-quantised input; tolerance = 1.25 x the error level measured on B200 for the
+two-pass sizes (profiles/r01_sweep_c3.json: 4.4e-4 at 2^20, 4.7e-4 at 2^24), below the reference's own level."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import tfft
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOL = 1.25 * 4.7e-4
+
+
+@pytest.mark.parametrize("lg,world", [(16, 1), (18, 2), (20, 2), (20, 4), (22, 8), (21, 4), (24, 2)])
+def test_ranks_on_one_gpu(lg, world):
+    n = 1 << lg
+    m = n // world
+    rng = np.random.default_rng(lg * 16 + world)
+    re, im = rng.standard_normal(n).astype(np.float16), rng.standard_normal(n).astype(np.float16)
+    want = np.fft.fft(re.astype(np.float64) + 1j * im.astype(np.float64)) / n
+    plans = [tfft.MgPlan(n, r, world) for r in range(world)]
+    tfft.MgPlan.connect_local(plans)
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    ins = [(torch.from_numpy(re[r * m:(r + 1) * m]).cuda(), torch.from_numpy(im[r * m:(r + 1) * m]).cuda())
+           for r in range(world)]
+    outs = [(torch.empty(m, dtype=torch.float16, device="cuda"), torch.empty(m, dtype=torch.float16, device="cuda"))
+            for _ in range(world)]
+    torch.cuda.synchronize()
+    for p in plans:
+        p.set_timeout_ms(20000)
+    for rep in range(2):                # the second exec reuses every buffer and advances the barrier epochs
+        for r, p in enumerate(plans):
+            p.exec(ins[r][0], ins[r][1], outs[r][0], outs[r][1], stream=streams[r].cuda_stream)
+    torch.cuda.synchronize()
+    for p in plans:
+        p.status()                      # raises on a barrier timeout
+    got = np.concatenate([o[0].cpu().numpy().astype(np.float64) + 1j * o[1].cpu().numpy().astype(np.float64)
+                          for o in outs])
+    err = np.linalg.norm(got - want) / np.linalg.norm(want)
+    assert err <= TOL, err
+    # the inputs are never written
+    for r in range(world):
+        assert bool(torch.equal(ins[r][0].cpu(), torch.from_numpy(re[r * m:(r + 1) * m])))
+    info = plans[0].info
+    assert info["exchanges"] == 3 and info["exchange_bytes_per_rank"] == 3 * (world - 1) * 4 * n // (world * world)
+    for p in plans:
+        p.close()
+
+
+def test_mg_argument_checks():
+    with pytest.raises(tfft.TfftError):
+        tfft.MgPlan(1 << 14, 0, 2)          # too short to split into 64 x 64 tiles per rank
+    with pytest.raises(tfft.TfftError):
+        tfft.MgPlan(1 << 20, 2, 2)          # rank out of range
+    with pytest.raises(tfft.TfftError):
+        tfft.MgPlan(1 << 20, 0, 3)          # world not a power of two
+    p = tfft.MgPlan(1 << 20, 0, 2)
+    x = torch.zeros(1 << 19, dtype=torch.float16, device="cuda")
+    with pytest.raises(tfft.TfftError):
+        p.exec(x, x)                        # not connected yet
+    p.close()
+
+
+def _torchrun(nproc, script, *args, timeout=600):
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+           "--master-addr", "127.0.0.1", "--master-port", "29617", script, *map(str, args)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert lines, r.stdout[-2000:]
+    return json.loads(lines[-1])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("lg", [20, 26])
+def test_two_gpus_sixstep_nccl_and_peer_store(lg):
+    out = _torchrun(2, os.path.join(ROOT, "tests", "_mg_worker.py"), lg)
+    assert out["world"] == 2
+    assert out["rel_l2_sixstep_nccl"] <= 1.25 * 6.5e-4, out   # three-pass level covers 2^26
+    assert out["rel_l2_mg_peer"] <= 1.25 * 6.5e-4, out
+    assert out["zero_copy_view_matches"]

@@ -21,6 +21,6 @@ for lg in range(16, 25):
     for lg1 in range(8, 13):
         if not (8 <= lg - lg1 <= 12):
             continue
-        env = dict(os.environ, TFFT_FOURSTEP_LG1=str(lg1))
+        env = dict(os.environ, TFFT_DEVELOPER="1", TFFT_FOURSTEP_LG1=str(lg1))
         r = subprocess.run([sys.executable, "-c", CHILD, str(lg)], env=env, capture_output=True, text=True)
         print(r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-300:], flush=True)
