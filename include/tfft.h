@@ -89,6 +89,12 @@ int tfft_plan_create_from_file(tfft_plan_t* plan, int64_t n, int64_t batch, uint
  * 1/(ny*nx).  The reference has no 2-D path. */
 int tfft_plan_create_2d(tfft_plan_t* plan, int64_t ny, int64_t nx, int64_t batch, uint32_t flags);
 
+/* Optional: do every one-time device initialisation of the plan now, on the current device (kernel module loading and
+ * the > 48 KiB shared-memory opt-in, upload of the constant tables), so that later tfft_exec calls only enqueue work.
+ * tfft_exec does the same lazily at first use; call this before capturing execs into a CUDA graph or before running
+ * them next to kernels that spin-wait on other streams (module loading can synchronise the device). */
+int tfft_plan_prepare(tfft_plan_t plan);
+
 int tfft_plan_info(tfft_plan_t plan, tfft_plan_info_t* info);
 int tfft_plan_destroy(tfft_plan_t plan);
 
@@ -147,6 +153,11 @@ int tfft_copy_runs(const void* src, void* dst, int64_t run, int64_t n0, int64_t 
  *                         stays in plan-owned planes (tfft_mg_plan_info: result_re / result_im, valid until the next
  *                         exec); pass out_re / out_im to have it copied out, or NULL for zero-copy use.
  *   tfft_mg_status        TFFT_E_TIMEOUT if some barrier gave up waiting for a peer (default 10 s; results invalid)
+ *   tfft_mg_exec_phase    one phase of tfft_mg_exec WITHOUT its flag barrier, for callers that order the ranks themselves
+ *                         (one host thread driving several GPUs with events; the single-GPU tests, which run the ranks
+ *                         of a phase one after the other on one stream): phase 0 = exchange 1, 1 = transforms over the
+ *                         first factor + exchange 2, 2 = transforms over the second factor + exchange 3, 3 = copy out.
+ *                         Every rank must have finished phase p before any rank starts phase p + 1.
  * All ranks must call tfft_mg_exec the same number of times. */
 #define TFFT_MG_HANDLE_BYTES 128
 typedef struct tfft_mg_plan_s* tfft_mg_plan_t;
@@ -167,6 +178,8 @@ int tfft_mg_plan_handle(tfft_mg_plan_t plan, void* handle);
 int tfft_mg_plan_connect(tfft_mg_plan_t plan, const void* handles);
 int tfft_mg_plan_info(tfft_mg_plan_t plan, tfft_mg_info_t* info);
 int tfft_mg_exec(tfft_mg_plan_t plan, const void* in_re, const void* in_im, void* out_re, void* out_im, void* stream);
+int tfft_mg_exec_phase(tfft_mg_plan_t plan, int32_t phase, const void* in_re, const void* in_im, void* out_re,
+                       void* out_im, void* stream);
 int tfft_mg_status(tfft_mg_plan_t plan);
 int tfft_mg_set_timeout_ms(tfft_mg_plan_t plan, int64_t milliseconds);
 int tfft_mg_plan_destroy(tfft_mg_plan_t plan);

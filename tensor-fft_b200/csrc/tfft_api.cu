@@ -648,6 +648,41 @@ bool prefetch_default(const tfft_plan_s* p, const Pass& ps, const UnitPlan& plan
   return plan.log2_elems == 15 && p->lg >= 23;
 }
 
+// First use of a pass on a device (caller holds g_upload_mutex): opt in to > 48 KiB of dynamic shared memory -- a
+// per-device attribute of the function (a process-wide call_once left every device but the first without it)
+// --, upload the constant tables and size the persistent grid.  cudaFuncSetAttribute also forces the (lazily loaded)
+// kernel module onto the device; tfft_plan_prepare runs this for every pass ahead of time.
+int ensure_pass_on_device(const Pass& ps, int dev, const void* entry, bool two_slot, const void* fn, int threads,
+                          uint32_t tmem_cols) {
+  if (ps.d_tables[dev]) return TFFT_OK;
+  cudaError_t e = cudaFuncSetAttribute(entry, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return e == cudaErrorInvalidDeviceFunction || e == cudaErrorNoKernelImageForDevice ? TFFT_E_NO_DEVICE : static_cast<int>(e);
+  }
+  uint4* d = nullptr;
+  e = cudaMalloc(&d, ps.tables.size());
+  if (e != cudaSuccess) { cudaGetLastError(); return e == cudaErrorMemoryAllocation ? TFFT_E_NOMEM : static_cast<int>(e); }
+  e = cudaMemcpy(d, ps.tables.data(), ps.tables.size(), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(d); return static_cast<int>(e); }
+  int per_sm = 0, sms = 0, smem_sm = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+  if (two_slot) {
+    per_sm = 1;   // two units in flight inside one CTA
+  } else {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, ps.smem);
+    const int by_smem = smem_sm / static_cast<int>(ps.smem + 1024);
+    if (per_sm < by_smem) per_sm = std::min(by_smem, 2);   // the API can under-report before the carve-out is set
+    const int tmem_limit = 512 / static_cast<int>(tmem_cols);   // tensor memory: 512 columns per SM
+    if (per_sm > tmem_limit) per_sm = tmem_limit;
+  }
+  if (per_sm < 1 || sms < 1) { cudaFree(d); return TFFT_E_UNSUPPORTED; }
+  ps.resident_ctas[dev] = per_sm * sms;
+  ps.d_tables[dev] = d;
+  return TFFT_OK;
+}
+
 int prepare_launch(const tfft_plan_s* p, const Pass& ps, const __half* src_re, const __half* src_im, int64_t in_stride,
                    int64_t out_stride, int tw_log2, int64_t tw_first_col, int dev, Prepared* out) {
   UnitStrides st = ps.strides;
@@ -701,36 +736,9 @@ int prepare_launch(const tfft_plan_s* p, const Pass& ps, const __half* src_re, c
   const uint32_t smem = fn2 ? smem2_layout(plan).total : ps.smem;
   const void* entry = fn2 ? reinterpret_cast<const void*>(fn2) : reinterpret_cast<const void*>(fn);
   static const bool debug = dev_env("TFFT_DEBUG") != nullptr;
-  cudaError_t e;
-  if (!ps.d_tables[dev]) {   // first use of this pass on this device (caller holds g_upload_mutex)
-    // opt in to > 48 KiB of dynamic shared memory: a per-device attribute of the function (a process-wide
-    // call_once left every device but the first without it)
-    e = cudaFuncSetAttribute(entry, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) {
-      cudaGetLastError();
-      return e == cudaErrorInvalidDeviceFunction || e == cudaErrorNoKernelImageForDevice ? TFFT_E_NO_DEVICE : static_cast<int>(e);
-    }
-    uint4* d = nullptr;
-    e = cudaMalloc(&d, ps.tables.size());
-    if (e != cudaSuccess) { cudaGetLastError(); return e == cudaErrorMemoryAllocation ? TFFT_E_NOMEM : static_cast<int>(e); }
-    e = cudaMemcpy(d, ps.tables.data(), ps.tables.size(), cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) { cudaFree(d); return static_cast<int>(e); }
-    int per_sm = 0, sms = 0, smem_sm = 0;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
-    if (fn2) {
-      per_sm = 1;   // two units in flight inside one CTA
-    } else {
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, ps.smem);
-      if (debug) fprintf(stderr, "tfft: occupancy api=%d smem/sm=%d\n", per_sm, smem_sm);
-      const int by_smem = smem_sm / static_cast<int>(ps.smem + 1024);
-      if (per_sm < by_smem) per_sm = std::min(by_smem, 2);   // the API can under-report before the carve-out is set
-      const int tmem_limit = 512 / static_cast<int>(plan.tmem_cols);   // tensor memory: 512 columns per SM
-      if (per_sm > tmem_limit) per_sm = tmem_limit;
-    }
-    if (per_sm < 1 || sms < 1) { cudaFree(d); return TFFT_E_UNSUPPORTED; }
-    ps.resident_ctas[dev] = per_sm * sms;
-    ps.d_tables[dev] = d;
+  {
+    const int rc = ensure_pass_on_device(ps, dev, entry, fn2 != nullptr, reinterpret_cast<const void*>(fn), threads, plan.tmem_cols);
+    if (rc != TFFT_OK) return rc;
   }
   out->tables = ps.d_tables[dev];
   out->grid = std::min<unsigned>(ps.n_units, static_cast<unsigned>(ps.resident_ctas[dev]));
@@ -913,6 +921,28 @@ int tfft_plan_create_2d(tfft_plan_t* out, int64_t ny, int64_t nx, int64_t batch,
     return rc;
   }
   *out = p;
+  return TFFT_OK;
+}
+
+int tfft_plan_prepare(tfft_plan_t p) {
+  if (!p) return TFFT_E_INVALID_ARG;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) { cudaGetLastError(); return TFFT_E_NO_DEVICE; }
+  if (dev < 0 || dev >= 16) return TFFT_E_UNSUPPORTED;
+  const bool allow2 = knob(p->tune.two_slot, "TFFT_NO_2SLOT", 1) != 0;
+  std::lock_guard<std::mutex> lock(g_upload_mutex);
+  for (const std::vector<Pass>* v : {&p->passes, &p->passes_strided})
+    for (const Pass& ps : *v) {
+      int threads = kThreads;
+      KernelFn fn = kernel_for(ps.plan, &threads);
+      if (!fn) return TFFT_E_UNSUPPORTED;
+      Kernel2Fn fn2 = kernel2_for(ps.plan, allow2);
+      const void* entry = fn2 ? reinterpret_cast<const void*>(fn2) : reinterpret_cast<const void*>(fn);
+      const int rc = ensure_pass_on_device(ps, dev, entry, fn2 != nullptr, reinterpret_cast<const void*>(fn), threads,
+                                           ps.plan.tmem_cols);
+      if (rc != TFFT_OK) return rc;
+    }
   return TFFT_OK;
 }
 

@@ -76,6 +76,15 @@ int tfft_mg_plan_create(tfft_mg_plan_t* out, int64_t n, int32_t rank, int32_t wo
   int rc = cuda_rc(cudaGetDevice(&p->device));
   if (rc == TFFT_OK) rc = tfft_plan_create(&p->fft1, n1, n2 / world, 0);
   if (rc == TFFT_OK) rc = tfft_plan_create(&p->fft2, n2, n1 / world, 0);
+  // everything lazy happens NOW: kernel loading can synchronise the device, which would deadlock against a peer's
+  // barrier kernel that is already spinning on this GPU (several ranks per GPU) or serialise the ranks' first exec
+  if (rc == TFFT_OK) rc = tfft_plan_prepare(p->fft1);
+  if (rc == TFFT_OK) rc = tfft_plan_prepare(p->fft2);
+  if (rc == TFFT_OK) {
+    cudaFuncAttributes fa;
+    rc = cuda_rc(cudaFuncGetAttributes(&fa, mg_transpose_send));
+    if (rc == TFFT_OK) rc = cuda_rc(cudaFuncGetAttributes(&fa, mg_barrier));
+  }
   if (rc == TFFT_OK) {
     p->flags_off = 6 * static_cast<size_t>(p->local) * sizeof(__half);
     p->bytes = p->flags_off + 4096;
@@ -156,7 +165,7 @@ int tfft_mg_plan_info(tfft_mg_plan_t p, tfft_mg_info_t* info) {
 }
 
 static int mg_exchange(tfft_mg_plan_t p, const __half* src_re, const __half* src_im, int which, int64_t rows_local,
-                       int64_t cols, cudaStream_t s) {
+                       int64_t cols, bool barrier, cudaStream_t s) {
   MgPeers peers;
   for (int r = 0; r < p->world; ++r) { peers.re[r] = p->plane(r, which); peers.im[r] = p->plane(r, which + 1); }
   const dim3 grid(static_cast<unsigned>(cols / 64), static_cast<unsigned>(rows_local / 64), 2);
@@ -164,11 +173,42 @@ static int mg_exchange(tfft_mg_plan_t p, const __half* src_re, const __half* src
   mg_transpose_send<<<grid, 256, 0, s>>>(src_re, src_im, peers, static_cast<int>(rows_local), static_cast<int>(cols),
                                          p->rank, p->world, cols);
   int rc = cuda_rc(cudaGetLastError());
-  if (rc != TFFT_OK) return rc;
+  if (rc != TFFT_OK || !barrier) return rc;
   MgFlags f;
   for (int r = 0; r < p->world; ++r) f.flags[r] = reinterpret_cast<uint32_t*>(p->peer[r] + p->flags_off);
   mg_barrier<<<1, 32, 0, s>>>(f, p->rank, p->world, ++p->epoch, p->timeout_ns, p->status_dev);
   return cuda_rc(cudaGetLastError());
+}
+
+// phase 0: exchange 1;  phase 1: transforms over i1 + exchange 2;  phase 2: transforms over i2 + exchange 3;
+// phase 3: copy the result out (if asked)
+static int mg_phase(tfft_mg_plan_t p, int phase, const void* in_re, const void* in_im, void* out_re, void* out_im,
+                    bool barrier, cudaStream_t s) {
+  const int64_t g = p->world, r1 = p->n1 / g, r2 = p->n2 / g;
+  __half *a_re = p->plane(p->rank, 0), *a_im = p->plane(p->rank, 1);
+  __half *b_re = p->plane(p->rank, 2), *b_im = p->plane(p->rank, 3);
+  __half *c_re = p->plane(p->rank, 4), *c_im = p->plane(p->rank, 5);
+  int rc = TFFT_OK;
+  switch (phase) {
+    case 0:   // my n1/g rows of n2 -> every rank gets its n2/g columns, transposed: A[i2_local][i1]
+      return mg_exchange(p, static_cast<const __half*>(in_re), static_cast<const __half*>(in_im), 0, r1, p->n2, barrier, s);
+    case 1:   // n2/g transforms over i1, times exp(-2*pi*i*k1*i2/n), in place; then A[i2_local][k1] -> B[k1_local][i2]
+      rc = tfft_exec_twiddled(p->fft1, a_re, a_im, a_re, a_im, p->n1, p->n1, p->lg, p->rank * r2, s);
+      if (rc == TFFT_OK) rc = mg_exchange(p, a_re, a_im, 2, r2, p->n1, barrier, s);
+      return rc;
+    case 2:   // n1/g transforms over i2, in place; then B[k1_local][k2] -> C[k2_local][k1] = X[k1 + n1*k2]: this rank's n/g slice
+      rc = tfft_exec(p->fft2, b_re, b_im, b_re, b_im, p->n2, p->n2, s);
+      if (rc == TFFT_OK) rc = mg_exchange(p, b_re, b_im, 4, r1, p->n2, barrier, s);
+      return rc;
+    case 3:
+      if (out_re && out_re != c_re)
+        rc = cuda_rc(cudaMemcpyAsync(out_re, c_re, p->local * sizeof(__half), cudaMemcpyDeviceToDevice, s));
+      if (rc == TFFT_OK && out_im && out_im != c_im)
+        rc = cuda_rc(cudaMemcpyAsync(out_im, c_im, p->local * sizeof(__half), cudaMemcpyDeviceToDevice, s));
+      return rc;
+    default:
+      return TFFT_E_INVALID_ARG;
+  }
 }
 
 int tfft_mg_exec(tfft_mg_plan_t p, const void* in_re, const void* in_im, void* out_re, void* out_im, void* stream_) {
@@ -176,25 +216,17 @@ int tfft_mg_exec(tfft_mg_plan_t p, const void* in_re, const void* in_im, void* o
   if (!p->connected) return TFFT_E_INVALID_ARG;
   if ((out_re == nullptr) != (out_im == nullptr)) return TFFT_E_INVALID_ARG;
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
-  const int64_t g = p->world, r1 = p->n1 / g, r2 = p->n2 / g;
-  __half *a_re = p->plane(p->rank, 0), *a_im = p->plane(p->rank, 1);
-  __half *b_re = p->plane(p->rank, 2), *b_im = p->plane(p->rank, 3);
-  __half *c_re = p->plane(p->rank, 4), *c_im = p->plane(p->rank, 5);
-  // exchange 1: my n1/g rows of n2 -> every rank gets its n2/g columns, transposed: A[i2_local][i1]
-  int rc = mg_exchange(p, static_cast<const __half*>(in_re), static_cast<const __half*>(in_im), 0, r1, p->n2, s);
-  // n2/g transforms over i1, times exp(-2*pi*i*k1*i2/n), in place
-  if (rc == TFFT_OK) rc = tfft_exec_twiddled(p->fft1, a_re, a_im, a_re, a_im, p->n1, p->n1, p->lg, p->rank * r2, s);
-  // exchange 2: A[i2_local][k1] -> B[k1_local][i2]
-  if (rc == TFFT_OK) rc = mg_exchange(p, a_re, a_im, 2, r2, p->n1, s);
-  // n1/g transforms over i2, in place
-  if (rc == TFFT_OK) rc = tfft_exec(p->fft2, b_re, b_im, b_re, b_im, p->n2, p->n2, s);
-  // exchange 3: B[k1_local][k2] -> C[k2_local][k1] = X[k1 + n1*k2], this rank's contiguous n/g slice
-  if (rc == TFFT_OK) rc = mg_exchange(p, b_re, b_im, 4, r1, p->n2, s);
-  if (rc == TFFT_OK && out_re && out_re != c_re)
-    rc = cuda_rc(cudaMemcpyAsync(out_re, c_re, p->local * sizeof(__half), cudaMemcpyDeviceToDevice, s));
-  if (rc == TFFT_OK && out_im && out_im != c_im)
-    rc = cuda_rc(cudaMemcpyAsync(out_im, c_im, p->local * sizeof(__half), cudaMemcpyDeviceToDevice, s));
+  int rc = TFFT_OK;
+  for (int phase = 0; phase < 4 && rc == TFFT_OK; ++phase) rc = mg_phase(p, phase, in_re, in_im, out_re, out_im, true, s);
   return rc;
+}
+
+int tfft_mg_exec_phase(tfft_mg_plan_t p, int32_t phase, const void* in_re, const void* in_im, void* out_re, void* out_im,
+                       void* stream_) {
+  if (!p || !p->connected || phase < 0 || phase > 3) return TFFT_E_INVALID_ARG;
+  if (phase == 0 && (!in_re || !in_im)) return TFFT_E_INVALID_ARG;
+  if ((out_re == nullptr) != (out_im == nullptr)) return TFFT_E_INVALID_ARG;
+  return mg_phase(p, phase, in_re, in_im, out_re, out_im, false, static_cast<cudaStream_t>(stream_));
 }
 
 int tfft_mg_status(tfft_mg_plan_t p) {

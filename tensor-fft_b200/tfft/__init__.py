@@ -52,7 +52,7 @@ EXPORTS = ("tfft_plan_create", "tfft_plan_create_2d", "tfft_plan_info", "tfft_pl
            "tfft_exec_twiddled", "tfft_exec_host", "tfft_error_string", "tfft_version", "tfft_fixture_sine",
            "tfft_error_stats", "tfft_transpose_blocks", "tfft_copy_runs", "tfft_plan_create_from_file",
            "tfft_mg_plan_create", "tfft_mg_plan_handle", "tfft_mg_plan_connect", "tfft_mg_plan_info", "tfft_mg_exec",
-           "tfft_mg_status", "tfft_mg_set_timeout_ms", "tfft_mg_plan_destroy")
+           "tfft_mg_status", "tfft_mg_set_timeout_ms", "tfft_mg_plan_destroy", "tfft_plan_prepare", "tfft_mg_exec_phase")
 
 TFFT_MG_HANDLE_BYTES = 128
 
@@ -78,6 +78,7 @@ def lib() -> ctypes.CDLL:
         L.tfft_plan_create_from_file.argtypes = [ctypes.POINTER(vp), i64, i64, u32, ctypes.c_char_p]
         L.tfft_plan_info.argtypes = [vp, ctypes.POINTER(_PlanInfo)]
         L.tfft_plan_destroy.argtypes = [vp]
+        L.tfft_plan_prepare.argtypes = [vp]
         L.tfft_exec.argtypes = [vp, vp, vp, vp, vp, i64, i64, vp]
         L.tfft_exec_twiddled.argtypes = [vp, vp, vp, vp, vp, i64, i64, ctypes.c_int32, i64, vp]
         L.tfft_exec_host.argtypes = [vp, vp, vp]
@@ -92,6 +93,7 @@ def lib() -> ctypes.CDLL:
         L.tfft_mg_plan_info.argtypes = [vp, ctypes.POINTER(_MgInfo)]
         L.tfft_mg_exec.argtypes = [vp, vp, vp, vp, vp, vp]
         L.tfft_mg_status.argtypes = [vp]
+        L.tfft_mg_exec_phase.argtypes = [vp, ctypes.c_int32, vp, vp, vp, vp, vp]
         L.tfft_mg_set_timeout_ms.argtypes = [vp, i64]
         L.tfft_mg_plan_destroy.argtypes = [vp]
         L.tfft_error_string.argtypes = [ctypes.c_int]
@@ -172,6 +174,10 @@ class NativePlan:
                                         out_im.data_ptr(), in_stride, out_stride, log2_total, first_col,
                                         ctypes.c_void_p(s)))
 
+    def prepare(self) -> None:
+        """tfft_plan_prepare: all lazy one-time device initialisation now (before graph capture / spin-waiting peers)."""
+        _check(lib().tfft_plan_prepare(self._h))
+
     def exec_host(self, host_in, host_out) -> None:
         """numpy float16 arrays of 2*n*batch values laid out [RE|IM] per transform."""
         _check(lib().tfft_exec_host(self._h, host_in.ctypes.data_as(ctypes.c_void_p),
@@ -240,6 +246,14 @@ class MgPlan:
         _check(lib().tfft_mg_exec(self._h, in_re.data_ptr(), in_im.data_ptr(),
                                   out_re.data_ptr() if out_re is not None else None,
                                   out_im.data_ptr() if out_im is not None else None, ctypes.c_void_p(s)))
+
+    def exec_phase(self, phase: int, in_re=None, in_im=None, out_re=None, out_im=None, stream=None) -> None:
+        """tfft_mg_exec_phase: one phase without its flag barrier (the caller orders the ranks)."""
+        import torch
+        s = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        ptr = lambda t: t.data_ptr() if t is not None else None   # noqa: E731
+        _check(lib().tfft_mg_exec_phase(self._h, phase, ptr(in_re), ptr(in_im), ptr(out_re), ptr(out_im),
+                                        ctypes.c_void_p(s)))
 
     def result(self):
         """Zero-copy torch views of the plan-owned result planes (valid until the next exec)."""

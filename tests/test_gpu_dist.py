@@ -1,9 +1,10 @@
 """GPU: ONE 1-D transform sharded over several ranks (BASELINE config C4) through the C ABI tfft_mg_*.
 
-* `test_ranks_on_one_gpu`: `world` ranks live in this process on ONE GPU, each with its own plan, buffers and stream;
-  the peers' buffers are plain device pointers.  Everything that runs on a multi-GPU box runs here too -- the tile
-  transposes that store into the owner's buffer, the flag barriers between the ranks, the twiddled and plain local
-  transforms -- so the driver's single-GPU test box covers the six-step end to end.
+* `test_ranks_on_one_gpu`: `world` ranks live in this process on ONE GPU, each with its own plan and buffers; the peers'
+  buffers are plain device pointers.  The ranks of a phase run one after the other on ONE stream (tfft_mg_exec_phase,
+  no flag barrier: kernels that spin on each other must never share a GPU), so everything else that runs on a
+  multi-GPU box runs here too -- the tile transposes that store into the owner's buffer, the peer tables, the twiddled
+  and plain local transforms, buffer reuse across execs.  world = 1 runs tfft_mg_exec itself, barrier kernel included.
 * `test_two_gpus_*`: two processes, one per GPU (torch.distributed.run, NCCL for the plumbing and for the NCCL
   all-to-all version SixStepPlan); skipped on a single-GPU box.
 Checked against the fp64 FFT of the fp16-quantised input; tolerance = 1.25 x the error level measured on B200 for the
@@ -24,7 +25,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TOL = 1.25 * 4.7e-4
 
 
-@pytest.mark.parametrize("lg,world", [(16, 1), (18, 2), (20, 2), (20, 4), (22, 8), (21, 4), (24, 2)])
+@pytest.mark.parametrize("lg,world", [(16, 1), (20, 1), (18, 2), (20, 2), (20, 4), (22, 8), (21, 4), (24, 2), (26, 8)])
 def test_ranks_on_one_gpu(lg, world):
     n = 1 << lg
     m = n // world
@@ -33,27 +34,30 @@ def test_ranks_on_one_gpu(lg, world):
     want = np.fft.fft(re.astype(np.float64) + 1j * im.astype(np.float64)) / n
     plans = [tfft.MgPlan(n, r, world) for r in range(world)]
     tfft.MgPlan.connect_local(plans)
-    streams = [torch.cuda.Stream() for _ in range(world)]
     ins = [(torch.from_numpy(re[r * m:(r + 1) * m]).cuda(), torch.from_numpy(im[r * m:(r + 1) * m]).cuda())
            for r in range(world)]
     outs = [(torch.empty(m, dtype=torch.float16, device="cuda"), torch.empty(m, dtype=torch.float16, device="cuda"))
             for _ in range(world)]
-    torch.cuda.synchronize()
-    for p in plans:
-        p.set_timeout_ms(20000)
-    for rep in range(2):                # the second exec reuses every buffer and advances the barrier epochs
-        for r, p in enumerate(plans):
-            p.exec(ins[r][0], ins[r][1], outs[r][0], outs[r][1], stream=streams[r].cuda_stream)
+    for rep in range(2):                # the second exec reuses every buffer
+        if world == 1:
+            plans[0].set_timeout_ms(5000)
+            plans[0].exec(ins[0][0], ins[0][1], outs[0][0], outs[0][1])
+        else:
+            for phase in range(4):
+                for r, p in enumerate(plans):
+                    p.exec_phase(phase, ins[r][0], ins[r][1], outs[r][0], outs[r][1])
     torch.cuda.synchronize()
     for p in plans:
         p.status()                      # raises on a barrier timeout
     got = np.concatenate([o[0].cpu().numpy().astype(np.float64) + 1j * o[1].cpu().numpy().astype(np.float64)
                           for o in outs])
     err = np.linalg.norm(got - want) / np.linalg.norm(want)
-    assert err <= TOL, err
+    assert err <= (TOL if lg <= 24 else 1.25 * 6.5e-4), err
     # the inputs are never written
     for r in range(world):
         assert bool(torch.equal(ins[r][0].cpu(), torch.from_numpy(re[r * m:(r + 1) * m])))
+    z_re, z_im = plans[-1].result()      # zero-copy view of the plan-owned result planes
+    assert bool(torch.equal(z_re, outs[-1][0])) and bool(torch.equal(z_im, outs[-1][1]))
     info = plans[0].info
     assert info["exchanges"] == 3 and info["exchange_bytes_per_rank"] == 3 * (world - 1) * 4 * n // (world * world)
     for p in plans:
