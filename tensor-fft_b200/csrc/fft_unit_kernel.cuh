@@ -806,11 +806,27 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
     tmem_alloc(tmem_slot, P.tmem_cols);
     tmem_relinquish();
   }
+  // row-mode TMA tiles: the tile of the CTA's first unit is requested before the constant tables are staged, so that its
+  // latency overlaps the table copy (matters for the latency of a single small transform, BASELINE config C1)
+  constexpr bool kEarlyFirstTile = LM == 1 || LM == 3;
   if (tid == 32) {
     mbar_init(bar, 1);
     mbar_init(bar + 1, 1);
     mbar_init(load_bar, 1);
     fence_mbar_init();
+    if (kEarlyFirstTile && blockIdx.x < P.n_units) {
+      pdl_wait();
+      const uint32_t unit = blockIdx.x, ub = unit >> P.upb_shift, uu = unit & ((1u << P.upb_shift) - 1u);
+      mbar_arrive_expect_tx(load_bar, 4u << LOG2E);
+      if (P.kron_bits) {
+        tma_load_5d(smem_u32(smem), &tmap_re, uu, ub * P.tma_batch_step, load_bar);
+        tma_load_5d(smem_u32(smem) + SL.plane_stride, &tmap_im, uu, ub * P.tma_batch_step, load_bar);
+      } else {
+        const uint32_t c3 = ub * P.tma_batch_step + (uu << P.log2_units);
+        tma_load_4d(smem_u32(smem), &tmap_re, 0, c3, load_bar);
+        tma_load_4d(smem_u32(smem) + SL.plane_stride, &tmap_im, 0, c3, load_bar);
+      }
+    }
   }
   for (uint32_t o = tid * 16; o < TL.total; o += NT * 16) sts128(table_base + o, ldg128(tables + (o >> 4)));
   tc_fence_before_sync();
@@ -868,7 +884,7 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
     } else if constexpr (LM == 1 || LM == 3) {
       // one tensor tile per plane: {64 rows, R kappa, M/64, U transforms}; transforms past the end of
       // the batch are out of bounds of the tensor map and arrive as zeros
-      if (tid == 0) {
+      if (tid == 0 && !(kEarlyFirstTile && unit == blockIdx.x)) {   // the first tile was requested during the setup
         fence_proxy_async_smem();   // earlier generic-proxy reads of the planes precede the async-proxy writes
         mbar_arrive_expect_tx(load_bar, 4u << LOG2E);
         if (P.kron_bits) {
