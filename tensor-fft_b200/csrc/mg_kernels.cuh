@@ -2,9 +2,9 @@
 // memory over NVLink (peer-mapped buffers, one process per GPU) and the flag barrier between the phases.  The reference
 // has no working multi-GPU path (its ComputeFFTMultiGPU, src/base/ComputeFFT.h:295-557, is commented-out replica code).
 //
-//   mg_transpose_send : the distributed transpose of one exchange as ONE kernel: 64 x 64 fp16 tiles of the local slab go
-//                       through shared memory and are stored transposed, as whole 128-byte lines, into the buffer of the
-//                       rank that owns those columns -- pack, all-to-all and unpack of the NCCL version in one pass.
+//   mg_transpose_send : the distributed transpose of one exchange as ONE kernel: 64 x 32 fp16 tiles of the local slab are
+//                       transposed in registers and stored, as whole 128-byte lines, into the buffer of the rank that
+//                       owns those columns -- pack, all-to-all and unpack of the NCCL version in one pass.
 //   mg_barrier        : every rank raises its flag on all peers (system-scope release after the data kernel of the same
 //                       stream has completed) and waits until all peers have raised theirs (acquire); bounded spin.
 #pragma once
@@ -23,40 +23,43 @@ struct MgPeers {
 
 // Local slab: `rows_local` rows of `cols` elements (both planes), rank `rank` of `world`.  Peer p owns columns
 // [p*cl, (p+1)*cl), cl = cols / world, and receives them transposed: dst_p[c][rank*rows_local + r] = src[r][p*cl + c],
-// dst row length = world * rows_local.  Grid: (cols/64, rows_local/64, 2 planes), 256 threads.
-// Tiles are visited peer-interleaved (consecutive CTAs target different peers, starting at rank+1) so that all NVLink
-// ports carry traffic at any moment.
+// dst row length = world * rows_local.
+// One warp moves a tile of 64 source rows x 32 source columns entirely in registers: lane (rg = lane / 4, ch = lane % 4)
+// loads the 8 x 8 block of rows 8*rg .. 8*rg+7, columns 8*ch .. 8*ch+7 (eight 16-byte loads; a warp instruction covers
+// 8 rows x 64 contiguous bytes), transposes it with byte permutes and stores eight 16-byte pieces; a warp store
+// instruction writes 4 destination rows x 128 contiguous bytes -- whole lines, which is what matters on NVLink.
+// Grid: (ceil(cols / 32 / 8), rows_local / 64, 2 planes), 256 threads.  Column groups are visited peer-interleaved
+// (consecutive warps target different peers, starting at rank + 1) so that all NVLink ports carry traffic at any moment.
 __global__ void __launch_bounds__(256)
 mg_transpose_send(const __half* __restrict__ src_re, const __half* __restrict__ src_im, const MgPeers peers,
                   int rows_local, int cols, int rank, int world, int64_t src_row_stride) {
-  __shared__ __align__(16) __half tile[64][72];   // 144-byte rows: 16-byte column reads spread over the banks
-  const int cl = cols / world, tiles_per_peer = cl / 64;
-  const int bx = blockIdx.x;
-  const int peer = (bx + rank + 1) % world;
-  const int tx = bx / world;                       // column tile inside the peer's block
-  (void)tiles_per_peer;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lin = blockIdx.x * 8 + warp;             // column group (32 columns) in peer-interleaved order
+  if (lin >= cols / 32) return;
+  const int cl = cols / world;
+  const int peer = (lin + rank + 1) % world;
+  const int cg = lin / world;                        // column group inside the peer's block
+  const int rg = lane >> 2, ch = lane & 3;
   const int plane = blockIdx.z;
-  const __half* s = (plane ? src_im : src_re) + static_cast<int64_t>(blockIdx.y) * 64 * src_row_stride +
-                    static_cast<int64_t>(peer) * cl + tx * 64;
+  const __half* s = (plane ? src_im : src_re) + (static_cast<int64_t>(blockIdx.y) * 64 + 8 * rg) * src_row_stride +
+                    static_cast<int64_t>(peer) * cl + cg * 32 + 8 * ch;
+  uint4 a[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = __ldcs(reinterpret_cast<const uint4*>(s + j * src_row_stride));
   const int64_t d_row = static_cast<int64_t>(world) * rows_local;
-  __half* d = (plane ? peers.im[peer] : peers.re[peer]) + static_cast<int64_t>(tx) * 64 * d_row +
-              static_cast<int64_t>(rank) * rows_local + blockIdx.y * 64;
-  const int t = threadIdx.x;
+  __half* d = (plane ? peers.im[peer] : peers.re[peer]) + (static_cast<int64_t>(cg) * 32 + 8 * ch) * d_row +
+              static_cast<int64_t>(rank) * rows_local + blockIdx.y * 64 + 8 * rg;
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int r = (t >> 3) + 32 * i, ch = t & 7;
-    // chunk ch of row r is kept at chunk position ch ^ (r / 8): the column reads below then hit 8 distinct bank groups
-    const uint4 v = __ldcs(reinterpret_cast<const uint4*>(s + r * src_row_stride + ch * 8));
-    *reinterpret_cast<uint4*>(&tile[r][(ch ^ ((r >> 3) & 7)) * 8]) = v;
-  }
-  __syncthreads();
+  for (int cc = 0; cc < 8; ++cc) {
+    const uint32_t sel = (cc & 1) ? 0x7632u : 0x5410u;
+    uint32_t w[4];
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int c = (t >> 3) + 32 * i, ch = t & 7;   // output row c (= source column), 8 consecutive source rows
-    __half v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = tile[ch * 8 + j][(((c >> 3) ^ ch) << 3) + (c & 7)];
-    *reinterpret_cast<uint4*>(d + c * d_row + ch * 8) = *reinterpret_cast<const uint4*>(v);
+    for (int i2 = 0; i2 < 4; ++i2) {
+      const uint32_t lo = reinterpret_cast<const uint32_t*>(&a[2 * i2])[cc >> 1];
+      const uint32_t hi = reinterpret_cast<const uint32_t*>(&a[2 * i2 + 1])[cc >> 1];
+      w[i2] = __byte_perm(lo, hi, sel);
+    }
+    *reinterpret_cast<uint4*>(d + cc * d_row) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
