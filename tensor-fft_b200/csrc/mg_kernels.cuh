@@ -75,7 +75,9 @@ __global__ void mg_barrier(const MgFlags f, int rank, int world, uint32_t epoch,
                            volatile int* status) {
   const int p = threadIdx.x;
   if (p >= world) return;
+#if !defined(TFFT_MG_BARRIER_VARIANT) || TFFT_MG_BARRIER_VARIANT == 0
   __threadfence_system();
+#endif
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f.flags[p] + rank), "r"(epoch) : "memory");
   const uint32_t* mine = f.flags[rank] + p;
   unsigned long long t0;
@@ -90,9 +92,13 @@ __global__ void mg_barrier(const MgFlags f, int rank, int world, uint32_t epoch,
       *status = static_cast<int>(epoch);
       break;
     }
+#if !defined(TFFT_MG_BARRIER_VARIANT) || TFFT_MG_BARRIER_VARIANT < 2
     __nanosleep(200);
+#endif
   }
+#if !defined(TFFT_MG_BARRIER_VARIANT) || TFFT_MG_BARRIER_VARIANT == 0
   __threadfence_system();
+#endif
 }
 
 }  // namespace tfft
