@@ -28,27 +28,29 @@ struct MgPeers {
 // loads the 8 x 8 block of rows 8*rg .. 8*rg+7, columns 8*ch .. 8*ch+7 (eight 16-byte loads; a warp instruction covers
 // 8 rows x 64 contiguous bytes), transposes it with byte permutes and stores eight 16-byte pieces; a warp store
 // instruction writes 4 destination rows x 128 contiguous bytes -- whole lines, which is what matters on NVLink.
-// Grid: (ceil(cols / 32 / 8), rows_local / 64, 2 planes), 256 threads.  Column groups are visited peer-interleaved
+// Grid: (rows_local / 64, ceil(cols / 32 / 8), 2 planes), 256 threads.  Column groups are visited peer-interleaved
 // (consecutive warps target different peers, starting at rank + 1) so that all NVLink ports carry traffic at any moment.
 __global__ void __launch_bounds__(256)
 mg_transpose_send(const __half* __restrict__ src_re, const __half* __restrict__ src_im, const MgPeers peers,
                   int rows_local, int cols, int rank, int world, int64_t src_row_stride) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int lin = blockIdx.x * 8 + warp;             // column group (32 columns) in peer-interleaved order
+  // blockIdx.x runs over the 64-row blocks (fastest), blockIdx.y over groups of 8 column groups: CTAs that run together
+  // write neighbouring 128-byte segments of the same destination rows
+  const int lin = blockIdx.y * 8 + warp;             // column group (32 columns) in peer-interleaved order
   if (lin >= cols / 32) return;
   const int cl = cols / world;
   const int peer = (lin + rank + 1) % world;
   const int cg = lin / world;                        // column group inside the peer's block
   const int rg = lane >> 2, ch = lane & 3;
   const int plane = blockIdx.z;
-  const __half* s = (plane ? src_im : src_re) + (static_cast<int64_t>(blockIdx.y) * 64 + 8 * rg) * src_row_stride +
+  const __half* s = (plane ? src_im : src_re) + (static_cast<int64_t>(blockIdx.x) * 64 + 8 * rg) * src_row_stride +
                     static_cast<int64_t>(peer) * cl + cg * 32 + 8 * ch;
   uint4 a[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) a[j] = __ldcs(reinterpret_cast<const uint4*>(s + j * src_row_stride));
   const int64_t d_row = static_cast<int64_t>(world) * rows_local;
   __half* d = (plane ? peers.im[peer] : peers.re[peer]) + (static_cast<int64_t>(cg) * 32 + 8 * ch) * d_row +
-              static_cast<int64_t>(rank) * rows_local + blockIdx.y * 64 + 8 * rg;
+              static_cast<int64_t>(rank) * rows_local + blockIdx.x * 64 + 8 * rg;
 #pragma unroll
   for (int cc = 0; cc < 8; ++cc) {
     const uint32_t sel = (cc & 1) ? 0x7632u : 0x5410u;

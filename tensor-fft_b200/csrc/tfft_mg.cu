@@ -168,7 +168,7 @@ static int mg_exchange(tfft_mg_plan_t p, const __half* src_re, const __half* src
                        int64_t cols, bool barrier, cudaStream_t s) {
   MgPeers peers;
   for (int r = 0; r < p->world; ++r) { peers.re[r] = p->plane(r, which); peers.im[r] = p->plane(r, which + 1); }
-  const dim3 grid(static_cast<unsigned>((cols / 32 + 7) / 8), static_cast<unsigned>(rows_local / 64), 2);
+  const dim3 grid(static_cast<unsigned>(rows_local / 64), static_cast<unsigned>((cols / 32 + 7) / 8), 2);
   if (grid.y > 65535) return TFFT_E_UNSUPPORTED;
   mg_transpose_send<<<grid, 256, 0, s>>>(src_re, src_im, peers, static_cast<int>(rows_local), static_cast<int>(cols),
                                          p->rank, p->world, cols);

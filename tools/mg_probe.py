@@ -78,6 +78,17 @@ def sm_copy():
     assert rc == 0, rc
 out["sm_peer_store_ms"] = round(timed(sm_copy), 4)
 out["sm_peer_store_gbs"] = round(nbytes / out["sm_peer_store_ms"] / 1e6, 1)
+# cold remote pages: the same SM copy kernel cycling over 6 different remote destinations (and sources)
+dsts = [torch.empty(nbytes // 2, dtype=torch.float16, device=f"cuda:{peer}") for _ in range(6)]
+srcs = [torch.empty(nbytes // 2, dtype=torch.float16, device=f"cuda:{local}") for _ in range(6)]
+for d_ in dsts:
+    d_.copy_(src)      # enables peer access / touches the mapping once
+sync()
+def cyc():
+    for i in range(6):
+        rc = L.tfft_copy_runs(srcs[i].data_ptr(), dsts[i].data_ptr(), run, cnt, 1, 1, run, 0, 0, run, 0, 0, s)
+        assert rc == 0, rc
+out["sm_peer_store_cycling6_ms_each"] = round(timed(cyc, iters=3) / 6, 4)
 dst2 = torch.empty_like(src)
 def sm_copy_local():
     rc = L.tfft_copy_runs(src.data_ptr(), dst2.data_ptr(), run, cnt, 1, 1, run, 0, 0, run, 0, 0, s)
