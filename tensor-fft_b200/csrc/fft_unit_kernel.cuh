@@ -237,10 +237,10 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 
 // column-mode tile {8 columns, R kappa, M rows, 1 batch}: coordinates (first column, 0, 0, batch)
 __device__ __forceinline__ void tma_load_4d_col(uint32_t dst, const CUtensorMap* map, uint32_t c0, uint32_t c3,
-                                                uint64_t* bar) {
+                                                uint64_t* bar, uint32_t c2 = 0) {
   asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %3, %4}], [%5];"
-      ::"r"(dst), "l"(map), "r"(c0), "r"(0), "r"(c3), "r"(ptx::smem_u32(bar))
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(0), "r"(c2), "r"(c3), "r"(ptx::smem_u32(bar))
       : "memory");
 }
 
@@ -301,7 +301,31 @@ __device__ __forceinline__ Cplx tw_lookup(const float2* tw_table, uint32_t x) {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// ---------------------------------------------------------------- thread-block cluster (CTA pair) helpers
+// Cluster units (UnitPlan::cluster): two CTAs share a 64K-element unit; the stage-1 epilogue stores into either CTA's
+// shared memory (distributed shared memory), everything else is local.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_map(uint32_t saddr, uint32_t rank) {   // shared::cta address -> CTA `rank`'s window
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {   // every thread of both CTAs; release / acquire at cluster scope
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void sts128_cluster(uint32_t caddr, uint4 v) {
+  asm volatile("st.shared::cluster.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(caddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 struct KernelCtx {
+  uint32_t cl_rank;        // cluster units: rank of this CTA in its pair (0 otherwise)
+  uint32_t cl_delta[2];    // shared::cluster address of CTA r's window minus this CTA's shared::cta base
   uint32_t sbase, s_re, s_im, taddr, lane_row, wgroup, lane_base;
   const float2* tw_table;
   const float2* ytw;       // Kronecker units: exp(-2*pi*i * k_y * y_lo / ny), k_y < 8, of the current unit
@@ -358,6 +382,10 @@ __device__ __forceinline__ uint32_t thread_map(const UnitPlan& P, const KernelCt
   constexpr uint32_t G = (1u << RHO) / 16;
   const UnitPlan::Epi& E = P.epi[ST];
   uint32_t dst = bit_sum(c.lane_row, E.dst, 0, 7), aux = bit_sum(c.lane_row, E.aux, 0, 7);
+  if (P.cluster && c.cl_rank) {   // the CTA's rank is an index bit: the input half in stage 1, the k_1 half afterwards
+    if (ST == 0) { dst += P.cl_in_dst; aux += P.cl_in_aux; }
+    else if (ST + 1 == static_cast<int>(P.stages)) aux += P.cl_out_aux;
+  }
   // warp-group bits: first the g bits (k_t[4], k_t[5]), then tile bits (row bits 7, 8)
   constexpr int kGBits = G >= 4 ? 2 : (G == 2 ? 1 : 0), kWBits = NG == 4 ? 2 : 1;
 #pragma unroll
@@ -394,7 +422,7 @@ __device__ __forceinline__ uint32_t thread_col(const UnitPlan& P, const KernelCt
   return col;
 }
 
-template <int ST, int RHO, bool LAST, uint32_t II, int NG = 2>
+template <int ST, int RHO, bool LAST, uint32_t II, int NG = 2, bool CL = false>
 __device__ __forceinline__ void epilogue_item(const UnitPlan& P, const KernelCtx& c, uint32_t dst_thr, uint32_t aux_thr,
                                               uint32_t col_thr, const TwSeed& seed, const uint32_t (&are)[16],
                                               const uint32_t (&aim)[16]) {
@@ -502,6 +530,17 @@ __device__ __forceinline__ void epilogue_item(const UnitPlan& P, const KernelCtx
       }
     }
   }
+  if constexpr (CL && ST == 0) {
+    // cluster unit, stage 1: the top bit of k_1 (bit RHO-4 of the 8-column chunk index 2g + h) selects the CTA whose
+    // stage-2 operand receives the chunk
+    const uint32_t da = (((2u * g) >> (RHO - 4)) & 1u) ? c.cl_delta[1] : c.cl_delta[0];
+    const uint32_t db = (((2u * g + 1u) >> (RHO - 4)) & 1u) ? c.cl_delta[1] : c.cl_delta[0];
+    sts128_cluster(c.s_re + dst + da, make_uint4(pre[0], pre[1], pre[2], pre[3]));
+    sts128_cluster(c.s_re + dst + E.dst_k[0] + db, make_uint4(pre[4], pre[5], pre[6], pre[7]));
+    sts128_cluster(c.s_im + dst + da, make_uint4(pim[0], pim[1], pim[2], pim[3]));
+    sts128_cluster(c.s_im + dst + E.dst_k[0] + db, make_uint4(pim[4], pim[5], pim[6], pim[7]));
+    return;
+  }
   sts128(c.s_re + dst, make_uint4(pre[0], pre[1], pre[2], pre[3]));
   sts128(c.s_re + dst + E.dst_k[0], make_uint4(pre[4], pre[5], pre[6], pre[7]));
   sts128(c.s_im + dst, make_uint4(pim[0], pim[1], pim[2], pim[3]));
@@ -511,7 +550,7 @@ __device__ __forceinline__ void epilogue_item(const UnitPlan& P, const KernelCtx
 // Software-pipelined item loop over items [II, END): the tensor-memory load of item II+1 is in flight
 // while item II is processed (tcgen05.wait::ld waits for ALL outstanding loads, so the next load is
 // issued right after the wait and before the arithmetic).
-template <int ST, int RHO, bool LAST, uint32_t II, uint32_t END, int NG = 2>
+template <int ST, int RHO, bool LAST, uint32_t II, uint32_t END, int NG = 2, bool CL = false>
 __device__ __forceinline__ void epilogue_range(const UnitPlan& P, const KernelCtx& c, uint32_t dst_thr,
                                                uint32_t aux_thr, uint32_t col_thr, const TwSeed& seed,
                                                uint32_t (&cre)[16], uint32_t (&cim)[16], uint32_t (&nre)[16],
@@ -519,8 +558,8 @@ __device__ __forceinline__ void epilogue_range(const UnitPlan& P, const KernelCt
   if constexpr (II < END) {
     ptx::tmem_ld_wait();                                            // item II has landed in (cre, cim)
     if constexpr (II + 1 < END) epilogue_load<RHO, II + 1, NG>(c, nre, nim);
-    epilogue_item<ST, RHO, LAST, II, NG>(P, c, dst_thr, aux_thr, col_thr, seed, cre, cim);
-    epilogue_range<ST, RHO, LAST, II + 1, END, NG>(P, c, dst_thr, aux_thr, col_thr, seed, nre, nim, cre, cim);
+    epilogue_item<ST, RHO, LAST, II, NG, CL>(P, c, dst_thr, aux_thr, col_thr, seed, cre, cim);
+    epilogue_range<ST, RHO, LAST, II + 1, END, NG, CL>(P, c, dst_thr, aux_thr, col_thr, seed, nre, nim, cre, cim);
   }
 }
 
@@ -634,8 +673,11 @@ __device__ __forceinline__ void stage_observe(uint64_t* bar, uint32_t (&phase)[2
 //         no leading barrier here.
 // EARLY2: the first half of this stage's UMMAs was already issued (and committed to bar[0]) by the previous stage's
 // mid() hook; only the second half is issued here (bar[1]) and the epilogue starts when both have completed.
+// CL: cluster unit (CTA pair).  Stage 1 waits at a cluster barrier between its MMAs and its epilogue (the partner's MMAs
+// must have consumed the partner's operand before this CTA stores into it); every later stage starts at a cluster barrier
+// instead of the CTA barrier (the partner's stores into this CTA's operand must have landed).
 template <int ST, int RHO, bool LAST, int LOG2E, int LM = 0, bool PIPE = false, class Hook = NoHook,
-          int ROLE = 0, int NG = 2, bool EARLY2 = false>
+          int ROLE = 0, int NG = 2, bool EARLY2 = false, bool CL = false>
 __device__ __forceinline__ void run_stage(const UnitPlan& P, const KernelCtx& c, uint32_t b1_saddr, uint64_t* bar,
                                           uint32_t (&phase)[2], int warp, int lane, long long* trace,
                                           uint32_t trace_unit, uint32_t tmap, uint32_t col_thr,
@@ -645,9 +687,16 @@ __device__ __forceinline__ void run_stage(const UnitPlan& P, const KernelCtx& c,
   constexpr uint32_t kItemsPerGroup = SS::kItemsPerGroup;
   constexpr bool kPipe = SS::kPipe;
   if (ROLE == 0 || ST > 0) {
-    fence_proxy_async_smem();   // generic-proxy / cp.async operand writes -> visible to the tensor core
-    tc_fence_before_sync();
-    group_sync(c);
+    if (CL && ST == 1) {
+      fence_proxy_async_all();   // this CTA's stores went into both CTAs' operands
+      tc_fence_before_sync();
+      cluster_sync_all();
+      fence_proxy_async_all();
+    } else {
+      fence_proxy_async_smem();   // generic-proxy / cp.async operand writes -> visible to the tensor core
+      tc_fence_before_sync();
+      group_sync(c);
+    }
     tc_fence_after_sync();
   }
   TFFT_TRACE_MARK(9 + 2 * ST);
@@ -690,9 +739,10 @@ __device__ __forceinline__ void run_stage(const UnitPlan& P, const KernelCtx& c,
       hook.after_half(0);
       hook.after_half(1);
     }
+    if (CL && ST == 0) cluster_sync_all();   // both CTAs' stage-1 MMAs have read their operands
     TFFT_TRACE_MARK(10 + 2 * ST);
     epilogue_load<RHO, 0, NG>(c, ra, rb);
-    epilogue_range<ST, RHO, LAST, 0, kItemsPerGroup, NG>(P, c, dst_thr, aux_thr, col_thr, seed, ra, rb, rc, rd);
+    epilogue_range<ST, RHO, LAST, 0, kItemsPerGroup, NG, CL>(P, c, dst_thr, aux_thr, col_thr, seed, ra, rb, rc, rd);
     phase[0]++;
     if (EARLY2) phase[1]++;
   }
@@ -765,7 +815,8 @@ __device__ __forceinline__ void store_phase(const UnitPlan& P, const KernelCtx& 
 // NT threads: 256 (two warp groups), or 512 (four warp groups) for the 32K-element units that run one CTA per SM
 // LM: how the stage-1 operand is loaded: 0 = 16-byte cp.async (any mode), 1 = one SWIZZLE_128B TMA tile per plane (row
 // mode), 2 = dense TMA tiles of 8 columns (column mode)
-template <int LOG2E, int RHO0, int RHO1, int RHO2, int LM, int NT = kThreads>
+// CL = 1: cluster units -- launched with a cluster dimension of 2; CTA pair c = blockIdx.x / 2 works on units c, c + gridDim.x/2, ...
+template <int LOG2E, int RHO0, int RHO1, int RHO2, int LM, int NT = kThreads, int CL = 0>
 __global__ void __launch_bounds__(NT, (LOG2E == 15 ? 1 : 2))
 fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ in_re,
                 const __half* __restrict__ in_im, __half* __restrict__ out_re, __half* __restrict__ out_im,
@@ -797,6 +848,10 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
   c.sync_threads = NT;
   c.mma_warp = 0;
   c.ytw = reinterpret_cast<const float2*>(smem + SL.ytw_off);
+  c.cl_rank = CL ? cluster_ctarank() : 0u;
+  c.cl_delta[0] = CL ? cluster_map(c.sbase, 0) - c.sbase : 0u;
+  c.cl_delta[1] = CL ? cluster_map(c.sbase, 1) - c.sbase : 0u;
+  const uint32_t first_unit = CL ? blockIdx.x >> 1 : blockIdx.x, unit_step = CL ? gridDim.x >> 1 : gridDim.x;
   uint32_t trace_unit = 0;
   (void)trace_unit;
 
@@ -814,17 +869,17 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
     mbar_init(bar + 1, 1);
     mbar_init(load_bar, 1);
     fence_mbar_init();
-    if (kEarlyFirstTile && blockIdx.x < P.n_units) {
+    if (kEarlyFirstTile && first_unit < P.n_units) {
       pdl_wait();
-      const uint32_t unit = blockIdx.x, ub = unit >> P.upb_shift, uu = unit & ((1u << P.upb_shift) - 1u);
+      const uint32_t unit = first_unit, ub = unit >> P.upb_shift, uu = unit & ((1u << P.upb_shift) - 1u);
       mbar_arrive_expect_tx(load_bar, 4u << LOG2E);
       if (P.kron_bits) {
         tma_load_5d(smem_u32(smem), &tmap_re, uu, ub * P.tma_batch_step, load_bar);
         tma_load_5d(smem_u32(smem) + SL.plane_stride, &tmap_im, uu, ub * P.tma_batch_step, load_bar);
       } else {
         const uint32_t c3 = ub * P.tma_batch_step + (uu << P.log2_units);
-        tma_load_4d(smem_u32(smem), &tmap_re, 0, c3, load_bar);
-        tma_load_4d(smem_u32(smem) + SL.plane_stride, &tmap_im, 0, c3, load_bar);
+        tma_load_4d(smem_u32(smem), &tmap_re, c.cl_rank * P.cl_load_c2, c3, load_bar);
+        tma_load_4d(smem_u32(smem) + SL.plane_stride, &tmap_im, c.cl_rank * P.cl_load_c2, c3, load_bar);
       }
     }
   }
@@ -832,6 +887,7 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
+  if (CL) cluster_sync_all();   // the partner CTA is resident and its barriers are initialised before anything is stored into it
   pdl_wait();   // the predecessor in the stream may have produced this kernel's input (or still read its output)
   c.taddr = *tmem_slot;
   uint32_t phase[2] = {0, 0}, load_phase = 0;
@@ -848,12 +904,12 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
   const TwSeed seed0 = thread_seed(P, 0, tmap0);
   const TwSeed seed1 = kStages == 3 ? thread_seed(P, 1, tmap1) : TwSeed();
 
-  for (uint32_t unit = blockIdx.x; unit < P.n_units; unit += gridDim.x) {
+  for (uint32_t unit = first_unit; unit < P.n_units; unit += unit_step) {
     const uint32_t ub = unit >> P.upb_shift, uu = unit & ((1u << P.upb_shift) - 1u);
-    const int64_t in_base =
-        static_cast<int64_t>(ub) * P.in_batch_stride + static_cast<int64_t>(uu) * P.in_unit_stride;
-    const int64_t out_base =
-        static_cast<int64_t>(ub) * P.out_batch_stride + static_cast<int64_t>(uu) * P.out_unit_stride;
+    const int64_t in_base = static_cast<int64_t>(ub) * P.in_batch_stride + static_cast<int64_t>(uu) * P.in_unit_stride +
+                            (CL ? static_cast<int64_t>(c.cl_rank) * P.cl_load_gofs : 0);
+    const int64_t out_base = static_cast<int64_t>(ub) * P.out_batch_stride + static_cast<int64_t>(uu) * P.out_unit_stride +
+                             (CL ? static_cast<int64_t>(c.cl_rank) * P.cl_out_gofs : 0);
     // row/row passes with a ragged batch: transforms past the end are loaded as zeros, never stored
     const uint32_t u_limit =
         P.n_transforms ? P.n_transforms - min(P.n_transforms, unit << P.log2_units) : 0xFFFFFFFFu;
@@ -872,10 +928,12 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
         constexpr uint32_t W = LM == 4 ? 16 : 8;
         fence_proxy_async_smem();
         mbar_arrive_expect_tx(load_bar, 4u << LOG2E);
-        const uint32_t group_bytes = (2 * W) << P.log2_len;
+        const uint32_t group_bytes = ((2 * W) << P.log2_len) >> CL;   // a cluster CTA loads half of the rows
         for (uint32_t ug = 0; ug < (1u << P.log2_units) / W; ++ug) {
-          tma_load_4d_col(c.s_re + ug * group_bytes, &tmap_re, (uu << P.log2_units) + W * ug, ub, load_bar);
-          tma_load_4d_col(c.s_im + ug * group_bytes, &tmap_im, (uu << P.log2_units) + W * ug, ub, load_bar);
+          tma_load_4d_col(c.s_re + ug * group_bytes, &tmap_re, (uu << P.log2_units) + W * ug, ub, load_bar,
+                          c.cl_rank * P.cl_load_c2);
+          tma_load_4d_col(c.s_im + ug * group_bytes, &tmap_im, (uu << P.log2_units) + W * ug, ub, load_bar,
+                          c.cl_rank * P.cl_load_c2);
         }
       }
       TFFT_TRACE_MARK(1);
@@ -884,7 +942,7 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
     } else if constexpr (LM == 1 || LM == 3) {
       // one tensor tile per plane: {64 rows, R kappa, M/64, U transforms}; transforms past the end of
       // the batch are out of bounds of the tensor map and arrive as zeros
-      if (tid == 0 && !(kEarlyFirstTile && unit == blockIdx.x)) {   // the first tile was requested during the setup
+      if (tid == 0 && !(kEarlyFirstTile && unit == first_unit)) {   // the first tile was requested during the setup
         fence_proxy_async_smem();   // earlier generic-proxy reads of the planes precede the async-proxy writes
         mbar_arrive_expect_tx(load_bar, 4u << LOG2E);
         if (P.kron_bits) {
@@ -892,8 +950,8 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
           tma_load_5d(c.s_im, &tmap_im, uu, ub * P.tma_batch_step, load_bar);
         } else {
           const uint32_t c3 = ub * P.tma_batch_step + (uu << P.log2_units);
-          tma_load_4d(c.s_re, &tmap_re, 0, c3, load_bar);
-          tma_load_4d(c.s_im, &tmap_im, 0, c3, load_bar);
+          tma_load_4d(c.s_re, &tmap_re, c.cl_rank * P.cl_load_c2, c3, load_bar);
+          tma_load_4d(c.s_im, &tmap_im, c.cl_rank * P.cl_load_c2, c3, load_bar);
         }
       }
       TFFT_TRACE_MARK(1);
@@ -945,7 +1003,7 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
     }
     TFFT_TRACE_MARK(2);
     // pull the next unit's input into L2 while this one is transformed and stored
-    const bool pf = P.prefetch_next && unit + gridDim.x < P.n_units;
+    const bool pf = !CL && P.prefetch_next && unit + gridDim.x < P.n_units;
     if (pf) {
       const uint32_t un = unit + gridDim.x, nb = un >> P.upb_shift, nu = un & ((1u << P.upb_shift) - 1u);
       if constexpr (LM == 2 || LM == 4) {
@@ -980,16 +1038,16 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
     }
 
     // ---------------------------------------------------------------- tensor-core stages
-    run_stage<0, RHO0, false, LOG2E, LM, false, NoHook, 0, NG>(P, c, table_base + TL.b_off[0], bar, phase, warp, lane,
-                                                                trace, trace_unit, tmap0, 0u, seed0);
+    run_stage<0, RHO0, false, LOG2E, LM, false, NoHook, 0, NG, false, CL != 0>(P, c, table_base + TL.b_off[0], bar, phase,
+                                                                                warp, lane, trace, trace_unit, tmap0, 0u, seed0);
     TFFT_TRACE_MARK(3);
     // 3-stage plans built with pipe_stage2: the epilogue of stage 2's first tile half overlaps the UMMAs of its second
     if (kStages == 3 && P.pipe_stage2)
-      run_stage<1, RHO1, kStages == 2, LOG2E, 0, true, NoHook, 0, NG>(P, c, table_base + TL.b_off[1], bar, phase, warp,
-                                                                          lane, trace, trace_unit, tmap1, col_thr, seed1);
+      run_stage<1, RHO1, kStages == 2, LOG2E, 0, true, NoHook, 0, NG, false, CL != 0>(
+          P, c, table_base + TL.b_off[1], bar, phase, warp, lane, trace, trace_unit, tmap1, col_thr, seed1);
     else
-      run_stage<1, RHO1, kStages == 2, LOG2E, 0, false, NoHook, 0, NG>(P, c, table_base + TL.b_off[1], bar, phase, warp,
-                                                                           lane, trace, trace_unit, tmap1, col_thr, seed1);
+      run_stage<1, RHO1, kStages == 2, LOG2E, 0, false, NoHook, 0, NG, false, CL != 0>(
+          P, c, table_base + TL.b_off[1], bar, phase, warp, lane, trace, trace_unit, tmap1, col_thr, seed1);
     TFFT_TRACE_MARK(4);
     if constexpr (kStages == 3)
       run_stage<2, (RHO2 ? RHO2 : 4), true, LOG2E, 0, false, NoHook, 0, NG>(P, c, table_base + TL.b_off[2], bar, phase,
@@ -1009,6 +1067,7 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
 
   // ------------------------------------------------------------------ teardown
   tc_fence_before_sync();
+  if (CL) cluster_sync_all();   // no CTA of a pair leaves while its partner could still address its shared memory
   __syncthreads();
   if (warp == 0) tmem_dealloc(c.taddr, P.tmem_cols);
 }

@@ -3,7 +3,7 @@
 #include "kernel_table.h"
 
 #ifndef TFFT_GROUP
-#error "build with -DTFFT_GROUP=0..4"
+#error "build with -DTFFT_GROUP=0..5"
 #endif
 
 namespace tfft {
@@ -19,6 +19,19 @@ namespace tfft {
 #define TFFT_KW(E, A, B, C) \
   {E, A, B, C, fft_unit_kernel<E, A, B, C, 0, 512>, fft_unit_kernel<E, A, B, C, 1, 512>, fft_unit_kernel<E, A, B, C, 2, 512>, 512}
 
+#if TFFT_GROUP == 5
+// cluster units: a CTA pair shares 2^16 elements (N = 65536 in one pass; 16 columns x 4096 for column passes)
+static const ClusterEntry g_cluster[] = {
+    {4, 6, 6, 1, fft_unit_kernel<15, 4, 6, 6, 1, 512, 1>},
+    {4, 6, 6, 0, fft_unit_kernel<15, 4, 6, 6, 0, 512, 1>},
+    {6, 6, 0, 4, fft_unit_kernel<15, 6, 6, 0, 4, 512, 1>},
+    {6, 6, 0, 0, fft_unit_kernel<15, 6, 6, 0, 0, 512, 1>},
+};
+const ClusterEntry* kernel_cluster_group(int* count) {
+  *count = static_cast<int>(sizeof(g_cluster) / sizeof(g_cluster[0]));
+  return g_cluster;
+}
+#else
 static const KernelEntry g_entries[] = {
 #if TFFT_GROUP == 0
     TFFT_KS(13, 4, 4, 0), TFFT_KSC(14, 4, 4, 0),                    // L = 2^8
@@ -56,5 +69,6 @@ const Kernel2Entry* kernel2_group(int* count) {
   return g_entries2;
 }
 #endif
+#endif   // TFFT_GROUP != 5
 
 }  // namespace tfft

@@ -23,6 +23,13 @@ struct Kernel2Entry {
   int r0, r1, r2;
   Kernel2Fn fn;
 };
+// Cluster units (UnitPlan::cluster): 512-thread CTAs launched as pairs; lm = load mode (0 cp.async, 1 row TMA tile, 4 column
+// TMA tiles of 16 columns)
+struct ClusterEntry {
+  int r0, r1, r2, lm;
+  KernelFn fn;
+};
+const ClusterEntry* kernel_cluster_group(int* count);
 constexpr int kKernelGroups = 5;
 // entries of group g (kernel_group.cu built with -DTFFT_GROUP=g)
 const KernelEntry* kernel_group_0(int* count);

@@ -40,7 +40,7 @@ struct Prepared {
   const uint4* tables = nullptr;
   unsigned grid = 0, block = 0;
   uint32_t smem = 0;
-  bool two_slot = false;
+  bool two_slot = false, cluster = false;
 };
 constexpr size_t kPreparedSlots = 4;
 
@@ -134,6 +134,17 @@ const char* dev_env(const char* name) {
 }
 // Kernel instantiations: one per (unit size, radix schedule) the planner can produce (kernel_table.h / kernel_group.cu).
 KernelFn kernel_for(const UnitPlan& p, int* threads) {
+  if (p.cluster) {   // CTA-pair units: 512-thread kernels of kernel_group.cu group 5
+    int count = 0;
+    const ClusterEntry* e = kernel_cluster_group(&count);
+    for (int i = 0; i < count; ++i)
+      if (e[i].r0 == static_cast<int>(p.log2_radix[0]) && e[i].r1 == static_cast<int>(p.log2_radix[1]) &&
+          e[i].r2 == static_cast<int>(p.stages == 3 ? p.log2_radix[2] : 0) && e[i].lm == static_cast<int>(p.tma_load)) {
+        *threads = 512;
+        return e[i].fn;
+      }
+    return nullptr;
+  }
   static const bool narrow = dev_env("TFFT_NARROW_32K") != nullptr;   // developer A/B: 256-thread CTAs for 32K-element units
   typedef const KernelEntry* (*GroupFn)(int*);
   static const GroupFn groups[kKernelGroups] = {kernel_group_0, kernel_group_1, kernel_group_2, kernel_group_3, kernel_group_4};
@@ -156,7 +167,7 @@ KernelFn kernel_for(const UnitPlan& p, int* threads) {
 
 // Two-slot variant (one CTA per SM, two units in flight, shared landing buffer) for 16K-element units
 Kernel2Fn kernel2_for(const UnitPlan& p, bool allowed = true) {
-  if (!allowed || p.tma_load != 1 || p.log2_elems != 14 || p.stages != 3) return nullptr;
+  if (!allowed || p.cluster || p.tma_load != 1 || p.log2_elems != 14 || p.stages != 3) return nullptr;
   if (smem2_layout(p).total > 227 * 1024) return nullptr;   // e.g. three distinct DFT matrices
   int count = 0;
   const Kernel2Entry* e = kernel2_group(&count);
@@ -202,6 +213,7 @@ int make_input_tensor_map(const UnitPlan& plan, const __half* base, int64_t tstr
     if (U >= 2) box[3] = static_cast<cuuint32_t>(U / 2);
     else box[2] = static_cast<cuuint32_t>(M / 128);
   }
+  if (plan.cluster) box[2] = static_cast<cuuint32_t>(M / 128);   // a cluster CTA loads the rows of one half of m
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(base), gdim, gstride, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -243,7 +255,8 @@ int make_col_tensor_map(const UnitPlan& plan, const __half* base, int64_t nstrid
   cuuint64_t gstride[3] = {M * static_cast<cuuint64_t>(nstride) * 2, static_cast<cuuint64_t>(nstride) * 2,
                            static_cast<cuuint64_t>(batch_stride) * 2};
   // mode 2: 8-column tiles, dense; mode 4: 16-column tiles (whole 32-byte sectors) as SWIZZLE_32B atoms
-  cuuint32_t box[4] = {plan.tma_load == 4 ? 16u : 8u, static_cast<cuuint32_t>(R), static_cast<cuuint32_t>(M), 1};
+  cuuint32_t box[4] = {plan.tma_load == 4 ? 16u : 8u, static_cast<cuuint32_t>(R),
+                       static_cast<cuuint32_t>(plan.cluster ? M / 2 : M), 1};   // a cluster CTA loads one half of m
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(base), gdim, gstride, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -254,20 +267,32 @@ int make_col_tensor_map(const UnitPlan& plan, const __half* base, int64_t nstrid
 
 // All kernels are launched with programmatic stream serialization: a kernel's CTAs may become resident while its
 // predecessor in the stream drains; the kernels themselves wait (griddepcontrol.wait) before they touch data.
-cudaError_t launch_pdl(const void* fn, unsigned grid, unsigned block, void** args, size_t smem, cudaStream_t stream) {
+cudaError_t launch_pdl(const void* fn, unsigned grid, unsigned block, void** args, size_t smem, cudaStream_t stream,
+                       bool cluster = false) {
   static const bool no_pdl = dev_env("TFFT_NO_PDL") != nullptr;
-  if (no_pdl) return cudaLaunchKernel(fn, dim3(grid), dim3(block), args, smem, stream);
+  if (no_pdl && !cluster) return cudaLaunchKernel(fn, dim3(grid), dim3(block), args, smem, stream);
   cudaLaunchConfig_t cfg;
   std::memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(block);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  unsigned na = 0;
+  if (!no_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (cluster) {   // CTA-pair units (UnitPlan::cluster)
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = na;
   return cudaLaunchKernelExC(&cfg, fn, args);
 }
 
@@ -282,6 +307,7 @@ struct Tuning {
   int prefetch = -1;       // L2 prefetch of the next unit                 (TFFT_PREFETCH)
   int fourstep_lg1 = -1;   // log2 of the column-pass length, N > 2^15     (TFFT_FOURSTEP_LG1)
   int tma_col = -1;        // TMA column tiles in four-step column passes  (TFFT_NO_TMA_COL)
+  int cluster = -1;        // CTA-pair units: N = 65536 in one pass, 16-column units for 4096-point column passes (TFFT_NO_CLUSTER)
 };
 int knob(int tuned, const char* env_off, int dflt) {   // env_off: variable whose presence switches the feature off
   if (tuned >= 0) return tuned;
@@ -393,6 +419,22 @@ int build_1d(tfft_plan_s* p) {
   if (p->flags & TFFT_INTERLEAVED) {
     if (lg > 24) return TFFT_E_UNSUPPORTED;   // three-pass sizes: planar only
   }
+  const bool use_cluster = knob(p->tune.cluster, "TFFT_NO_CLUSTER", 1) != 0 && !(p->flags & TFFT_INTERLEAVED);
+  if (lg == 16 && use_cluster) {
+    // N = 65536 in ONE pass (BASELINE north_star (2)): a unit of 2^16 elements shared by a CTA pair -- each CTA loads the
+    // rows of one half of m = n mod 4096, runs the radix-16 stage on them and hands the outputs of the other half of k_1
+    // to its partner through distributed shared memory; the two radix-64 stages and the store are local
+    UnitShape sh;
+    sh.log2_len = 16;
+    sh.log2_units = 0;
+    sh.cluster = true;
+    sh.tma_load = knob(p->tune.tma, "TFFT_NO_TMA", 1) != 0;
+    UnitStrides st;
+    st.n_transforms = static_cast<uint32_t>(batch);
+    st.units_per_batch = 0x7FFFFFFFu;
+    if (!add_pass(p, sh, st, static_cast<uint32_t>(batch), 0, 1, true, true)) return TFFT_E_UNSUPPORTED;
+    return TFFT_OK;
+  }
   int three_from = 25;   // developer knob: three passes from this log2 length on (>= 24: all factors >= 256)
   if (const char* e = dev_env("TFFT_THREEPASS_LG")) three_from = std::min(25, std::max(24, atoi(e)));   // four-step covers <= 2^24 only
   if (lg >= three_from && !(p->flags & TFFT_INTERLEAVED)) {
@@ -489,6 +531,8 @@ int build_1d(tfft_plan_s* p) {
     // 2048-point columns: 16 columns per unit (32K elements, 16-column tiles) instead of 8 (measured at 2^23 = 2048 x 4096:
     // 2.23 -> 1.87 ms)
     if (lg1 == 11 && dev_env("TFFT_COL2048_U8") == nullptr) sh.log2_units = 4;
+    // 4096-point columns: 16 columns per unit (32-byte pieces on both sides instead of 16-byte ones) as a CTA-pair unit
+    if (lg1 == 12 && use_cluster) { sh.log2_units = 4; sh.cluster = true; }
     sh.in_mode = kColMode;
     sh.out_mode = kColMode;
     sh.tma_load = knob(p->tune.tma_col, "TFFT_NO_TMA_COL", 1) && !interleaved;   // column tiles {8 columns, R, M} by TMA
@@ -617,6 +661,8 @@ int build_2d(tfft_plan_s* p, std::vector<Pass>* passes, bool allow_tma) {
     // passes (row stride <= 8 KiB) gain 1-4 % from the tiles and keep them.
     sh.tma_load = dev_env("TFFT_TMA_COL_2D") != nullptr;
     if (lg2 == 11 && dev_env("TFFT_2D_COL_U16")) sh.log2_units = 4;   // developer knob: 16 columns x 2048 (32-byte pieces)
+    // 4096-point columns: CTA-pair units of 16 columns (32-byte pieces)
+    if (lg2 == 12 && knob(p->tune.cluster, "TFFT_NO_CLUSTER", 1) != 0) { sh.log2_units = 4; sh.cluster = true; }
     const int64_t U = int64_t(1) << sh.log2_units;
     UnitStrides st;
     st.in_nstride = nx << yb; st.out_nstride = nx << yb;
@@ -668,7 +714,27 @@ int ensure_pass_on_device(const Pass& ps, int dev, const void* entry, bool two_s
   int per_sm = 0, sms = 0, smem_sm = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
-  if (two_slot) {
+  if (ps.plan.cluster) {
+    // resident CTA pairs: the pairs must fit the GPCs, so ask the runtime instead of multiplying
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(static_cast<unsigned>(2 * sms));
+    cfg.blockDim = dim3(static_cast<unsigned>(threads));
+    cfg.dynamicSmemBytes = ps.smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int clusters = 0;
+    e = cudaOccupancyMaxActiveClusters(&clusters, fn, &cfg);
+    if (e != cudaSuccess || clusters < 1) { cudaGetLastError(); cudaFree(d); return TFFT_E_UNSUPPORTED; }
+    ps.resident_ctas[dev] = 2 * clusters;
+    ps.d_tables[dev] = d;
+    return TFFT_OK;
+  } else if (two_slot) {
     per_sm = 1;   // two units in flight inside one CTA
   } else {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, ps.smem);
@@ -741,7 +807,9 @@ int prepare_launch(const tfft_plan_s* p, const Pass& ps, const __half* src_re, c
     if (rc != TFFT_OK) return rc;
   }
   out->tables = ps.d_tables[dev];
-  out->grid = std::min<unsigned>(ps.n_units, static_cast<unsigned>(ps.resident_ctas[dev]));
+  out->grid = plan.cluster ? 2u * std::min<unsigned>(ps.n_units, static_cast<unsigned>(ps.resident_ctas[dev]) / 2u)
+                           : std::min<unsigned>(ps.n_units, static_cast<unsigned>(ps.resident_ctas[dev]));
+  out->cluster = plan.cluster != 0;
   out->block = fn2 ? static_cast<unsigned>(kCta2Threads) : static_cast<unsigned>(threads);
   out->smem = smem;
   out->fn = entry;
@@ -808,7 +876,7 @@ int launch_pass(const tfft_plan_s* p, const Pass& ps, const __half* src_re, cons
     e = launch_pdl(L.fn, L.grid, L.block, args2, L.smem, stream);
   } else {
     void* args[] = {&L.plan, &src_re, &src_im, &dst_re, &dst_im, &L.tables, &trace, &L.tmap_re, &L.tmap_im};
-    e = launch_pdl(L.fn, L.grid, L.block, args, L.smem, stream);
+    e = launch_pdl(L.fn, L.grid, L.block, args, L.smem, stream, L.cluster);
   }
   return e == cudaSuccess ? TFFT_OK : static_cast<int>(e);
 }
@@ -876,6 +944,7 @@ int tfft_plan_create_from_file(tfft_plan_t* out, int64_t n, int64_t batch, uint3
       else if (kl == 8 && !strncmp(tok, "prefetch", 8)) t.prefetch = v;
       else if (kl == 3 && !strncmp(tok, "lg1", 3)) t.fourstep_lg1 = v;
       else if (kl == 7 && !strncmp(tok, "tma_col", 7)) t.tma_col = v;
+      else if (kl == 7 && !strncmp(tok, "cluster", 7)) t.cluster = v;
     }
     rc = plan_create_tuned(out, n, batch, flags, t);
     break;

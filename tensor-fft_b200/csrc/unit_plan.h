@@ -52,6 +52,10 @@ struct UnitShape {
   int kron_bits = 0;         // 2-D row pass: the U = 2^kron_bits transforms of a unit are rows y_lo + u*(ny/U) of one image
                              // and the LAST tensor stage also transforms across them (DFT matrix = F_x (x) F_y), i.e.
                              // the unit computes a 2-D DFT of size U x L.  Needs kron_bits == log2_units, row modes.
+  bool cluster = false;      // the unit holds 2^16 elements and is shared by a pair of CTAs (thread-block cluster of 2): CTA r
+                             // loads the half of the rows whose highest not-yet-transformed index bit (the top bit of m_1)
+                             // is r, runs stage 1 on it, and its stage-1 epilogue stores every output whose top k_1 bit is d
+                             // into CTA d's shared memory (distributed shared memory); stages 2.. and the store are local
   bool pipe_stage2 = false;  // 3-stage plans: make the top row bit of stages 2 and 3 the same logical bit (k_1's
                              // top bit), so that the epilogue of the first half of stage 2's tiles only writes into
                              // the already consumed first half of the operand planes (MMA / epilogue overlap)
@@ -73,6 +77,12 @@ struct UnitPlan {
   uint32_t il_swap;                        // interleaved + inverse: the pairs are read / written as (im, re)
   uint32_t il_in, il_out;                  // TFFT_INTERLEAVED: this pass reads / writes half2 (re, im) elements (cp.async
                                            // load path only); the element offsets of the plan are doubled on the fly
+  uint32_t cluster;                        // 1: CTA-pair unit (UnitShape::cluster); the fields below are the rank-1 constants
+  uint32_t cl_in_dst, cl_in_aux;           //   stage-1 epilogue: destination bytes / twiddle integer of the input half bit
+  uint32_t cl_out_aux;                     //   last stage: output-index weight of the top k_1 bit (tw_mode 2)
+  uint32_t cl_load_c2;                     //   TMA loads: dim-2 tile coordinate of rank 1 (row tiles: M/128; column tiles: M/2)
+  uint32_t cl_load_gofs;                   //   cp.async loads: global element offset of rank 1's rows (fill_strides)
+  uint32_t cl_out_gofs;                    //   store: global element offset of rank 1's outputs (fill_strides)
   uint32_t prefetch_next;                  // 1: pull the next unit's input into L2 during this unit's stages
   uint32_t tma_load;                       // 4: column-mode input, >= 16 columns per unit: tiles {16 columns, R kappa, M rows} per
                                            //    16-column group as SWIZZLE_32B atoms: row = (u&15) + 16*(m + M*(u>>4)), element
@@ -153,6 +163,8 @@ struct PlanBuildInfo {   // host-only by-products, used by fill_strides and the 
                                             // a Kronecker last stage: rho - kron_bits)
   int kron_bits = 0;
   int lo_bit[kMaxStages] = {0, 0, 0};       // n_t = n bits [lo_bit, lo_bit + rho)
+  bool cluster = false;
+  LBit cin = {LBit::R, 0, 0}, cout = {LBit::K, 1, 0};   // cluster units: the input half bit and the output half bit
   std::string error;
 };
 
@@ -171,6 +183,7 @@ inline int radix_schedule(int log2_len, int* rho, int kron_bits = 0) {
     case 13: rho[0] = 4; rho[1] = 4; rho[2] = 5; return 3;
     case 14: rho[0] = 4; rho[1] = 5; rho[2] = 5; return 3;
     case 15: rho[0] = 5; rho[1] = 5; rho[2] = 5; return 3;
+    case 16: rho[0] = 4; rho[1] = 6; rho[2] = 6; return 3;   // cluster units only (one CTA pair per transform)
     default: return 0;
   }
 }
@@ -192,14 +205,21 @@ inline bool build_unit_plan(const UnitShape& shape, UnitPlan* plan, PlanBuildInf
   std::memset(plan, 0, sizeof(*plan));
   const int lg = shape.log2_len;
   const int ups = shape.log2_units;
-  const int eps = lg + ups;
+  const bool cl = shape.cluster;
+  const int eps = lg + ups - (cl ? 1 : 0);   // elements per CTA
   int* rho = info->rho;
   const int kb = shape.kron_bits;
+  if (cl && (kb || lg + ups != 16 || shape.in_mode != shape.out_mode)) {
+    info->error = "cluster units hold 2^16 elements, same mode in and out, no Kronecker stage"; return false;
+  }
+  if (!cl && lg > 15) { info->error = "length must be 2^8 .. 2^15"; return false; }
+  info->cluster = cl;
+  plan->cluster = cl ? 1u : 0u;
   if (kb && (kb != ups || shape.in_mode != kRowMode || shape.out_mode != kRowMode || lg < 8)) {
     info->error = "Kronecker units need kron_bits == log2_units and row modes"; return false;
   }
   const int s = radix_schedule(kb ? eps : lg, rho, kb);
-  if (s == 0) { info->error = "length must be 2^8 .. 2^15"; return false; }
+  if (s == 0) { info->error = "length must be 2^8 .. 2^15 (2^16 for cluster units)"; return false; }
   if (eps < 13 || eps > 15) { info->error = "unit must hold 2^13 .. 2^15 elements"; return false; }
   int* rx = info->rx;
   for (int t = 0; t < s; ++t) rx[t] = rho[t] - (t == s - 1 ? kb : 0);
@@ -224,12 +244,18 @@ inline bool build_unit_plan(const UnitShape& shape, UnitPlan* plan, PlanBuildInf
   plan->tma_load = shape.tma_load ? (shape.in_mode == kColMode ? (ups >= 4 ? 4u : 2u) : ((lg - rho[0]) < 6 ? 3u : 1u)) : 0u;
   // the first-half epilogue of stage 2 writes the first half of stage 3's layout, which must lie inside the half of
   // stage 2's layout that its first-half MMAs have consumed: padded plane sizes shrink with the radix, so R_3 >= R_2
-  const bool pipe2 = shape.pipe_stage2 && s == 3 && rho[2] >= rho[1];
+  const bool pipe2 = shape.pipe_stage2 && s == 3 && rho[2] >= rho[1] && !cl;
   plan->pipe_stage2 = pipe2 ? 1u : 0u;
   {
     int lo = lg;
     for (int t = 0; t < s; ++t) { lo -= rx[t]; info->lo_bit[t] = lo; }
   }
+  if (cl) {
+    if (info->lo_bit[0] < 1) { info->error = "cluster unit: stage 1 leaves no index bit to split on"; return false; }
+    info->cin = {LBit::R, 0, (uint8_t)(info->lo_bit[0] - 1)};
+    info->cout = {LBit::K, 1, (uint8_t)(rho[0] - 1)};
+  }
+  const LBit cin = info->cin, cout = info->cout;
   uint32_t max_plane = 0;
   for (int t = 0; t < s; ++t) {
     plan->log2_radix[t] = rho[t];
@@ -265,6 +291,7 @@ inline bool build_unit_plan(const UnitShape& shape, UnitPlan* plan, PlanBuildInf
     for (int b = 3; b < ups; ++b) lb.push_back({LBit::U, 0, (uint8_t)b});
     for (int i = 0; i < lg; ++i) lb.push_back({LBit::R, 0, (uint8_t)i});
   }
+  if (cl) lb.erase(lb.begin() + find_bit(lb, cin));   // the CTA's rank
   plan->load_item_bits = static_cast<uint32_t>(lb.size());
   std::vector<LBit> writer_varying(lb.begin(), lb.begin() + 3);
 
@@ -286,6 +313,11 @@ inline bool build_unit_plan(const UnitShape& shape, UnitPlan* plan, PlanBuildInf
     for (int i = 0; i < info->lo_bit[t - 1]; ++i) all.push_back({LBit::R, 0, (uint8_t)i});
     for (int tt = 1; tt < t; ++tt)
       for (int i = 0; i < rho[tt - 1]; ++i) all.push_back({LBit::K, (uint8_t)tt, (uint8_t)i});
+    if (cl) {   // stage 1 works on one half of m_1, the later stages on one half of k_1: that bit is the CTA's rank
+      const int drop = find_bit(all, t == 1 ? cin : cout);
+      if (drop < 0) { info->error = "cluster bit missing"; return false; }
+      all.erase(all.begin() + drop);
+    }
     if (!(kb && t == s))
       for (int b = 0; b < ups; ++b) all.push_back({LBit::U, 0, (uint8_t)b});
     std::vector<LBit> rest;
@@ -372,6 +404,7 @@ inline bool build_unit_plan(const UnitShape& shape, UnitPlan* plan, PlanBuildInf
     for (size_t i = 3; i < addr_bits.size() && g.size() < 3; ++i) {
       const LBit& b = addr_bits[i];
       if (b.kind == LBit::K && b.stage == s && b.idx < 3) continue;
+      if (cl && b == cout) continue;
       g.push_back(b);
     }
     bool used[3] = {false, false, false};
@@ -433,8 +466,15 @@ inline bool build_unit_plan(const UnitShape& shape, UnitPlan* plan, PlanBuildInf
     }
     for (int i = 3; i < rho[t - 1]; ++i) {
       const LBit kb = {LBit::K, (uint8_t)t, (uint8_t)i};
+      if (cl && kb == cout) { e.dst_k[i - 3] = 0; continue; }   // selects the destination CTA, not an address
       e.dst_k[i - 3] = t < s ? row_pos_bytes(t + 1, find_bit(info->row_bits[t], kb)) : staging_contrib(kb);
     }
+    if (cl && t == 1) {
+      int p;
+      plan->cl_in_dst = is_kbit_of_stage(cin, 2, &p) ? k_bit_bytes(p) : row_pos_bytes(2, find_bit(info->row_bits[1], cin));
+      plan->cl_in_aux = 1u << cin.idx;
+    }
+    if (cl && t == s) plan->cl_out_aux = 1u << find_bit(obits, cout);
     if (t < s) {
       e.tw_mode = 1;
       // N_t = 2^(lo_bit[t-1] + rho_t); unit angle 2*pi/L: x = m_t * (L / N_t) * k
@@ -467,6 +507,12 @@ inline bool build_unit_plan(const UnitShape& shape, UnitPlan* plan, PlanBuildInf
     }
   }
 
+  if (cl) {
+    const uint32_t M = 1u << info->lo_bit[0];   // rows per K line of stage 1
+    plan->cl_load_c2 = shape.in_mode == kRowMode ? M / 128 : M / 2;
+    if (shape.tma_load && shape.in_mode == kRowMode && M < 128) { info->error = "cluster row tiles need M >= 128"; return false; }
+  }
+
   // ---------------- store maps
   {
     std::vector<LBit>& sb = info->store_bits;
@@ -474,6 +520,7 @@ inline bool build_unit_plan(const UnitShape& shape, UnitPlan* plan, PlanBuildInf
     for (size_t i = 3; i < addr_bits.size(); ++i) {
       const LBit& b = addr_bits[i];
       if (b.kind == LBit::K && b.stage == s && b.idx < 3) continue;
+      if (cl && b == cout) continue;
       sb.push_back(b);
     }
     plan->store_item_bits = static_cast<uint32_t>(sb.size());
@@ -529,6 +576,10 @@ inline void fill_strides(const UnitStrides& st, const PlanBuildInfo& info, UnitP
   };
   for (size_t i = 0; i < info.store_bits.size(); ++i) plan->store_gofs[i] = out_contrib(info.store_bits[i]);
   for (int i = 0; i < 3; ++i) plan->store_cg[i] = out_contrib({LBit::K, (uint8_t)s, (uint8_t)i});
+  if (info.cluster) {
+    plan->cl_load_gofs = in_contrib(info.cin);
+    plan->cl_out_gofs = out_contrib(info.cout);
+  }
   plan->in_batch_stride = st.in_batch_stride; plan->in_unit_stride = st.in_unit_stride;
   plan->out_batch_stride = st.out_batch_stride; plan->out_unit_stride = st.out_unit_stride;
   plan->units_per_batch = st.units_per_batch;

@@ -47,6 +47,7 @@ int plansim_run_ex(int log2_len, int log2_units, int in_mode_flags, int out_mode
   const int in_mode = in_mode_flags & 1;
   shape.in_mode = (AxisMode)in_mode; shape.out_mode = (AxisMode)out_mode; shape.tma_load = (in_mode_flags & 2) != 0;
   shape.pipe_stage2 = (in_mode_flags & 4) != 0;
+  shape.cluster = (in_mode_flags & 8) != 0;   // CTA-pair unit: both ranks are simulated, stage-1 stores cross between them
   UnitPlan P; PlanBuildInfo info;
   if (!build_unit_plan(shape, &P, &info)) { fprintf(stderr, "plan error: %s\n", info.error.c_str()); return -1; }
   UnitStrides st;
@@ -66,53 +67,60 @@ int plansim_run_ex(int log2_len, int log2_units, int in_mode_flags, int out_mode
     const int64_t ibase = (unit / P.units_per_batch) * P.in_batch_stride + (unit % P.units_per_batch) * P.in_unit_stride;
     const int64_t obase = (unit / P.units_per_batch) * P.out_batch_stride + (unit % P.units_per_batch) * P.out_unit_stride;
     const uint32_t col_base = ((unit % P.units_per_batch) / P.col_div) * P.col_base_stride;
-    std::vector<double> sre(smem_halves, NAN), sim(smem_halves, NAN);
-    // ---------------- load: TMA tensor tile {64 rows, R kappa, M/64, U} with 128-byte swizzle ...
+    const int nranks = P.cluster ? 2 : 1;
+    std::vector<double> pre_[2], pim_[2];   // operand planes of the (up to two) CTAs
+    for (int rk = 0; rk < nranks; ++rk) { pre_[rk].assign(smem_halves, NAN); pim_[rk].assign(smem_halves, NAN); }
+    // ---------------- load (per CTA): TMA tensor tile ... or 16-byte copies
+    for (int rk = 0; rk < nranks; ++rk) {
+    std::vector<double>& sre = pre_[rk];
+    std::vector<double>& sim = pim_[rk];
+    const int R0 = 1 << P.log2_radix[0];
+    const int64_t Mfull = L / R0, Mloc = Mfull >> (P.cluster ? 1 : 0), m0 = rk * Mloc;   // a cluster CTA loads one half of m
     if (P.tma_load == 4) {   // column mode, 16-column tiles as SWIZZLE_32B atoms: row = (u&15) + 16*(m + M*(u>>4))
-      const int R = 1 << P.log2_radix[0];
-      const int64_t M = L / R, U = int64_t(1) << P.log2_units;
+      const int R = R0;
+      const int64_t U = int64_t(1) << P.log2_units;
       for (int64_t u = 0; u < U; ++u)
-        for (int64_t m = 0; m < M; ++m)
+        for (int64_t m = 0; m < Mloc; ++m)
           for (int kap = 0; kap < R; ++kap) {
-            const int64_t row = (u & 15) + 16 * (m + M * (u >> 4));
+            const int64_t row = (u & 15) + 16 * (m + Mloc * (u >> 4));
             uint32_t off = (uint32_t)((row >> 4) * 32 * R + kap * 32 + (row & 15) * 2);
             off ^= ((off >> 7) & 1u) << 4;
-            const int64_t a = ibase + u + (kap * M + m) * strides9[1];
+            const int64_t a = ibase + u + (kap * Mfull + m0 + m) * strides9[1];
             sre[off / 2] = rh(in_re[a], h); sim[off / 2] = rh(in_im[a], h);
           }
     } else if (P.tma_load == 2) {   // column mode: tiles {8 columns, R kappa, M rows} per 8-column group, dense, no swizzle
-      const int R = 1 << P.log2_radix[0];
-      const int64_t M = L / R, U = int64_t(1) << P.log2_units;
+      const int R = R0;
+      const int64_t U = int64_t(1) << P.log2_units;
       for (int64_t ug = 0; ug < U / 8; ++ug)
-        for (int64_t m = 0; m < M; ++m)
+        for (int64_t m = 0; m < Mloc; ++m)
           for (int kap = 0; kap < R; ++kap)
             for (int cc = 0; cc < 8; ++cc) {
-              const uint32_t off = (uint32_t)((((ug * M + m) * R + kap) * 8 + cc) * 2);
-              const int64_t a = ibase + ug * 8 + cc + (kap * M + m) * strides9[1];
+              const uint32_t off = (uint32_t)((((ug * Mloc + m) * R + kap) * 8 + cc) * 2);
+              const int64_t a = ibase + ug * 8 + cc + (kap * Mfull + m0 + m) * strides9[1];
               sre[off / 2] = rh(in_re[a], h); sim[off / 2] = rh(in_im[a], h);
             }
     } else if (P.tma_load == 3) {   // SWIZZLE_32B atoms of 16 rows: dense [atom][kappa][16 rows], byte bit 4 ^= bit 7
-      const int R = 1 << P.log2_radix[0];
-      const int64_t M = L / R, U = int64_t(1) << P.log2_units;
+      const int R = R0;
+      const int64_t U = int64_t(1) << P.log2_units;
       for (int64_t u = 0; u < U; ++u)
-        for (int64_t m = 0; m < M; ++m)
+        for (int64_t m = 0; m < Mloc; ++m)
           for (int kap = 0; kap < R; ++kap) {
-            const int64_t row = u * M + m;
+            const int64_t row = u * Mloc + m;
             uint32_t off = (uint32_t)((row >> 4) * 32 * R + kap * 32 + (row & 15) * 2);
             off ^= ((off >> 7) & 1u) << 4;
-            const int64_t a = ibase + u * strides9[0] + kap * M + m;
+            const int64_t a = ibase + u * strides9[0] + kap * Mfull + m0 + m;
             sre[off / 2] = rh(in_re[a], h); sim[off / 2] = rh(in_im[a], h);
           }
     } else if (P.tma_load) {
-      const int R = 1 << P.log2_radix[0];
-      const int64_t M = L / R, U = int64_t(1) << P.log2_units;
+      const int R = R0;
+      const int64_t U = int64_t(1) << P.log2_units;
       for (int64_t u = 0; u < U; ++u)
-        for (int64_t m = 0; m < M; ++m)
+        for (int64_t m = 0; m < Mloc; ++m)
           for (int kap = 0; kap < R; ++kap) {
-            const int64_t row = u * M + m;
+            const int64_t row = u * Mloc + m;
             const uint32_t off = (uint32_t)((row >> 6) * 128 * R + (kap >> 3) * 1024 + (kap & 7) * 128 +
                                             ((((row >> 3) & 7) ^ (kap & 7)) << 4) + (row & 7) * 2);
-            const int64_t a = ibase + u * strides9[0] + kap * M + m;
+            const int64_t a = ibase + u * strides9[0] + kap * Mfull + m0 + m;
             sre[off / 2] = rh(in_re[a], h); sim[off / 2] = rh(in_im[a], h);
           }
     }
@@ -122,7 +130,7 @@ int plansim_run_ex(int log2_len, int log2_units, int in_mode_flags, int out_mode
       uint32_t addr[8];
       for (uint32_t dq = 0; dq < 8; ++dq) {
         uint32_t q = q0 + dq;
-        uint32_t g = bitsum(q, P.load_gofs, P.load_item_bits);
+        uint32_t g = bitsum(q, P.load_gofs, P.load_item_bits) + rk * P.cl_load_gofs;
         uint32_t so = bitsum(q, P.load_sofs, P.load_item_bits);
         addr[dq] = so;
         if (so + 16 > P.plane_bytes) { fprintf(stderr, "load dst out of range\n"); return -2; }
@@ -134,15 +142,20 @@ int plansim_run_ex(int log2_len, int log2_units, int in_mode_flags, int out_mode
       }
       conflicts[0] += qw_conflict(addr);
     }
+    }   // rank (load)
     // ---------------- MMA stages
     for (int t = 1; t <= s; ++t) {
       const UnitPlan::Epi& E = P.epi[t - 1];
       const int rho = P.log2_radix[t - 1], R = 1 << rho;
       const int rowbits = P.log2_elems - rho;
       const uint32_t S = P.chunk_stride[t - 1];
-      std::vector<double> nre(smem_halves, NAN), nim(smem_halves, NAN);
+      std::vector<double> nre_[2], nim_[2];
+      for (int rk = 0; rk < nranks; ++rk) { nre_[rk].assign(smem_halves, NAN); nim_[rk].assign(smem_halves, NAN); }
       const uint32_t rows = 1u << rowbits;
       if (rows != P.n_tiles[t - 1] * 128) { fprintf(stderr, "tile count mismatch\n"); return -5; }
+      for (int rk = 0; rk < nranks; ++rk) {
+      const std::vector<double>& sre = pre_[rk];
+      const std::vector<double>& sim = pim_[rk];
       for (uint32_t row0 = 0; row0 < rows; row0 += 8) {
         uint32_t addr[8];
         for (uint32_t dr = 0; dr < 8; ++dr) {
@@ -176,6 +189,10 @@ int plansim_run_ex(int log2_len, int log2_units, int in_mode_flags, int out_mode
           uint32_t dst = bitsum(row, E.dst, rowbits);
           uint32_t aux = bitsum(row, E.aux, rowbits);
           uint32_t col = bitsum(row, E.col, rowbits);
+          if (P.cluster && rk) {   // the CTA's rank is an index bit (input half in stage 1, k_1 half afterwards)
+            if (t == 1) { dst += P.cl_in_dst; aux += P.cl_in_aux; }
+            else if (t == s) aux += P.cl_out_aux;
+          }
           addr[dr] = dst;
           // MMA / epilogue overlap of stage 2: first-half rows may only write into the consumed first half
           if (P.pipe_stage2 && t == 2 && row < rows / 2) {
@@ -192,15 +209,21 @@ int plansim_run_ex(int log2_len, int log2_units, int in_mode_flags, int out_mode
             uint32_t o = dst + bitsum((uint32_t)(k >> 3), E.dst_k, 3);
             if (o + 16 > P.plane_bytes) { fprintf(stderr, "dst out of range\n"); return -2; }
             o = o / 2 + (k & 7);
-            if (!std::isnan(nre[o])) { fprintf(stderr, "stage %d: destination written twice\n", t); return -3; }
-            nre[o] = rh(v.real(), h); nim[o] = rh(v.imag(), h);
+            // cluster stage 1: the top k_1 bit picks the CTA that receives the chunk
+            const int tgt = (P.cluster && t == 1) ? (int)(((uint32_t)(k >> 3) >> (rho - 4)) & 1u) : rk;
+            if (!std::isnan(nre_[tgt][o])) { fprintf(stderr, "stage %d: destination written twice\n", t); return -3; }
+            nre_[tgt][o] = rh(v.real(), h); nim_[tgt][o] = rh(v.imag(), h);
           }
         }
         conflicts[1] += qw_conflict(addr);
       }
-      sre.swap(nre); sim.swap(nim);
+      }   // rank (stage)
+      for (int rk = 0; rk < nranks; ++rk) { pre_[rk].swap(nre_[rk]); pim_[rk].swap(nim_[rk]); }
     }
     // ---------------- store
+    for (int rk = 0; rk < nranks; ++rk) {
+    const std::vector<double>& sre = pre_[rk];
+    const std::vector<double>& sim = pim_[rk];
     const uint32_t n_sitems = 1u << P.store_item_bits;
     for (uint32_t q0 = 0; q0 < n_sitems; q0 += 8) {
       for (int x = 0; x < 8; ++x) {
@@ -208,7 +231,7 @@ int plansim_run_ex(int log2_len, int log2_units, int in_mode_flags, int out_mode
         for (uint32_t dq = 0; dq < 8; ++dq) {
           uint32_t q = q0 + dq;
           uint32_t so = bitsum(q, P.store_sofs, P.store_item_bits) + bitsum(x, P.store_xs, 3);
-          uint32_t g = bitsum(q, P.store_gofs, P.store_item_bits);
+          uint32_t g = bitsum(q, P.store_gofs, P.store_item_bits) + rk * P.cl_out_gofs;
           addr[dq] = so;
           for (int c = 0; c < 8; ++c) {
             int64_t a = obase + g + x + bitsum(c, P.store_cg, 3);
@@ -220,6 +243,7 @@ int plansim_run_ex(int log2_len, int log2_units, int in_mode_flags, int out_mode
         conflicts[2] += qw_conflict(addr);
       }
     }
+    }   // rank (store)
   }
   return conflicts[0] + conflicts[1] + conflicts[2];
 }

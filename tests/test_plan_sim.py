@@ -190,3 +190,43 @@ def test_two_d_passes_with_tiled_intermediate(sim, lgy, lgx, yb, flags):
     got = (o_re + 1j * o_im).reshape(ny, nx)
     assert rc1 == 0 and rc2 == 0 and c1 == [0, 0, 0] and list(conf)[:3] == [0, 0, 0]
     assert np.linalg.norm(got - want) / np.linalg.norm(want) < 1e-13
+
+
+@pytest.mark.parametrize("flags", [8, 10])
+def test_cluster_unit_single_pass_65536(sim, flags):
+    """N = 65536 in ONE pass: a unit of 2^16 elements shared by a CTA pair (flag 8).  CTA r loads the rows with m-half r,
+    its stage-1 epilogue stores the outputs with top k_1 bit d into CTA d, stages 2-3 and the store are local.
+    flags: 8 = 16-byte copies, 10 = + TMA row tiles."""
+    rc, conf, err = _rows(sim, 16, 0, n_units=2, flags=flags)
+    assert rc == 0 and conf == [0, 0, 0]
+    assert err < 1e-13
+
+
+def test_cluster_unit_predicted_fp16_error(sim):
+    rc, _, err = _rows(sim, 16, 0, n_units=1, h=1, flags=10)
+    assert rc == 0 and err < 6e-4
+
+
+@pytest.mark.parametrize("lg1,lg2,tma", [(12, 8, 2), (12, 8, 0), (12, 10, 2)])
+def test_four_step_with_cluster_column_units(sim, lg1, lg2, tma):
+    """Four-step N = N1*N2 whose column pass (length N1 = 4096) runs on cluster units of 16 columns (32-byte pieces):
+    column pass with the fused twiddle on CTA pairs, then the ordinary row pass with transposed store."""
+    N1, N2 = 1 << lg1, 1 << lg2
+    N = N1 * N2
+    rng = np.random.default_rng(6)
+    re, im = rng.standard_normal(N), rng.standard_normal(N)
+    t_re, t_im, o_re, o_im = np.zeros(N), np.zeros(N), np.zeros(N), np.zeros(N)
+    u1, U1 = 4, 16
+    conf = (ctypes.c_int * 4)()
+    st = (ctypes.c_int64 * 9)(0, N2, 0, N2, 0, U1, 0, U1, 1 << 30)
+    rc1 = sim.plansim_run(lg1, u1, 1 | tma | 8, 1, st, lg1 + lg2, N2 // U1, re.ctypes.data_as(dp), im.ctypes.data_as(dp),
+                          t_re.ctypes.data_as(dp), t_im.ctypes.data_as(dp), 0, conf)
+    c1 = list(conf)[:3]
+    u2 = 14 - lg2
+    U2 = 1 << u2
+    st = (ctypes.c_int64 * 9)(N2, 1, 0, N1, 0, U2 * N2, 0, U2, 1 << 30)
+    rc2 = sim.plansim_run(lg2, u2, 0, 1, st, 0, N1 // U2, t_re.ctypes.data_as(dp), t_im.ctypes.data_as(dp),
+                          o_re.ctypes.data_as(dp), o_im.ctypes.data_as(dp), 0, conf)
+    want = np.fft.fft(re + 1j * im) / N
+    assert rc1 == 0 and rc2 == 0 and c1 == [0, 0, 0]
+    assert np.linalg.norm(o_re + 1j * o_im - want) / np.linalg.norm(want) < 1e-13
