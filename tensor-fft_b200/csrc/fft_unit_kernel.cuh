@@ -321,7 +321,8 @@ __device__ __forceinline__ void sts128_cluster(uint32_t caddr, uint4 v) {
   asm volatile("st.shared::cluster.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(caddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                : "memory");
 }
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// generic-proxy stores into either CTA's shared memory -> visible to the async proxy (tensor core) of the owning CTA
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async.shared::cluster;" ::: "memory"); }
 
 struct KernelCtx {
   uint32_t cl_rank;        // cluster units: rank of this CTA in its pair (0 otherwise)

@@ -307,7 +307,7 @@ struct Tuning {
   int prefetch = -1;       // L2 prefetch of the next unit                 (TFFT_PREFETCH)
   int fourstep_lg1 = -1;   // log2 of the column-pass length, N > 2^15     (TFFT_FOURSTEP_LG1)
   int tma_col = -1;        // TMA column tiles in four-step column passes  (TFFT_NO_TMA_COL)
-  int cluster = -1;        // CTA-pair units: N = 65536 in one pass, 16-column units for 4096-point column passes (TFFT_NO_CLUSTER)
+  int cluster = -1;        // CTA-pair units: N = 65536 in one pass, 16-column units for 4096-point column passes (off unless 1)
 };
 int knob(int tuned, const char* env_off, int dflt) {   // env_off: variable whose presence switches the feature off
   if (tuned >= 0) return tuned;
@@ -419,7 +419,10 @@ int build_1d(tfft_plan_s* p) {
   if (p->flags & TFFT_INTERLEAVED) {
     if (lg > 24) return TFFT_E_UNSUPPORTED;   // three-pass sizes: planar only
   }
-  const bool use_cluster = knob(p->tune.cluster, "TFFT_NO_CLUSTER", 1) != 0 && !(p->flags & TFFT_INTERLEAVED);
+  // CTA-pair units are OFF by default: measured on B200 they are correct but not faster (N = 65536 x 4096: 1.08 ms in one
+  // pass against 0.97 ms in two; 2^24: 2.24 against 2.19 ms).  Tuner key cluster=1 (or the developer variable
+  // TFFT_CLUSTER) switches them on.
+  const bool use_cluster = (p->tune.cluster > 0 || (p->tune.cluster < 0 && dev_env("TFFT_CLUSTER"))) && !(p->flags & TFFT_INTERLEAVED);
   if (lg == 16 && use_cluster) {
     // N = 65536 in ONE pass (BASELINE north_star (2)): a unit of 2^16 elements shared by a CTA pair -- each CTA loads the
     // rows of one half of m = n mod 4096, runs the radix-16 stage on them and hands the outputs of the other half of k_1
@@ -662,7 +665,7 @@ int build_2d(tfft_plan_s* p, std::vector<Pass>* passes, bool allow_tma) {
     sh.tma_load = dev_env("TFFT_TMA_COL_2D") != nullptr;
     if (lg2 == 11 && dev_env("TFFT_2D_COL_U16")) sh.log2_units = 4;   // developer knob: 16 columns x 2048 (32-byte pieces)
     // 4096-point columns: CTA-pair units of 16 columns (32-byte pieces)
-    if (lg2 == 12 && knob(p->tune.cluster, "TFFT_NO_CLUSTER", 1) != 0) { sh.log2_units = 4; sh.cluster = true; }
+    if (lg2 == 12 && dev_env("TFFT_CLUSTER")) { sh.log2_units = 4; sh.cluster = true; }   // developer knob, see build_1d
     const int64_t U = int64_t(1) << sh.log2_units;
     UnitStrides st;
     st.in_nstride = nx << yb; st.out_nstride = nx << yb;

@@ -235,3 +235,32 @@ def test_reference_single_benchmark_runs_from_a_tuner_file(tmp_path):
     for p in outs:
         with open(os.path.join(ROOT, "gpurun_out", "shim_" + p), "w") as f:
             f.write((tmp_path / p).read_text())
+
+
+@pytest.mark.parametrize("lg,b", [(16, 5), (16, 300), (22, 2), (24, 1)])
+def test_cluster_units_through_the_tuner_file(tmp_path, lg, b):
+    """Tuner key cluster=1: units of 2^16 elements shared by a CTA pair (thread-block cluster of 2, stage-1 outputs
+    exchanged through distributed shared memory).  N = 65536 then runs in ONE HBM pass (passes == 1, input preserved);
+    for 2^22 / 2^24 the 4096-point column pass uses 16-column units.  Same guard as the default plans."""
+    n = 1 << lg
+    re, im = O.gauss_fixture(n, b, seed=1600 + lg)
+    f = tmp_path / "TunerResults.dat"
+    f.write_text(f"{n} 256 8 8 256 cluster=1\n")
+    x = _planar(re, im)
+    keep = x.clone()
+    plan = tfft.NativePlan(n, b, 0, tuner_file=str(f))
+    assert plan.info["passes"] == (1 if lg == 16 else 2)
+    y = torch.full_like(x, float("nan"))
+    plan.exec(x, x[n:], y, y[n:], 2 * n, 2 * n)
+    torch.cuda.synchronize()
+    if lg == 16:
+        assert bool(torch.equal(x, keep))                 # a single pass never writes its input
+    nb = min(b, 4)
+    o = y.view(b, 2, n)[:nb].cpu().numpy().astype(np.float64)
+    w_re, w_im = O.fft_f64(re[:nb].astype(np.float64), im[:nb].astype(np.float64))
+    err = O.error_stats(o[:, 0], o[:, 1], w_re, w_im)["rel_l2"]
+    assert err <= GUARD * (4.05e-4 if lg == 16 else MEASURED[lg]), err
+    # last transform too (ragged CTA-pair waves)
+    ol = y.view(b, 2, n)[b - 1].cpu().numpy().astype(np.float64)
+    wl_re, wl_im = O.fft_f64(re[b - 1:].astype(np.float64), im[b - 1:].astype(np.float64))
+    assert O.error_stats(ol[0], ol[1], wl_re[0], wl_im[0])["rel_l2"] <= GUARD * (4.05e-4 if lg == 16 else MEASURED[lg])
