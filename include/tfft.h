@@ -123,7 +123,11 @@ int tfft_exec_twiddled(tfft_plan_t plan, const void* in_re, const void* in_im, v
 /* Whole reference call sequence with HOST buffers: CopyDataHostToDevice -> ComputeFFT ->
  * CopyResultsDeviceToHost (src/base/DataHandler.h:45-70,124-153).  host_in / host_out hold,
  * per transform, [RE(n) | IM(n)] halves (2*n*batch values each).  Uses plan-owned device
- * buffers; synchronises before returning like the reference's batch overload does. */
+ * buffers (a ring of four 16 MiB slots per direction, not the whole batch) and three plan-owned streams: upload,
+ * transform and download of consecutive chunks overlap.  Synchronises before returning like the reference's batch
+ * overload does.  Pass PINNED host memory (cudaHostAlloc / cudaHostRegister): with pageable buffers every chunk copy
+ * blocks the calling thread and the three-stage pipeline degenerates to serial copies (results are the same).
+ * Calls on one plan are serialised internally. */
 int tfft_exec_host(tfft_plan_t plan, const void* host_in, void* host_out);
 
 /* Pack / unpack kernels of the all-to-all exchanges of the multi-GPU 1-D transform (nothing in the
