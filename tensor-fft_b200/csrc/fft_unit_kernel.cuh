@@ -164,9 +164,12 @@ __device__ __forceinline__ f32x2 unpack_half2(uint32_t v) {
 // Device tables (built on the host, tfft_api.cu make_tables; staged into shared memory once per CTA):
 //   [0, 512)    TWlo[j]  = exp(-2*pi*i * j / L),        j < 64
 //   [512, 4608) TWhi[j]  = exp(-2*pi*i * 64*j / L),     j < L/64 <= 512
-//   then for every distinct radix R of the plan the B operands B1 = [Fr | Fi] / R and
-//   B2 = [-Fi | Fr] / R (fp16, K-major SWIZZLE_NONE: Bmath[kappa][n] at
-//   (n>>3)*16R + (kappa>>3)*128 + (n&7)*16 + (kappa&7)*2 bytes), F = exp(-2*pi*i*kappa*k/R).
+//   then for every distinct radix R of the plan ONE matrix T = [Fr | Fi | -Fr] / R of 3R columns (fp16, K-major
+//   SWIZZLE_NONE: Tmath[kappa][n] at (n>>3)*16R + (kappa>>3)*128 + (n&7)*16 + (kappa&7)*2 bytes), F = exp(-2*pi*i*kappa*k/R).
+//   The two B operands of a stage are windows of it: B1 = [Fr | Fi] = columns 0 .. 2R-1 and B2' = [Fi | -Fr] = columns
+//   R .. 3R-1; D = A_re * B1 + (-A_im) * B2' with the tensor core negating A (instruction-descriptor bit 13), which is
+//   A_re*[Fr|Fi] + A_im*[-Fi|Fr].  6 R^2 bytes per radix instead of 8 R^2 (24 KiB instead of 32 KiB for R = 64: two
+//   16K-element CTAs of a 2048-point plan fit one SM).  -DTFFT_TWO_MATRICES builds the round-1 layout [Fr|Fi], [-Fi|Fr].
 struct TableLayout {
   uint32_t b_off[kMaxStages];   // byte offset of B1 of stage t (B2 follows at + 4*R*R)
   uint32_t total;               // multiple of 16
@@ -182,7 +185,11 @@ __host__ __device__ inline TableLayout table_layout(const UnitPlan& p) {
       if (p.log2_radix[u] == p.log2_radix[t]) { l.b_off[t] = l.b_off[u]; found = true; break; }
     if (!found) {
       l.b_off[t] = off;
+#ifdef TFFT_TWO_MATRICES
       off += 8u << (2 * p.log2_radix[t]);   // 2 matrices of 2R x R halves
+#else
+      off += 6u << (2 * p.log2_radix[t]);   // one matrix of 3R x R halves
+#endif
     }
   }
   l.total = off;
@@ -626,7 +633,13 @@ __device__ __forceinline__ void stage_issue(const KernelCtx& c, uint32_t b1_sadd
   constexpr uint32_t kTileStep = (SW128 || SW32) ? (2 * 128 * R) / 16 : S;   // descriptor address units (16 B) per tile
   constexpr uint32_t kKStep = SW128 ? 2048 / 16 : SW32 ? 512 / 16 : 16;      // ... per 16-wide K step
   const uint64_t db1 = make_smem_desc(b1_saddr, kKGroupStride, 16 * R);
+#ifdef TFFT_TWO_MATRICES
   const uint64_t db2 = make_smem_desc(b1_saddr + 4 * R * R, kKGroupStride, 16 * R);
+  constexpr uint32_t idesc2 = idesc;
+#else
+  const uint64_t db2 = make_smem_desc(b1_saddr + 2 * R * R, kKGroupStride, 16 * R);   // columns R .. 3R-1: [Fi | -Fr]
+  constexpr uint32_t idesc2 = idesc | (1u << 13);                                       // negate A: (-A_im) * [Fi | -Fr]
+#endif
   constexpr uint32_t kTileBegin = PART == 2 ? kTiles / 2 : 0, kTileEnd = PART == 1 ? kTiles / 2 : kTiles;
 #pragma unroll
   for (uint32_t tile = kTileBegin; tile < kTileEnd; ++tile) {
@@ -645,7 +658,7 @@ __device__ __forceinline__ void stage_issue(const KernelCtx& c, uint32_t b1_sadd
       umma_f16_ss(d, da_re + (tile * kTileStep + j * kKStep), db1 + j * 16, idesc, j > 0 ? 1u : 0u);
 #pragma unroll
     for (uint32_t j = 0; j < kSteps; ++j)
-      umma_f16_ss(d, da_im + (tile * kTileStep + j * kKStep), db2 + j * 16, idesc, 1u);
+      umma_f16_ss(d, da_im + (tile * kTileStep + j * kKStep), db2 + j * 16, idesc2, 1u);
     if (PART == 0 && kPipe && tile + 1 == kTiles / 2) umma_commit(bar);     // first half of the tiles
   }
   if (PART == 1) umma_commit(bar);

@@ -100,13 +100,17 @@ std::vector<uint8_t> make_tables(const UnitPlan& plan, bool unscaled) {
   for (uint32_t t = 0; t < plan.stages; ++t) {
     const int rho = static_cast<int>(plan.log2_radix[t]), R = 1 << rho;
     __half* b1 = reinterpret_cast<__half*>(host.data() + TL.b_off[t]);
-    __half* b2 = b1 + 2 * R * R;
     // Kronecker last stage (2-D row pass): K index = (kappa_x low, kappa_y high), output column = (k_x low, k_y high),
     // F = F_x[kappa_x][k_x] * F_y[kappa_y][k_y]
     const int ybits = (plan.kron_bits && t + 1 == plan.stages) ? static_cast<int>(plan.kron_bits) : 0;
     const int Rx = R >> ybits, Ry = 1 << ybits;
+#ifdef TFFT_TWO_MATRICES
+    const int ncols = 4 * R;   // [Fr | Fi] then [-Fi | Fr], each 2R columns
+#else
+    const int ncols = 3 * R;   // [Fr | Fi | -Fr]
+#endif
     for (int kap = 0; kap < R; ++kap)
-      for (int n = 0; n < 2 * R; ++n) {
+      for (int n = 0; n < ncols; ++n) {
         double c, s;
         const int k = n % R;
         // phase / R = kap_x*k_x/Rx + kap_y*k_y/Ry
@@ -114,9 +118,15 @@ std::vector<uint8_t> make_tables(const UnitPlan& plan, bool unscaled) {
         // 1/R per stage = the reference's "sequential scaling"; TFFT_UNSCALED (cuFFT convention) leaves it out
         const double sc = unscaled ? 1.0 : 1.0 / R;
         const float fr = static_cast<float>(c * sc), fi = static_cast<float>(s * sc);
+#ifdef TFFT_TWO_MATRICES
+        const int m = n / (2 * R), nn = n % (2 * R);
+        const float v = m == 0 ? (nn < R ? fr : fi) : (nn < R ? -fi : fr);
+        const uint32_t off = static_cast<uint32_t>(m) * 2 * R * R + (nn >> 3) * (8 * R) + (kap >> 3) * 64 + (nn & 7) * 8 + (kap & 7);
+#else
+        const float v = n < R ? fr : (n < 2 * R ? fi : -fr);
         const uint32_t off = (n >> 3) * (8 * R) + (kap >> 3) * 64 + (n & 7) * 8 + (kap & 7);   // in halves
-        b1[off] = __float2half_rn(n < R ? fr : fi);
-        b2[off] = __float2half_rn(n < R ? -fi : fr);
+#endif
+        b1[off] = __float2half_rn(v);
       }
   }
   return host;
@@ -358,7 +368,7 @@ namespace {
 // (256 tensor-memory columns, two CTAs per SM) unless the length or its tables need otherwise.
 int unit_log2_elems(int lg) {
   if (lg == 15) return 15;
-  if (lg == 11) return 13;   // radix 32 + 64 matrices (40 KiB): keep two CTAs per SM
+  if (lg == 11) return dev_env("TFFT_U2048_16K") ? 14 : 13;   // radix 32 + 64 matrices: 8K-element units (developer A/B: 16K)
   return 14;
 }
 // transforms per unit for a row/row pass, never padding a small batch beyond the 8K-element minimum
