@@ -368,7 +368,9 @@ namespace {
 // (256 tensor-memory columns, two CTAs per SM) unless the length or its tables need otherwise.
 int unit_log2_elems(int lg) {
   if (lg == 15) return 15;
-  if (lg == 11) return dev_env("TFFT_U2048_16K") ? 14 : 13;   // radix 32 + 64 matrices: 8K-element units (developer A/B: 16K)
+  // 2048 = 32 * 64: with one 3R-column matrix per radix (30 KiB of tables) two 16K-element CTAs fit an SM; measured on
+  // B200 0.389 ms per GiB against 0.434 ms with the 8K-element units of round 1 (developer A/B: TFFT_U2048_8K)
+  if (lg == 11) return dev_env("TFFT_U2048_8K") ? 13 : 14;
   return 14;
 }
 // transforms per unit for a row/row pass, never padding a small batch beyond the 8K-element minimum

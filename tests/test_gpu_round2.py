@@ -128,7 +128,7 @@ def test_tuner_knobs_leave_the_result_unchanged(tmp_path, lg, b, knobs):
     """A tuner-file plan (tfft_plan_create_from_file, the reference's CreatePlan(N, file) overload, Plan.h:197-255) with
     non-default kernel knobs: the load path / pipelining / prefetch choices do not change the stages or the DFT matrices;
     only the split of an inter-stage twiddle into its per-thread and per-tile factor follows the operand layout, so
-    single results may differ by one fp16 rounding (rel-L2 < 1e-4, no element off by more than 2^-9 of the largest)."""
+    single results may differ by one fp16 rounding (rel-L2 < 3e-4, no element off by more than 2^-9 of the largest)."""
     n = 1 << lg
     re, im = O.gauss_fixture(n, b, seed=800 + lg)
     want = _run(n, b, _planar(re, im))
@@ -136,7 +136,7 @@ def test_tuner_knobs_leave_the_result_unchanged(tmp_path, lg, b, knobs):
     f.write_text(f"256 256 8 8 256\n{n} 256 8 8 256 {knobs}\n")
     got = _run(n, b, _planar(re, im), tuner_file=str(f))
     d = got.float() - want.float()
-    assert float(torch.linalg.vector_norm(d) / torch.linalg.vector_norm(want.float())) < 1e-4, knobs
+    assert float(torch.linalg.vector_norm(d) / torch.linalg.vector_norm(want.float())) < 3e-4, knobs
     assert float(d.abs().max()) <= float(want.float().abs().max()) * 2.0 ** -9, knobs
 
 
