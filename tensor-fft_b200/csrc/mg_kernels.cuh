@@ -22,8 +22,11 @@ struct MgPeers {
 };
 
 // Local slab: `rows_local` rows of `cols` elements (both planes), rank `rank` of `world`.  Peer p owns columns
-// [p*cl, (p+1)*cl), cl = cols / world, and receives them transposed: dst_p[c][rank*rows_local + r] = src[r][p*cl + c],
-// dst row length = world * rows_local.
+// [p*cl, (p+1)*cl), cl = cols / world, and receives them transposed into its staging buffer, SOURCE-RANK MAJOR:
+// stage_p[rank][c][r] = src[r][p*cl + c] -- one contiguous block of cl * rows_local elements per source rank.  (Writing
+// the row-major matrix dst_p[c][rank*rows_local + r] directly scatters 128-byte..4-KiB pieces over every page of the
+// peer's buffer; measured at 8 GPUs that costs 0.13 ms per exchange over the 0.19 ms the same bytes take when the
+// destination is contiguous.)  mg_unpack then builds the row-major matrix locally.
 // One warp moves a tile of 64 source rows x 32 source columns entirely in registers: lane (rg = lane / 4, ch = lane % 4)
 // loads the 8 x 8 block of rows 8*rg .. 8*rg+7, columns 8*ch .. 8*ch+7 (eight 16-byte loads; a warp instruction covers
 // 8 rows x 64 contiguous bytes), transposes it with byte permutes and stores eight 16-byte pieces; a warp store
@@ -48,9 +51,9 @@ mg_transpose_send(const __half* __restrict__ src_re, const __half* __restrict__ 
   uint4 a[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) a[j] = __ldcs(reinterpret_cast<const uint4*>(s + j * src_row_stride));
-  const int64_t d_row = static_cast<int64_t>(world) * rows_local;
-  __half* d = (plane ? peers.im[peer] : peers.re[peer]) + (static_cast<int64_t>(cg) * 32 + 8 * ch) * d_row +
-              static_cast<int64_t>(rank) * rows_local + blockIdx.x * 64 + 8 * rg;
+  const int64_t d_row = rows_local;
+  __half* d = (plane ? peers.im[peer] : peers.re[peer]) + static_cast<int64_t>(rank) * cl * rows_local +
+              (static_cast<int64_t>(cg) * 32 + 8 * ch) * d_row + blockIdx.x * 64 + 8 * rg;
 #pragma unroll
   for (int cc = 0; cc < 8; ++cc) {
     const uint32_t sel = (cc & 1) ? 0x7632u : 0x5410u;
@@ -63,6 +66,19 @@ mg_transpose_send(const __half* __restrict__ src_re, const __half* __restrict__ 
     }
     *reinterpret_cast<uint4*>(d + cc * d_row) = make_uint4(w[0], w[1], w[2], w[3]);
   }
+}
+
+// dst[c][q*rows_local + r] = stage[q][c][r] for q < world, c < cl: runs of rows_local elements (both planes: blockIdx.z).
+// One warp per run.  Grid: (ceil(cl / 8), world, 2), 256 threads.
+__global__ void __launch_bounds__(256)
+mg_unpack(const __half* __restrict__ st_re, const __half* __restrict__ st_im, __half* __restrict__ dst_re,
+          __half* __restrict__ dst_im, int rows_local, int cl, int world) {
+  const int lane = threadIdx.x & 31, c = blockIdx.x * 8 + (threadIdx.x >> 5), q = blockIdx.y;
+  if (c >= cl) return;
+  const __half* s = (blockIdx.z ? st_im : st_re) + (static_cast<int64_t>(q) * cl + c) * rows_local;
+  __half* d = (blockIdx.z ? dst_im : dst_re) + static_cast<int64_t>(c) * world * rows_local + static_cast<int64_t>(q) * rows_local;
+  for (int k = lane; k < rows_local / 8; k += 32)
+    reinterpret_cast<uint4*>(d)[k] = __ldcs(reinterpret_cast<const uint4*>(s) + k);
 }
 
 struct MgFlags {

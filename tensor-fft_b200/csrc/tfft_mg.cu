@@ -43,12 +43,17 @@ struct tfft_mg_plan_s {
   int64_t n = 0, n1 = 0, n2 = 0, local = 0;   // local = n / world elements per rank and plane
   int lg = 0, rank = 0, world = 1, device = 0;
   tfft_plan_t fft1 = nullptr, fft2 = nullptr;
-  char* base = nullptr;                        // [A_re | A_im | B_re | B_im | C_re | C_im | flags]
+  char* base = nullptr;                        // [S0_re | S0_im | S1_re | S1_im | W_re | W_im | C_re | C_im | flags]
+                                               // S0/S1: staging planes the peers store into (source-rank major); W: this
+                                               // rank's working matrix (row major, transforms run in place); C: the result
   size_t bytes = 0, flags_off = 0;
   char* peer[kMgMaxRanks] = {};
   bool opened[kMgMaxRanks] = {};
   bool connected = false;
   uint32_t epoch = 0;
+  uint32_t parity = 0;                         // execs alternate the staging planes: exchange e of an exec lands in S[(e + parity) & 1],
+                                               // so that exchange 1 of the next exec never targets the planes a slower
+                                               // peer is still unpacking from exchange 3 of this one
   int* status_host = nullptr;
   int* status_dev = nullptr;
   unsigned long long timeout_ns = 10ull * 1000 * 1000 * 1000;
@@ -84,9 +89,10 @@ int tfft_mg_plan_create(tfft_mg_plan_t* out, int64_t n, int32_t rank, int32_t wo
     cudaFuncAttributes fa;
     rc = cuda_rc(cudaFuncGetAttributes(&fa, mg_transpose_send));
     if (rc == TFFT_OK) rc = cuda_rc(cudaFuncGetAttributes(&fa, mg_barrier));
+    if (rc == TFFT_OK) rc = cuda_rc(cudaFuncGetAttributes(&fa, mg_unpack));
   }
   if (rc == TFFT_OK) {
-    p->flags_off = 6 * static_cast<size_t>(p->local) * sizeof(__half);
+    p->flags_off = 8 * static_cast<size_t>(p->local) * sizeof(__half);
     p->bytes = p->flags_off + 4096;
     rc = cuda_rc(cudaMalloc(&p->base, p->bytes));
   }
@@ -159,49 +165,71 @@ int tfft_mg_plan_info(tfft_mg_plan_t p, tfft_mg_info_t* info) {
   info->rank = p->rank; info->world = p->world; info->exchanges = 3;
   info->exchange_bytes_per_rank = 3 * static_cast<int64_t>(p->world - 1) * 4 * p->local / p->world;
   info->device_bytes = static_cast<int64_t>(p->bytes);
-  info->result_re = p->base + 4 * static_cast<size_t>(p->local) * sizeof(__half);
-  info->result_im = p->base + 5 * static_cast<size_t>(p->local) * sizeof(__half);
+  info->result_re = p->base + 6 * static_cast<size_t>(p->local) * sizeof(__half);
+  info->result_im = p->base + 7 * static_cast<size_t>(p->local) * sizeof(__half);
   return TFFT_OK;
 }
 
-static int mg_exchange(tfft_mg_plan_t p, const __half* src_re, const __half* src_im, int which, int64_t rows_local,
+// stage planes (source-rank major: [q][c][r]) -> row-major matrix [c][q*rows_local + r]; the slab that was sent had
+// rows_local rows of cols columns on every rank, so this rank received cl = cols/world rows of world*rows_local elements
+static int mg_unpack_stage(tfft_mg_plan_t p, int stage, int dst, int64_t rows_local, int64_t cols, cudaStream_t s) {
+  const int64_t cl = cols / p->world;
+  const dim3 grid(static_cast<unsigned>((cl + 7) / 8), static_cast<unsigned>(p->world), 2);
+  mg_unpack<<<grid, 256, 0, s>>>(p->plane(p->rank, stage), p->plane(p->rank, stage + 1), p->plane(p->rank, dst),
+                                 p->plane(p->rank, dst + 1), static_cast<int>(rows_local), static_cast<int>(cl), p->world);
+  return cuda_rc(cudaGetLastError());
+}
+
+// One exchange: transpose-send my slab into the peers' staging planes `stage` (0: S0, 2: S1), flag barrier, then unpack
+// my own staging planes into the row-major matrix dst (plane index `dst`: 4 = W, 6 = C).
+static int mg_exchange(tfft_mg_plan_t p, const __half* src_re, const __half* src_im, int stage, int dst, int64_t rows_local,
                        int64_t cols, bool barrier, cudaStream_t s) {
   MgPeers peers;
-  for (int r = 0; r < p->world; ++r) { peers.re[r] = p->plane(r, which); peers.im[r] = p->plane(r, which + 1); }
+  for (int r = 0; r < p->world; ++r) { peers.re[r] = p->plane(r, stage); peers.im[r] = p->plane(r, stage + 1); }
   const dim3 grid(static_cast<unsigned>(rows_local / 64), static_cast<unsigned>((cols / 32 + 7) / 8), 2);
   if (grid.y > 65535) return TFFT_E_UNSUPPORTED;
   mg_transpose_send<<<grid, 256, 0, s>>>(src_re, src_im, peers, static_cast<int>(rows_local), static_cast<int>(cols),
                                          p->rank, p->world, cols);
   int rc = cuda_rc(cudaGetLastError());
-  if (rc != TFFT_OK || !barrier) return rc;
-  MgFlags f;
-  for (int r = 0; r < p->world; ++r) f.flags[r] = reinterpret_cast<uint32_t*>(p->peer[r] + p->flags_off);
-  mg_barrier<<<1, 32, 0, s>>>(f, p->rank, p->world, ++p->epoch, p->timeout_ns, p->status_dev);
-  return cuda_rc(cudaGetLastError());
+  if (rc != TFFT_OK) return rc;
+  if (barrier) {
+    MgFlags f;
+    for (int r = 0; r < p->world; ++r) f.flags[r] = reinterpret_cast<uint32_t*>(p->peer[r] + p->flags_off);
+    mg_barrier<<<1, 32, 0, s>>>(f, p->rank, p->world, ++p->epoch, p->timeout_ns, p->status_dev);
+    rc = cuda_rc(cudaGetLastError());
+    if (rc != TFFT_OK) return rc;
+    return mg_unpack_stage(p, stage, dst, rows_local, cols, s);
+  }
+  return TFFT_OK;   // phase-stepped callers unpack at the start of the next phase (after every rank has sent)
 }
 
-// phase 0: exchange 1;  phase 1: transforms over i1 + exchange 2;  phase 2: transforms over i2 + exchange 3;
-// phase 3: copy the result out (if asked)
+// phase 0: exchange 1;  phase 1: [unpack] transforms over i1 + exchange 2;  phase 2: [unpack] transforms over i2 + exchange 3;
+// phase 3: [unpack] copy the result out (if asked).  The unpacks in brackets run here only for phase-stepped callers
+// (tfft_mg_exec_phase: no barrier inside the exchange, so the exchange cannot unpack what the peers have not sent yet).
 static int mg_phase(tfft_mg_plan_t p, int phase, const void* in_re, const void* in_im, void* out_re, void* out_im,
                     bool barrier, cudaStream_t s) {
   const int64_t g = p->world, r1 = p->n1 / g, r2 = p->n2 / g;
-  __half *a_re = p->plane(p->rank, 0), *a_im = p->plane(p->rank, 1);
-  __half *b_re = p->plane(p->rank, 2), *b_im = p->plane(p->rank, 3);
-  __half *c_re = p->plane(p->rank, 4), *c_im = p->plane(p->rank, 5);
+  __half *w_re = p->plane(p->rank, 4), *w_im = p->plane(p->rank, 5);
+  __half *c_re = p->plane(p->rank, 6), *c_im = p->plane(p->rank, 7);
   int rc = TFFT_OK;
+  if (phase == 0) p->parity ^= 1u;
+  const int sa = static_cast<int>(p->parity & 1u) * 2, sb = 2 - sa;   // staging planes of exchanges 1 and 3 / of exchange 2
   switch (phase) {
-    case 0:   // my n1/g rows of n2 -> every rank gets its n2/g columns, transposed: A[i2_local][i1]
-      return mg_exchange(p, static_cast<const __half*>(in_re), static_cast<const __half*>(in_im), 0, r1, p->n2, barrier, s);
-    case 1:   // n2/g transforms over i1, times exp(-2*pi*i*k1*i2/n), in place; then A[i2_local][k1] -> B[k1_local][i2]
-      rc = tfft_exec_twiddled(p->fft1, a_re, a_im, a_re, a_im, p->n1, p->n1, p->lg, p->rank * r2, s);
-      if (rc == TFFT_OK) rc = mg_exchange(p, a_re, a_im, 2, r2, p->n1, barrier, s);
+    case 0:   // my n1/g rows of n2 -> every rank gets its n2/g columns, transposed: W[i2_local][i1]
+      return mg_exchange(p, static_cast<const __half*>(in_re), static_cast<const __half*>(in_im), sa, 4, r1, p->n2, barrier, s);
+    case 1:   // n2/g transforms over i1, times exp(-2*pi*i*k1*i2/n), in place; then W[i2_local][k1] -> W'[k1_local][i2]
+      if (!barrier) rc = mg_unpack_stage(p, sa, 4, r1, p->n2, s);
+      if (rc == TFFT_OK) rc = tfft_exec_twiddled(p->fft1, w_re, w_im, w_re, w_im, p->n1, p->n1, p->lg, p->rank * r2, s);
+      if (rc == TFFT_OK) rc = mg_exchange(p, w_re, w_im, sb, 4, r2, p->n1, barrier, s);
       return rc;
-    case 2:   // n1/g transforms over i2, in place; then B[k1_local][k2] -> C[k2_local][k1] = X[k1 + n1*k2]: this rank's n/g slice
-      rc = tfft_exec(p->fft2, b_re, b_im, b_re, b_im, p->n2, p->n2, s);
-      if (rc == TFFT_OK) rc = mg_exchange(p, b_re, b_im, 4, r1, p->n2, barrier, s);
+    case 2:   // n1/g transforms over i2, in place; then W[k1_local][k2] -> C[k2_local][k1] = X[k1 + n1*k2]: this rank's n/g slice
+      if (!barrier) rc = mg_unpack_stage(p, sb, 4, r2, p->n1, s);
+      if (rc == TFFT_OK) rc = tfft_exec(p->fft2, w_re, w_im, w_re, w_im, p->n2, p->n2, s);
+      if (rc == TFFT_OK) rc = mg_exchange(p, w_re, w_im, sa, 6, r1, p->n2, barrier, s);
       return rc;
     case 3:
-      if (out_re && out_re != c_re)
+      if (!barrier) rc = mg_unpack_stage(p, sa, 6, r1, p->n2, s);
+      if (rc == TFFT_OK && out_re && out_re != c_re)
         rc = cuda_rc(cudaMemcpyAsync(out_re, c_re, p->local * sizeof(__half), cudaMemcpyDeviceToDevice, s));
       if (rc == TFFT_OK && out_im && out_im != c_im)
         rc = cuda_rc(cudaMemcpyAsync(out_im, c_im, p->local * sizeof(__half), cudaMemcpyDeviceToDevice, s));
