@@ -26,7 +26,8 @@ struct MgPeers {
 // stage_p[rank][c][r] = src[r][p*cl + c] -- one contiguous block of cl * rows_local elements per source rank.  (Writing
 // the row-major matrix dst_p[c][rank*rows_local + r] directly scatters 128-byte..4-KiB pieces over every page of the
 // peer's buffer; measured at 8 GPUs that costs 0.13 ms per exchange over the 0.19 ms the same bytes take when the
-// destination is contiguous.)  mg_unpack then builds the row-major matrix locally.
+// destination is contiguous.)  mg_unpack then builds the row-major matrix locally.  With staged == 0 the kernel writes
+// the row-major matrix directly (no unpack pass): cheaper for 2 ranks, where the scattered stores cost nothing.
 // One warp moves a tile of 64 source rows x 32 source columns entirely in registers: lane (rg = lane / 4, ch = lane % 4)
 // loads the 8 x 8 block of rows 8*rg .. 8*rg+7, columns 8*ch .. 8*ch+7 (eight 16-byte loads; a warp instruction covers
 // 8 rows x 64 contiguous bytes), transposes it with byte permutes and stores eight 16-byte pieces; a warp store
@@ -35,7 +36,7 @@ struct MgPeers {
 // (consecutive warps target different peers, starting at rank + 1) so that all NVLink ports carry traffic at any moment.
 __global__ void __launch_bounds__(256)
 mg_transpose_send(const __half* __restrict__ src_re, const __half* __restrict__ src_im, const MgPeers peers,
-                  int rows_local, int cols, int rank, int world, int64_t src_row_stride) {
+                  int rows_local, int cols, int rank, int world, int64_t src_row_stride, int staged) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // blockIdx.x runs over the 64-row blocks (fastest), blockIdx.y over groups of 8 column groups: CTAs that run together
   // write neighbouring 128-byte segments of the same destination rows
@@ -51,8 +52,10 @@ mg_transpose_send(const __half* __restrict__ src_re, const __half* __restrict__ 
   uint4 a[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) a[j] = __ldcs(reinterpret_cast<const uint4*>(s + j * src_row_stride));
-  const int64_t d_row = rows_local;
-  __half* d = (plane ? peers.im[peer] : peers.re[peer]) + static_cast<int64_t>(rank) * cl * rows_local +
+  // staged: stage_p[rank][c][r] (contiguous block per source rank); direct: the row-major matrix dst_p[c][rank*rows_local + r]
+  const int64_t d_row = staged ? rows_local : static_cast<int64_t>(world) * rows_local;
+  __half* d = (plane ? peers.im[peer] : peers.re[peer]) +
+              (staged ? static_cast<int64_t>(rank) * cl * rows_local : static_cast<int64_t>(rank) * rows_local) +
               (static_cast<int64_t>(cg) * 32 + 8 * ch) * d_row + blockIdx.x * 64 + 8 * rg;
 #pragma unroll
   for (int cc = 0; cc < 8; ++cc) {

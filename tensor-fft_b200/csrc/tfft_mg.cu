@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <unistd.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -51,6 +52,7 @@ struct tfft_mg_plan_s {
   bool opened[kMgMaxRanks] = {};
   bool connected = false;
   uint32_t epoch = 0;
+  bool staged = false;                         // exchanges go through source-rank-major staging planes + a local unpack (world > 2)
   uint32_t parity = 0;                         // execs alternate the staging planes: exchange e of an exec lands in S[(e + parity) & 1],
                                                // so that exchange 1 of the next exec never targets the planes a slower
                                                // peer is still unpacking from exchange 3 of this one
@@ -108,6 +110,10 @@ int tfft_mg_plan_create(tfft_mg_plan_t* out, int64_t n, int32_t rank, int32_t wo
     return rc;
   }
   p->peer[rank] = p->base;
+  // direct row-major peer stores for 1-2 ranks (measured at 2 GPUs: 1.71 ms against 2.26 ms staged), staging above
+  // (measured at 8 GPUs: the scattered stores cost 0.13 ms per exchange); TFFT_MG_STAGED=0/1 (developer) forces one
+  p->staged = world > 2;
+  if (const char* e = getenv("TFFT_DEVELOPER") ? getenv("TFFT_MG_STAGED") : nullptr) p->staged = atoi(e) != 0;
   if (world == 1) p->connected = true;
   *out = p;
   return TFFT_OK;
@@ -180,8 +186,9 @@ static int mg_unpack_stage(tfft_mg_plan_t p, int stage, int dst, int64_t rows_lo
   return cuda_rc(cudaGetLastError());
 }
 
-// One exchange: transpose-send my slab into the peers' staging planes `stage` (0: S0, 2: S1), flag barrier, then unpack
-// my own staging planes into the row-major matrix dst (plane index `dst`: 4 = W, 6 = C).
+// One exchange.  Staged: transpose-send my slab into the peers' staging planes `stage` (0: S0, 2: S1), flag barrier, then
+// unpack my own staging planes into the row-major matrix `dst` (4 = W, 6 = C).  Direct: transpose-send straight into the
+// peers' row-major planes `stage` (0, 2 or 6), flag barrier.
 static int mg_exchange(tfft_mg_plan_t p, const __half* src_re, const __half* src_im, int stage, int dst, int64_t rows_local,
                        int64_t cols, bool barrier, cudaStream_t s) {
   MgPeers peers;
@@ -189,7 +196,7 @@ static int mg_exchange(tfft_mg_plan_t p, const __half* src_re, const __half* src
   const dim3 grid(static_cast<unsigned>(rows_local / 64), static_cast<unsigned>((cols / 32 + 7) / 8), 2);
   if (grid.y > 65535) return TFFT_E_UNSUPPORTED;
   mg_transpose_send<<<grid, 256, 0, s>>>(src_re, src_im, peers, static_cast<int>(rows_local), static_cast<int>(cols),
-                                         p->rank, p->world, cols);
+                                         p->rank, p->world, cols, p->staged ? 1 : 0);
   int rc = cuda_rc(cudaGetLastError());
   if (rc != TFFT_OK) return rc;
   if (barrier) {
@@ -198,37 +205,48 @@ static int mg_exchange(tfft_mg_plan_t p, const __half* src_re, const __half* src
     mg_barrier<<<1, 32, 0, s>>>(f, p->rank, p->world, ++p->epoch, p->timeout_ns, p->status_dev);
     rc = cuda_rc(cudaGetLastError());
     if (rc != TFFT_OK) return rc;
-    return mg_unpack_stage(p, stage, dst, rows_local, cols, s);
+    if (p->staged) return mg_unpack_stage(p, stage, dst, rows_local, cols, s);
   }
-  return TFFT_OK;   // phase-stepped callers unpack at the start of the next phase (after every rank has sent)
+  return TFFT_OK;   // staged + phase-stepped callers: unpacked at the start of the next phase (after every rank has sent)
 }
 
-// phase 0: exchange 1;  phase 1: [unpack] transforms over i1 + exchange 2;  phase 2: [unpack] transforms over i2 + exchange 3;
-// phase 3: [unpack] copy the result out (if asked).  The unpacks in brackets run here only for phase-stepped callers
-// (tfft_mg_exec_phase: no barrier inside the exchange, so the exchange cannot unpack what the peers have not sent yet).
+// phase 0: exchange 1;  phase 1: transforms over i1 + exchange 2;  phase 2: transforms over i2 + exchange 3;  phase 3: copy
+// the result out (if asked).
+// Staged plans (world > 2): the peers store into staging planes S[(e + parity) & 1] of exchange e; this rank unpacks them
+// into its working matrix W (exchanges 1, 2; the transforms run in place on W) or into the result C (exchange 3).  For
+// phase-stepped callers (no barrier inside the exchange) the unpack runs at the start of the next phase.
+// Direct plans (1-2 ranks): exchange 1 stores the row-major matrix into the peers' S0, transforms in place there, exchange 2
+// into S1, exchange 3 into C.
 static int mg_phase(tfft_mg_plan_t p, int phase, const void* in_re, const void* in_im, void* out_re, void* out_im,
                     bool barrier, cudaStream_t s) {
   const int64_t g = p->world, r1 = p->n1 / g, r2 = p->n2 / g;
-  __half *w_re = p->plane(p->rank, 4), *w_im = p->plane(p->rank, 5);
   __half *c_re = p->plane(p->rank, 6), *c_im = p->plane(p->rank, 7);
   int rc = TFFT_OK;
   if (phase == 0) p->parity ^= 1u;
-  const int sa = static_cast<int>(p->parity & 1u) * 2, sb = 2 - sa;   // staging planes of exchanges 1 and 3 / of exchange 2
+  // planes the exchanges target (sa: exchanges 1 and 3 when staged, exchange 1 when direct; sb: exchange 2) and the
+  // row-major matrices the two transforms run on
+  const int sa = p->staged ? static_cast<int>(p->parity & 1u) * 2 : 0, sb = 2 - sa;
+  const int m1 = p->staged ? 4 : 0, m2 = p->staged ? 4 : 2, x3 = p->staged ? sa : 6;
+  const bool lazy_unpack = p->staged && !barrier;
   switch (phase) {
-    case 0:   // my n1/g rows of n2 -> every rank gets its n2/g columns, transposed: W[i2_local][i1]
+    case 0:   // my n1/g rows of n2 -> every rank gets its n2/g columns, transposed: M1[i2_local][i1]
       return mg_exchange(p, static_cast<const __half*>(in_re), static_cast<const __half*>(in_im), sa, 4, r1, p->n2, barrier, s);
-    case 1:   // n2/g transforms over i1, times exp(-2*pi*i*k1*i2/n), in place; then W[i2_local][k1] -> W'[k1_local][i2]
-      if (!barrier) rc = mg_unpack_stage(p, sa, 4, r1, p->n2, s);
-      if (rc == TFFT_OK) rc = tfft_exec_twiddled(p->fft1, w_re, w_im, w_re, w_im, p->n1, p->n1, p->lg, p->rank * r2, s);
-      if (rc == TFFT_OK) rc = mg_exchange(p, w_re, w_im, sb, 4, r2, p->n1, barrier, s);
+    case 1:   // n2/g transforms over i1, times exp(-2*pi*i*k1*i2/n), in place; then M1[i2_local][k1] -> M2[k1_local][i2]
+      if (lazy_unpack) rc = mg_unpack_stage(p, sa, 4, r1, p->n2, s);
+      if (rc == TFFT_OK)
+        rc = tfft_exec_twiddled(p->fft1, p->plane(p->rank, m1), p->plane(p->rank, m1 + 1), p->plane(p->rank, m1),
+                                p->plane(p->rank, m1 + 1), p->n1, p->n1, p->lg, p->rank * r2, s);
+      if (rc == TFFT_OK) rc = mg_exchange(p, p->plane(p->rank, m1), p->plane(p->rank, m1 + 1), sb, 4, r2, p->n1, barrier, s);
       return rc;
-    case 2:   // n1/g transforms over i2, in place; then W[k1_local][k2] -> C[k2_local][k1] = X[k1 + n1*k2]: this rank's n/g slice
-      if (!barrier) rc = mg_unpack_stage(p, sb, 4, r2, p->n1, s);
-      if (rc == TFFT_OK) rc = tfft_exec(p->fft2, w_re, w_im, w_re, w_im, p->n2, p->n2, s);
-      if (rc == TFFT_OK) rc = mg_exchange(p, w_re, w_im, sa, 6, r1, p->n2, barrier, s);
+    case 2:   // n1/g transforms over i2, in place; then M2[k1_local][k2] -> C[k2_local][k1] = X[k1 + n1*k2]: this rank's n/g slice
+      if (lazy_unpack) rc = mg_unpack_stage(p, sb, 4, r2, p->n1, s);
+      if (rc == TFFT_OK)
+        rc = tfft_exec(p->fft2, p->plane(p->rank, m2), p->plane(p->rank, m2 + 1), p->plane(p->rank, m2),
+                       p->plane(p->rank, m2 + 1), p->n2, p->n2, s);
+      if (rc == TFFT_OK) rc = mg_exchange(p, p->plane(p->rank, m2), p->plane(p->rank, m2 + 1), x3, 6, r1, p->n2, barrier, s);
       return rc;
     case 3:
-      if (!barrier) rc = mg_unpack_stage(p, sa, 6, r1, p->n2, s);
+      if (lazy_unpack) rc = mg_unpack_stage(p, sa, 6, r1, p->n2, s);
       if (rc == TFFT_OK && out_re && out_re != c_re)
         rc = cuda_rc(cudaMemcpyAsync(out_re, c_re, p->local * sizeof(__half), cudaMemcpyDeviceToDevice, s));
       if (rc == TFFT_OK && out_im && out_im != c_im)

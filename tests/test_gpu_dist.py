@@ -25,8 +25,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TOL = 1.25 * 4.7e-4
 
 
-@pytest.mark.parametrize("lg,world", [(16, 1), (20, 1), (18, 2), (20, 2), (20, 4), (22, 8), (21, 4), (24, 2), (26, 8)])
-def test_ranks_on_one_gpu(lg, world):
+@pytest.mark.parametrize("lg,world,staged", [(16, 1, None), (20, 1, None), (18, 2, None), (20, 2, None), (20, 4, None),
+                                             (22, 8, None), (21, 4, None), (24, 2, None), (26, 8, None),
+                                             (20, 2, "1"), (22, 4, "0"), (20, 1, "1")])
+def test_ranks_on_one_gpu(lg, world, staged, monkeypatch):
+    """staged: None = the plan's own choice of exchange layout (direct row-major peer stores for 1-2 ranks, source-rank-major
+    staging + local unpack above), "0" / "1" = the other one forced (developer variable TFFT_MG_STAGED)."""
+    if staged is not None:
+        monkeypatch.setenv("TFFT_MG_STAGED", staged)
     n = 1 << lg
     m = n // world
     rng = np.random.default_rng(lg * 16 + world)
