@@ -115,6 +115,15 @@ int tfft_exec(tfft_plan_t plan, const void* in_re, const void* in_im, void* out_
 int tfft_exec_twiddled(tfft_plan_t plan, const void* in_re, const void* in_im, void* out_re, void* out_im,
                        int64_t in_stride, int64_t out_stride, int32_t log2_total, int64_t first_col, void* stream);
 
+/* tfft_exec_twiddled for an input whose transforms are SEGMENTED: every transform is cut into `segments` equal pieces and
+ * piece q of transform b starts at in + q*segment_stride + b*in_stride (the exchange buffers of the multi-GPU transform are
+ * source-rank major: one block per sending rank).  The gather happens inside the TMA load of the transform (a 5-D tensor
+ * map), not in a separate pass.  log2_total = 0: no twiddle.  Only for single-pass plans with n >= 2048 and `segments`
+ * dividing the first radix (16 or 32); TFFT_E_UNSUPPORTED otherwise (callers then gather with a copy). */
+int tfft_exec_segmented(tfft_plan_t plan, const void* in_re, const void* in_im, void* out_re, void* out_im,
+                        int64_t in_stride, int64_t out_stride, int32_t segments, int64_t segment_stride,
+                        int32_t log2_total, int64_t first_col, void* stream);
+
 /* In-place execution: for single-pass sizes (n <= 32768) out_re == in_re and out_im == in_im (same strides) is legal --
  * every CTA reads its transforms completely before it writes them.  Multi-pass sizes run in place on the INPUT planes
  * by design (see TFFT_PRESERVE_INPUT) but their final pass is a transposition: out must not alias in.  2-D plans: out

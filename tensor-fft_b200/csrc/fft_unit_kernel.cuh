@@ -892,8 +892,13 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
         tma_load_5d(smem_u32(smem) + SL.plane_stride, &tmap_im, uu, ub * P.tma_batch_step, load_bar);
       } else {
         const uint32_t c3 = ub * P.tma_batch_step + (uu << P.log2_units);
-        tma_load_4d(smem_u32(smem), &tmap_re, c.cl_rank * P.cl_load_c2, c3, load_bar);
-        tma_load_4d(smem_u32(smem) + SL.plane_stride, &tmap_im, c.cl_rank * P.cl_load_c2, c3, load_bar);
+        if (P.tma_seg) {
+          tma_load_5d(smem_u32(smem), &tmap_re, 0, c3, load_bar);
+          tma_load_5d(smem_u32(smem) + SL.plane_stride, &tmap_im, 0, c3, load_bar);
+        } else {
+          tma_load_4d(smem_u32(smem), &tmap_re, c.cl_rank * P.cl_load_c2, c3, load_bar);
+          tma_load_4d(smem_u32(smem) + SL.plane_stride, &tmap_im, c.cl_rank * P.cl_load_c2, c3, load_bar);
+        }
       }
     }
   }
@@ -964,8 +969,13 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
           tma_load_5d(c.s_im, &tmap_im, uu, ub * P.tma_batch_step, load_bar);
         } else {
           const uint32_t c3 = ub * P.tma_batch_step + (uu << P.log2_units);
-          tma_load_4d(c.s_re, &tmap_re, c.cl_rank * P.cl_load_c2, c3, load_bar);
-          tma_load_4d(c.s_im, &tmap_im, c.cl_rank * P.cl_load_c2, c3, load_bar);
+          if (P.tma_seg) {   // segmented input (multi-GPU staging planes): 5-D map {64, kappa_lo, segment, M/64, transform}
+            tma_load_5d(c.s_re, &tmap_re, 0, c3, load_bar);
+            tma_load_5d(c.s_im, &tmap_im, 0, c3, load_bar);
+          } else {
+            tma_load_4d(c.s_re, &tmap_re, c.cl_rank * P.cl_load_c2, c3, load_bar);
+            tma_load_4d(c.s_im, &tmap_im, c.cl_rank * P.cl_load_c2, c3, load_bar);
+          }
         }
       }
       TFFT_TRACE_MARK(1);
@@ -1209,6 +1219,11 @@ fft_unit_kernel_2slot(const __grid_constant__ UnitPlan P, __half* __restrict__ o
       return;
     }
     const uint32_t c3 = qb * P.tma_batch_step + (qu << P.log2_units) + h * half_c3;
+    if (P.tma_seg) {   // segmented input (multi-GPU staging planes): 5-D map {64, kappa_lo, segment, M/64, transform}
+      tma_load_5d(c.a_re + off, &tmap_re, h * half_c2, c3, full);
+      tma_load_5d(c.a_im + off, &tmap_im, h * half_c2, c3, full);
+      return;
+    }
     tma_load_4d(c.a_re + off, &tmap_re, h * half_c2, c3, full);
     tma_load_4d(c.a_im + off, &tmap_im, h * half_c2, c3, full);
     if (pf) {

@@ -32,8 +32,8 @@ using namespace tfft;
 struct Prepared {
   int dev = -1;
   const void *sre = nullptr, *sim = nullptr;
-  int64_t in_stride = 0, out_stride = 0, tw_first_col = 0;
-  int tw_log2 = 0;
+  int64_t in_stride = 0, out_stride = 0, tw_first_col = 0, seg_stride = 0;
+  int tw_log2 = 0, segs = 0;
   UnitPlan plan;
   alignas(64) CUtensorMap tmap_re, tmap_im;
   const void* fn = nullptr;
@@ -227,6 +227,31 @@ int make_input_tensor_map(const UnitPlan& plan, const __half* base, int64_t tstr
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(base), gdim, gstride, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? TFFT_OK : TFFT_E_INVALID_ARG;
+}
+
+// Segmented input (tfft_exec_segmented): element n of transform t lies at base + (n / seg_len) * seg_stride + t * tstride +
+// n % seg_len with seg_len = L / segs.  With n = kappa*M + m (M = L/R rows per K line, seg_len = kl*M, kl = R/segs):
+// dims {64 (m low), kl (kappa low, stride M), segs (stride seg_stride), M/64 (stride 64), transforms (stride tstride)} --
+// the box lands in shared memory exactly like the 4-D tile {64, R, M/64, U} because (kappa_lo, segment) enumerate kappa.
+int make_seg_tensor_map(const UnitPlan& plan, const __half* base, int64_t tstride, int64_t n_transforms, int segs,
+                        int64_t seg_stride, CUtensorMap* out, bool half_box) {
+  EncodeTiledFn encode = get_encode_fn();
+  if (!encode) return TFFT_E_UNSUPPORTED;
+  const uint64_t L = uint64_t(1) << plan.log2_len, R = uint64_t(1) << plan.log2_radix[0], M = L / R;
+  const uint64_t U = uint64_t(1) << plan.log2_units, kl = R / static_cast<uint64_t>(segs);
+  cuuint64_t gdim[5] = {64, kl, static_cast<cuuint64_t>(segs), M / 64, static_cast<cuuint64_t>(n_transforms)};
+  cuuint64_t gstride[4] = {M * 2, static_cast<cuuint64_t>(seg_stride) * 2, 128, static_cast<cuuint64_t>(tstride) * 2};
+  cuuint32_t box[5] = {64, static_cast<cuuint32_t>(kl), static_cast<cuuint32_t>(segs), static_cast<cuuint32_t>(M / 64),
+                       static_cast<cuuint32_t>(U)};
+  if (half_box) {   // two-slot kernel: one box = half of a unit's stage-1 tiles
+    if (U >= 2) box[4] = static_cast<cuuint32_t>(U / 2);
+    else box[3] = static_cast<cuuint32_t>(M / 128);
+  }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<__half*>(base), gdim, gstride, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? TFFT_OK : TFFT_E_INVALID_ARG;
 }
@@ -765,7 +790,8 @@ int ensure_pass_on_device(const Pass& ps, int dev, const void* entry, bool two_s
 }
 
 int prepare_launch(const tfft_plan_s* p, const Pass& ps, const __half* src_re, const __half* src_im, int64_t in_stride,
-                   int64_t out_stride, int tw_log2, int64_t tw_first_col, int dev, Prepared* out) {
+                   int64_t out_stride, int tw_log2, int64_t tw_first_col, int segs, int64_t seg_stride, int dev,
+                   Prepared* out) {
   UnitStrides st = ps.strides;
   if (tw_log2) {   // fused output twiddle: column index of transform b = first_col + b
     st.pass1_log2n = static_cast<uint32_t>(tw_log2);
@@ -809,6 +835,12 @@ int prepare_launch(const tfft_plan_s* p, const Pass& ps, const __half* src_re, c
                                 : (prefetch_default(p, ps, plan) ? 1u : 0u);
   }
   plan.col_first = static_cast<uint32_t>(tw_first_col);
+  if (segs > 0) {   // tfft_exec_segmented: only for the row tiles of 64-row atoms, whole K lines per segment
+    const int R0 = 1 << plan.log2_radix[0];
+    if (plan.tma_load != 1 || plan.cluster || plan.kron_bits || ps.kind != 0 || R0 % segs != 0) return TFFT_E_UNSUPPORTED;
+    plan.tma_seg = 1;
+    plan.prefetch_next = 0;
+  }
   const bool allow2 = knob(p->tune.two_slot, "TFFT_NO_2SLOT", 1) != 0;
   int threads = kThreads;
   KernelFn fn = kernel_for(plan, &threads);
@@ -845,6 +877,10 @@ int prepare_launch(const tfft_plan_s* p, const Pass& ps, const __half* src_re, c
     } else if (plan.kron_bits) {
       rc = make_kron_tensor_map(plan, src_re, p->ny, p->batch, plan.tma_batch_step, &out->tmap_re, half_box);
       if (rc == TFFT_OK) rc = make_kron_tensor_map(plan, src_im, p->ny, p->batch, plan.tma_batch_step, &out->tmap_im, half_box);
+    } else if (plan.tma_seg) {
+      const int64_t nt = plan.n_transforms ? plan.n_transforms : n_tr;
+      rc = make_seg_tensor_map(plan, src_re, st.in_tstride, nt, segs, seg_stride, &out->tmap_re, half_box);
+      if (rc == TFFT_OK) rc = make_seg_tensor_map(plan, src_im, st.in_tstride, nt, segs, seg_stride, &out->tmap_im, half_box);
     } else {
       rc = make_input_tensor_map(plan, src_re, st.in_tstride, plan.n_transforms ? plan.n_transforms : n_tr, &out->tmap_re, half_box);
       if (rc == TFFT_OK)
@@ -859,12 +895,13 @@ int prepare_launch(const tfft_plan_s* p, const Pass& ps, const __half* src_re, c
   out->sre = src_re; out->sim = src_im;
   out->in_stride = in_stride; out->out_stride = out_stride;
   out->tw_log2 = tw_log2; out->tw_first_col = tw_first_col;
+  out->segs = segs; out->seg_stride = seg_stride;
   return TFFT_OK;
 }
 
 int launch_pass(const tfft_plan_s* p, const Pass& ps, const __half* src_re, const __half* src_im, __half* dst_re,
                 __half* dst_im, int64_t in_stride, int64_t out_stride, cudaStream_t stream, int tw_log2 = 0,
-                int64_t tw_first_col = 0) {
+                int64_t tw_first_col = 0, int segs = 0, int64_t seg_stride = 0) {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) { cudaGetLastError(); return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? TFFT_E_NO_DEVICE : static_cast<int>(e); }
@@ -875,11 +912,14 @@ int launch_pass(const tfft_plan_s* p, const Pass& ps, const __half* src_re, cons
     const Prepared* hit = nullptr;
     for (const Prepared& c : ps.prepared)
       if (c.dev == dev && c.sre == src_re && c.sim == src_im && c.in_stride == in_stride && c.out_stride == out_stride &&
-          c.tw_log2 == tw_log2 && c.tw_first_col == tw_first_col) { hit = &c; break; }
+          c.tw_log2 == tw_log2 && c.tw_first_col == tw_first_col && c.segs == segs && c.seg_stride == seg_stride) {
+        hit = &c;
+        break;
+      }
     if (hit) {
       L = *hit;
     } else {
-      const int rc = prepare_launch(p, ps, src_re, src_im, in_stride, out_stride, tw_log2, tw_first_col, dev, &L);
+      const int rc = prepare_launch(p, ps, src_re, src_im, in_stride, out_stride, tw_log2, tw_first_col, segs, seg_stride, dev, &L);
       if (rc != TFFT_OK) return rc;
       if (ps.prepared.size() < kPreparedSlots) ps.prepared.push_back(L);
       else ps.prepared[ps.prepared_next++ % kPreparedSlots] = L;
@@ -1145,6 +1185,26 @@ int tfft_exec_twiddled(tfft_plan_t p, const void* in_re, const void* in_im, void
   return launch_pass(p, p->passes[0], static_cast<const __half*>(in_re), static_cast<const __half*>(in_im),
                      static_cast<__half*>(out_re), static_cast<__half*>(out_im), in_stride, out_stride,
                      static_cast<cudaStream_t>(stream_), log2_total, first_col);
+}
+
+int tfft_exec_segmented(tfft_plan_t p, const void* in_re, const void* in_im, void* out_re, void* out_im, int64_t in_stride,
+                        int64_t out_stride, int32_t segments, int64_t segment_stride, int32_t log2_total, int64_t first_col,
+                        void* stream_) {
+  if (!p || !in_re || !in_im || !out_re || !out_im || segments < 1) return TFFT_E_INVALID_ARG;
+  if (p->passes.size() != 1 || (p->flags & (TFFT_INVERSE | TFFT_INTERLEAVED)) || p->n % segments) return TFFT_E_UNSUPPORTED;
+  if (log2_total && (log2_total < p->lg || log2_total > 30)) return TFFT_E_UNSUPPORTED;
+  if (log2_total && (first_col < 0 || first_col + p->batch > (int64_t(1) << (log2_total - p->lg)))) return TFFT_E_INVALID_ARG;
+  if (!aligned16(in_re) || !aligned16(in_im) || !aligned16(out_re) || !aligned16(out_im)) return TFFT_E_INVALID_ARG;
+  const int64_t seg_len = p->n / segments;
+  if ((in_stride & 7) || (out_stride & 7) || (segment_stride & 7) || in_stride < seg_len || out_stride < p->n) return TFFT_E_INVALID_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return TFFT_E_NO_DEVICE;
+  }
+  return launch_pass(p, p->passes[0], static_cast<const __half*>(in_re), static_cast<const __half*>(in_im),
+                     static_cast<__half*>(out_re), static_cast<__half*>(out_im), in_stride, out_stride,
+                     static_cast<cudaStream_t>(stream_), log2_total, first_col, segments, segment_stride);
 }
 
 // Host-buffer path.  The batch is cut into chunks of whole transforms; upload, transform and download of consecutive

@@ -52,6 +52,8 @@ struct tfft_mg_plan_s {
   bool opened[kMgMaxRanks] = {};
   bool connected = false;
   uint32_t epoch = 0;
+  int fuse1 = -1, fuse2 = -1;                  // staged plans: the transform gathers its input from the staging planes in its
+                                               // TMA load (tfft_exec_segmented); -1 = not tried yet, 0 = unsupported shape
   bool staged = false;                         // exchanges go through source-rank-major staging planes + a local unpack (world > 2)
   uint32_t parity = 0;                         // execs alternate the staging planes: exchange e of an exec lands in S[(e + parity) & 1],
                                                // so that exchange 1 of the next exec never targets the planes a slower
@@ -187,10 +189,10 @@ static int mg_unpack_stage(tfft_mg_plan_t p, int stage, int dst, int64_t rows_lo
 }
 
 // One exchange.  Staged: transpose-send my slab into the peers' staging planes `stage` (0: S0, 2: S1), flag barrier, then
-// unpack my own staging planes into the row-major matrix `dst` (4 = W, 6 = C).  Direct: transpose-send straight into the
-// peers' row-major planes `stage` (0, 2 or 6), flag barrier.
-static int mg_exchange(tfft_mg_plan_t p, const __half* src_re, const __half* src_im, int stage, int dst, int64_t rows_local,
-                       int64_t cols, bool barrier, cudaStream_t s) {
+// -- if unpack_dst >= 0 -- unpack my own staging planes into the row-major matrix unpack_dst (4 = W, 6 = C).  Direct:
+// transpose-send straight into the peers' row-major planes `stage` (0, 2 or 6), flag barrier.
+static int mg_exchange(tfft_mg_plan_t p, const __half* src_re, const __half* src_im, int stage, int unpack_dst,
+                       int64_t rows_local, int64_t cols, bool barrier, cudaStream_t s) {
   MgPeers peers;
   for (int r = 0; r < p->world; ++r) { peers.re[r] = p->plane(r, stage); peers.im[r] = p->plane(r, stage + 1); }
   const dim3 grid(static_cast<unsigned>(rows_local / 64), static_cast<unsigned>((cols / 32 + 7) / 8), 2);
@@ -205,16 +207,35 @@ static int mg_exchange(tfft_mg_plan_t p, const __half* src_re, const __half* src
     mg_barrier<<<1, 32, 0, s>>>(f, p->rank, p->world, ++p->epoch, p->timeout_ns, p->status_dev);
     rc = cuda_rc(cudaGetLastError());
     if (rc != TFFT_OK) return rc;
-    if (p->staged) return mg_unpack_stage(p, stage, dst, rows_local, cols, s);
+    if (p->staged && unpack_dst >= 0) return mg_unpack_stage(p, stage, unpack_dst, rows_local, cols, s);
   }
-  return TFFT_OK;   // staged + phase-stepped callers: unpacked at the start of the next phase (after every rank has sent)
+  return TFFT_OK;
 }
 
-// phase 0: exchange 1;  phase 1: transforms over i1 + exchange 2;  phase 2: transforms over i2 + exchange 3;  phase 3: copy
-// the result out (if asked).
-// Staged plans (world > 2): the peers store into staging planes S[(e + parity) & 1] of exchange e; this rank unpacks them
-// into its working matrix W (exchanges 1, 2; the transforms run in place on W) or into the result C (exchange 3).  For
-// phase-stepped callers (no barrier inside the exchange) the unpack runs at the start of the next phase.
+// The transforms of a staged plan: gather the input from the staging planes `stage` inside the TMA load when the shape
+// allows (tfft_exec_segmented), else unpack into W first and transform in place.  rows_local / cols describe the slab the
+// PEERS sent (this rank received cols/world transforms of world*rows_local elements).
+static int mg_staged_fft(tfft_mg_plan_t p, tfft_plan_t fft, int* fuse, int stage, int64_t rows_local, int64_t cols, int64_t n,
+                         int log2_total, int64_t first_col, cudaStream_t s) {
+  __half *w_re = p->plane(p->rank, 4), *w_im = p->plane(p->rank, 5);
+  const int64_t cl = cols / p->world;
+  if (*fuse != 0) {
+    const int rc = tfft_exec_segmented(fft, p->plane(p->rank, stage), p->plane(p->rank, stage + 1), w_re, w_im, rows_local, n,
+                                       p->world, cl * rows_local, log2_total, first_col, s);
+    if (rc != TFFT_E_UNSUPPORTED) { *fuse = 1; return rc; }
+    *fuse = 0;
+  }
+  int rc = mg_unpack_stage(p, stage, 4, rows_local, cols, s);
+  if (rc != TFFT_OK) return rc;
+  return log2_total ? tfft_exec_twiddled(fft, w_re, w_im, w_re, w_im, n, n, log2_total, first_col, s)
+                    : tfft_exec(fft, w_re, w_im, w_re, w_im, n, n, s);
+}
+
+// phase 0: exchange 1;  phase 1: transforms over i1 + exchange 2;  phase 2: transforms over i2 + exchange 3;  phase 3:
+// result in place (+ copy out if asked).
+// Staged plans (world > 2): the peers store into staging planes S[(e + parity) & 1] of exchange e; the transforms read them
+// (gathering in their TMA load) and write the working matrix W, which the next exchange sends; exchange 3 is unpacked
+// into the result C (after its barrier; for phase-stepped callers in phase 3).
 // Direct plans (1-2 ranks): exchange 1 stores the row-major matrix into the peers' S0, transforms in place there, exchange 2
 // into S1, exchange 3 into C.
 static int mg_phase(tfft_mg_plan_t p, int phase, const void* in_re, const void* in_im, void* out_re, void* out_im,
@@ -223,30 +244,32 @@ static int mg_phase(tfft_mg_plan_t p, int phase, const void* in_re, const void* 
   __half *c_re = p->plane(p->rank, 6), *c_im = p->plane(p->rank, 7);
   int rc = TFFT_OK;
   if (phase == 0) p->parity ^= 1u;
-  // planes the exchanges target (sa: exchanges 1 and 3 when staged, exchange 1 when direct; sb: exchange 2) and the
-  // row-major matrices the two transforms run on
   const int sa = p->staged ? static_cast<int>(p->parity & 1u) * 2 : 0, sb = 2 - sa;
-  const int m1 = p->staged ? 4 : 0, m2 = p->staged ? 4 : 2, x3 = p->staged ? sa : 6;
-  const bool lazy_unpack = p->staged && !barrier;
   switch (phase) {
-    case 0:   // my n1/g rows of n2 -> every rank gets its n2/g columns, transposed: M1[i2_local][i1]
-      return mg_exchange(p, static_cast<const __half*>(in_re), static_cast<const __half*>(in_im), sa, 4, r1, p->n2, barrier, s);
-    case 1:   // n2/g transforms over i1, times exp(-2*pi*i*k1*i2/n), in place; then M1[i2_local][k1] -> M2[k1_local][i2]
-      if (lazy_unpack) rc = mg_unpack_stage(p, sa, 4, r1, p->n2, s);
-      if (rc == TFFT_OK)
-        rc = tfft_exec_twiddled(p->fft1, p->plane(p->rank, m1), p->plane(p->rank, m1 + 1), p->plane(p->rank, m1),
-                                p->plane(p->rank, m1 + 1), p->n1, p->n1, p->lg, p->rank * r2, s);
-      if (rc == TFFT_OK) rc = mg_exchange(p, p->plane(p->rank, m1), p->plane(p->rank, m1 + 1), sb, 4, r2, p->n1, barrier, s);
+    case 0:   // my n1/g rows of n2 -> every rank gets its n2/g columns, transposed
+      return mg_exchange(p, static_cast<const __half*>(in_re), static_cast<const __half*>(in_im), sa, -1, r1, p->n2, barrier, s);
+    case 1:   // n2/g transforms over i1, times exp(-2*pi*i*k1*i2/n); then M1[i2_local][k1] -> peers
+      if (p->staged) {
+        rc = mg_staged_fft(p, p->fft1, &p->fuse1, sa, r1, p->n2, p->n1, p->lg, p->rank * r2, s);
+        if (rc == TFFT_OK) rc = mg_exchange(p, p->plane(p->rank, 4), p->plane(p->rank, 5), sb, -1, r2, p->n1, barrier, s);
+      } else {
+        rc = tfft_exec_twiddled(p->fft1, p->plane(p->rank, 0), p->plane(p->rank, 1), p->plane(p->rank, 0), p->plane(p->rank, 1),
+                                p->n1, p->n1, p->lg, p->rank * r2, s);
+        if (rc == TFFT_OK) rc = mg_exchange(p, p->plane(p->rank, 0), p->plane(p->rank, 1), 2, -1, r2, p->n1, barrier, s);
+      }
       return rc;
-    case 2:   // n1/g transforms over i2, in place; then M2[k1_local][k2] -> C[k2_local][k1] = X[k1 + n1*k2]: this rank's n/g slice
-      if (lazy_unpack) rc = mg_unpack_stage(p, sb, 4, r2, p->n1, s);
-      if (rc == TFFT_OK)
-        rc = tfft_exec(p->fft2, p->plane(p->rank, m2), p->plane(p->rank, m2 + 1), p->plane(p->rank, m2),
-                       p->plane(p->rank, m2 + 1), p->n2, p->n2, s);
-      if (rc == TFFT_OK) rc = mg_exchange(p, p->plane(p->rank, m2), p->plane(p->rank, m2 + 1), x3, 6, r1, p->n2, barrier, s);
+    case 2:   // n1/g transforms over i2; then M2[k1_local][k2] -> C[k2_local][k1] = X[k1 + n1*k2]: this rank's n/g slice
+      if (p->staged) {
+        rc = mg_staged_fft(p, p->fft2, &p->fuse2, sb, r2, p->n1, p->n2, 0, 0, s);
+        if (rc == TFFT_OK) rc = mg_exchange(p, p->plane(p->rank, 4), p->plane(p->rank, 5), sa, 6, r1, p->n2, barrier, s);
+      } else {
+        rc = tfft_exec(p->fft2, p->plane(p->rank, 2), p->plane(p->rank, 3), p->plane(p->rank, 2), p->plane(p->rank, 3), p->n2,
+                       p->n2, s);
+        if (rc == TFFT_OK) rc = mg_exchange(p, p->plane(p->rank, 2), p->plane(p->rank, 3), 6, -1, r1, p->n2, barrier, s);
+      }
       return rc;
     case 3:
-      if (lazy_unpack) rc = mg_unpack_stage(p, sa, 6, r1, p->n2, s);
+      if (p->staged && !barrier) rc = mg_unpack_stage(p, sa, 6, r1, p->n2, s);   // phase-stepped callers
       if (rc == TFFT_OK && out_re && out_re != c_re)
         rc = cuda_rc(cudaMemcpyAsync(out_re, c_re, p->local * sizeof(__half), cudaMemcpyDeviceToDevice, s));
       if (rc == TFFT_OK && out_im && out_im != c_im)

@@ -83,6 +83,10 @@ struct UnitPlan {
   uint32_t cl_load_c2;                     //   TMA loads: dim-2 tile coordinate of rank 1 (row tiles: M/128; column tiles: M/2)
   uint32_t cl_load_gofs;                   //   cp.async loads: global element offset of rank 1's rows (fill_strides)
   uint32_t cl_out_gofs;                    //   store: global element offset of rank 1's outputs (fill_strides)
+  uint32_t tma_seg;                        // 1 (row tiles of 64-row atoms only): every input transform is split into equal
+                                           // segments lying segment_stride apart (multi-GPU staging planes, source-rank
+                                           // major); the tensor map is 5-D {64, kappa_lo, segment, M/64, transform} and the
+                                           // tile coordinates are (0, 0, 0, c2, c3)
   uint32_t prefetch_next;                  // 1: pull the next unit's input into L2 during this unit's stages
   uint32_t tma_load;                       // 4: column-mode input, >= 16 columns per unit: tiles {16 columns, R kappa, M rows} per
                                            //    16-column group as SWIZZLE_32B atoms: row = (u&15) + 16*(m + M*(u>>4)), element

@@ -52,7 +52,7 @@ EXPORTS = ("tfft_plan_create", "tfft_plan_create_2d", "tfft_plan_info", "tfft_pl
            "tfft_exec_twiddled", "tfft_exec_host", "tfft_error_string", "tfft_version", "tfft_fixture_sine",
            "tfft_error_stats", "tfft_transpose_blocks", "tfft_copy_runs", "tfft_plan_create_from_file",
            "tfft_mg_plan_create", "tfft_mg_plan_handle", "tfft_mg_plan_connect", "tfft_mg_plan_info", "tfft_mg_exec",
-           "tfft_mg_status", "tfft_mg_set_timeout_ms", "tfft_mg_plan_destroy", "tfft_plan_prepare", "tfft_mg_exec_phase")
+           "tfft_mg_status", "tfft_mg_set_timeout_ms", "tfft_mg_plan_destroy", "tfft_plan_prepare", "tfft_mg_exec_phase", "tfft_exec_segmented")
 
 TFFT_MG_HANDLE_BYTES = 128
 
@@ -82,6 +82,7 @@ def lib() -> ctypes.CDLL:
         L.tfft_exec.argtypes = [vp, vp, vp, vp, vp, i64, i64, vp]
         L.tfft_exec_twiddled.argtypes = [vp, vp, vp, vp, vp, i64, i64, ctypes.c_int32, i64, vp]
         L.tfft_exec_host.argtypes = [vp, vp, vp]
+        L.tfft_exec_segmented.argtypes = [vp, vp, vp, vp, vp, i64, i64, ctypes.c_int32, i64, ctypes.c_int32, i64, vp]
         fp, dp = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)
         L.tfft_fixture_sine.argtypes = [vp, vp, i64, i64, i64, fp, fp, ctypes.c_int32, vp]
         L.tfft_error_stats.argtypes = [vp, vp, vp, vp, i64, dp, vp]
@@ -173,6 +174,15 @@ class NativePlan:
         _check(lib().tfft_exec_twiddled(self._h, in_re.data_ptr(), in_im.data_ptr(), out_re.data_ptr(),
                                         out_im.data_ptr(), in_stride, out_stride, log2_total, first_col,
                                         ctypes.c_void_p(s)))
+
+    def exec_segmented(self, in_re, in_im, out_re, out_im, in_stride: int, out_stride: int, segments: int,
+                       segment_stride: int, log2_total: int = 0, first_col: int = 0, stream=None) -> None:
+        """tfft_exec_segmented: piece q of transform b at in + q*segment_stride + b*in_stride (gathered by the TMA load)."""
+        import torch
+        s = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        _check(lib().tfft_exec_segmented(self._h, in_re.data_ptr(), in_im.data_ptr(), out_re.data_ptr(), out_im.data_ptr(),
+                                         in_stride, out_stride, segments, segment_stride, log2_total, first_col,
+                                         ctypes.c_void_p(s)))
 
     def prepare(self) -> None:
         """tfft_plan_prepare: all lazy one-time device initialisation now (before graph capture / spin-waiting peers)."""

@@ -264,3 +264,32 @@ def test_cluster_units_through_the_tuner_file(tmp_path, lg, b):
     ol = y.view(b, 2, n)[b - 1].cpu().numpy().astype(np.float64)
     wl_re, wl_im = O.fft_f64(re[b - 1:].astype(np.float64), im[b - 1:].astype(np.float64))
     assert O.error_stats(ol[0], ol[1], wl_re[0], wl_im[0])["rel_l2"] <= GUARD * (4.05e-4 if lg == 16 else MEASURED[lg])
+
+
+@pytest.mark.parametrize("lg,b,segs,lgt", [(11, 64, 8, 0), (12, 32, 4, 24), (13, 24, 16, 0), (14, 16, 8, 28), (14, 5, 2, 0),
+                                           (15, 4, 8, 0), (10, 16, 4, 0)])
+def test_exec_segmented_gathers_in_the_tma_load(lg, b, segs, lgt):
+    """tfft_exec_segmented: piece q of transform t at in + q*segment_stride + t*in_stride (the source-rank-major staging planes
+    of the multi-GPU transform).  Must equal tfft_exec_twiddled on the gathered input bit for bit; shapes whose row tiles
+    are not 64-row atoms (n <= 1024) answer TFFT_E_UNSUPPORTED."""
+    n = 1 << lg
+    seg = n // segs
+    re, im = O.gauss_fixture(n, b, seed=1700 + lg)
+    # staging layout [q][t][r]
+    st_re = torch.from_numpy(np.ascontiguousarray(re.reshape(b, segs, seg).transpose(1, 0, 2))).cuda().reshape(-1)
+    st_im = torch.from_numpy(np.ascontiguousarray(im.reshape(b, segs, seg).transpose(1, 0, 2))).cuda().reshape(-1)
+    g_re, g_im = torch.from_numpy(re).cuda().reshape(-1), torch.from_numpy(im).cuda().reshape(-1)
+    plan = tfft.NativePlan(n, b)
+    want_re, want_im = torch.empty_like(g_re), torch.empty_like(g_im)
+    if lgt:
+        plan.exec_twiddled(g_re, g_im, want_re, want_im, n, n, lgt, 3)
+    else:
+        plan.exec(g_re, g_im, want_re, want_im, n, n)
+    out_re, out_im = torch.full_like(g_re, float("nan")), torch.full_like(g_im, float("nan"))
+    if lg <= 10:
+        with pytest.raises(tfft.TfftError):
+            plan.exec_segmented(st_re, st_im, out_re, out_im, seg, n, segs, b * seg, lgt, 3 if lgt else 0)
+        return
+    plan.exec_segmented(st_re, st_im, out_re, out_im, seg, n, segs, b * seg, lgt, 3 if lgt else 0)
+    torch.cuda.synchronize()
+    assert bool(torch.equal(out_re, want_re)) and bool(torch.equal(out_im, want_im))
