@@ -28,14 +28,15 @@
 namespace tfft {
 
 constexpr int kThreads = 256;
-// -DTFFT_TW_TABLE: the round-1 inter-stage twiddle seeds (two-level shared-memory table, two divergent LDS.64 per seed).
-// Default: per-thread seeds in registers times per-tile factors from kernel-parameter space -- no shared-memory loads
-// in the epilogue (profiles/r02_*: the table lookups were the only instructions with excess shared wavefronts).
-#ifdef TFFT_TW_TABLE
-constexpr uint32_t kTwTableBytes = 512 + 4096;   // [TWlo: 64 float2 | TWhi: 512 float2]
-#else
-constexpr uint32_t kTwTableBytes = 0;
-#endif
+// Inter-stage twiddle seeds, two implementations chosen per plan shape (measured on B200, same box A/B):
+//   3-stage plans (N = 8192 .. 32768, the two-slot kernel): per-thread seeds in registers times per-tile factors from
+//     kernel-parameter space -- no shared-memory loads in the epilogue (C2 -5 %; the table lookups were the only
+//     instructions with excess shared wavefronts and sat at the head of every item's dependency chain);
+//   2-stage plans (N <= 4096 and every pass of a multi-pass plan): the round-1 two-level shared-memory table (two LDS.64
+//     per seed).  With two CTAs per SM the lookup latency is hidden and the seed registers cost spills:
+//     N = 1024 0.430 against 0.467 ms per GiB, 2^16 .. 2^20 2 - 4 % (profiles/r02_twiddle_seed_ab.txt).
+constexpr uint32_t kTwTableBytesMax = 512 + 4096;   // [TWlo: 64 float2 | TWhi: 512 float2]
+__host__ __device__ inline uint32_t tw_table_bytes(const UnitPlan& p) { return p.stages == 3 ? 0u : kTwTableBytesMax; }
 
 // ---------------------------------------------------------------- packed fp32 pairs (FFMA2)
 // Blackwell issues two fp32 FMAs per lane per instruction on 64-bit register pairs
@@ -176,7 +177,7 @@ struct TableLayout {
 };
 __host__ __device__ inline TableLayout table_layout(const UnitPlan& p) {
   TableLayout l;
-  uint32_t off = kTwTableBytes;
+  uint32_t off = tw_table_bytes(p);
   for (uint32_t t = 0; t < kMaxStages; ++t) l.b_off[t] = 0;
   for (uint32_t t = 0; t < p.stages; ++t) {
     bool found = false;
@@ -430,7 +431,7 @@ __device__ __forceinline__ uint32_t thread_col(const UnitPlan& P, const KernelCt
   return col;
 }
 
-template <int ST, int RHO, bool LAST, uint32_t II, int NG = 2, bool CL = false>
+template <int ST, int RHO, bool LAST, uint32_t II, int NG = 2, bool CL = false, bool TWT = false>
 __device__ __forceinline__ void epilogue_item(const UnitPlan& P, const KernelCtx& c, uint32_t dst_thr, uint32_t aux_thr,
                                               uint32_t col_thr, const TwSeed& seed, const uint32_t (&are)[16],
                                               const uint32_t (&aim)[16]) {
@@ -475,7 +476,7 @@ __device__ __forceinline__ void epilogue_item(const UnitPlan& P, const KernelCtx
       return;
     }
     if (!LAST) {
-#ifdef TFFT_TW_TABLE
+     if constexpr (TWT) {   // two-level shared-memory table (2-stage plans)
       const uint32_t idx = aux << E.tw_shift;                       // unit angle 2*pi/L
       const Cplx w1 = tw_lookup(c.tw_table, idx);
       s2 = cmul(w1, w1);
@@ -486,7 +487,7 @@ __device__ __forceinline__ void epilogue_item(const UnitPlan& P, const KernelCtx
         t0 = tw_lookup(c.tw_table, (idx * 16u * g) & ((1u << P.log2_len) - 1u));
         t1 = cmul(t0, w1);
       }
-#else
+     } else {
       // w1 = exp(-2*pi*i*m/N_t) of this row = (per-thread seed) * (factor of the tile, warp-uniform, parameter space)
       (void)aux;
       const Cplx w1 = cmul(seed.w, {E.tile_tw[kTileHi][0], E.tile_tw[kTileHi][1]});
@@ -503,7 +504,7 @@ __device__ __forceinline__ void epilogue_item(const UnitPlan& P, const KernelCtx
         if (g2) t0 = cmul(t0, cmul(w16, w16));
         t1 = cmul(t0, w1);
       }
-#endif
+     }
     } else {
       const uint64_t col = col_thr + bit_sum_c<(kTileHi >> kTileShift), kMaxRowBits - 7 - kTileShift>(E.col, 7 + kTileShift) + c.col_base;
       const uint64_t mask = (uint64_t(1) << E.tw_log2n) - 1u;
@@ -558,7 +559,7 @@ __device__ __forceinline__ void epilogue_item(const UnitPlan& P, const KernelCtx
 // Software-pipelined item loop over items [II, END): the tensor-memory load of item II+1 is in flight
 // while item II is processed (tcgen05.wait::ld waits for ALL outstanding loads, so the next load is
 // issued right after the wait and before the arithmetic).
-template <int ST, int RHO, bool LAST, uint32_t II, uint32_t END, int NG = 2, bool CL = false>
+template <int ST, int RHO, bool LAST, uint32_t II, uint32_t END, int NG = 2, bool CL = false, bool TWT = false>
 __device__ __forceinline__ void epilogue_range(const UnitPlan& P, const KernelCtx& c, uint32_t dst_thr,
                                                uint32_t aux_thr, uint32_t col_thr, const TwSeed& seed,
                                                uint32_t (&cre)[16], uint32_t (&cim)[16], uint32_t (&nre)[16],
@@ -566,8 +567,8 @@ __device__ __forceinline__ void epilogue_range(const UnitPlan& P, const KernelCt
   if constexpr (II < END) {
     ptx::tmem_ld_wait();                                            // item II has landed in (cre, cim)
     if constexpr (II + 1 < END) epilogue_load<RHO, II + 1, NG>(c, nre, nim);
-    epilogue_item<ST, RHO, LAST, II, NG, CL>(P, c, dst_thr, aux_thr, col_thr, seed, cre, cim);
-    epilogue_range<ST, RHO, LAST, II + 1, END, NG, CL>(P, c, dst_thr, aux_thr, col_thr, seed, nre, nim, cre, cim);
+    epilogue_item<ST, RHO, LAST, II, NG, CL, TWT>(P, c, dst_thr, aux_thr, col_thr, seed, cre, cim);
+    epilogue_range<ST, RHO, LAST, II + 1, END, NG, CL, TWT>(P, c, dst_thr, aux_thr, col_thr, seed, nre, nim, cre, cim);
   }
 }
 
@@ -691,7 +692,7 @@ __device__ __forceinline__ void stage_observe(uint64_t* bar, uint32_t (&phase)[2
 // must have consumed the partner's operand before this CTA stores into it); every later stage starts at a cluster barrier
 // instead of the CTA barrier (the partner's stores into this CTA's operand must have landed).
 template <int ST, int RHO, bool LAST, int LOG2E, int LM = 0, bool PIPE = false, class Hook = NoHook,
-          int ROLE = 0, int NG = 2, bool EARLY2 = false, bool CL = false>
+          int ROLE = 0, int NG = 2, bool EARLY2 = false, bool CL = false, bool TWT = false>
 __device__ __forceinline__ void run_stage(const UnitPlan& P, const KernelCtx& c, uint32_t b1_saddr, uint64_t* bar,
                                           uint32_t (&phase)[2], int warp, int lane, long long* trace,
                                           uint32_t trace_unit, uint32_t tmap, uint32_t col_thr,
@@ -738,12 +739,12 @@ __device__ __forceinline__ void run_stage(const UnitPlan& P, const KernelCtx& c,
     if (hook_warp && elect_one()) hook.after_half(0);
     TFFT_TRACE_MARK(10 + 2 * ST);
     epilogue_load<RHO, 0, NG>(c, ra, rb);
-    epilogue_range<ST, RHO, LAST, 0, kHalf, NG>(P, c, dst_thr, aux_thr, col_thr, seed, ra, rb, rc, rd);
+    epilogue_range<ST, RHO, LAST, 0, kHalf, NG, false, TWT>(P, c, dst_thr, aux_thr, col_thr, seed, ra, rb, rc, rd);
     hook.mid(warp, lane);
     warp_wait(bar + 1, phase[1] & 1u, lane);
     if (hook_warp && elect_one()) hook.after_half(1);
     epilogue_load<RHO, kHalf, NG>(c, ra, rb);
-    epilogue_range<ST, RHO, LAST, kHalf, kItemsPerGroup, NG>(P, c, dst_thr, aux_thr, col_thr, seed, ra, rb, rc, rd);
+    epilogue_range<ST, RHO, LAST, kHalf, kItemsPerGroup, NG, false, TWT>(P, c, dst_thr, aux_thr, col_thr, seed, ra, rb, rc, rd);
     phase[0]++;
     phase[1]++;
   } else {
@@ -756,7 +757,7 @@ __device__ __forceinline__ void run_stage(const UnitPlan& P, const KernelCtx& c,
     if (CL && ST == 0) cluster_sync_all();   // both CTAs' stage-1 MMAs have read their operands
     TFFT_TRACE_MARK(10 + 2 * ST);
     epilogue_load<RHO, 0, NG>(c, ra, rb);
-    epilogue_range<ST, RHO, LAST, 0, kItemsPerGroup, NG, CL>(P, c, dst_thr, aux_thr, col_thr, seed, ra, rb, rc, rd);
+    epilogue_range<ST, RHO, LAST, 0, kItemsPerGroup, NG, CL, TWT>(P, c, dst_thr, aux_thr, col_thr, seed, ra, rb, rc, rd);
     phase[0]++;
     if (EARLY2) phase[1]++;
   }
@@ -920,7 +921,8 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
   const uint32_t tmap0 = thread_map<0, RHO0, NG>(P, c), tmap1 = thread_map<1, RHO1, NG>(P, c);
   const uint32_t tmap2 = kStages == 3 ? thread_map<2, (RHO2 ? RHO2 : 4), NG>(P, c) : 0u;
   const uint32_t col_thr = kStages == 3 ? thread_col<2, (RHO2 ? RHO2 : 4), NG>(P, c) : thread_col<1, RHO1, NG>(P, c);
-  const TwSeed seed0 = thread_seed(P, 0, tmap0);
+  constexpr bool kTwt = kStages == 2;   // 2-stage plans take their twiddle seeds from the shared-memory table
+  const TwSeed seed0 = kTwt ? TwSeed() : thread_seed(P, 0, tmap0);
   const TwSeed seed1 = kStages == 3 ? thread_seed(P, 1, tmap1) : TwSeed();
 
   for (uint32_t unit = first_unit; unit < P.n_units; unit += unit_step) {
@@ -1062,8 +1064,8 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
     }
 
     // ---------------------------------------------------------------- tensor-core stages
-    run_stage<0, RHO0, false, LOG2E, LM, false, NoHook, 0, NG, false, CL != 0>(P, c, table_base + TL.b_off[0], bar, phase,
-                                                                                warp, lane, trace, trace_unit, tmap0, 0u, seed0);
+    run_stage<0, RHO0, false, LOG2E, LM, false, NoHook, 0, NG, false, CL != 0, kTwt>(
+        P, c, table_base + TL.b_off[0], bar, phase, warp, lane, trace, trace_unit, tmap0, 0u, seed0);
     TFFT_TRACE_MARK(3);
     // 3-stage plans built with pipe_stage2: the epilogue of stage 2's first tile half overlaps the UMMAs of its second
     if (kStages == 3 && P.pipe_stage2)

@@ -87,12 +87,12 @@ std::vector<uint8_t> make_tables(const UnitPlan& plan, bool unscaled) {
     *c = std::cos(a); *s = std::sin(a);
   };
   float2* tw = reinterpret_cast<float2*>(host.data());
-  for (int j = 0; j < 64 && kTwTableBytes; ++j) {
+  for (int j = 0; j < 64 && tw_table_bytes(plan); ++j) {
     double c, s;
     unit(j, L, &c, &s);
     tw[j] = make_float2(static_cast<float>(c), static_cast<float>(s));
   }
-  for (int64_t j = 0; j < 512 && kTwTableBytes; ++j) {
+  for (int64_t j = 0; j < 512 && tw_table_bytes(plan); ++j) {
     double c, s;
     unit((64 * j) % L, L, &c, &s);
     tw[64 + j] = make_float2(static_cast<float>(c), static_cast<float>(s));
