@@ -108,3 +108,43 @@ def test_tuner_file_plan_creation(tmp_path):
     assert L.tfft_plan_create_from_file(ctypes.byref(h), 8192, 1, 0, str(f).encode()) == -6
     assert L.tfft_plan_create_from_file(ctypes.byref(h), 8192, 1, 0, b"/nonexistent/file") == -2
     assert b"tuner file" in L.tfft_error_string(-6)
+
+
+def test_multi_gpu_and_segmented_entry_points_fail_loudly_without_gpu():
+    """The round-2 entry points (tfft_mg_*, tfft_exec_segmented, tfft_plan_prepare) validate their arguments on the host and
+    answer with an error -- never a CPU result -- when there is no device."""
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    L = tfft.lib()
+    h = ctypes.c_void_p()
+    assert L.tfft_mg_plan_create(ctypes.byref(h), 1 << 20, 0, 3, 0) == -2          # world not a power of two
+    assert L.tfft_mg_plan_create(ctypes.byref(h), 1 << 20, 2, 2, 0) == -2          # rank out of range
+    assert L.tfft_mg_plan_create(ctypes.byref(h), 1 << 12, 0, 2, 0) == -1          # too short to shard
+    assert L.tfft_mg_plan_create(ctypes.byref(h), 1 << 20, 0, 2, 0) == -3          # TFFT_E_NO_DEVICE
+    assert not h.value
+    p = tfft.NativePlan(16384, 4)
+    with pytest.raises(tfft.TfftError):
+        p.prepare()                                                                 # needs the device
+    buf = (ctypes.c_uint16 * 64)()
+    a = ctypes.addressof(buf)
+    a += (-a) % 16
+    rc = L.tfft_exec_segmented(p._h, a, a, a, a, 2048, 16384, 8, 8192, 0, 0, None)
+    assert rc == -3                                                                 # arguments fine, no device
+    assert L.tfft_exec_segmented(p._h, a, a, a, a, 2048, 16384, 0, 8192, 0, 0, None) == -2   # segments < 1
+    assert L.tfft_exec_segmented(p._h, a + 2, a, a, a, 2048, 16384, 8, 8192, 0, 0, None) == -2   # misaligned
+    assert b"barrier" in L.tfft_error_string(-7)
+    p.close()
+
+
+def test_cluster_tuner_key_builds_a_single_pass_plan(tmp_path):
+    f = tmp_path / "TunerResults.dat"
+    f.write_text("65536 256 8 8 256 cluster=1\n4194304 256 8 8 256 cluster=1 lg1=12\n")
+    p = tfft.NativePlan(65536, 7, tuner_file=str(f))
+    assert p.info["passes"] == 1 and p.info["algorithmic_bytes"] == 8 * 65536 * 7      # one HBM pass on CTA-pair units
+    assert p.info["smem_bytes"] <= 227 * 1024 and p.info["tmem_columns"] == 512
+    q = tfft.NativePlan(65536, 7)
+    assert q.info["passes"] == 2                                                        # default: four-step
+    r = tfft.NativePlan(1 << 22, 1, tuner_file=str(f))
+    assert r.info["passes"] == 2 and r.info["transforms_per_cta"] == 16                 # 16 columns per CTA pair
+    for x in (p, q, r):
+        x.close()
