@@ -550,7 +550,9 @@ int build_1d(tfft_plan_s* p) {
   // column-pass length 2^lg1, measured per size on B200 (tools/tune_fourstep.py): the balanced split except where it
   // would produce 2048-point units (40 KiB of DFT matrices -> one 16K-element CTA per SM): 2^19 = 512 x 1024 (-9 %),
   // 2^21 = 4096 x 512 (-3 %), 2^22 = 4096 x 1024 (-26 %); 2^23 = 2048 x 4096 with 16-column units (-16 %)
-  static const int kLg1[9] = {8, 9, 9, 9, 10, 12, 12, 11, 12};   // lg = 16 .. 24
+  // round 2 (tools/tune.py, gpurun_out/t27_tune.log -> profiles/r02_TunerResults.dat): 2^21 = 2048 x 1024 (1.24 ms against 1.42 ms
+  // for 4096 x 512) now that two 16K-element CTAs of a 2048-point plan share an SM; the other sizes keep their split
+  static const int kLg1[9] = {8, 9, 9, 9, 10, 11, 12, 11, 12};   // lg = 16 .. 24
   if (lg < 16 || lg > 24) return TFFT_E_INVALID_SIZE;
   int lg1 = kLg1[lg - 16];
   {   // tuner file / developer knob: length 2^lg1 of the column pass
