@@ -293,3 +293,35 @@ def test_exec_segmented_gathers_in_the_tma_load(lg, b, segs, lgt):
     plan.exec_segmented(st_re, st_im, out_re, out_im, seg, n, segs, b * seg, lgt, 3 if lgt else 0)
     torch.cuda.synchronize()
     assert bool(torch.equal(out_re, want_re)) and bool(torch.equal(out_im, want_im))
+
+
+@pytest.mark.parametrize("lg,b", [(12, 1), (14, 64), (20, 2)])
+def test_exec_can_be_captured_into_a_cuda_graph(lg, b):
+    """tfft_plan_prepare does every lazy device initialisation up front, so a later exec only enqueues kernels and can be
+    recorded by stream capture (launch-bound loops of small transforms replay as one graph launch)."""
+    n = 1 << lg
+    re, im = O.gauss_fixture(n, b, seed=1900 + lg)
+    x = _planar(re, im)
+    src = x.clone()
+    plan = tfft.NativePlan(n, b, tfft.TFFT_PRESERVE_INPUT if lg > 15 else 0)
+    plan.prepare()
+    want = torch.empty_like(x)
+    plan.exec(x, x[n:], want, want[n:], 2 * n, 2 * n)          # also fills the plan's launch cache for these buffers
+    torch.cuda.synchronize()
+    y = torch.zeros_like(x)
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        plan.exec(x, x[n:], y, y[n:], 2 * n, 2 * n)            # warm-up on the capture stream
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g, stream=s):
+            for _ in range(4):
+                plan.exec(x, x[n:], y, y[n:], 2 * n, 2 * n)
+    y.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    assert bool(torch.equal(y, want)) and bool(torch.equal(x, src))
+    g.replay()
+    torch.cuda.synchronize()
+    assert bool(torch.equal(y, want))
