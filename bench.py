@@ -252,6 +252,20 @@ def extra_c1(O):
         torch.cuda.synchronize()
         lat.append((time.perf_counter() - t0) * 1e6)
     row["ours_isolated_launch_to_done_us"] = round(float(np.median(lat)), 2)
+    # the same 100 launches recorded once into a CUDA graph (tfft_plan_prepare makes exec capturable) and replayed
+    try:
+        plan.prepare()
+        g, st = torch.cuda.CUDAGraph(), torch.cuda.Stream()
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
+            plan.exec(x, x[n:], y, y[n:], 2 * n, 2 * n)
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g, stream=st):
+                for _ in range(100):
+                    plan.exec(x, x[n:], y, y[n:], 2 * n, 2 * n)
+        row["ours_cuda_graph_us"] = round(float(np.median([timed(g.replay, warm=1, iters=5) * 1e3 / 100 for _ in range(5)])), 3)
+    except Exception as e:  # noqa
+        row["ours_cuda_graph_error"] = repr(e)[:120]
     try:
         xc = torch.view_as_complex(torch.randn(n, 2, device="cuda", dtype=torch.float16).contiguous())
         row["cufft_fp16_us"] = round(group(lambda: torch.fft.fft(xc)), 3)
