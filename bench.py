@@ -310,6 +310,26 @@ def extra_c3(peak):
         if passes > 1:   # multi-pass sizes consume their input: refill for the next size
             x.copy_(torch.randn(2 * total, generator=g, device="cuda").to(torch.float16))
         del plan
+    # N = 65536: the default two-pass plan and the opt-in single-pass plan on CTA-pair units (tuner key cluster=1)
+    try:
+        import tempfile
+        n, b = 65536, total // 65536
+        for label, knobs in (("two passes (default)", ""), ("one pass, CTA-pair units (cluster=1)", " cluster=1")):
+            with tempfile.NamedTemporaryFile("w", suffix=".dat", delete=False) as f:
+                f.write(f"{n} 256 8 8 256{knobs}\n")
+            plan = tfft.NativePlan(n, b, tuner_file=f.name)
+            os.unlink(f.name)
+            passes = plan.info["passes"]
+            ms = timed(lambda: plan.exec(x, x[n:], y, y[n:], 2 * n, 2 * n), warm=3, iters=10)
+            gbs = 8.0 * n * b * passes / (ms * 1e-3) / 1e9
+            rows.append({"log2n": 16, "batch": b, "plan": label, "passes": passes, "ms": round(ms, 4),
+                         "gflops": round(5.0 * n * 16 * b / (ms * 1e-3) / 1e9, 1), "hbm_gbs": round(gbs, 1),
+                         "frac": round(gbs / peak, 4)})
+            if passes > 1:
+                x.copy_(torch.randn(2 * total, generator=g, device="cuda").to(torch.float16))
+            del plan
+    except Exception as e:  # noqa
+        rows.append({"log2n": 16, "error": repr(e)[:160]})
     return rows
 
 
