@@ -24,6 +24,23 @@ static uint32_t bitsum(uint32_t q, const uint32_t* c, int nbits) {
   for (int i = 0; i < nbits; ++i) if (q >> i & 1) s += c[i];
   return s;
 }
+// Excess wavefronts of one warp-wide LDS.64 (32 lanes, 8 bytes each, byte offsets `off` into the table): the access is
+// served in as many wavefronts as the busiest of the 32 four-byte banks has DISTINCT words; ideal = ceil(distinct words / 32)
+#include <set>
+#include <map>
+static int lds64_excess(const uint32_t* off) {
+  std::map<int, std::set<uint32_t>> banks;
+  std::set<uint32_t> words;
+  for (int l = 0; l < 32; ++l)
+    for (int hw = 0; hw < 2; ++hw) {
+      const uint32_t w = (off[l] >> 2) + hw;
+      banks[w & 31].insert(w);
+      words.insert(w);
+    }
+  size_t worst = 0;
+  for (auto& b : banks) worst = std::max(worst, b.second.size());
+  return (int)worst - (int)((words.size() + 31) / 32);
+}
 // conflicts of one quarter-warp of 16-byte accesses: max lanes per 16-byte bank group - 1
 static int qw_conflict(const uint32_t* addr) {
   int cnt[8] = {0};
@@ -62,6 +79,8 @@ int plansim_run_ex(int log2_len, int log2_units, int in_mode_flags, int out_mode
   const int s = P.stages;
   const int64_t L = int64_t(1) << P.log2_len;
   conflicts[0] = conflicts[1] = conflicts[2] = conflicts[3] = 0;
+  int lookups = 0;   // warp-wide LDS.64 table lookups modelled (for reference; conflicts[3] is their excess wavefronts)
+  (void)lookups;
   const uint32_t smem_halves = P.plane_bytes / 2;
   for (int unit = 0; unit < n_units; ++unit) {
     const int64_t ibase = (unit / P.units_per_batch) * P.in_batch_stride + (unit % P.units_per_batch) * P.in_unit_stride;
@@ -153,6 +172,26 @@ int plansim_run_ex(int log2_len, int log2_units, int in_mode_flags, int out_mode
       for (int rk = 0; rk < nranks; ++rk) { nre_[rk].assign(smem_halves, NAN); nim_[rk].assign(smem_halves, NAN); }
       const uint32_t rows = 1u << rowbits;
       if (rows != P.n_tiles[t - 1] * 128) { fprintf(stderr, "tile count mismatch\n"); return -5; }
+      // Twiddle-table lookups of the epilogue (2-stage plans only; 3-stage plans keep their seeds in registers): per
+      // item a warp of 32 consecutive rows reads TWlo[x & 63], TWhi[x >> 6] for x = aux << tw_shift and, for radix 32 / 64,
+      // for x * 16 g.  conflicts[3] accumulates the EXCESS wavefronts of these LDS.64 (0 = conflict free).
+      if (t < s && s == 2 && E.tw_mode == 1 && unit == 0) {
+        for (uint32_t row0 = 0; row0 < rows; row0 += 32)
+          for (int gq = 0; gq < R / 16; ++gq) {   // one item = (32 rows of a tile, column group g)
+            uint32_t lo[32], hi[32], lo2[32], hi2[32];
+            for (int l = 0; l < 32; ++l) {
+              const uint32_t x = bitsum(row0 + l, E.aux, rowbits) << E.tw_shift;        // seed w1
+              const uint32_t x2 = (x * 16u * gq) & ((1u << P.log2_len) - 1u);           // seed t0 = w1^(16 g)
+              lo[l] = 8u * (x & 63u);
+              hi[l] = 8u * (64u + (x >> 6));
+              lo2[l] = 8u * (x2 & 63u);
+              hi2[l] = 8u * (64u + (x2 >> 6));
+            }
+            conflicts[3] += lds64_excess(lo) + lds64_excess(hi);
+            lookups += 2;
+            if (R > 16) { conflicts[3] += lds64_excess(lo2) + lds64_excess(hi2); lookups += 2; }
+          }
+      }
       for (int rk = 0; rk < nranks; ++rk) {
       const std::vector<double>& sre = pre_[rk];
       const std::vector<double>& sim = pim_[rk];

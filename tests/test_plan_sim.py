@@ -230,3 +230,25 @@ def test_four_step_with_cluster_column_units(sim, lg1, lg2, tma):
     want = np.fft.fft(re + 1j * im) / N
     assert rc1 == 0 and rc2 == 0 and c1 == [0, 0, 0]
     assert np.linalg.norm(o_re + 1j * o_im - want) / np.linalg.norm(want) < 1e-13
+
+
+@pytest.mark.parametrize("lg,ups,bound", [(8, 6, 0), (8, 5, 0), (9, 5, 0), (10, 4, 96), (11, 3, 96), (12, 2, 128), (12, 1, 64)])
+def test_twiddle_table_lookups_are_modelled(sim, lg, ups, bound):
+    """The only shared-memory accesses besides the 16-byte operand stores and staging loads are the LDS.64 lookups of the
+    two-level twiddle table in the epilogue of 2-stage plans (3-stage plans keep their seeds in registers).  The simulator
+    counts their EXCESS wavefronts per unit (conflicts[3]): none for a radix-16 first stage; for radix 32 / 64 the second
+    lookup (x * 16 g) folds lanes onto the same banks -- bounded, and measured on hardware as the only instructions with
+    `L1 Wavefronts Shared Excessive` > 0 (profiles/r02_ncu_c2.txt discussion in DESIGN.md 3)."""
+    n, U = 1 << lg, 1 << ups
+    tot = U * n
+    rng = np.random.default_rng(1)
+    re, im = rng.standard_normal(tot), rng.standard_normal(tot)
+    ore, oim = np.zeros(tot), np.zeros(tot)
+    st = (ctypes.c_int64 * 9)(n, 1, n, 1, 0, U * n, 0, U * n, 1 << 30)
+    conf = (ctypes.c_int * 4)()
+    rc = sim.plansim_run(lg, ups, 2, 0, st, 0, 1, re.ctypes.data_as(dp), im.ctypes.data_as(dp),
+                         ore.ctypes.data_as(dp), oim.ctypes.data_as(dp), 0, conf)
+    assert rc == 0 and list(conf)[:3] == [0, 0, 0]
+    assert 0 <= conf[3] <= bound, conf[3]
+    if bound == 0:
+        assert conf[3] == 0
