@@ -269,6 +269,18 @@ def extra_c1(O):
     try:
         xc = torch.view_as_complex(torch.randn(n, 2, device="cuda", dtype=torch.float16).contiguous())
         row["cufft_fp16_us"] = round(group(lambda: torch.fft.fft(xc)), 3)
+        try:   # the same through a CUDA graph (both stream-launch numbers above are bound by the Python launch path)
+            gc, sc = torch.cuda.CUDAGraph(), torch.cuda.Stream()
+            sc.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(sc):
+                yc = torch.fft.fft(xc)
+                torch.cuda.synchronize()
+                with torch.cuda.graph(gc, stream=sc):
+                    for _ in range(100):
+                        yc = torch.fft.fft(xc)
+            row["cufft_fp16_cuda_graph_us"] = round(float(np.median([timed(gc.replay, warm=1, iters=5) * 1e3 / 100 for _ in range(5)])), 3)
+        except Exception as e:  # noqa
+            row["cufft_fp16_cuda_graph_error"] = repr(e)[:120]
     except Exception as e:  # noqa
         row["cufft_fp16_error"] = repr(e)[:120]
     try:
