@@ -172,7 +172,8 @@ int tfft_copy_runs(const void* src, void* dst, int64_t run, int64_t n0, int64_t 
  *                         of a phase one after the other on one stream): phase 0 = exchange 1, 1 = transforms over the
  *                         first factor + exchange 2, 2 = transforms over the second factor + exchange 3, 3 = copy out.
  *                         Every rank must have finished phase p before any rank starts phase p + 1.
- * All ranks must call tfft_mg_exec the same number of times. */
+ * All ranks must call tfft_mg_exec the same number of times.  Destroy a plan only after every rank has finished its last
+ * exec (synchronise the streams, then a barrier of the caller's transport): peers store into each other's buffers. */
 #define TFFT_MG_HANDLE_BYTES 128
 typedef struct tfft_mg_plan_s* tfft_mg_plan_t;
 typedef struct tfft_mg_info_s {

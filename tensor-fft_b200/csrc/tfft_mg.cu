@@ -24,6 +24,7 @@ struct Blob {   // what a rank publishes (<= TFFT_MG_HANDLE_BYTES)
   uint64_t magic;
   int64_t n;
   int32_t rank, world, pid, device;
+  int32_t staged, reserved;   // exchange layout of the exporting rank: every rank of a transform must use the same one
   uint64_t base;    // device pointer in the exporting process (used directly by ranks living in the same process)
   uint64_t bytes;
   cudaIpcMemHandle_t ipc;
@@ -61,7 +62,7 @@ struct tfft_mg_plan_s {
   int* status_host = nullptr;
   int* status_dev = nullptr;
   unsigned long long timeout_ns = 10ull * 1000 * 1000 * 1000;
-  __half* plane(int r, int which) const {      // which: 0..5 as in the layout above, on rank r
+  __half* plane(int r, int which) const {      // which: 0..7 as in the layout above, on rank r
     return reinterpret_cast<__half*>(peer[r] + static_cast<size_t>(which) * local * sizeof(__half));
   }
 };
@@ -127,6 +128,7 @@ int tfft_mg_plan_handle(tfft_mg_plan_t p, void* handle) {
   std::memset(&b, 0, sizeof(b));
   b.magic = kBlobMagic; b.n = p->n; b.rank = p->rank; b.world = p->world; b.pid = static_cast<int32_t>(getpid());
   b.device = p->device; b.base = reinterpret_cast<uint64_t>(p->base); b.bytes = p->bytes;
+  b.staged = p->staged ? 1 : 0;
   const int rc = cuda_rc(cudaIpcGetMemHandle(&b.ipc, p->base));
   if (rc != TFFT_OK) return rc;
   std::memset(handle, 0, TFFT_MG_HANDLE_BYTES);
@@ -141,7 +143,9 @@ int tfft_mg_plan_connect(tfft_mg_plan_t p, const void* handles) {
   for (int r = 0; r < p->world; ++r) {
     Blob b;
     std::memcpy(&b, h + static_cast<size_t>(r) * TFFT_MG_HANDLE_BYTES, sizeof(b));
-    if (b.magic != kBlobMagic || b.rank != r || b.world != p->world || b.n != p->n || b.bytes != p->bytes) return TFFT_E_INVALID_ARG;
+    if (b.magic != kBlobMagic || b.rank != r || b.world != p->world || b.n != p->n || b.bytes != p->bytes ||
+        b.staged != (p->staged ? 1 : 0))
+      return TFFT_E_INVALID_ARG;
     if (r == p->rank) continue;
     if (b.pid == static_cast<int32_t>(getpid())) {
       // ranks that live in this process (one host thread per GPU, or several ranks on one GPU in the tests)
