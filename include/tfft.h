@@ -48,9 +48,9 @@ enum {
   TFFT_INVERSE = 2,
   TFFT_UNSCALED = 4,
   /* interleaved layout (cuFFT's half2 / the reference's CuFFTTest.h:25-57 buffers): in_re and out_re point to arrays of
-   * (re, im) fp16 pairs, in_im / out_im are ignored, strides count complex elements.  1-D, N <= 2^24; these plans load
-   * with 16-byte vector loads instead of TMA tiles (the split into planes happens in registers) and multi-pass sizes own
-   * a planar scratch buffer. */
+   * (re, im) fp16 pairs, in_im / out_im are ignored, strides count complex elements.  Every size and the 2-D plans; these
+   * plans load with 16-byte vector loads instead of TMA tiles (the split into planes happens in registers), multi-pass
+   * 1-D sizes own a planar scratch buffer (the input is preserved), 2-D plans keep their intermediate in the output array. */
   TFFT_INTERLEAVED = 8
 };
 

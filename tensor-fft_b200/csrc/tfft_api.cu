@@ -453,9 +453,6 @@ int build_1d(tfft_plan_s* p) {
     p->passes.back().il_in = p->passes.back().il_out = (p->flags & TFFT_INTERLEAVED) != 0;
     return TFFT_OK;
   }
-  if (p->flags & TFFT_INTERLEAVED) {
-    if (lg > 24) return TFFT_E_UNSUPPORTED;   // three-pass sizes: planar only
-  }
   // CTA-pair units are OFF by default: measured on B200 they are correct but not faster (N = 65536 x 4096: 1.08 ms in one
   // pass against 0.97 ms in two; 2^24: 2.24 against 2.19 ms).  Tuner key cluster=1 (or the developer variable
   // TFFT_CLUSTER) switches them on.
@@ -477,10 +474,12 @@ int build_1d(tfft_plan_s* p) {
   }
   int three_from = 25;   // developer knob: three passes from this log2 length on (>= 24: all factors >= 256)
   if (const char* e = dev_env("TFFT_THREEPASS_LG")) three_from = std::min(25, std::max(24, atoi(e)));   // four-step covers <= 2^24 only
-  if (lg >= three_from && !(p->flags & TFFT_INTERLEAVED)) {
+  if (lg >= three_from) {
     // TFFT_PRESERVE_INPUT: pass A writes into a plan-owned scratch of ONE transform (the batch is looped), passes B
-    // and C work from there; without the flag passes A and B run in place on the input planes
-    const bool preserve3 = (p->flags & TFFT_PRESERVE_INPUT) != 0;
+    // and C work from there; without the flag passes A and B run in place on the input planes.  TFFT_INTERLEAVED: pass A
+    // reads half2 pairs and pass C writes them, the scratch between them is planar
+    const bool il3 = (p->flags & TFFT_INTERLEAVED) != 0;
+    const bool preserve3 = (p->flags & TFFT_PRESERVE_INPUT) != 0 || il3;
     const int mid = preserve3 ? 2 : 0;
     // three passes: n = N1 * Na * Nb (each 2^8 .. 2^12), one transform at a time (exec loops over the batch).
     //   A: N2 = Na*Nb strided length-N1 transforms, times exp(-2*pi*i*k1*n2/n)            (column mode, in place)
@@ -498,7 +497,7 @@ int build_1d(tfft_plan_s* p) {
       sh.in_mode = kColMode; sh.out_mode = kColMode;
       // column tiles by TMA as in the four-step pass: -5 % up to 2^27, +12 % at 2^28 / 2^29 (row strides of 1 MiB and
       // more), measured with tools/bench_large.py
-      sh.tma_load = lg <= 27 && knob(p->tune.tma_col, "TFFT_NO_TMA_COL", 1) != 0;
+      sh.tma_load = lg <= 27 && knob(p->tune.tma_col, "TFFT_NO_TMA_COL", 1) != 0 && !il3;
       const int64_t U = int64_t(1) << sh.log2_units;
       UnitStrides st;
       st.in_nstride = N2; st.out_nstride = N2; st.in_unit_stride = U; st.out_unit_stride = U;
@@ -507,6 +506,7 @@ int build_1d(tfft_plan_s* p) {
       st.pass1_log2n = lg;
       if (!add_pass(p, sh, st, static_cast<uint32_t>(N2 / U), 0, mid, true, true)) return TFFT_E_UNSUPPORTED;
       p->passes.back().own_batch_strides = true;
+      p->passes.back().il_in = il3;
     }
     {
       UnitShape sh;
@@ -534,6 +534,7 @@ int build_1d(tfft_plan_s* p) {
       st.units_per_batch = static_cast<uint32_t>(Na);
       if (!add_pass(p, sh, st, static_cast<uint32_t>((N1 / U) * Na), mid, 1, true, true)) return TFFT_E_UNSUPPORTED;
       p->passes.back().own_batch_strides = true;
+      p->passes.back().il_out = il3;
     }
     if (preserve3) {
       p->workspace_bytes = 2 * n * static_cast<int64_t>(sizeof(__half));   // one transform: exec loops over the batch
@@ -670,7 +671,8 @@ int build_2d(tfft_plan_s* p, std::vector<Pass>* passes, bool allow_tma) {
     sh.log2_units = yb ? yb : std::min(lgy, std::max(13 - lgx, unit_log2_elems(lgx) - lgx));
     int rho[kMaxStages];
     radix_schedule(yb ? lgx + yb : lgx, rho);
-    sh.tma_load = allow_tma && (lgx - rho[0]) >= 4 && knob(p->tune.tma, "TFFT_NO_TMA", 1);   // 128-byte or 32-byte atoms
+    const bool il2 = (p->flags & TFFT_INTERLEAVED) != 0;   // half2 images: register-split loads, no TMA tiles
+    sh.tma_load = allow_tma && !il2 && (lgx - rho[0]) >= 4 && knob(p->tune.tma, "TFFT_NO_TMA", 1);   // 128-byte or 32-byte atoms
     sh.pipe_stage2 = sh.tma_load && lgx + yb >= 13 && knob(p->tune.pipe, "TFFT_NO_PIPE", 1);
     const int64_t U = int64_t(1) << sh.log2_units;
     UnitStrides st;
@@ -689,6 +691,7 @@ int build_2d(tfft_plan_s* p, std::vector<Pass>* passes, bool allow_tma) {
     }
     ok = add_pass(p, passes, sh, st, static_cast<uint32_t>(batch * (ny / U)), 0, tiled ? 2 : 1, true, true);
     if (ok) passes->back().kind = 1;
+    if (ok) passes->back().il_in = passes->back().il_out = il2;   // interleaved in, interleaved intermediate in the output array
   }
   if (ok) {
     const int lg2 = lgy - yb;
@@ -716,6 +719,7 @@ int build_2d(tfft_plan_s* p, std::vector<Pass>* passes, bool allow_tma) {
     st.units_per_batch = static_cast<uint32_t>((nx << yb) / U);
     ok = add_pass(p, passes, sh, st, static_cast<uint32_t>(batch * ((nx << yb) / U)), tiled ? 2 : 1, 1, true, true);
     if (ok) passes->back().kind = 2;
+    if (ok) passes->back().il_in = passes->back().il_out = (p->flags & TFFT_INTERLEAVED) != 0;   // in place on the half2 output
   }
   if (ok && tiled && !p->workspace) {
     p->workspace_bytes = 2 * p->n * batch * static_cast<int64_t>(sizeof(__half));
@@ -1033,7 +1037,6 @@ int tfft_plan_create_2d(tfft_plan_t* out, int64_t ny, int64_t nx, int64_t batch,
   if (!out) return TFFT_E_INVALID_ARG;
   *out = nullptr;
   if (ilog2_exact(ny) < 8 || ilog2_exact(nx) < 8 || ny * nx > (int64_t(1) << 30)) return TFFT_E_INVALID_SIZE;
-  if (flags & TFFT_INTERLEAVED) return TFFT_E_UNSUPPORTED;   // 2-D: planar only
   if (batch < 1 || batch > (int64_t(1) << 20)) return TFFT_E_INVALID_ARG;
   tfft_plan_s* p = new (std::nothrow) tfft_plan_s;
   if (!p) return TFFT_E_NOMEM;
@@ -1148,10 +1151,11 @@ int tfft_exec(tfft_plan_t p, const void* in_re, const void* in_im, void* out_re,
   }
   for (int64_t ob = 0; ob < outer; ++ob)
   for (const Pass& ps : *passes) {
-    const __half* ire = static_cast<const __half*>(in_re) + ob * in_stride;
-    const __half* iim = static_cast<const __half*>(in_im) + ob * in_stride;
-    __half* ore = static_cast<__half*>(out_re) + ob * out_stride;
-    __half* oim = static_cast<__half*>(out_im) + ob * out_stride;
+    const int64_t il = (p->flags & TFFT_INTERLEAVED) ? 2 : 1;   // interleaved strides count complex elements = 2 halves
+    const __half* ire = static_cast<const __half*>(in_re) + ob * in_stride * il;
+    const __half* iim = static_cast<const __half*>(in_im) + ob * in_stride * il;
+    __half* ore = static_cast<__half*>(out_re) + ob * out_stride * il;
+    __half* oim = static_cast<__half*>(out_im) + ob * out_stride * il;
     const __half *sre, *sim;
     __half *dre, *dim;
     int64_t is, os;

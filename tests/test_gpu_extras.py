@@ -134,11 +134,15 @@ def test_interleaved_layout_equals_planar_bit_for_bit(lg, b, flags):
         assert np.array_equal(h_out.view(np.uint16), out.cpu().numpy().view(np.uint16))
 
 
-def test_interleaved_unsupported_combinations_fail_loudly():
+def test_interleaved_with_twiddled_and_segmented_exec_fails_loudly():
+    """Round 2 supports TFFT_INTERLEAVED for every size and for 2-D (tests/test_gpu_round2.py); what stays planar-only are
+    the building blocks of the multi-GPU transform."""
+    plan = tfft.NativePlan(4096, 4, tfft.TFFT_INTERLEAVED)
+    x = torch.zeros(2 * 4096 * 4, dtype=torch.float16, device="cuda")
     with pytest.raises(tfft.TfftError):
-        tfft.NativePlan(1 << 25, 1, tfft.TFFT_INTERLEAVED)
+        plan.exec_twiddled(x, x, x, x, 4096, 4096, 20, 0)
     with pytest.raises(tfft.TfftError):
-        tfft.NativePlan(256 * 256, 1, tfft.TFFT_INTERLEAVED, shape2d=(256, 256))
+        plan.exec_segmented(x, x, x, x, 512, 4096, 8, 2048)
 
 
 def test_dependent_launches_back_to_back_are_ordered():

@@ -325,3 +325,51 @@ def test_exec_can_be_captured_into_a_cuda_graph(lg, b):
     g.replay()
     torch.cuda.synchronize()
     assert bool(torch.equal(y, want))
+
+
+def _close_to_rounding(got, want):
+    d = got.float() - want.float()
+    assert float(torch.linalg.vector_norm(d) / torch.linalg.vector_norm(want.float())) < 3e-4
+    assert float(d.abs().max()) <= float(want.float().abs().max()) * 2.0 ** -9
+
+
+@pytest.mark.parametrize("lg,b,flags", [(25, 2, 0), (26, 1, tfft.TFFT_INVERSE)])
+def test_interleaved_three_pass(lg, b, flags):
+    """TFFT_INTERLEAVED above 2^24 (round 1: unsupported): pass A reads half2 pairs, pass C writes them, planar scratch in
+    between; same stages as the planar plan, input preserved."""
+    n = 1 << lg
+    g = torch.Generator(device="cuda"); g.manual_seed(lg)
+    planar = torch.randn(b * 2 * n, generator=g, device="cuda").to(torch.float16)
+    inter = planar.view(b, 2, n).permute(0, 2, 1).contiguous().view(-1)         # (b, n, 2)
+    keep = inter.clone()
+    want = torch.empty_like(planar)
+    tfft.NativePlan(n, b, flags | tfft.TFFT_PRESERVE_INPUT).exec(planar, planar[n:], want, want[n:], 2 * n, 2 * n)
+    out = torch.full_like(inter, float("nan"))
+    plan = tfft.NativePlan(n, b, flags | tfft.TFFT_INTERLEAVED)
+    assert plan.info["passes"] == 3
+    plan.exec(inter, inter, out, out, n, n)
+    torch.cuda.synchronize()
+    assert bool(torch.equal(inter, keep))
+    got = out.view(b, n, 2)
+    _close_to_rounding(got[:, :, 0], want.view(b, 2, n)[:, 0])
+    _close_to_rounding(got[:, :, 1], want.view(b, 2, n)[:, 1])
+
+
+@pytest.mark.parametrize("ny,nx,b,flags", [(512, 1024, 3, 0), (8192, 4096, 1, 0), (2048, 2048, 2, tfft.TFFT_INVERSE)])
+def test_interleaved_two_d(ny, nx, b, flags):
+    """TFFT_INTERLEAVED 2-D plans (round 1: unsupported): half2 images in and out, the intermediate lives in the output."""
+    n = ny * nx
+    g = torch.Generator(device="cuda"); g.manual_seed(ny + nx)
+    planar = torch.randn(b * 2 * n, generator=g, device="cuda").to(torch.float16)
+    inter = planar.view(b, 2, n).permute(0, 2, 1).contiguous().view(-1)
+    keep = inter.clone()
+    want = torch.empty_like(planar)
+    tfft.NativePlan(n, b, flags, shape2d=(ny, nx)).exec(planar, planar[n:], want, want[n:], 2 * n, 2 * n)
+    out = torch.full_like(inter, float("nan"))
+    plan = tfft.NativePlan(n, b, flags | tfft.TFFT_INTERLEAVED, shape2d=(ny, nx))
+    plan.exec(inter, inter, out, out, n, n)
+    torch.cuda.synchronize()
+    assert bool(torch.equal(inter, keep))
+    got = out.view(b, n, 2)
+    _close_to_rounding(got[:, :, 0], want.view(b, 2, n)[:, 0])
+    _close_to_rounding(got[:, :, 1], want.view(b, 2, n)[:, 1])
