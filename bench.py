@@ -447,6 +447,18 @@ def comparison_points(O):
         del xc
     except Exception as e:  # noqa
         out["cufft_fp16"] = {"error": repr(e)[:160]}
+    try:   # our own interleaved (half2) plans: cuFFT's layout, register-split loads instead of TMA tiles
+        import tfft
+        xi = torch.randn(BATCH * N * 2, device="cuda", dtype=torch.float16)
+        yi = torch.empty_like(xi)
+        pl = tfft.NativePlan(N, BATCH, tfft.TFFT_INTERLEAVED)
+        ms = timed(lambda: pl.exec(xi, xi, yi, yi, N, N), warm=3, iters=20)
+        out["ours_interleaved"] = {"value": round(FLOP_PER_TRANSFORM * BATCH / (ms * 1e-3) / 1e9, 1), "unit": "GFLOP/s",
+                                   "ms_per_step": round(ms, 4), "what": "tfft_exec with TFFT_INTERLEAVED (half2 in / out, "
+                                   "1/N scaled), N=16384 x 4096, data resident"}
+        del xi, yi, pl
+    except Exception as e:  # noqa
+        out["ours_interleaved"] = {"error": repr(e)[:160]}
     try:
         if O is not None and O.ref_lib() is not None:
             k_ms, e_ms = O.ref_bench_gpu(N, BATCH, 3, 1, mode=0, use_batch_api=False)
