@@ -764,9 +764,15 @@ __device__ __forceinline__ void run_stage(const UnitPlan& P, const KernelCtx& c,
 }
 
 // Store phase: 16-byte shared loads of 8 staging chunks, 8x8 in-register transpose, 16-byte global stores.
-template <int LOG2E, int NT = kThreads>
+// pump(): called by every thread, warp-converged, before each plane of each item (the ring kernel advances its loads and
+// stage-1 UMMAs of the next unit from there).
+struct NoPump {
+  __device__ __forceinline__ void operator()() const {}
+};
+template <int LOG2E, int NT = kThreads, class Pump = NoPump>
 __device__ __forceinline__ void store_phase(const UnitPlan& P, const KernelCtx& c, __half* gre, __half* gim, int tid,
-                                            uint32_t st_s_lo, uint32_t st_g_lo, uint32_t st_u_lo, uint32_t u_limit) {
+                                            uint32_t st_s_lo, uint32_t st_g_lo, uint32_t st_u_lo, uint32_t u_limit,
+                                            const Pump& pump = Pump()) {
   constexpr uint32_t kStoreBlocks = (1u << LOG2E) / 64;            // 8x8 blocks per plane
   constexpr uint32_t kStoreItems = kStoreBlocks >= NT ? kStoreBlocks / NT : 1;
   constexpr int TB = NT == 512 ? 9 : 8;                            // item q = tid + NT * i
@@ -806,6 +812,7 @@ __device__ __forceinline__ void store_phase(const UnitPlan& P, const KernelCtx& 
     }
 #pragma unroll
     for (int plane = 0; plane < 2; ++plane) {
+      pump();
       const uint32_t sp = plane ? c.s_im : c.s_re;
       __half* gp = plane ? gim : gre;
       uint4 a[8];
@@ -926,11 +933,13 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
   const TwSeed seed1 = kStages == 3 ? thread_seed(P, 1, tmap1) : TwSeed();
 
   for (uint32_t unit = first_unit; unit < P.n_units; unit += unit_step) {
-    const uint32_t ub = unit >> P.upb_shift, uu = unit & ((1u << P.upb_shift) - 1u);
+    // outer batch level (batched three-pass plans; b3_shift = 31 otherwise: b3 = 0), then (batch, unit in batch)
+    const uint32_t b3 = unit >> P.b3_shift, unit_lo = unit & ((1u << P.b3_shift) - 1u);
+    const uint32_t ub = unit_lo >> P.upb_shift, uu = unit_lo & ((1u << P.upb_shift) - 1u);
     const int64_t in_base = static_cast<int64_t>(ub) * P.in_batch_stride + static_cast<int64_t>(uu) * P.in_unit_stride +
-                            (CL ? static_cast<int64_t>(c.cl_rank) * P.cl_load_gofs : 0);
+                            static_cast<int64_t>(b3) * P.in_b3_stride + (CL ? static_cast<int64_t>(c.cl_rank) * P.cl_load_gofs : 0);
     const int64_t out_base = static_cast<int64_t>(ub) * P.out_batch_stride + static_cast<int64_t>(uu) * P.out_unit_stride +
-                             (CL ? static_cast<int64_t>(c.cl_rank) * P.cl_out_gofs : 0);
+                             static_cast<int64_t>(b3) * P.out_b3_stride + (CL ? static_cast<int64_t>(c.cl_rank) * P.cl_out_gofs : 0);
     // row/row passes with a ragged batch: transforms past the end are loaded as zeros, never stored
     const uint32_t u_limit =
         P.n_transforms ? P.n_transforms - min(P.n_transforms, unit << P.log2_units) : 0xFFFFFFFFu;
@@ -951,10 +960,10 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
         mbar_arrive_expect_tx(load_bar, 4u << LOG2E);
         const uint32_t group_bytes = ((2 * W) << P.log2_len) >> CL;   // a cluster CTA loads half of the rows
         for (uint32_t ug = 0; ug < (1u << P.log2_units) / W; ++ug) {
-          tma_load_4d_col(c.s_re + ug * group_bytes, &tmap_re, (uu << P.log2_units) + W * ug, ub, load_bar,
-                          c.cl_rank * P.cl_load_c2);
-          tma_load_4d_col(c.s_im + ug * group_bytes, &tmap_im, (uu << P.log2_units) + W * ug, ub, load_bar,
-                          c.cl_rank * P.cl_load_c2);
+          tma_load_4d_col(c.s_re + ug * group_bytes, &tmap_re, (uu << P.log2_units) + W * ug, ub + b3 * P.tma_b3_step,
+                          load_bar, c.cl_rank * P.cl_load_c2);
+          tma_load_4d_col(c.s_im + ug * group_bytes, &tmap_im, (uu << P.log2_units) + W * ug, ub + b3 * P.tma_b3_step,
+                          load_bar, c.cl_rank * P.cl_load_c2);
         }
       }
       TFFT_TRACE_MARK(1);
@@ -1029,7 +1038,7 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
     }
     TFFT_TRACE_MARK(2);
     // pull the next unit's input into L2 while this one is transformed and stored
-    const bool pf = !CL && P.prefetch_next && unit + gridDim.x < P.n_units;
+    const bool pf = !CL && P.prefetch_next && P.b3_shift == 31 && unit + gridDim.x < P.n_units;
     if (pf) {
       const uint32_t un = unit + gridDim.x, nb = un >> P.upb_shift, nu = un & ((1u << P.upb_shift) - 1u);
       if constexpr (LM == 2 || LM == 4) {
@@ -1096,6 +1105,254 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
   if (CL) cluster_sync_all();   // no CTA of a pair leaves while its partner could still address its shared memory
   __syncthreads();
   if (warp == 0) tmem_dealloc(c.taddr, P.tmem_cols);
+}
+
+
+// ==========================================================================================
+// Landing-ring kernel (32K-element units, TMA input, one 512-thread CTA per SM; UnitShape::ring).
+// The single-unit kernel above is a serial chain -- wait for the tile, stage 1, stage 2 (3), store -- and a 32K-element
+// unit leaves no room for a second unit in shared memory.  Here the stage-1 operand does not land in the working planes
+// but in a separate ring of two 32 KiB slots (a QUARTER of the unit each: re and im part of 16 KiB), and the stage-1
+// accumulators of unit q+1 only need tensor memory, which is free as soon as the last epilogue of unit q has drained it.
+// So while the 16 warps run the store phase of unit q, one thread (warp 0's elected lane, polling between its store
+// items) issues the stage-1 UMMAs of unit q+1 part by part and re-requests each ring slot the moment its UMMAs have
+// completed: the global loads and the stage-1 tensor work of the next unit disappear under the store phase, and the
+// ring runs up to two parts ahead of the UMMAs (the first two parts of unit q+2 are in flight during stages 2.. of
+// unit q+1).  Shared memory: [plane_re | plane_im | ring 64 KiB | tables | barriers]; the planes only hold the stage >= 2
+// operands and the staging (dense for 8-column output, see unit_plan.h), which is what makes the ring fit.
+// Part p of a unit = the top two row bits of the stage-1 operand = the UMMA tiles [p*T/4, (p+1)*T/4).
+struct SmemRingLayout {
+  uint32_t plane_stride, land_off, table_off, bar_off, total;
+};
+constexpr uint32_t kRingSlotBytes = 32768, kRingPartBytes = 16384;
+__host__ __device__ inline SmemRingLayout smem_ring_layout(const UnitPlan& p) {
+  SmemRingLayout l;
+  l.plane_stride = (p.plane_bytes + 1023u) & ~1023u;
+  l.land_off = 2 * l.plane_stride;
+  l.table_off = l.land_off + 2 * kRingSlotBytes;
+  l.bar_off = l.table_off + table_layout(p).total;
+  l.total = l.bar_off + 128;   // [0,16) stage barriers, [16,32) full[2], [32,64) part_done[4], [64,72) tensor-memory slot
+  return l;
+}
+
+// stage-1 UMMAs of part p (runtime) of a unit, A operand in a ring slot; one thread
+template <int RHO, int LM>
+__device__ __forceinline__ void ring_issue_part(uint32_t taddr, uint32_t land_re, uint32_t land_im, uint32_t b1_saddr,
+                                                uint32_t p, uint64_t* done_bar) {
+  using namespace ptx;
+  constexpr uint32_t R = 1u << RHO, kSteps = R / 16, kTiles = 32768u / R / 128u, kTilesPerPart = kTiles / 4;
+  static_assert(kTilesPerPart >= 1, "a part holds at least one tile");
+  constexpr bool SW128 = LM == 1;
+  constexpr uint32_t idesc = make_idesc_f16(128, 2 * R, /*a_mn=*/1, /*b_mn=*/0), idesc2 = idesc | (1u << 13);
+  constexpr uint64_t kSw128 = uint64_t(2) << 61;
+  const uint64_t da_re = SW128 ? (make_smem_desc(land_re, 128 * R, 1024) | kSw128) : make_smem_desc(land_re, kKGroupStride, 16 * R);
+  const uint64_t da_im = SW128 ? (make_smem_desc(land_im, 128 * R, 1024) | kSw128) : make_smem_desc(land_im, kKGroupStride, 16 * R);
+  constexpr uint32_t kTileStep = 16 * R;                    // 256R bytes per 128-row tile, in 16-byte descriptor units
+  constexpr uint32_t kKStep = SW128 ? 2048 / 16 : 16;       // per 16-wide K step
+  const uint64_t db1 = make_smem_desc(b1_saddr, kKGroupStride, 16 * R);
+  const uint64_t db2 = make_smem_desc(b1_saddr + 2 * R * R, kKGroupStride, 16 * R);   // columns R .. 3R-1: [Fi | -Fr]
+#pragma unroll
+  for (uint32_t tt = 0; tt < kTilesPerPart; ++tt) {
+    const uint32_t d = taddr + (p * kTilesPerPart + tt) * 2 * R;
+#pragma unroll
+    for (uint32_t j = 0; j < kSteps; ++j)
+      umma_f16_ss(d, da_re + (tt * kTileStep + j * kKStep), db1 + j * 16, idesc, j > 0 ? 1u : 0u);
+#pragma unroll
+    for (uint32_t j = 0; j < kSteps; ++j)
+      umma_f16_ss(d, da_im + (tt * kTileStep + j * kKStep), db2 + j * 16, idesc2, 1u);
+  }
+  umma_commit(done_bar);
+}
+
+// LM: 1 = row tiles of 64-row SWIZZLE_128B atoms, 2 = column tiles of 8 columns
+template <int RHO0, int RHO1, int RHO2, int LM>
+__global__ void __launch_bounds__(512, 1)
+fft_unit_kernel_ring(const __grid_constant__ UnitPlan P, __half* __restrict__ out_re, __half* __restrict__ out_im,
+                     const uint4* __restrict__ tables, const __grid_constant__ CUtensorMap tmap_re,
+                     const __grid_constant__ CUtensorMap tmap_im, long long* __restrict__ trace) {
+  using namespace ptx;
+#ifdef TFFT_TWO_MATRICES
+  static_assert(RHO0 < 0, "the ring kernel uses the 3R-column DFT matrices");
+#endif
+  constexpr int LOG2E = 15, NT = 512, NG = 4, TB = 9;
+  constexpr int kStages = RHO2 ? 3 : 2;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const SmemRingLayout SL = smem_ring_layout(P);
+  const TableLayout TL = table_layout(P);
+  KernelCtx c;
+  c.sbase = smem_u32(smem);
+  c.s_re = c.sbase;
+  c.s_im = c.sbase + SL.plane_stride;
+  c.a_re = c.s_re;
+  c.a_im = c.s_im;
+  c.tw_table = reinterpret_cast<const float2*>(smem + SL.table_off);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SL.bar_off);
+  uint64_t* bar = bars;             // UMMA completion of stages 2.. (two barriers: tile halves)
+  uint64_t* full = bars + 2;        // full[s]: the part in ring slot s has landed
+  uint64_t* part_done = bars + 4;   // part_done[p]: the stage-1 UMMAs of part p of a unit have completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  const uint32_t table_base = c.sbase + SL.table_off;
+  const uint32_t land = c.sbase + SL.land_off;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  c.lane_row = static_cast<uint32_t>((warp & 3) * 32 + lane);
+  c.lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+  c.wgroup = static_cast<uint32_t>(warp >> 2);
+  c.bar_id = 0;
+  c.sync_threads = NT;
+  c.mma_warp = 0;
+  c.ytw = nullptr;
+  c.cl_rank = 0;
+  c.cl_delta[0] = c.cl_delta[1] = 0;
+  uint32_t trace_unit = 0;
+  (void)trace_unit;
+  (void)TB;
+
+  const uint32_t first_unit = blockIdx.x, unit_step = gridDim.x;
+  const uint32_t my_units = first_unit < P.n_units ? (P.n_units - first_unit + unit_step - 1) / unit_step : 0u;
+  const uint32_t total_parts = 4 * my_units;
+
+  // part g of this CTA: unit first_unit + (g >> 2) * unit_step, part g & 3, ring slot g & 1
+  auto request = [&](uint32_t g) {
+    const uint32_t unit = first_unit + (g >> 2) * unit_step, p = g & 3u, slot = g & 1u;
+    const uint32_t ub = unit >> P.upb_shift, uu = unit & ((1u << P.upb_shift) - 1u);
+    uint64_t* fb = full + slot;
+    mbar_arrive_expect_tx(fb, kRingSlotBytes);
+    const uint32_t dre = land + slot * kRingSlotBytes, dim = dre + kRingPartBytes;
+    if constexpr (LM == 2) {   // {8 columns, R kappa, M/4 rows, 1 batch}; no L2 hint: the pass runs in place
+      tma_load_4d_col(dre, &tmap_re, uu << P.log2_units, ub, fb, p * P.ring_c2_step);
+      tma_load_4d_col(dim, &tmap_im, uu << P.log2_units, ub, fb, p * P.ring_c2_step);
+    } else {                   // {64 rows, R kappa, a quarter of (M/64, U)}
+      const uint32_t c3 = ub * P.tma_batch_step + (uu << P.log2_units) + p * P.ring_c3_step;
+      tma_load_4d(dre, &tmap_re, p * P.ring_c2_step, c3, fb);
+      tma_load_4d(dim, &tmap_im, p * P.ring_c2_step, c3, fb);
+    }
+  };
+
+  // ------------------------------------------------------------------ setup (once per CTA)
+  pdl_launch_dependents();
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  if (tid == 32) {
+    for (int i = 0; i < 8; ++i) mbar_init(bars + i, 1);
+    fence_mbar_init();
+    pdl_wait();
+    if (total_parts) {   // the first two parts are requested before the constant tables are staged
+      request(0);
+      request(1);
+    }
+  }
+  for (uint32_t o = tid * 16; o < TL.total; o += NT * 16) sts128(table_base + o, ldg128(tables + (o >> 4)));
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  pdl_wait();
+  c.taddr = *tmem_slot;
+  uint32_t phase[2] = {0, 0}, phase1[2] = {0, 0};
+
+  const uint32_t st_s_lo = bit_sum(tid, P.store_sofs, 0, TB), st_g_lo = bit_sum(tid, P.store_gofs, 0, TB);
+  const uint32_t st_u_lo = bit_sum(tid, P.store_uval, 0, TB);
+  const uint32_t tmap0 = thread_map<0, RHO0, NG>(P, c), tmap1 = thread_map<1, RHO1, NG>(P, c);
+  const uint32_t tmap2 = kStages == 3 ? thread_map<2, (RHO2 ? RHO2 : 4), NG>(P, c) : 0u;
+  const uint32_t col_thr = kStages == 3 ? thread_col<2, (RHO2 ? RHO2 : 4), NG>(P, c) : thread_col<1, RHO1, NG>(P, c);
+  constexpr bool kTwt = kStages == 2;
+  const TwSeed seed0 = kTwt ? TwSeed() : thread_seed(P, 0, tmap0);
+  const TwSeed seed1 = kStages == 3 ? thread_seed(P, 1, tmap1) : TwSeed();
+  const uint32_t b_saddr0 = table_base + TL.b_off[0], b_saddr1 = table_base + TL.b_off[1],
+                 b_saddr2 = table_base + TL.b_off[2];
+
+  // Ring state, live in warp 0's elected lane only: parts requested / issued / observed complete (indices over all
+  // parts of this CTA).  Invariants: dn <= is <= rq <= min(total, dn + 2), so a barrier is never tested more than
+  // one phase behind.
+  uint32_t rq = total_parts ? 2u : 0u, is = 0, dn = 0;
+  auto step = [&](uint32_t issue_limit) -> bool {
+    bool progress = false;
+    if (dn < is && mbar_test(part_done + (dn & 3u), (dn >> 2) & 1u)) {
+      ++dn;
+      progress = true;
+    }
+    if (rq < total_parts && rq < dn + 2) {
+      request(rq);
+      ++rq;
+      progress = true;
+    }
+    if (is < rq && is < issue_limit && mbar_test(full + (is & 1u), (is >> 1) & 1u)) {
+      const uint32_t lre = land + (is & 1u) * kRingSlotBytes;
+      ring_issue_part<RHO0, LM>(c.taddr, lre, lre + kRingPartBytes, b_saddr0, is & 3u, part_done + (is & 3u));
+      ++is;
+      progress = true;
+    }
+    return progress;
+  };
+
+  uint32_t q = 0;
+  for (uint32_t unit = first_unit; unit < P.n_units; unit += unit_step, ++q) {
+    const uint32_t ub = unit >> P.upb_shift, uu = unit & ((1u << P.upb_shift) - 1u);
+    const int64_t out_base = static_cast<int64_t>(ub) * P.out_batch_stride + static_cast<int64_t>(uu) * P.out_unit_stride;
+    const uint32_t u_limit =
+        P.n_transforms ? P.n_transforms - min(P.n_transforms, unit << P.log2_units) : 0xFFFFFFFFu;
+    c.col_base = (uu >> P.col_shift) * P.col_base_stride + P.col_first;
+
+    // ---------------------------------------------------------------- stage 1
+    // all four parts of this unit issued and complete (after the first unit that already happened under the previous
+    // store phase), and the ring two parts ahead
+    TFFT_TRACE_MARK(0);
+    if (warp == 0) {
+      __syncwarp();
+      if (elect_one()) {
+        const uint32_t need = 4 * (q + 1);
+        while (dn < need) step(need);
+        while (step(need)) {}
+      }
+      __syncwarp();
+    }
+    TFFT_TRACE_MARK(1);
+    TFFT_TRACE_MARK(2);
+    run_stage<0, RHO0, false, LOG2E, LM, false, NoHook, 1, NG, false, false, kTwt>(
+        P, c, b_saddr0, part_done + 3, phase1, warp, lane, trace, trace_unit, tmap0, 0u, seed0);
+    TFFT_TRACE_MARK(3);
+    // ---------------------------------------------------------------- stages 2 (3): in place on the working planes
+    if (kStages == 3 && P.pipe_stage2)
+      run_stage<1, RHO1, kStages == 2, LOG2E, 0, true, NoHook, 0, NG>(P, c, b_saddr1, bar, phase, warp, lane, trace,
+                                                                       trace_unit, tmap1, col_thr, seed1);
+    else
+      run_stage<1, RHO1, kStages == 2, LOG2E, 0, false, NoHook, 0, NG>(P, c, b_saddr1, bar, phase, warp, lane, trace,
+                                                                        trace_unit, tmap1, col_thr, seed1);
+    TFFT_TRACE_MARK(4);
+    if constexpr (kStages == 3)
+      run_stage<2, (RHO2 ? RHO2 : 4), true, LOG2E, 0, false, NoHook, 0, NG>(P, c, b_saddr2, bar, phase, warp, lane, trace,
+                                                                             trace_unit, tmap2, col_thr);
+    TFFT_TRACE_MARK(5);
+    tc_fence_before_sync();   // the accumulators are drained: the next unit's stage-1 UMMAs may overwrite them
+    __syncthreads();
+    tc_fence_after_sync();
+    TFFT_TRACE_MARK(6);
+
+    // ---------------------------------------------------------------- store phase, with the next unit's stage 1 under it
+    const uint32_t issue_limit = 4 * (q + 2);
+    auto pump = [&]() {
+      if (warp == 0) {
+        __syncwarp();
+        if (elect_one()) {
+          while (step(issue_limit)) {}
+        }
+        __syncwarp();
+      }
+    };
+    store_phase<LOG2E, NT>(P, c, out_re + (P.il_out ? 2 * out_base : out_base), out_im + out_base, tid, st_s_lo, st_g_lo,
+                           st_u_lo, u_limit, pump);
+    TFFT_TRACE_MARK(7);
+    __syncthreads();   // staging fully read before the next unit's stage-1 epilogue overwrites it
+    TFFT_TRACE_MARK(8);
+    trace_unit++;
+  }
+
+  // ------------------------------------------------------------------ teardown
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(c.taddr, 512);
 }
 
 // ==========================================================================================

@@ -3,7 +3,7 @@
 #include "kernel_table.h"
 
 #ifndef TFFT_GROUP
-#error "build with -DTFFT_GROUP=0..5"
+#error "build with -DTFFT_GROUP=0..6"
 #endif
 
 namespace tfft {
@@ -19,7 +19,18 @@ namespace tfft {
 #define TFFT_KW(E, A, B, C) \
   {E, A, B, C, fft_unit_kernel<E, A, B, C, 0, 512>, fft_unit_kernel<E, A, B, C, 1, 512>, fft_unit_kernel<E, A, B, C, 2, 512>, 512}
 
-#if TFFT_GROUP == 5
+#if TFFT_GROUP == 6
+// landing-ring kernels: 4096 x 8 columns (four-step / 2-D column passes), 8 rows x 4096 (four-step row pass), N = 32768
+static const RingEntry g_ring[] = {
+    {6, 6, 0, 2, fft_unit_kernel_ring<6, 6, 0, 2>},
+    {6, 6, 0, 1, fft_unit_kernel_ring<6, 6, 0, 1>},
+    {5, 5, 5, 1, fft_unit_kernel_ring<5, 5, 5, 1>},
+};
+const RingEntry* kernel_ring_group(int* count) {
+  *count = static_cast<int>(sizeof(g_ring) / sizeof(g_ring[0]));
+  return g_ring;
+}
+#elif TFFT_GROUP == 5
 // cluster units: a CTA pair shares 2^16 elements (N = 65536 in one pass; 16 columns x 4096 for column passes)
 static const ClusterEntry g_cluster[] = {
     {4, 6, 6, 1, fft_unit_kernel<15, 4, 6, 6, 1, 512, 1>},
@@ -69,6 +80,6 @@ const Kernel2Entry* kernel2_group(int* count) {
   return g_entries2;
 }
 #endif
-#endif   // TFFT_GROUP != 5
+#endif   // TFFT_GROUP < 5
 
 }  // namespace tfft

@@ -30,6 +30,13 @@ struct ClusterEntry {
   KernelFn fn;
 };
 const ClusterEntry* kernel_cluster_group(int* count);
+// Landing-ring kernels (UnitPlan::ring): 32K-element units, 512 threads, two-slot calling convention; lm = load mode (1 row
+// tiles of 64-row atoms, 2 column tiles of 8 columns)
+struct RingEntry {
+  int r0, r1, r2, lm;
+  Kernel2Fn fn;
+};
+const RingEntry* kernel_ring_group(int* count);
 constexpr int kKernelGroups = 5;
 // entries of group g (kernel_group.cu built with -DTFFT_GROUP=g)
 const KernelEntry* kernel_group_0(int* count);

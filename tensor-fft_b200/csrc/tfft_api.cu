@@ -40,7 +40,7 @@ struct Prepared {
   const uint4* tables = nullptr;
   unsigned grid = 0, block = 0;
   uint32_t smem = 0;
-  bool two_slot = false, cluster = false;
+  bool two_slot = false, cluster = false;   // two_slot: the two-slot calling convention (two-slot and landing-ring kernels)
 };
 constexpr size_t kPreparedSlots = 4;
 
@@ -56,6 +56,8 @@ struct Pass {
   int src = 0, dst = 0;    // 0 = user input planes, 1 = user output planes, 2 = plan workspace
   bool in_stride_is_user = false, out_stride_is_user = false;
   bool own_batch_strides = false;   // three-pass plans: the batch level of the unit addressing is internal
+  bool outer_batch = false;         // batched three-pass plans: the transforms of the batch are an outer level of the unit
+                                    // index (UnitPlan::b3_shift), in/out stride apart
   bool il_in = false, il_out = false;   // TFFT_INTERLEAVED: the pass reads / writes half2 elements
   int kind = 0;                     // 0: 1-D passes; 1: 2-D row pass (row mode, unit = U rows of one image); 2: 2-D column pass
   mutable std::vector<Prepared> prepared;   // launch cache (see prepare_launch), guarded by g_upload_mutex
@@ -188,6 +190,18 @@ Kernel2Fn kernel2_for(const UnitPlan& p, bool allowed = true) {
   return nullptr;
 }
 
+// Landing-ring variant (32K-element units, stage-1 operand in a separate ring; fft_unit_kernel_ring)
+Kernel2Fn kernel_ring_for(const UnitPlan& p) {
+  if (!p.ring) return nullptr;
+  int count = 0;
+  const RingEntry* e = kernel_ring_group(&count);
+  for (int i = 0; i < count; ++i)
+    if (e[i].r0 == static_cast<int>(p.log2_radix[0]) && e[i].r1 == static_cast<int>(p.log2_radix[1]) &&
+        e[i].r2 == static_cast<int>(p.stages == 3 ? p.log2_radix[2] : 0) && e[i].lm == static_cast<int>(p.tma_load))
+      return e[i].fn;
+  return nullptr;
+}
+
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link dependency on libcuda)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -224,6 +238,10 @@ int make_input_tensor_map(const UnitPlan& plan, const __half* base, int64_t tstr
     else box[2] = static_cast<cuuint32_t>(M / 128);
   }
   if (plan.cluster) box[2] = static_cast<cuuint32_t>(M / 128);   // a cluster CTA loads the rows of one half of m
+  if (plan.ring) {   // landing-ring units: one box = a quarter of the unit's stage-1 tiles
+    if (U >= 4) box[3] = static_cast<cuuint32_t>(U / 4);
+    else box[2] = static_cast<cuuint32_t>(M / 256);
+  }
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(base), gdim, gstride, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -291,7 +309,7 @@ int make_col_tensor_map(const UnitPlan& plan, const __half* base, int64_t nstrid
                            static_cast<cuuint64_t>(batch_stride) * 2};
   // mode 2: 8-column tiles, dense; mode 4: 16-column tiles (whole 32-byte sectors) as SWIZZLE_32B atoms
   cuuint32_t box[4] = {plan.tma_load == 4 ? 16u : 8u, static_cast<cuuint32_t>(R),
-                       static_cast<cuuint32_t>(plan.cluster ? M / 2 : M), 1};   // a cluster CTA loads one half of m
+                       static_cast<cuuint32_t>(plan.cluster ? M / 2 : plan.ring ? M / 4 : M), 1};   // cluster CTA: one half of m; ring unit: quarters
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(base), gdim, gstride, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -343,6 +361,7 @@ struct Tuning {
   int fourstep_lg1 = -1;   // log2 of the column-pass length, N > 2^15     (TFFT_FOURSTEP_LG1)
   int tma_col = -1;        // TMA column tiles in four-step column passes  (TFFT_NO_TMA_COL)
   int cluster = -1;        // CTA-pair units: N = 65536 in one pass, 16-column units for 4096-point column passes (off unless 1)
+  int ring = -1;           // landing-ring kernel for 32K-element TMA units (TFFT_NO_RING)
 };
 int knob(int tuned, const char* env_off, int dflt) {   // env_off: variable whose presence switches the feature off
   if (tuned >= 0) return tuned;
@@ -416,7 +435,7 @@ bool add_pass(tfft_plan_s* p, std::vector<Pass>* out, const UnitShape& shape, co
   ps.strides = st;
   ps.strides.n_units = n_units;
   ps.n_units = n_units;
-  ps.smem = smem_layout(ps.plan).total;
+  ps.smem = ps.plan.ring ? smem_ring_layout(ps.plan).total : smem_layout(ps.plan).total;
   ps.tables = make_tables(ps.plan, (p->flags & TFFT_UNSCALED) != 0);
   ps.src = src;
   ps.dst = dst;
@@ -444,6 +463,10 @@ int build_1d(tfft_plan_s* p) {
       const bool small_ok = (lg - rho[0]) >= 4 && dev_env("TFFT_NO_TMA_SMALL") == nullptr;
       sh.tma_load = ((lg - rho[0]) >= 6 || small_ok) && knob(p->tune.tma, "TFFT_NO_TMA", 1) && !(p->flags & TFFT_INTERLEAVED);
       sh.pipe_stage2 = sh.tma_load && lg >= 13 && knob(p->tune.pipe, "TFFT_NO_PIPE", 1);
+      // N = 32768 (one 32K-element unit per CTA): the landing-ring kernel is opt-in (tuner key ring=2).  Measured on B200:
+      // 0.6145 against 0.6111 ms per GiB -- the row-mode store phase (2.5 us) is too short to hide the chain "stage-1
+      // UMMAs of the first half -> request the second half -> its latency -> its UMMAs" of a two-slot ring
+      sh.ring = lg == 15 && sh.tma_load && sh.log2_units == 0 && p->tune.ring >= 2;
     }
     UnitStrides st;
     st.n_transforms = static_cast<uint32_t>(batch);
@@ -472,7 +495,12 @@ int build_1d(tfft_plan_s* p) {
     if (!add_pass(p, sh, st, static_cast<uint32_t>(batch), 0, 1, true, true)) return TFFT_E_UNSUPPORTED;
     return TFFT_OK;
   }
-  int three_from = 25;   // developer knob: three passes from this log2 length on (>= 24: all factors >= 256)
+  // Three passes from 2^24 on (256 x 256 x 256: every piece of every pass is 128 bytes or more).  The four-step plan of 2^24
+  // (4096 x 4096) moves 16-byte pieces in three of its four global access patterns, which the memory system sustains at
+  // 2.4 - 3.2 TB/s only (probe/colio_probe.cu); measured on B200, batch 16: 2.11 ms in two passes, see DESIGN for three.
+  // A tuner file that names a four-step split (lg1=) or CTA-pair units (cluster=1) for 2^24 keeps the two-pass plan;
+  // developer knob TFFT_THREEPASS_LG=25.
+  int three_from = (p->tune.fourstep_lg1 >= 0 || use_cluster) ? 25 : 24;
   if (const char* e = dev_env("TFFT_THREEPASS_LG")) three_from = std::min(25, std::max(24, atoi(e)));   // four-step covers <= 2^24 only
   if (lg >= three_from) {
     // TFFT_PRESERVE_INPUT: pass A writes into a plan-owned scratch of ONE transform (the batch is looped), passes B
@@ -490,7 +518,12 @@ int build_1d(tfft_plan_s* p) {
     const int lg2 = lg - lg1, la = (lg2 + 1) / 2, lb = lg2 - la;
     if (lg1 > 12 || la > 12 || lb < 8) return TFFT_E_INVALID_SIZE;
     const int64_t N1 = int64_t(1) << lg1, N2 = int64_t(1) << lg2, Na = int64_t(1) << la, Nb = int64_t(1) << lb;
-    p->loop_batch = true;
+    // Without a scratch (the default: passes A and B in place) the whole batch runs in three launches: the transform index
+    // is an outer level of the unit index.  With TFFT_PRESERVE_INPUT / TFFT_INTERLEAVED the batch is looped (the scratch
+    // holds one transform).
+    const bool batched3 = !preserve3 && batch > 1 && batch * (N2 >> 3) < (int64_t(1) << 31) && dev_env("TFFT_THREEPASS_LOOP") == nullptr;
+    p->loop_batch = !batched3;
+    const uint32_t nb3 = batched3 ? static_cast<uint32_t>(batch) : 1u;
     {
       UnitShape sh;
       sh.log2_len = lg1; sh.log2_units = std::max(3, unit_log2_elems(lg1) - lg1);
@@ -504,24 +537,29 @@ int build_1d(tfft_plan_s* p) {
       st.units_per_batch = static_cast<uint32_t>(N2 / U);
       st.col_base_stride = static_cast<uint32_t>(U);
       st.pass1_log2n = lg;
-      if (!add_pass(p, sh, st, static_cast<uint32_t>(N2 / U), 0, mid, true, true)) return TFFT_E_UNSUPPORTED;
+      if (batched3) st.b3_units = static_cast<uint32_t>(N2 / U);
+      if (!add_pass(p, sh, st, nb3 * static_cast<uint32_t>(N2 / U), 0, mid, true, true)) return TFFT_E_UNSUPPORTED;
       p->passes.back().own_batch_strides = true;
+      p->passes.back().outer_batch = batched3;
       p->passes.back().il_in = il3;
     }
     {
       UnitShape sh;
       sh.log2_len = la; sh.log2_units = std::max(3, unit_log2_elems(la) - la);
       sh.in_mode = kColMode; sh.out_mode = kColMode;
-      sh.tma_load = lg <= 27 && knob(p->tune.tma_col, "TFFT_NO_TMA_COL", 1) != 0;
+      // batched: 16-byte cp.async (the tile's batch coordinate is taken by k1; a fifth dimension is not built)
+      sh.tma_load = lg <= 27 && knob(p->tune.tma_col, "TFFT_NO_TMA_COL", 1) != 0 && !batched3;
       const int64_t U = int64_t(1) << sh.log2_units;
       UnitStrides st;
       st.in_nstride = Nb; st.out_nstride = Nb; st.in_unit_stride = U; st.out_unit_stride = U;
       st.in_batch_stride = N2; st.out_batch_stride = N2;
+      if (batched3) st.b3_units = static_cast<uint32_t>(N1 * (Nb / U));
       st.units_per_batch = static_cast<uint32_t>(Nb / U);
       st.col_base_stride = static_cast<uint32_t>(U);
       st.pass1_log2n = lg2;
-      if (!add_pass(p, sh, st, static_cast<uint32_t>(N1 * (Nb / U)), mid, mid, true, true)) return TFFT_E_UNSUPPORTED;
+      if (!add_pass(p, sh, st, nb3 * static_cast<uint32_t>(N1 * (Nb / U)), mid, mid, true, true)) return TFFT_E_UNSUPPORTED;
       p->passes.back().own_batch_strides = true;
+      p->passes.back().outer_batch = batched3;
     }
     {
       UnitShape sh;
@@ -532,8 +570,10 @@ int build_1d(tfft_plan_s* p) {
       st.in_tstride = N2; st.in_unit_stride = Nb; st.in_batch_stride = U * N2;
       st.out_nstride = N1 * Na; st.out_unit_stride = N1; st.out_batch_stride = U;
       st.units_per_batch = static_cast<uint32_t>(Na);
-      if (!add_pass(p, sh, st, static_cast<uint32_t>((N1 / U) * Na), mid, 1, true, true)) return TFFT_E_UNSUPPORTED;
+      if (batched3) st.b3_units = static_cast<uint32_t>((N1 / U) * Na);
+      if (!add_pass(p, sh, st, nb3 * static_cast<uint32_t>((N1 / U) * Na), mid, 1, true, true)) return TFFT_E_UNSUPPORTED;
       p->passes.back().own_batch_strides = true;
+      p->passes.back().outer_batch = batched3;
       p->passes.back().il_out = il3;
     }
     if (preserve3) {
@@ -579,6 +619,8 @@ int build_1d(tfft_plan_s* p) {
     sh.in_mode = kColMode;
     sh.out_mode = kColMode;
     sh.tma_load = knob(p->tune.tma_col, "TFFT_NO_TMA_COL", 1) && !interleaved;   // column tiles {8 columns, R, M} by TMA
+    // 4096-point columns (8 columns, 32K elements, one CTA per SM): landing-ring kernel
+    sh.ring = lg1 == 12 && sh.log2_units == 3 && !sh.cluster && sh.tma_load && knob(p->tune.ring, "TFFT_NO_RING", 1);
     const int64_t U = int64_t(1) << sh.log2_units;
     UnitStrides st;
     st.in_nstride = N2; st.out_nstride = N2;
@@ -606,7 +648,12 @@ int build_1d(tfft_plan_s* p) {
     // a whole number of rows; otherwise tfft_exec takes the cp.async twin of this pass from passes_strided)
     // Measured on B200 (C3 sizes): -8 .. -13 % for row lengths up to 1024 (2^16 .. 2^22), +10 .. +22 % for 2048 / 4096
     // (2^23, 2^24), so only the former use tiles.
-    const bool row_tma = lg2 <= 10 && knob(p->tune.tma, "TFFT_NO_TMA", 1) && dev_env("TFFT_NO_TMA_PASS2") == nullptr;
+    // 4096-point rows (8 per unit, 32K elements) through the landing-ring kernel: opt-in (tuner key ring=2).  Measured on
+    // B200 it is much SLOWER (2^23: 2.31 against 1.84 ms, 2^24: 2.66 against 2.16 ms): this pass already runs at the rate
+    // the memory system sustains for 128-byte reads + 16-byte scattered writes (probe/colio_probe.cu: 15 - 16 us per unit
+    // for the bare traffic, 17 us measured), and overlapping its reads with its writes makes that traffic slower
+    const bool row_ring = lg2 == 12 && !interleaved && p->tune.ring >= 2 && knob(p->tune.tma, "TFFT_NO_TMA", 1);
+    const bool row_tma = (lg2 <= 10 || row_ring) && knob(p->tune.tma, "TFFT_NO_TMA", 1) && dev_env("TFFT_NO_TMA_PASS2") == nullptr;
     if (row_tma) {
       const Pass first = p->passes.back();
       if (!add_pass(p, sh, st, static_cast<uint32_t>(batch * (N1 / U)), preserve ? 2 : 0, 1, !preserve, true))
@@ -616,6 +663,7 @@ int build_1d(tfft_plan_s* p) {
       p->passes_strided.push_back(p->passes.back());
       p->passes.pop_back();
       sh.tma_load = true;
+      sh.ring = row_ring;
     }
     if (!add_pass(p, sh, st, static_cast<uint32_t>(batch * (N1 / U)), preserve ? 2 : 0, 1, !preserve, true))
       return TFFT_E_UNSUPPORTED;
@@ -705,6 +753,8 @@ int build_2d(tfft_plan_s* p, std::vector<Pass>* passes, bool allow_tma) {
     // (2 MiB jumps) before m, while the cp.async units of neighbouring CTAs sweep the rows together.  Four-step column
     // passes (row stride <= 8 KiB) gain 1-4 % from the tiles and keep them.
     sh.tma_load = dev_env("TFFT_TMA_COL_2D") != nullptr;
+    // developer knob: 4096-point columns through the landing-ring kernel (TMA column tiles, hidden under the store phase)
+    if (lg2 == 12 && dev_env("TFFT_RING_2D") && !(p->flags & TFFT_INTERLEAVED)) { sh.tma_load = allow_tma; sh.ring = allow_tma; }
     if (lg2 == 11 && dev_env("TFFT_2D_COL_U16")) sh.log2_units = 4;   // developer knob: 16 columns x 2048 (32-byte pieces)
     // 4096-point columns: CTA-pair units of 16 columns (32-byte pieces)
     if (lg2 == 12 && dev_env("TFFT_CLUSTER")) { sh.log2_units = 4; sh.cluster = true; }   // developer knob, see build_1d
@@ -820,6 +870,10 @@ int prepare_launch(const tfft_plan_s* p, const Pass& ps, const __half* src_re, c
   } else if (!ps.own_batch_strides) {   // four-step passes: the batch level carries the user's (or workspace) transform stride
     st.in_batch_stride = in_stride;
     st.out_batch_stride = out_stride;
+  } else if (ps.outer_batch) {   // batched three-pass plans: the outer level carries it
+    st.in_b3_stride = in_stride;
+    st.out_b3_stride = out_stride;
+    st.tma_b3_step = 1;          // column tiles (pass A only: its own batch level is unused): batch coordinate = b3
   }
   if (ps.kind == 0 && (ps.plan.tma_load == 1 || ps.plan.tma_load == 3) && st.units_per_batch != 0x7FFFFFFFu) {
     // four-step row pass: transform t of batch b at b*batch_stride + t*tstride (tfft_exec checked divisibility)
@@ -841,6 +895,12 @@ int prepare_launch(const tfft_plan_s* p, const Pass& ps, const __half* src_re, c
                                 : (prefetch_default(p, ps, plan) ? 1u : 0u);
   }
   plan.col_first = static_cast<uint32_t>(tw_first_col);
+  bool ring_fallback = false;
+  if (segs > 0 && plan.ring) {   // segmented input: the single-unit kernel (same plan; row-mode staging is the same)
+    if (plan.out_mode != kRowMode) return TFFT_E_UNSUPPORTED;
+    plan.ring = 0;
+    ring_fallback = true;
+  }
   if (segs > 0) {   // tfft_exec_segmented: only for the row tiles of 64-row atoms, whole K lines per segment
     const int R0 = 1 << plan.log2_radix[0];
     if (plan.tma_load != 1 || plan.cluster || plan.kron_bits || ps.kind != 0 || R0 % segs != 0) return TFFT_E_UNSUPPORTED;
@@ -851,8 +911,14 @@ int prepare_launch(const tfft_plan_s* p, const Pass& ps, const __half* src_re, c
   int threads = kThreads;
   KernelFn fn = kernel_for(plan, &threads);
   if (!fn) return TFFT_E_UNSUPPORTED;
-  Kernel2Fn fn2 = kernel2_for(plan, allow2);
-  const uint32_t smem = fn2 ? smem2_layout(plan).total : ps.smem;
+  Kernel2Fn fn2 = plan.ring ? kernel_ring_for(plan) : kernel2_for(plan, allow2);
+  if (plan.ring && !fn2) return TFFT_E_UNSUPPORTED;
+  const uint32_t smem = (fn2 && !plan.ring) ? smem2_layout(plan).total : ring_fallback ? smem_layout(plan).total : ps.smem;
+  if (ring_fallback && cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            227 * 1024) != cudaSuccess) {
+    cudaGetLastError();
+    return TFFT_E_UNSUPPORTED;
+  }
   const void* entry = fn2 ? reinterpret_cast<const void*>(fn2) : reinterpret_cast<const void*>(fn);
   static const bool debug = dev_env("TFFT_DEBUG") != nullptr;
   {
@@ -863,7 +929,7 @@ int prepare_launch(const tfft_plan_s* p, const Pass& ps, const __half* src_re, c
   out->grid = plan.cluster ? 2u * std::min<unsigned>(ps.n_units, static_cast<unsigned>(ps.resident_ctas[dev]) / 2u)
                            : std::min<unsigned>(ps.n_units, static_cast<unsigned>(ps.resident_ctas[dev]));
   out->cluster = plan.cluster != 0;
-  out->block = fn2 ? static_cast<unsigned>(kCta2Threads) : static_cast<unsigned>(threads);
+  out->block = plan.ring ? 512u : fn2 ? static_cast<unsigned>(kCta2Threads) : static_cast<unsigned>(threads);
   out->smem = smem;
   out->fn = entry;
   out->two_slot = fn2 != nullptr;
@@ -878,8 +944,11 @@ int prepare_launch(const tfft_plan_s* p, const Pass& ps, const __half* src_re, c
     if (plan.tma_load == 2 || plan.tma_load == 4) {
       const int64_t columns = static_cast<int64_t>(plan.units_per_batch) << plan.log2_units;
       const int64_t batches = (ps.n_units + plan.units_per_batch - 1) / plan.units_per_batch;
-      rc = make_col_tensor_map(plan, src_re, st.in_nstride, columns, batches, plan.in_batch_stride, &out->tmap_re);
-      if (rc == TFFT_OK) rc = make_col_tensor_map(plan, src_im, st.in_nstride, columns, batches, plan.in_batch_stride, &out->tmap_im);
+      // batched three-pass pass A: one "batch" per transform of the user's batch, in_stride apart
+      const int64_t bstride = ps.outer_batch ? in_stride : plan.in_batch_stride;
+      if (ps.outer_batch && plan.units_per_batch != st.b3_units) return TFFT_E_UNSUPPORTED;
+      rc = make_col_tensor_map(plan, src_re, st.in_nstride, columns, batches, bstride, &out->tmap_re);
+      if (rc == TFFT_OK) rc = make_col_tensor_map(plan, src_im, st.in_nstride, columns, batches, bstride, &out->tmap_im);
     } else if (plan.kron_bits) {
       rc = make_kron_tensor_map(plan, src_re, p->ny, p->batch, plan.tma_batch_step, &out->tmap_re, half_box);
       if (rc == TFFT_OK) rc = make_kron_tensor_map(plan, src_im, p->ny, p->batch, plan.tma_batch_step, &out->tmap_im, half_box);
@@ -1006,6 +1075,7 @@ int tfft_plan_create_from_file(tfft_plan_t* out, int64_t n, int64_t batch, uint3
       else if (kl == 3 && !strncmp(tok, "lg1", 3)) t.fourstep_lg1 = v;
       else if (kl == 7 && !strncmp(tok, "tma_col", 7)) t.tma_col = v;
       else if (kl == 7 && !strncmp(tok, "cluster", 7)) t.cluster = v;
+      else if (kl == 4 && !strncmp(tok, "ring", 4)) t.ring = v;
     }
     rc = plan_create_tuned(out, n, batch, flags, t);
     break;
@@ -1066,7 +1136,8 @@ int tfft_plan_prepare(tfft_plan_t p) {
       int threads = kThreads;
       KernelFn fn = kernel_for(ps.plan, &threads);
       if (!fn) return TFFT_E_UNSUPPORTED;
-      Kernel2Fn fn2 = kernel2_for(ps.plan, allow2);
+      Kernel2Fn fn2 = ps.plan.ring ? kernel_ring_for(ps.plan) : kernel2_for(ps.plan, allow2);
+      if (ps.plan.ring && !fn2) return TFFT_E_UNSUPPORTED;
       const void* entry = fn2 ? reinterpret_cast<const void*>(fn2) : reinterpret_cast<const void*>(fn);
       const int rc = ensure_pass_on_device(ps, dev, entry, fn2 != nullptr, reinterpret_cast<const void*>(fn), threads,
                                            ps.plan.tmem_cols);

@@ -56,6 +56,9 @@ struct UnitShape {
                              // loads the half of the rows whose highest not-yet-transformed index bit (the top bit of m_1)
                              // is r, runs stage 1 on it, and its stage-1 epilogue stores every output whose top k_1 bit is d
                              // into CTA d's shared memory (distributed shared memory); stages 2.. and the store are local
+  bool ring = false;         // 32K-element units with TMA input: the stage-1 operand lands in a separate ring of two quarter
+                             // tiles (64 KiB) instead of the working planes, so that the loads and the stage-1 MMAs of
+                             // unit q+1 run under the store phase of unit q (fft_unit_kernel_ring)
   bool pipe_stage2 = false;  // 3-stage plans: make the top row bit of stages 2 and 3 the same logical bit (k_1's
                              // top bit), so that the epilogue of the first half of stage 2's tiles only writes into
                              // the already consumed first half of the operand planes (MMA / epilogue overlap)
@@ -87,6 +90,8 @@ struct UnitPlan {
                                            // segments lying segment_stride apart (multi-GPU staging planes, source-rank
                                            // major); the tensor map is 5-D {64, kappa_lo, segment, M/64, transform} and the
                                            // tile coordinates are (0, 0, 0, c2, c3)
+  uint32_t ring;                           // 1: landing-ring unit (UnitShape::ring): the unit is loaded as four parts (quarter
+  uint32_t ring_c2_step, ring_c3_step;     //   of the stage-1 tiles each); part p starts at tile coordinates (c2, c3) + p * step
   uint32_t prefetch_next;                  // 1: pull the next unit's input into L2 during this unit's stages
   uint32_t tma_load;                       // 4: column-mode input, >= 16 columns per unit: tiles {16 columns, R kappa, M rows} per
                                            //    16-column group as SWIZZLE_32B atoms: row = (u&15) + 16*(m + M*(u>>4)), element
@@ -141,6 +146,11 @@ struct UnitPlan {
                                                //   + ((unit & mask) << log2_units)   (0: the unit index alone, 1-D batches)
   uint32_t n_units;                            // total units of the launch (persistent CTAs loop over them)
   uint32_t n_transforms;                       // != 0 (row/row passes): transforms >= n_transforms are masked
+  // outer batch level (three-pass plans, whose own "batch" level is an index of the transform): unit = b3 << b3_shift | rest,
+  // rest decomposes as above; b3_shift = 31: none
+  uint32_t b3_shift;
+  uint32_t tma_b3_step;                        // column tiles: batch coordinate = unit / upb + b3 * tma_b3_step
+  int64_t in_b3_stride, out_b3_stride;
   uint32_t col_base_stride;   // tw_mode 2: col_base = ((unit % upb) / col_div) * col_base_stride
   uint32_t col_div;
   uint32_t col_first;         // tw_mode 2: added to every column index (tfft_exec_twiddled)
@@ -246,6 +256,22 @@ inline bool build_unit_plan(const UnitShape& shape, UnitPlan* plan, PlanBuildInf
   }
   // column mode: tiles of 16 columns (full 32-byte sectors, SWIZZLE_32B atoms) when the unit has >= 16 columns
   plan->tma_load = shape.tma_load ? (shape.in_mode == kColMode ? (ups >= 4 ? 4u : 2u) : ((lg - rho[0]) < 6 ? 3u : 1u)) : 0u;
+  if (shape.ring) {
+    // parts = the top two row bits of the stage-1 operand (natural row order: m, then u)
+    const uint32_t M = 1u << (lg - rho[0]);
+    if (cl || kb || eps != 15 || (plan->tma_load != 1 && plan->tma_load != 2)) {
+      info->error = "ring units: 2^15 elements, TMA tiles of 64-row atoms or 8-column tiles, no cluster / Kronecker stage"; return false;
+    }
+    plan->ring = 1;
+    if (plan->tma_load == 2) {
+      if (ups != 3 || M < 4) { info->error = "ring units: column tiles need exactly 8 columns"; return false; }
+      plan->ring_c2_step = M / 4;
+    } else if (ups >= 2) {
+      plan->ring_c3_step = (1u << ups) / 4;
+    } else if (ups == 0 && M >= 256) {
+      plan->ring_c2_step = M / 256;
+    } else { info->error = "ring units: 1 or >= 4 transforms per unit"; return false; }
+  }
   // the first-half epilogue of stage 2 writes the first half of stage 3's layout, which must lie inside the half of
   // stage 2's layout that its first-half MMAs have consumed: padded plane sizes shrink with the radix, so R_3 >= R_2
   const bool pipe2 = shape.pipe_stage2 && s == 3 && rho[2] >= rho[1] && !cl;
@@ -268,7 +294,7 @@ inline bool build_unit_plan(const UnitShape& shape, UnitPlan* plan, PlanBuildInf
     plan->n_tiles[t] = rows / 128;
     plan->chunk_stride[t] = (16u << rho[t]) + ((t == 0 && plan->tma_load == 2) ? 0u : 16u);
     const uint32_t pb = (rows / 8) * plan->chunk_stride[t];
-    if (pb > max_plane) max_plane = pb;
+    if (pb > max_plane && !(shape.ring && t == 0)) max_plane = pb;   // ring units: stage 1 reads the landing ring
   }
   {
     uint32_t need = (1u << eps) / 64, c = 32;
@@ -396,6 +422,7 @@ inline bool build_unit_plan(const UnitShape& shape, UnitPlan* plan, PlanBuildInf
     for (auto& b : obits) addr_bits.push_back(b);
   }
   for (int i = 0; i < 3; ++i) info->store_x[i] = addr_bits[i];
+  bool dense_staging = false;
   std::vector<LBit> chunk_logical = info->row_bits[s - 1];
   for (int i = 3; i < rho[s - 1]; ++i) chunk_logical.push_back({LBit::K, (uint8_t)s, (uint8_t)i});
   {
@@ -417,6 +444,11 @@ inline bool build_unit_plan(const UnitShape& shape, UnitPlan* plan, PlanBuildInf
       int p = find_bit(sc, b);
       if (p >= 0) used[p] = true; else gnew.push_back(b);
     }
+    // ring units: when every lane-varying bit of the store phase already is an in-run bit of the staging (column-mode
+    // output of 8-column units: G = the three lowest output-index bits = the in-chunk row bits of the last stage) the
+    // 16-byte padding per 128-byte run is not needed, and the planes must stay at 64 KiB + operand padding to leave
+    // room for the landing ring
+    dense_staging = shape.ring && gnew.empty();
     // positions 3,4,5 have residues 1,2,4 (chunk address = d + (d >> 3)); place new G bits on free residues
     LBit mid[3] = {}; bool mid_set[3] = {false, false, false};
     for (auto& b : gnew) {
@@ -439,14 +471,14 @@ inline bool build_unit_plan(const UnitShape& shape, UnitPlan* plan, PlanBuildInf
     }
     for (auto& b : rest) sc.push_back(b);
     const uint32_t nchunks = 1u << sc.size();
-    const uint32_t sb = (nchunks + (nchunks >> 3)) * 16;
+    const uint32_t sb = (nchunks + (dense_staging ? 0u : (nchunks >> 3))) * 16;
     if (sb > max_plane) max_plane = sb;
   }
   plan->plane_bytes = (max_plane + 127u) & ~127u;
   auto staging_contrib = [&](const LBit& b) -> uint32_t {
     int pd = find_bit(info->stage_chunk_bits, b);
     if (pd < 0) return 0;
-    uint32_t c = (1u << pd) + (pd >= 3 ? (1u << (pd - 3)) : 0u);
+    uint32_t c = (1u << pd) + ((pd >= 3 && !dense_staging) ? (1u << (pd - 3)) : 0u);
     return c * 16;
   };
 
@@ -550,6 +582,9 @@ struct UnitStrides {
   uint32_t n_transforms = 0;
   uint32_t pass1_log2n = 0;  // != 0: multiply outputs by exp(-2*pi*i*o*(col_base+u)/2^pass1_log2n)
   uint32_t tma_batch_step = 0;
+  uint32_t b3_units = 0;       // != 0 (power of two): units per outer batch element, which lie in/out_b3_stride apart
+  int64_t in_b3_stride = 0, out_b3_stride = 0;
+  uint32_t tma_b3_step = 0;
   int64_t out_hi_stride = 0;   // tiled row-mode output (2-D row pass writing the column units' operand order):
   int out_hi_from = 0;         //   output-index bit i >= out_hi_from has stride out_hi_stride << (i - out_hi_from)
   uint32_t kron_log2n = 0;   // Kronecker units, != 0: multiply output row k_y by exp(-2*pi*i*k_y*col_base/2^kron_log2n)
@@ -594,6 +629,11 @@ inline void fill_strides(const UnitStrides& st, const PlanBuildInfo& info, UnitP
   for (uint32_t i = 0; i < 31; ++i)
     if (st.col_div == (1u << i)) plan->col_shift = i;
   plan->tma_batch_step = st.tma_batch_step;
+  plan->b3_shift = 31;
+  for (uint32_t i = 0; i < 31; ++i)
+    if (st.b3_units == (1u << i)) plan->b3_shift = i;
+  plan->in_b3_stride = st.in_b3_stride; plan->out_b3_stride = st.out_b3_stride;
+  plan->tma_b3_step = st.tma_b3_step;
   plan->n_units = st.n_units;
   plan->col_base_stride = st.col_base_stride;
   plan->col_div = st.col_div ? st.col_div : 1;

@@ -65,6 +65,7 @@ int plansim_run_ex(int log2_len, int log2_units, int in_mode_flags, int out_mode
   shape.in_mode = (AxisMode)in_mode; shape.out_mode = (AxisMode)out_mode; shape.tma_load = (in_mode_flags & 2) != 0;
   shape.pipe_stage2 = (in_mode_flags & 4) != 0;
   shape.cluster = (in_mode_flags & 8) != 0;   // CTA-pair unit: both ranks are simulated, stage-1 stores cross between them
+  shape.ring = (in_mode_flags & 16) != 0;     // landing-ring unit: stage-1 operand outside the planes, dense staging for 8-column output
   UnitPlan P; PlanBuildInfo info;
   if (!build_unit_plan(shape, &P, &info)) { fprintf(stderr, "plan error: %s\n", info.error.c_str()); return -1; }
   UnitStrides st;
@@ -81,7 +82,17 @@ int plansim_run_ex(int log2_len, int log2_units, int in_mode_flags, int out_mode
   conflicts[0] = conflicts[1] = conflicts[2] = conflicts[3] = 0;
   int lookups = 0;   // warp-wide LDS.64 table lookups modelled (for reference; conflicts[3] is their excess wavefronts)
   (void)lookups;
-  const uint32_t smem_halves = P.plane_bytes / 2;
+  // ring units keep the stage-1 operand in the landing ring (a unit = 64 KiB per plane), not in the planes
+  const uint32_t smem_halves = (P.ring ? (P.plane_bytes > 65536u ? P.plane_bytes : 65536u) : P.plane_bytes) / 2;
+  if (P.ring) {   // the kernel's carve-up (smem_ring_layout): planes + 64 KiB ring + tables + barriers within 227 KiB
+    uint32_t tables = P.stages == 3 ? 0u : 4608u;
+    for (uint32_t t = 0; t < P.stages; ++t) {
+      bool seen = false;
+      for (uint32_t u = 0; u < t; ++u) seen = seen || P.log2_radix[u] == P.log2_radix[t];
+      if (!seen) tables += 6u << (2 * P.log2_radix[t]);
+    }
+    if (2u * ((P.plane_bytes + 1023u) & ~1023u) + 65536u + tables + 128u > 227u * 1024u) { fprintf(stderr, "ring unit does not fit shared memory\n"); return -8; }
+  }
   for (int unit = 0; unit < n_units; ++unit) {
     const int64_t ibase = (unit / P.units_per_batch) * P.in_batch_stride + (unit % P.units_per_batch) * P.in_unit_stride;
     const int64_t obase = (unit / P.units_per_batch) * P.out_batch_stride + (unit % P.units_per_batch) * P.out_unit_stride;

@@ -93,6 +93,38 @@ def test_four_step_passes(sim, lg1, lg2, u1, u2, tma):
     assert np.linalg.norm(o_re + 1j * o_im - want) / np.linalg.norm(want) < 1e-13
 
 
+def test_ring_units(sim):
+    """Landing-ring units (flag 16; fft_unit_kernel_ring): N = 32768 in one unit, and the two 4096-point passes of
+    2^24 = 4096 x 4096 (8 columns in place with dense staging; 8 rows per unit from row tiles, stored transposed)."""
+    rc, conf, err = _rows(sim, 15, 0, flags=2 | 4 | 16)
+    assert rc == 0 and conf == [0, 0, 0] and err < 1e-13
+    lg1 = lg2 = 12
+    N1, N2 = 1 << lg1, 1 << lg2
+    N = N1 * N2
+    rng = np.random.default_rng(7)
+    # only a few units of each pass are simulated (a full 2^24 pass is slow on the CPU): 2 column units, 2 row units
+    re, im = rng.standard_normal(N), rng.standard_normal(N)
+    t_re, t_im = re.copy(), im.copy()
+    conf = (ctypes.c_int * 4)()
+    st = (ctypes.c_int64 * 9)(0, N2, 0, N2, 0, 8, 0, 8, 1 << 30)
+    rc1 = sim.plansim_run(lg1, 3, 1 | 2 | 16, 1, st, lg1 + lg2, 2, re.ctypes.data_as(dp), im.ctypes.data_as(dp),
+                          t_re.ctypes.data_as(dp), t_im.ctypes.data_as(dp), 0, conf)
+    assert rc1 == 0 and list(conf)[:3] == [0, 0, 0]
+    x = (re + 1j * im).reshape(N1, N2)[:, :16]
+    k1, n2 = np.arange(N1)[:, None], np.arange(16)[None, :]
+    want = np.fft.fft(x, axis=0) / N1 * np.exp(-2j * np.pi * k1 * n2 / N)
+    got = (t_re + 1j * t_im).reshape(N1, N2)[:, :16]
+    assert np.linalg.norm(got - want) / np.linalg.norm(want) < 1e-13
+    o_re, o_im = np.zeros(N), np.zeros(N)
+    st = (ctypes.c_int64 * 9)(N2, 1, 0, N1, 0, 8 * N2, 0, 8, 1 << 30)
+    rc2 = sim.plansim_run(lg2, 3, 2 | 16, 1, st, 0, 2, re.ctypes.data_as(dp), im.ctypes.data_as(dp),
+                          o_re.ctypes.data_as(dp), o_im.ctypes.data_as(dp), 0, conf)
+    assert rc2 == 0 and list(conf)[:3] == [0, 0, 0]
+    want = (np.fft.fft((re + 1j * im).reshape(N1, N2)[:16], axis=1) / N2).T      # X[k1 + N1*k2], k1 < 16
+    got = (o_re + 1j * o_im).reshape(N2, N1)[:, :16]
+    assert np.linalg.norm(got - want) / np.linalg.norm(want) < 1e-13
+
+
 @pytest.mark.parametrize("lgy,lgx,yb,flags", [(9, 12, 1, 6), (10, 11, 2, 0)])
 def test_two_d_passes(sim, lgy, lgx, yb, flags):
     """2-D ny x nx: row pass on Kronecker units (U = 2^yb rows y_lo + u*ny/U, last tensor stage = F_x (x) F_y, row
