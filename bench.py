@@ -319,6 +319,8 @@ def extra_c3(peak):
         rows.append({"log2n": lg, "batch": b, "passes": passes, "ms": round(ms, 4),
                      "gflops": round(5.0 * n * lg * b / (ms * 1e-3) / 1e9, 1), "hbm_gbs": round(gbs, 1),
                      "frac": round(gbs / peak, 4)})
+        if passes > 2:   # 2^24 runs as three passes of 256: also the fraction a two-pass plan would be judged by
+            rows[-1]["frac_two_pass_basis"] = round(8.0 * n * b * 2 / (ms * 1e-3) / 1e9 / peak, 4)
         if passes > 1:   # multi-pass sizes consume their input: refill for the next size
             x.copy_(torch.randn(2 * total, generator=g, device="cuda").to(torch.float16))
         del plan

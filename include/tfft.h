@@ -59,7 +59,7 @@ typedef struct tfft_plan_info_s {
   int64_t batch;             /* transforms per exec                                                */
   int32_t r16_stages;        /* tensor-core radix-16 stages per pass                               */
   int32_t tail_radix;        /* 1, 2, 4 or 8: CUDA-core radix fused into the load phase            */
-  int32_t passes;            /* HBM round trips: 1 (N <= 2^15), 2 (<= 2^24), 3 above                */
+  int32_t passes;            /* HBM round trips: 1 (N <= 2^15), 2 (<= 2^23), 3 from 2^24 on          */
   int32_t results_in_results;/* always 1: results land in the output planes (Plan.h:25)            */
   int32_t amount_of_r16_steps; /* reference-compatible: log2(N)/4 - 1   (Plan.h:99)                */
   int32_t amount_of_r2_steps;  /* reference-compatible: log2(N) % 4     (Plan.h:100)               */
@@ -82,7 +82,11 @@ int tfft_plan_create(tfft_plan_t* plan, int64_t n, int64_t batch, uint32_t flags
  * (written by src/testing/FileWriter.h:250-269; those four columns are accepted and ignored) optionally followed by
  * `key=value` knobs of the B200 kernels: tma, pipe, two_slot, prefetch (0/1), lg1 (log2 of the four-step column-pass
  * length), tma_col (0/1), cluster (1: units of 2^16 elements shared by a CTA pair through distributed shared memory --
- * N = 65536 in ONE HBM pass, 16-column units for 4096-point column passes; off by default).  tools/tune.py measures and writes such a file.  TFFT_E_NOT_IN_FILE when no line matches.
+ * N = 65536 in ONE HBM pass, 16-column units for 4096-point column passes; off by default), ring
+ * (landing-ring kernel for 32K-element units: 1 = the 4096-point column pass of four-step plans, the default; 0 = off;
+ * 2 = also N = 32768 and the 4096-point row pass, where it does not pay).  For n = 2^24 a line that names lg1 or cluster
+ * keeps the two-pass (four-step) plan instead of the default three passes of 256.
+ * tools/tune.py measures and writes such a file.  TFFT_E_NOT_IN_FILE when no line matches.
  * The environment variable TFFT_TUNER_FILE makes tfft_plan_create consult a file the same way. */
 int tfft_plan_create_from_file(tfft_plan_t* plan, int64_t n, int64_t batch, uint32_t flags, const char* path);
 
