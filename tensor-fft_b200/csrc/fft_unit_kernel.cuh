@@ -252,6 +252,16 @@ __device__ __forceinline__ void tma_load_4d_col(uint32_t dst, const CUtensorMap*
       : "memory");
 }
 
+// 5-D column-mode tile {W columns, R kappa, M rows, 1 batch, 1 outer batch}: batched three-pass plans, whose passes have a
+// batch level of their own (UnitPlan::tma_b3_step == 2)
+__device__ __forceinline__ void tma_load_5d_col(uint32_t dst, const CUtensorMap* map, uint32_t c0, uint32_t c2, uint32_t c3,
+                                                uint32_t c4, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(0), "r"(c2), "r"(c3), "r"(c4), "r"(ptx::smem_u32(bar))
+      : "memory");
+}
+
 // 4-D TMA tile load {64 rows, R kappa, M/64, U transforms} -> SWIZZLE_128B stage-1 operand plane
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t c2, uint32_t c3,
                                             uint64_t* bar) {
@@ -886,6 +896,29 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
   // row-mode TMA tiles: the tile of the CTA's first unit is requested before the constant tables are staged, so that its
   // latency overlaps the table copy (matters for the latency of a single small transform, BASELINE config C1)
   constexpr bool kEarlyFirstTile = LM == 1 || LM == 3;
+  // row-mode tile of a unit (one thread): one tensor tile per plane
+  auto request_row_tile = [&](uint32_t unit) {
+    const uint32_t b3 = unit >> P.b3_shift, unit_lo = unit & ((1u << P.b3_shift) - 1u);
+    const uint32_t ub = unit_lo >> P.upb_shift, uu = unit_lo & ((1u << P.upb_shift) - 1u);
+    mbar_arrive_expect_tx(load_bar, 4u << LOG2E);
+    if (P.kron_bits) {   // 5-D map {64, R, M/64, y_lo, u + step * image}
+      tma_load_5d(c.s_re, &tmap_re, uu, ub * P.tma_batch_step, load_bar);
+      tma_load_5d(c.s_im, &tmap_im, uu, ub * P.tma_batch_step, load_bar);
+    } else if (P.tma_row5) {   // last pass of a three-pass plan: 5-D map {16 | 64, R, M/16 | M/64, column block, transform}
+      const uint32_t c4 = (ub << P.log2_units) + b3 * P.tma_b3_step;
+      tma_load_5d(c.s_re, &tmap_re, uu, c4, load_bar);
+      tma_load_5d(c.s_im, &tmap_im, uu, c4, load_bar);
+    } else {
+      const uint32_t c3 = ub * P.tma_batch_step + (uu << P.log2_units);
+      if (P.tma_seg) {   // segmented input (multi-GPU staging planes): 5-D map {64, kappa_lo, segment, M/64, transform}
+        tma_load_5d(c.s_re, &tmap_re, 0, c3, load_bar);
+        tma_load_5d(c.s_im, &tmap_im, 0, c3, load_bar);
+      } else {
+        tma_load_4d(c.s_re, &tmap_re, c.cl_rank * P.cl_load_c2, c3, load_bar);
+        tma_load_4d(c.s_im, &tmap_im, c.cl_rank * P.cl_load_c2, c3, load_bar);
+      }
+    }
+  };
   if (tid == 32) {
     mbar_init(bar, 1);
     mbar_init(bar + 1, 1);
@@ -893,21 +926,7 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
     fence_mbar_init();
     if (kEarlyFirstTile && first_unit < P.n_units) {
       pdl_wait();
-      const uint32_t unit = first_unit, ub = unit >> P.upb_shift, uu = unit & ((1u << P.upb_shift) - 1u);
-      mbar_arrive_expect_tx(load_bar, 4u << LOG2E);
-      if (P.kron_bits) {
-        tma_load_5d(smem_u32(smem), &tmap_re, uu, ub * P.tma_batch_step, load_bar);
-        tma_load_5d(smem_u32(smem) + SL.plane_stride, &tmap_im, uu, ub * P.tma_batch_step, load_bar);
-      } else {
-        const uint32_t c3 = ub * P.tma_batch_step + (uu << P.log2_units);
-        if (P.tma_seg) {
-          tma_load_5d(smem_u32(smem), &tmap_re, 0, c3, load_bar);
-          tma_load_5d(smem_u32(smem) + SL.plane_stride, &tmap_im, 0, c3, load_bar);
-        } else {
-          tma_load_4d(smem_u32(smem), &tmap_re, c.cl_rank * P.cl_load_c2, c3, load_bar);
-          tma_load_4d(smem_u32(smem) + SL.plane_stride, &tmap_im, c.cl_rank * P.cl_load_c2, c3, load_bar);
-        }
-      }
+      request_row_tile(first_unit);
     }
   }
   for (uint32_t o = tid * 16; o < TL.total; o += NT * 16) sts128(table_base + o, ldg128(tables + (o >> 4)));
@@ -960,10 +979,17 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
         mbar_arrive_expect_tx(load_bar, 4u << LOG2E);
         const uint32_t group_bytes = ((2 * W) << P.log2_len) >> CL;   // a cluster CTA loads half of the rows
         for (uint32_t ug = 0; ug < (1u << P.log2_units) / W; ++ug) {
-          tma_load_4d_col(c.s_re + ug * group_bytes, &tmap_re, (uu << P.log2_units) + W * ug, ub + b3 * P.tma_b3_step,
-                          load_bar, c.cl_rank * P.cl_load_c2);
-          tma_load_4d_col(c.s_im + ug * group_bytes, &tmap_im, (uu << P.log2_units) + W * ug, ub + b3 * P.tma_b3_step,
-                          load_bar, c.cl_rank * P.cl_load_c2);
+          if (P.tma_b3_step == 2) {   // 5-D map: (batch of the pass, outer batch)
+            tma_load_5d_col(c.s_re + ug * group_bytes, &tmap_re, (uu << P.log2_units) + W * ug, c.cl_rank * P.cl_load_c2, ub, b3,
+                            load_bar);
+            tma_load_5d_col(c.s_im + ug * group_bytes, &tmap_im, (uu << P.log2_units) + W * ug, c.cl_rank * P.cl_load_c2, ub, b3,
+                            load_bar);
+          } else {
+            tma_load_4d_col(c.s_re + ug * group_bytes, &tmap_re, (uu << P.log2_units) + W * ug, ub + b3 * P.tma_b3_step,
+                            load_bar, c.cl_rank * P.cl_load_c2);
+            tma_load_4d_col(c.s_im + ug * group_bytes, &tmap_im, (uu << P.log2_units) + W * ug, ub + b3 * P.tma_b3_step,
+                            load_bar, c.cl_rank * P.cl_load_c2);
+          }
         }
       }
       TFFT_TRACE_MARK(1);
@@ -974,20 +1000,7 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
       // the batch are out of bounds of the tensor map and arrive as zeros
       if (tid == 0 && !(kEarlyFirstTile && unit == first_unit)) {   // the first tile was requested during the setup
         fence_proxy_async_smem();   // earlier generic-proxy reads of the planes precede the async-proxy writes
-        mbar_arrive_expect_tx(load_bar, 4u << LOG2E);
-        if (P.kron_bits) {
-          tma_load_5d(c.s_re, &tmap_re, uu, ub * P.tma_batch_step, load_bar);
-          tma_load_5d(c.s_im, &tmap_im, uu, ub * P.tma_batch_step, load_bar);
-        } else {
-          const uint32_t c3 = ub * P.tma_batch_step + (uu << P.log2_units);
-          if (P.tma_seg) {   // segmented input (multi-GPU staging planes): 5-D map {64, kappa_lo, segment, M/64, transform}
-            tma_load_5d(c.s_re, &tmap_re, 0, c3, load_bar);
-            tma_load_5d(c.s_im, &tmap_im, 0, c3, load_bar);
-          } else {
-            tma_load_4d(c.s_re, &tmap_re, c.cl_rank * P.cl_load_c2, c3, load_bar);
-            tma_load_4d(c.s_im, &tmap_im, c.cl_rank * P.cl_load_c2, c3, load_bar);
-          }
-        }
+        request_row_tile(unit);
       }
       TFFT_TRACE_MARK(1);
       mbar_wait(load_bar, load_phase & 1u);

@@ -56,6 +56,7 @@ struct Pass {
   int src = 0, dst = 0;    // 0 = user input planes, 1 = user output planes, 2 = plan workspace
   bool in_stride_is_user = false, out_stride_is_user = false;
   bool own_batch_strides = false;   // three-pass plans: the batch level of the unit addressing is internal
+  bool row5 = false;                // last pass of a three-pass plan with TMA row tiles (5-D map, UnitPlan::tma_row5)
   bool outer_batch = false;         // batched three-pass plans: the transforms of the batch are an outer level of the unit
                                     // index (UnitPlan::b3_shift), in/out stride apart
   bool il_in = false, il_out = false;   // TFFT_INTERLEAVED: the pass reads / writes half2 elements
@@ -249,6 +250,29 @@ int make_input_tensor_map(const UnitPlan& plan, const __half* base, int64_t tstr
   return r == CUDA_SUCCESS ? TFFT_OK : TFFT_E_INVALID_ARG;
 }
 
+// Row tiles of the last pass of a three-pass plan: transform t (a row of the N1 x N2 matrix, tstride = N2 apart) and column
+// block cb (block_stride = Nb apart) start at base + t*tstride + cb*block_stride; element n = kappa*M + m of the length-Nb
+// transform.  Dims {16 | 64 (m low), R kappa (stride M), M/16 | M/64, column blocks, transforms}, box {.., 1, U}: lands
+// exactly like the 4-D tile of a contiguous batch.
+int make_row5_tensor_map(const UnitPlan& plan, const __half* base, int64_t tstride, int64_t n_transforms, int64_t blocks,
+                         int64_t block_stride, CUtensorMap* out) {
+  EncodeTiledFn encode = get_encode_fn();
+  if (!encode) return TFFT_E_UNSUPPORTED;
+  const uint64_t L = uint64_t(1) << plan.log2_len, R = uint64_t(1) << plan.log2_radix[0], M = L / R;
+  const uint64_t U = uint64_t(1) << plan.log2_units;
+  const uint64_t atom = plan.tma_load == 3 ? 16 : 64;
+  cuuint64_t gdim[5] = {atom, R, M / atom, static_cast<cuuint64_t>(blocks), static_cast<cuuint64_t>(n_transforms)};
+  cuuint64_t gstride[4] = {M * 2, atom * 2, static_cast<cuuint64_t>(block_stride) * 2, static_cast<cuuint64_t>(tstride) * 2};
+  cuuint32_t box[5] = {static_cast<cuuint32_t>(atom), static_cast<cuuint32_t>(R), static_cast<cuuint32_t>(M / atom), 1,
+                       static_cast<cuuint32_t>(U)};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<__half*>(base), gdim, gstride, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      plan.tma_load == 3 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? TFFT_OK : TFFT_E_INVALID_ARG;
+}
+
 // Segmented input (tfft_exec_segmented): element n of transform t lies at base + (n / seg_len) * seg_stride + t * tstride +
 // n % seg_len with seg_len = L / segs.  With n = kappa*M + m (M = L/R rows per K line, seg_len = kl*M, kl = R/segs):
 // dims {64 (m low), kl (kappa low, stride M), segs (stride seg_stride), M/64 (stride 64), transforms (stride tstride)} --
@@ -298,20 +322,23 @@ int make_kron_tensor_map(const UnitPlan& plan, const __half* base, int64_t ny, i
 // Column-mode input (four-step column pass, 2-D column pass): element n of column c of batch b at
 // base + b*batch_stride + c + n*nstride, n = kappa*M + m.  Dims {columns, R kappa (stride M*nstride), M rows (stride
 // nstride), batches}; box {8, R, M, 1}, no swizzle: the tile lands as dense 16-byte chunks [m][kappa][8 columns].
+// outer > 0 (batched three-pass pass B): a fifth dimension of `outer` user transforms, outer_stride apart.
 int make_col_tensor_map(const UnitPlan& plan, const __half* base, int64_t nstride, int64_t columns, int64_t batches,
-                        int64_t batch_stride, CUtensorMap* out) {
+                        int64_t batch_stride, CUtensorMap* out, int64_t outer = 0, int64_t outer_stride = 0) {
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) return TFFT_E_UNSUPPORTED;
   const uint64_t L = uint64_t(1) << plan.log2_len, R = uint64_t(1) << plan.log2_radix[0], M = L / R;
   if (batches <= 1 || batch_stride <= 0) batch_stride = static_cast<int64_t>(L) * nstride;
-  cuuint64_t gdim[4] = {static_cast<cuuint64_t>(columns), R, M, static_cast<cuuint64_t>(batches < 1 ? 1 : batches)};
-  cuuint64_t gstride[3] = {M * static_cast<cuuint64_t>(nstride) * 2, static_cast<cuuint64_t>(nstride) * 2,
-                           static_cast<cuuint64_t>(batch_stride) * 2};
+  cuuint64_t gdim[5] = {static_cast<cuuint64_t>(columns), R, M, static_cast<cuuint64_t>(batches < 1 ? 1 : batches),
+                        static_cast<cuuint64_t>(outer < 1 ? 1 : outer)};
+  cuuint64_t gstride[4] = {M * static_cast<cuuint64_t>(nstride) * 2, static_cast<cuuint64_t>(nstride) * 2,
+                           static_cast<cuuint64_t>(batch_stride) * 2,
+                           static_cast<cuuint64_t>(outer_stride > 0 ? outer_stride : batch_stride) * 2};
   // mode 2: 8-column tiles, dense; mode 4: 16-column tiles (whole 32-byte sectors) as SWIZZLE_32B atoms
-  cuuint32_t box[4] = {plan.tma_load == 4 ? 16u : 8u, static_cast<cuuint32_t>(R),
-                       static_cast<cuuint32_t>(plan.cluster ? M / 2 : plan.ring ? M / 4 : M), 1};   // cluster CTA: one half of m; ring unit: quarters
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(base), gdim, gstride, box, estr,
+  cuuint32_t box[5] = {plan.tma_load == 4 ? 16u : 8u, static_cast<cuuint32_t>(R),
+                       static_cast<cuuint32_t>(plan.cluster ? M / 2 : plan.ring ? M / 4 : M), 1, 1};   // cluster CTA: one half of m; ring unit: quarters
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, outer > 0 ? 5 : 4, const_cast<__half*>(base), gdim, gstride, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE,
                       plan.tma_load == 4 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE,
                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -547,8 +574,8 @@ int build_1d(tfft_plan_s* p) {
       UnitShape sh;
       sh.log2_len = la; sh.log2_units = std::max(3, unit_log2_elems(la) - la);
       sh.in_mode = kColMode; sh.out_mode = kColMode;
-      // batched: 16-byte cp.async (the tile's batch coordinate is taken by k1; a fifth dimension is not built)
-      sh.tma_load = lg <= 27 && knob(p->tune.tma_col, "TFFT_NO_TMA_COL", 1) != 0 && !batched3;
+      // batched: the tile's batch coordinate is taken by k1, the transform of the batch is a fifth dimension of the map
+      sh.tma_load = lg <= 27 && knob(p->tune.tma_col, "TFFT_NO_TMA_COL", 1) != 0;
       const int64_t U = int64_t(1) << sh.log2_units;
       UnitStrides st;
       st.in_nstride = Nb; st.out_nstride = Nb; st.in_unit_stride = U; st.out_unit_stride = U;
@@ -571,9 +598,26 @@ int build_1d(tfft_plan_s* p) {
       st.out_nstride = N1 * Na; st.out_unit_stride = N1; st.out_batch_stride = U;
       st.units_per_batch = static_cast<uint32_t>(Na);
       if (batched3) st.b3_units = static_cast<uint32_t>((N1 / U) * Na);
+      // Row tiles by TMA for rows up to 1024 points, as in the four-step row pass (5-D map: column block, matrix row).
+      // Measured on B200 (ncu, 2^24 x 16): this pass 538 us with 16-byte cp.async against 409 us for the same shape as
+      // the row pass of 2^16.  The batched plan needs the transform stride to be a whole number of matrix rows; tfft_exec
+      // takes the cp.async twin (passes_strided) otherwise.
+      const bool row_tma = lb <= 10 && knob(p->tune.tma, "TFFT_NO_TMA", 1) && dev_env("TFFT_NO_TMA_PASS2") == nullptr;
+      if (row_tma) {
+        const std::vector<Pass> head(p->passes.begin(), p->passes.end());
+        if (!add_pass(p, sh, st, nb3 * static_cast<uint32_t>((N1 / U) * Na), mid, 1, true, true)) return TFFT_E_UNSUPPORTED;
+        p->passes.back().own_batch_strides = true;
+        p->passes.back().outer_batch = batched3;
+        p->passes.back().il_out = il3;
+        p->passes_strided = head;
+        p->passes_strided.push_back(p->passes.back());
+        p->passes.pop_back();
+        sh.tma_load = true;
+      }
       if (!add_pass(p, sh, st, nb3 * static_cast<uint32_t>((N1 / U) * Na), mid, 1, true, true)) return TFFT_E_UNSUPPORTED;
       p->passes.back().own_batch_strides = true;
       p->passes.back().outer_batch = batched3;
+      p->passes.back().row5 = row_tma;
       p->passes.back().il_out = il3;
     }
     if (preserve3) {
@@ -873,9 +917,14 @@ int prepare_launch(const tfft_plan_s* p, const Pass& ps, const __half* src_re, c
   } else if (ps.outer_batch) {   // batched three-pass plans: the outer level carries it
     st.in_b3_stride = in_stride;
     st.out_b3_stride = out_stride;
-    st.tma_b3_step = 1;          // column tiles (pass A only: its own batch level is unused): batch coordinate = b3
+    // column tiles: pass A's own batch level is unused (batch coordinate = b3, 4-D map); pass B's is k1 (5-D map)
+    st.tma_b3_step = st.units_per_batch == st.b3_units ? 1u : 2u;
   }
-  if (ps.kind == 0 && (ps.plan.tma_load == 1 || ps.plan.tma_load == 3) && st.units_per_batch != 0x7FFFFFFFu) {
+  if (ps.row5) {   // tfft_exec checked that in_stride is a whole number of matrix rows (in_tstride = N2)
+    st.tma_row5 = true;
+    st.tma_b3_step = ps.outer_batch ? static_cast<uint32_t>(in_stride / st.in_tstride) : 0u;
+  }
+  if (ps.kind == 0 && (ps.plan.tma_load == 1 || ps.plan.tma_load == 3) && st.units_per_batch != 0x7FFFFFFFu && !ps.row5) {
     // four-step row pass: transform t of batch b at b*batch_stride + t*tstride (tfft_exec checked divisibility)
     const int64_t batches = (ps.n_units + st.units_per_batch - 1) / st.units_per_batch;
     st.tma_batch_step = static_cast<uint32_t>(batches > 1 ? st.in_batch_stride / st.in_tstride : 0);
@@ -945,10 +994,24 @@ int prepare_launch(const tfft_plan_s* p, const Pass& ps, const __half* src_re, c
       const int64_t columns = static_cast<int64_t>(plan.units_per_batch) << plan.log2_units;
       const int64_t batches = (ps.n_units + plan.units_per_batch - 1) / plan.units_per_batch;
       // batched three-pass pass A: one "batch" per transform of the user's batch, in_stride apart
-      const int64_t bstride = ps.outer_batch ? in_stride : plan.in_batch_stride;
-      if (ps.outer_batch && plan.units_per_batch != st.b3_units) return TFFT_E_UNSUPPORTED;
-      rc = make_col_tensor_map(plan, src_re, st.in_nstride, columns, batches, bstride, &out->tmap_re);
-      if (rc == TFFT_OK) rc = make_col_tensor_map(plan, src_im, st.in_nstride, columns, batches, bstride, &out->tmap_im);
+      if (ps.outer_batch && st.tma_b3_step == 2) {   // pass B: (k1, transform of the batch)
+        const int64_t inner = st.b3_units / plan.units_per_batch, outer = ps.n_units / st.b3_units;
+        rc = make_col_tensor_map(plan, src_re, st.in_nstride, columns, inner, plan.in_batch_stride, &out->tmap_re, outer, in_stride);
+        if (rc == TFFT_OK)
+          rc = make_col_tensor_map(plan, src_im, st.in_nstride, columns, inner, plan.in_batch_stride, &out->tmap_im, outer, in_stride);
+      } else {
+        const int64_t bstride = ps.outer_batch ? in_stride : plan.in_batch_stride;
+        rc = make_col_tensor_map(plan, src_re, st.in_nstride, columns, batches, bstride, &out->tmap_re);
+        if (rc == TFFT_OK) rc = make_col_tensor_map(plan, src_im, st.in_nstride, columns, batches, bstride, &out->tmap_im);
+      }
+    } else if (ps.row5) {
+      // transforms along the matrix rows: N1 per user transform, user transforms tma_b3_step rows apart
+      const int64_t per = static_cast<int64_t>(ps.outer_batch ? st.b3_units : ps.n_units) / plan.units_per_batch * U;
+      const int64_t outer = ps.outer_batch ? ps.n_units / st.b3_units : 1;
+      const int64_t total = static_cast<int64_t>(st.tma_b3_step) * (outer - 1) + per;
+      rc = make_row5_tensor_map(plan, src_re, st.in_tstride, total, plan.units_per_batch, st.in_unit_stride, &out->tmap_re);
+      if (rc == TFFT_OK)
+        rc = make_row5_tensor_map(plan, src_im, st.in_tstride, total, plan.units_per_batch, st.in_unit_stride, &out->tmap_im);
     } else if (plan.kron_bits) {
       rc = make_kron_tensor_map(plan, src_re, p->ny, p->batch, plan.tma_batch_step, &out->tmap_re, half_box);
       if (rc == TFFT_OK) rc = make_kron_tensor_map(plan, src_im, p->ny, p->batch, plan.tma_batch_step, &out->tmap_im, half_box);
@@ -1216,6 +1279,9 @@ int tfft_exec(tfft_plan_t p, const void* in_re, const void* in_im, void* out_re,
   if (!p->ny && p->passes.size() == 2 && !p->passes_strided.empty() && p->batch > 1 && p->passes[1].src == 0 &&
       in_stride % p->passes[1].strides.in_tstride != 0)
     passes = &p->passes_strided;   // four-step row pass: the batch stride is not a whole number of rows
+  if (!p->ny && p->passes.size() == 3 && !p->passes_strided.empty() && p->passes[2].outer_batch &&
+      in_stride % p->passes[2].strides.in_tstride != 0)
+    passes = &p->passes_strided;   // batched three-pass row pass: the transform stride is not a whole number of matrix rows
   if (p->ny && p->batch > 1 && p->passes.front().plan.tma_load && !tma_ok_2d()) {
     if (p->passes_strided.empty()) return TFFT_E_UNSUPPORTED;
     passes = &p->passes_strided;

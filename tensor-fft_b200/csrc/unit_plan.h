@@ -149,7 +149,12 @@ struct UnitPlan {
   // outer batch level (three-pass plans, whose own "batch" level is an index of the transform): unit = b3 << b3_shift | rest,
   // rest decomposes as above; b3_shift = 31: none
   uint32_t b3_shift;
-  uint32_t tma_b3_step;                        // column tiles: batch coordinate = unit / upb + b3 * tma_b3_step
+  uint32_t tma_b3_step;                        // column tiles: 1: batch coordinate = unit / upb + b3 (4-D map); 2: 5-D map,
+                                               // coordinates (unit / upb, b3).  Row tiles (tma_row5): transform
+                                               // coordinate = (unit / upb) * U + b3 * tma_b3_step
+  uint32_t tma_row5;                           // 1: row tiles through a 5-D map {rows, kappa, row atoms, unit % upb, transform}
+                                               // (last pass of a three-pass plan: the unit's transforms lie a whole row of
+                                               // the N1 x N2 matrix apart, unit % upb selects the column block)
   int64_t in_b3_stride, out_b3_stride;
   uint32_t col_base_stride;   // tw_mode 2: col_base = ((unit % upb) / col_div) * col_base_stride
   uint32_t col_div;
@@ -585,6 +590,7 @@ struct UnitStrides {
   uint32_t b3_units = 0;       // != 0 (power of two): units per outer batch element, which lie in/out_b3_stride apart
   int64_t in_b3_stride = 0, out_b3_stride = 0;
   uint32_t tma_b3_step = 0;
+  bool tma_row5 = false;
   int64_t out_hi_stride = 0;   // tiled row-mode output (2-D row pass writing the column units' operand order):
   int out_hi_from = 0;         //   output-index bit i >= out_hi_from has stride out_hi_stride << (i - out_hi_from)
   uint32_t kron_log2n = 0;   // Kronecker units, != 0: multiply output row k_y by exp(-2*pi*i*k_y*col_base/2^kron_log2n)
@@ -634,6 +640,7 @@ inline void fill_strides(const UnitStrides& st, const PlanBuildInfo& info, UnitP
     if (st.b3_units == (1u << i)) plan->b3_shift = i;
   plan->in_b3_stride = st.in_b3_stride; plan->out_b3_stride = st.out_b3_stride;
   plan->tma_b3_step = st.tma_b3_step;
+  plan->tma_row5 = st.tma_row5 ? 1u : 0u;
   plan->n_units = st.n_units;
   plan->col_base_stride = st.col_base_stride;
   plan->col_div = st.col_div ? st.col_div : 1;

@@ -123,6 +123,34 @@ def test_three_pass_batched_equals_looped(monkeypatch, lg, b):
         assert float(torch.linalg.vector_norm(got - want) / torch.linalg.vector_norm(want)) <= GUARD * 6.5e-4, i
 
 
+def test_three_pass_batched_with_a_ragged_transform_stride():
+    """The batched three-pass plan loads its last pass through a 5-D tensor map whose transform coordinate folds the user's
+    batch (stride = a whole number of matrix rows).  A stride that is not (2n + 8) takes the cp.async twin of that pass:
+    same stages, same result up to the operand-layout dependent split of a twiddle (one fp16 rounding)."""
+    n, b = 1 << 24, 2
+    g = torch.Generator(device="cuda"); g.manual_seed(77)
+    x0 = torch.randn(b, 2, n, generator=g, device="cuda").to(torch.float16)
+    plan = tfft.NativePlan(n, b)
+    x = x0.clone().view(-1)
+    y = torch.full_like(x, float("nan"))
+    plan.exec(x, x[n:], y, y[n:], 2 * n, 2 * n)
+    stride = 2 * n + 8
+    xs = torch.zeros(b * stride, dtype=torch.float16, device="cuda")
+    for i in range(b):
+        xs[i * stride:i * stride + 2 * n] = x0[i].reshape(-1)
+    ys = torch.full_like(xs, float("nan"))
+    plan.exec(xs, xs[n:], ys, ys[n:], stride, stride)
+    torch.cuda.synchronize()
+    for i in range(b):
+        got = ys[i * stride:i * stride + 2 * n].float()
+        want = y[i * 2 * n:(i + 1) * 2 * n].float()
+        d = got - want
+        assert float(torch.linalg.vector_norm(d) / torch.linalg.vector_norm(want)) < 3e-4, i
+        ref = torch.fft.fft(torch.complex(x0[i, 0].float(), x0[i, 1].float())) / n
+        gc = torch.complex(got[:n], got[n:])
+        assert float(torch.linalg.vector_norm(gc - ref) / torch.linalg.vector_norm(ref)) <= GUARD * 6.5e-4, i
+
+
 def test_three_pass_from_2_24_developer_knob(monkeypatch):
     monkeypatch.setenv("TFFT_THREEPASS_LG", "24")
     n = 1 << 24
