@@ -113,6 +113,25 @@ __device__ __forceinline__ Cplx twiddle64(uint64_t x, uint32_t log2n) {
   return cmul(hi, lo);
 }
 
+// Inter-pass twiddles (tw_mode 2: exp(-2*pi*i * o * column / N), two per work item in the last epilogue of a column
+// pass): the phase fraction is exact in fp32 up to 24 bits (split in two exact parts above), so one range-reduced
+// MUFU sine / cosine (absolute error < 5e-7, three orders below an fp16 ulp) replaces two sincospif polynomials --
+// in the 4096 x 8-column pass those were 20 % of the executed instructions.  -DTFFT_EXACT_TWIDDLE keeps sincospif.
+__device__ __forceinline__ Cplx twiddle_fast64(uint64_t x, uint32_t log2n) {
+#ifdef TFFT_EXACT_TWIDDLE
+  return twiddle64(x, log2n);
+#else
+  // f = x / 2^log2n in [0, 1): high and low 12-bit parts are exact, their sum is rounded once (6e-8)
+  const float hi = static_cast<float>(static_cast<uint32_t>(x >> 12)) * __uint_as_float((127u + 12u - log2n) << 23);
+  const float lo = static_cast<float>(static_cast<uint32_t>(x & 0xFFFu)) * __uint_as_float((127u - log2n) << 23);
+  float f = hi + lo;
+  f -= (f >= 0.5f) ? 1.0f : 0.0f;   // [-0.5, 0.5): the argument of the MUFU stays inside [-pi, pi]
+  float s, c;
+  __sincosf(-6.283185307179586f * f, &s, &c);
+  return {c, s};
+#endif
+}
+
 __device__ __forceinline__ uint32_t bit_sum(uint32_t q, const uint32_t* contrib, int first, int count) {
   uint32_t s = 0;
 #pragma unroll
@@ -518,8 +537,8 @@ __device__ __forceinline__ void epilogue_item(const UnitPlan& P, const KernelCtx
     } else {
       const uint64_t col = col_thr + bit_sum_c<(kTileHi >> kTileShift), kMaxRowBits - 7 - kTileShift>(E.col, 7 + kTileShift) + c.col_base;
       const uint64_t mask = (uint64_t(1) << E.tw_log2n) - 1u;
-      const Cplx w1 = twiddle64((E.tw_kw * col) & mask, E.tw_log2n);
-      t0 = twiddle64(((aux + 16u * g * E.tw_kw) * col) & mask, E.tw_log2n);
+      const Cplx w1 = twiddle_fast64((E.tw_kw * col) & mask, E.tw_log2n);
+      t0 = twiddle_fast64(((aux + 16u * g * E.tw_kw) * col) & mask, E.tw_log2n);
       t1 = cmul(t0, w1);
       s2 = cmul(w1, w1);
     }
