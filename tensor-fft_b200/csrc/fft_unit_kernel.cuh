@@ -639,7 +639,7 @@ __device__ __forceinline__ void stage_issue(const KernelCtx& c, uint32_t b1_sadd
   using namespace ptx;
   using SS = StageShape<RHO, LOG2E, PIPE, NG>;
   constexpr uint32_t R = SS::R, kSteps = SS::kSteps, kTiles = SS::kTiles;
-  constexpr bool SW128 = LM == 1 && ST == 0;
+  constexpr bool SW128 = (LM == 1 || LM == 5) && ST == 0;   // 5: column tiles of 64 columns, the same atoms of 64 rows
   constexpr bool SW32 = (LM == 3 || LM == 4) && ST == 0;   // 16-row atoms: LBO = atom stride 32R, SBO = K-group stride 256
   constexpr uint32_t S = (LM == 2 && ST == 0) ? 16 * R : SS::S;   // column tiles loaded by TMA are dense: no padding
   constexpr bool kPipe = SS::kPipe;
@@ -990,10 +990,10 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
 
     // ---------------------------------------------------------------- load phase
     TFFT_TRACE_MARK(0);
-    if constexpr (LM == 2 || LM == 4) {
-      // per group of W = 8 (16) columns one tile {W columns, R kappa, M rows, 1 batch} per plane, dense: [group][m][kappa][W]
+    if constexpr (LM == 2 || LM == 4 || LM == 5) {
+      // per group of W = 8 (16, 64) columns one tile {W columns, R kappa, M rows, 1 batch} per plane, dense: [group][m][kappa][W]
       if (tid == 0) {
-        constexpr uint32_t W = LM == 4 ? 16 : 8;
+        constexpr uint32_t W = LM == 5 ? 64 : LM == 4 ? 16 : 8;
         fence_proxy_async_smem();
         mbar_arrive_expect_tx(load_bar, 4u << LOG2E);
         const uint32_t group_bytes = ((2 * W) << P.log2_len) >> CL;   // a cluster CTA loads half of the rows
@@ -1073,8 +1073,8 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
     const bool pf = !CL && P.prefetch_next && P.b3_shift == 31 && unit + gridDim.x < P.n_units;
     if (pf) {
       const uint32_t un = unit + gridDim.x, nb = un >> P.upb_shift, nu = un & ((1u << P.upb_shift) - 1u);
-      if constexpr (LM == 2 || LM == 4) {
-        constexpr uint32_t W = LM == 4 ? 16 : 8;
+      if constexpr (LM == 2 || LM == 4 || LM == 5) {
+        constexpr uint32_t W = LM == 5 ? 64 : LM == 4 ? 16 : 8;
         if (tid == 0)
           for (uint32_t ug = 0; ug < (1u << P.log2_units) / W; ++ug) {
             tma_prefetch_4d_col(&tmap_re, (nu << P.log2_units) + W * ug, nb);

@@ -8,16 +8,20 @@
 
 namespace tfft {
 
-#define TFFT_KT(E, A, B, C) {E, A, B, C, fft_unit_kernel<E, A, B, C, 0>, fft_unit_kernel<E, A, B, C, 1>, nullptr, kThreads}
+#define TFFT_KT(E, A, B, C) {E, A, B, C, fft_unit_kernel<E, A, B, C, 0>, fft_unit_kernel<E, A, B, C, 1>, nullptr, nullptr, kThreads}
 // N <= 1024: the row tile uses SWIZZLE_32B atoms (load mode 3)
-#define TFFT_KS(E, A, B, C) {E, A, B, C, fft_unit_kernel<E, A, B, C, 0>, fft_unit_kernel<E, A, B, C, 3>, nullptr, kThreads}
+#define TFFT_KS(E, A, B, C) {E, A, B, C, fft_unit_kernel<E, A, B, C, 0>, fft_unit_kernel<E, A, B, C, 3>, nullptr, nullptr, kThreads}
 #define TFFT_KSC(E, A, B, C) /* column passes of these lengths have >= 16 columns per unit: 16-column tiles (mode 4) */ \
-  {E, A, B, C, fft_unit_kernel<E, A, B, C, 0>, fft_unit_kernel<E, A, B, C, 3>, fft_unit_kernel<E, A, B, C, 4>, kThreads}
+  {E, A, B, C, fft_unit_kernel<E, A, B, C, 0>, fft_unit_kernel<E, A, B, C, 3>, fft_unit_kernel<E, A, B, C, 4>, nullptr, kThreads}
+// 256-point columns: 64 columns per 16K-element unit -> also the 64-column tiles (mode 5)
+#define TFFT_KSC64(E, A, B, C) \
+  {E, A, B, C, fft_unit_kernel<E, A, B, C, 0>, fft_unit_kernel<E, A, B, C, 3>, fft_unit_kernel<E, A, B, C, 4>, \
+   fft_unit_kernel<E, A, B, C, 5>, kThreads}
 #define TFFT_KTC(E, A, B, C) \
-  {E, A, B, C, fft_unit_kernel<E, A, B, C, 0>, fft_unit_kernel<E, A, B, C, 1>, fft_unit_kernel<E, A, B, C, 2>, kThreads}
+  {E, A, B, C, fft_unit_kernel<E, A, B, C, 0>, fft_unit_kernel<E, A, B, C, 1>, fft_unit_kernel<E, A, B, C, 2>, nullptr, kThreads}
 // 32K-element units (one CTA per SM): 512 threads = four warp groups
 #define TFFT_KW(E, A, B, C) \
-  {E, A, B, C, fft_unit_kernel<E, A, B, C, 0, 512>, fft_unit_kernel<E, A, B, C, 1, 512>, fft_unit_kernel<E, A, B, C, 2, 512>, 512}
+  {E, A, B, C, fft_unit_kernel<E, A, B, C, 0, 512>, fft_unit_kernel<E, A, B, C, 1, 512>, fft_unit_kernel<E, A, B, C, 2, 512>, nullptr, 512}
 
 #if TFFT_GROUP == 6
 // landing-ring kernels: 4096 x 8 columns (four-step / 2-D column passes), 8 rows x 4096 (four-step row pass), N = 32768
@@ -45,14 +49,14 @@ const ClusterEntry* kernel_cluster_group(int* count) {
 #else
 static const KernelEntry g_entries[] = {
 #if TFFT_GROUP == 0
-    TFFT_KS(13, 4, 4, 0), TFFT_KSC(14, 4, 4, 0),                    // L = 2^8
+    TFFT_KS(13, 4, 4, 0), TFFT_KSC64(14, 4, 4, 0),                  // L = 2^8
     TFFT_KS(13, 4, 5, 0), TFFT_KSC(14, 4, 5, 0),                    // 2^9
 #elif TFFT_GROUP == 1
     TFFT_KS(13, 5, 5, 0), TFFT_KSC(14, 5, 5, 0),                    // 2^10
     TFFT_KT(13, 5, 6, 0), TFFT_KTC(14, 5, 6, 0),                    // 2^11
 #elif TFFT_GROUP == 2
     TFFT_KT(13, 6, 6, 0), TFFT_KT(14, 6, 6, 0), TFFT_KW(15, 6, 6, 0), TFFT_KTC(15, 6, 6, 0),  // 2^12
-    {15, 5, 6, 0, fft_unit_kernel<15, 5, 6, 0, 0, 512>, nullptr, fft_unit_kernel<15, 5, 6, 0, 4, 512>, 512},   // 16 columns x 2^11
+    {15, 5, 6, 0, fft_unit_kernel<15, 5, 6, 0, 0, 512>, nullptr, fft_unit_kernel<15, 5, 6, 0, 4, 512>, nullptr, 512},   // 16 columns x 2^11
 #elif TFFT_GROUP == 3
     TFFT_KT(13, 4, 4, 5), TFFT_KT(14, 4, 4, 5),                     // 2^13
     TFFT_KT(14, 4, 5, 5),                                           // 2^14

@@ -171,7 +171,7 @@ KernelFn kernel_for(const UnitPlan& p, int* threads) {
           !(narrow && k.threads == 512)) {
         *threads = k.threads;
         // tma_load 2 / 4: the entry's column-tile kernel; 1 / 3: its row-tile kernel
-        return (p.tma_load == 2 || p.tma_load == 4) ? k.fn_tma_col : (p.tma_load ? k.fn_tma : k.fn);
+        return p.tma_load == 5 ? k.fn_tma_col64 : (p.tma_load == 2 || p.tma_load == 4) ? k.fn_tma_col : (p.tma_load ? k.fn_tma : k.fn);
       }
     }
   }
@@ -335,12 +335,13 @@ int make_col_tensor_map(const UnitPlan& plan, const __half* base, int64_t nstrid
                            static_cast<cuuint64_t>(batch_stride) * 2,
                            static_cast<cuuint64_t>(outer_stride > 0 ? outer_stride : batch_stride) * 2};
   // mode 2: 8-column tiles, dense; mode 4: 16-column tiles (whole 32-byte sectors) as SWIZZLE_32B atoms
-  cuuint32_t box[5] = {plan.tma_load == 4 ? 16u : 8u, static_cast<cuuint32_t>(R),
+  cuuint32_t box[5] = {plan.tma_load == 5 ? 64u : plan.tma_load == 4 ? 16u : 8u, static_cast<cuuint32_t>(R),
                        static_cast<cuuint32_t>(plan.cluster ? M / 2 : plan.ring ? M / 4 : M), 1, 1};   // cluster CTA: one half of m; ring unit: quarters
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, outer > 0 ? 5 : 4, const_cast<__half*>(base), gdim, gstride, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE,
-                      plan.tma_load == 4 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                      plan.tma_load == 5 ? CU_TENSOR_MAP_SWIZZLE_128B
+                      : plan.tma_load == 4 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE,
                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? TFFT_OK : TFFT_E_INVALID_ARG;
 }
@@ -558,6 +559,7 @@ int build_1d(tfft_plan_s* p) {
       // column tiles by TMA as in the four-step pass: -5 % up to 2^27, +12 % at 2^28 / 2^29 (row strides of 1 MiB and
       // more), measured with tools/bench_large.py
       sh.tma_load = lg <= 27 && knob(p->tune.tma_col, "TFFT_NO_TMA_COL", 1) != 0 && !il3;
+      sh.no_col64 = p->tune.tma_col == 2 || dev_env("TFFT_NO_COL64") != nullptr;
       const int64_t U = int64_t(1) << sh.log2_units;
       UnitStrides st;
       st.in_nstride = N2; st.out_nstride = N2; st.in_unit_stride = U; st.out_unit_stride = U;
@@ -576,6 +578,7 @@ int build_1d(tfft_plan_s* p) {
       sh.in_mode = kColMode; sh.out_mode = kColMode;
       // batched: the tile's batch coordinate is taken by k1, the transform of the batch is a fifth dimension of the map
       sh.tma_load = lg <= 27 && knob(p->tune.tma_col, "TFFT_NO_TMA_COL", 1) != 0;
+      sh.no_col64 = p->tune.tma_col == 2 || dev_env("TFFT_NO_COL64") != nullptr;
       const int64_t U = int64_t(1) << sh.log2_units;
       UnitStrides st;
       st.in_nstride = Nb; st.out_nstride = Nb; st.in_unit_stride = U; st.out_unit_stride = U;
@@ -662,7 +665,9 @@ int build_1d(tfft_plan_s* p) {
     if (lg1 == 12 && use_cluster) { sh.log2_units = 4; sh.cluster = true; }
     sh.in_mode = kColMode;
     sh.out_mode = kColMode;
-    sh.tma_load = knob(p->tune.tma_col, "TFFT_NO_TMA_COL", 1) && !interleaved;   // column tiles {8 columns, R, M} by TMA
+    sh.tma_load = knob(p->tune.tma_col, "TFFT_NO_TMA_COL", 1) && !interleaved;   // column tiles {8 | 16 | 64 columns, R, M} by TMA
+    // tuner key tma_col=2: 16-column tiles even where 64-column tiles (whole 128-byte lines, 256-point columns) exist
+    sh.no_col64 = p->tune.tma_col == 2 || dev_env("TFFT_NO_COL64") != nullptr;
     // 4096-point columns (8 columns, 32K elements, one CTA per SM): landing-ring kernel
     sh.ring = lg1 == 12 && sh.log2_units == 3 && !sh.cluster && sh.tma_load && knob(p->tune.ring, "TFFT_NO_RING", 1);
     const int64_t U = int64_t(1) << sh.log2_units;
@@ -990,7 +995,7 @@ int prepare_launch(const tfft_plan_s* p, const Pass& ps, const __half* src_re, c
     const int64_t n_tr = tma_extent ? tma_extent : static_cast<int64_t>(ps.n_units) << plan.log2_units;
     const bool half_box = fn2 != nullptr;   // half-tile boxes: no other kernel may run these maps
     int rc;
-    if (plan.tma_load == 2 || plan.tma_load == 4) {
+    if (plan.tma_load == 2 || plan.tma_load == 4 || plan.tma_load == 5) {
       const int64_t columns = static_cast<int64_t>(plan.units_per_batch) << plan.log2_units;
       const int64_t batches = (ps.n_units + plan.units_per_batch - 1) / plan.units_per_batch;
       // batched three-pass pass A: one "batch" per transform of the user's batch, in_stride apart

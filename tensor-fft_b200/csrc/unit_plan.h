@@ -56,6 +56,7 @@ struct UnitShape {
                              // loads the half of the rows whose highest not-yet-transformed index bit (the top bit of m_1)
                              // is r, runs stage 1 on it, and its stage-1 epilogue stores every output whose top k_1 bit is d
                              // into CTA d's shared memory (distributed shared memory); stages 2.. and the store are local
+  bool no_col64 = false;     // column-mode TMA tiles: never the 64-column SWIZZLE_128B tiles (tma_load 5), developer A/B
   bool ring = false;         // 32K-element units with TMA input: the stage-1 operand lands in a separate ring of two quarter
                              // tiles (64 KiB) instead of the working planes, so that the loads and the stage-1 MMAs of
                              // unit q+1 run under the store phase of unit q (fft_unit_kernel_ring)
@@ -93,7 +94,10 @@ struct UnitPlan {
   uint32_t ring;                           // 1: landing-ring unit (UnitShape::ring): the unit is loaded as four parts (quarter
   uint32_t ring_c2_step, ring_c3_step;     //   of the stage-1 tiles each); part p starts at tile coordinates (c2, c3) + p * step
   uint32_t prefetch_next;                  // 1: pull the next unit's input into L2 during this unit's stages
-  uint32_t tma_load;                       // 4: column-mode input, >= 16 columns per unit: tiles {16 columns, R kappa, M rows} per
+  uint32_t tma_load;                       // 5: column-mode input, >= 64 columns per unit: tiles {64 columns, R kappa, M rows} per
+                                           //    64-column group as SWIZZLE_128B atoms (whole 128-byte lines): row = (u&63) +
+                                           //    64*(m + M*(u>>6)), element (row, kappa) as in mode 1
+                                           // 4: column-mode input, >= 16 columns per unit: tiles {16 columns, R kappa, M rows} per
                                            //    16-column group as SWIZZLE_32B atoms: row = (u&15) + 16*(m + M*(u>>4)), element
                                            //    (row, kappa) as in mode 3
                                            // 3: row-mode input with 16 or 32 rows per K line: SWIZZLE_32B MN-major atoms of
@@ -260,7 +264,8 @@ inline bool build_unit_plan(const UnitShape& shape, UnitPlan* plan, PlanBuildInf
     info->error = "column-mode TMA load: more than 256 rows per K line"; return false;
   }
   // column mode: tiles of 16 columns (full 32-byte sectors, SWIZZLE_32B atoms) when the unit has >= 16 columns
-  plan->tma_load = shape.tma_load ? (shape.in_mode == kColMode ? (ups >= 4 ? 4u : 2u) : ((lg - rho[0]) < 6 ? 3u : 1u)) : 0u;
+  plan->tma_load = shape.tma_load ? (shape.in_mode == kColMode ? ((ups >= 6 && !shape.no_col64 && !cl) ? 5u : ups >= 4 ? 4u : 2u)
+                                                               : ((lg - rho[0]) < 6 ? 3u : 1u)) : 0u;
   if (shape.ring) {
     // parts = the top two row bits of the stage-1 operand (natural row order: m, then u)
     const uint32_t M = 1u << (lg - rho[0]);
@@ -340,7 +345,8 @@ inline bool build_unit_plan(const UnitShape& shape, UnitPlan* plan, PlanBuildInf
     if (t == 1) {
       for (int i = 0; i < 3; ++i)
         rb.push_back(shape.in_mode == kRowMode ? LBit{LBit::R, 0, (uint8_t)i} : LBit{LBit::U, 0, (uint8_t)i});
-      if (plan->tma_load == 4) rb.push_back({LBit::U, 0, 3});   // 16 columns = one atom of 16 rows
+      if (plan->tma_load == 4 || plan->tma_load == 5) rb.push_back({LBit::U, 0, 3});   // 16 columns = one atom of 16 rows
+      if (plan->tma_load == 5) { rb.push_back({LBit::U, 0, 4}); rb.push_back({LBit::U, 0, 5}); }   // 64 columns = one atom of 64 rows
     } else {
       for (int i = 0; i < 3; ++i) rb.push_back({LBit::K, (uint8_t)(t - 1), (uint8_t)i});
     }

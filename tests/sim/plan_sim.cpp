@@ -65,6 +65,7 @@ int plansim_run_ex(int log2_len, int log2_units, int in_mode_flags, int out_mode
   shape.in_mode = (AxisMode)in_mode; shape.out_mode = (AxisMode)out_mode; shape.tma_load = (in_mode_flags & 2) != 0;
   shape.pipe_stage2 = (in_mode_flags & 4) != 0;
   shape.cluster = (in_mode_flags & 8) != 0;   // CTA-pair unit: both ranks are simulated, stage-1 stores cross between them
+  shape.no_col64 = (in_mode_flags & 32) != 0; // column tiles: 16-column SWIZZLE_32B tiles even for >= 64 columns
   shape.ring = (in_mode_flags & 16) != 0;     // landing-ring unit: stage-1 operand outside the planes, dense staging for 8-column output
   UnitPlan P; PlanBuildInfo info;
   if (!build_unit_plan(shape, &P, &info)) { fprintf(stderr, "plan error: %s\n", info.error.c_str()); return -1; }
@@ -106,7 +107,19 @@ int plansim_run_ex(int log2_len, int log2_units, int in_mode_flags, int out_mode
     std::vector<double>& sim = pim_[rk];
     const int R0 = 1 << P.log2_radix[0];
     const int64_t Mfull = L / R0, Mloc = Mfull >> (P.cluster ? 1 : 0), m0 = rk * Mloc;   // a cluster CTA loads one half of m
-    if (P.tma_load == 4) {   // column mode, 16-column tiles as SWIZZLE_32B atoms: row = (u&15) + 16*(m + M*(u>>4))
+    if (P.tma_load == 5) {   // column mode, 64-column tiles as SWIZZLE_128B atoms: row = (u&63) + 64*(m + M*(u>>6))
+      const int R = R0;
+      const int64_t U = int64_t(1) << P.log2_units;
+      for (int64_t u = 0; u < U; ++u)
+        for (int64_t m = 0; m < Mloc; ++m)
+          for (int kap = 0; kap < R; ++kap) {
+            const int64_t row = (u & 63) + 64 * (m + Mloc * (u >> 6));
+            const uint32_t off = (uint32_t)((row >> 6) * 128 * R + (kap >> 3) * 1024 + (kap & 7) * 128 +
+                                            ((((row >> 3) & 7) ^ (kap & 7)) << 4) + (row & 7) * 2);
+            const int64_t a = ibase + u + (kap * Mfull + m0 + m) * strides9[1];
+            sre[off / 2] = rh(in_re[a], h); sim[off / 2] = rh(in_im[a], h);
+          }
+    } else if (P.tma_load == 4) {   // column mode, 16-column tiles as SWIZZLE_32B atoms: row = (u&15) + 16*(m + M*(u>>4))
       const int R = R0;
       const int64_t U = int64_t(1) << P.log2_units;
       for (int64_t u = 0; u < U; ++u)
@@ -218,7 +231,7 @@ int plansim_run_ex(int log2_len, int log2_units, int in_mode_flags, int out_mode
               off = (row >> 4) * 32 * R + kap * 32 + (row & 15) * 2;
               off ^= ((off >> 7) & 1u) << 4;
             }
-            if (t == 1 && P.tma_load == 1)
+            if (t == 1 && (P.tma_load == 1 || P.tma_load == 5))
               off = (row >> 6) * 128 * R + (kap >> 3) * 1024 + (kap & 7) * 128 + ((((row >> 3) & 7) ^ (kap & 7)) << 4) + (row & 7) * 2;
             a[kap] = cd(sre[off / 2], sim[off / 2]);
             if (std::isnan(sre[off / 2])) { fprintf(stderr, "stage %d reads an unwritten operand slot\n", t); return -6; }

@@ -68,7 +68,7 @@ def test_predicted_fp16_error_below_reference(sim, lg, ups, ref_level):
     assert rc == 0 and err < ref_level
 
 
-@pytest.mark.parametrize("lg1,lg2,u1,u2,tma", [(8, 8, 5, 5, 0), (8, 8, 6, 6, 2), (10, 10, 4, 4, 0), (11, 11, 3, 3, 0),
+@pytest.mark.parametrize("lg1,lg2,u1,u2,tma", [(8, 8, 5, 5, 0), (8, 8, 6, 6, 2), (8, 8, 6, 6, 2 | 32), (10, 10, 4, 4, 0), (11, 11, 3, 3, 0),
                                                (12, 10, 3, 4, 0), (9, 8, 5, 6, 2), (12, 9, 3, 5, 2), (11, 9, 3, 5, 2),
                                                (10, 8, 4, 6, 2)])
 def test_four_step_passes(sim, lg1, lg2, u1, u2, tma):
@@ -86,7 +86,7 @@ def test_four_step_passes(sim, lg1, lg2, u1, u2, tma):
     c1 = list(conf)[:3]
     st = (ctypes.c_int64 * 9)(N2, 1, 0, N1, 0, U2 * N2, 0, U2, 1 << 30)
     # pass 2 (contiguous rows in, transposed out): cp.async chunks or, with tma, row tiles (SWIZZLE_32B / 128B atoms)
-    rc2 = sim.plansim_run(lg2, u2, tma, 1, st, 0, N1 // U2, t_re.ctypes.data_as(dp), t_im.ctypes.data_as(dp),
+    rc2 = sim.plansim_run(lg2, u2, tma & 2, 1, st, 0, N1 // U2, t_re.ctypes.data_as(dp), t_im.ctypes.data_as(dp),
                           o_re.ctypes.data_as(dp), o_im.ctypes.data_as(dp), 0, conf)
     want = np.fft.fft(re + 1j * im) / N
     assert rc1 == 0 and rc2 == 0 and c1 == [0, 0, 0] and list(conf)[:3] == [0, 0, 0]   # tma: column tiles loaded by TMA
