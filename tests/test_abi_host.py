@@ -148,3 +148,19 @@ def test_cluster_tuner_key_builds_a_single_pass_plan(tmp_path):
     assert r.info["passes"] == 2 and r.info["transforms_per_cta"] == 16                 # 16 columns per CTA pair
     for x in (p, q, r):
         x.close()
+
+
+def test_round2_second_session_tuner_keys(tmp_path):
+    """ring (landing-ring kernel) and tma_col=2 (no 64-column tiles) are accepted; a four-step split or cluster=1 keeps 2^24
+    on the two-pass plan, the default is three passes; every plan stays inside the 227 KiB / 512 columns of an SM."""
+    f = tmp_path / "TunerResults.dat"
+    f.write_text("4194304 256 8 8 256 ring=0\n32768 256 8 8 256 ring=2\n65536 256 8 8 256 tma_col=2\n16777216 256 8 8 256 lg1=12\n")
+    for n, passes in ((1 << 22, 2), (32768, 1), (65536, 2), (1 << 24, 2)):
+        p = tfft.NativePlan(n, 3, tuner_file=str(f))
+        assert p.info["passes"] == passes, n
+        assert p.info["smem_bytes"] <= 227 * 1024 and p.info["tmem_columns"] <= 512
+        p.close()
+    for n, passes in ((1 << 22, 2), (1 << 24, 3), (1 << 26, 3)):
+        p = tfft.NativePlan(n, 3)
+        assert p.info["passes"] == passes and p.info["smem_bytes"] <= 227 * 1024
+        p.close()
