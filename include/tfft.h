@@ -81,7 +81,7 @@ int tfft_plan_create(tfft_plan_t* plan, int64_t n, int64_t batch, uint32_t flags
  * from the line of `path` that starts with n.  Line format: the reference's `N mode base_warps r16_warps r2_block`
  * (written by src/testing/FileWriter.h:250-269; those four columns are accepted and ignored) optionally followed by
  * `key=value` knobs of the B200 kernels: tma, pipe, two_slot, prefetch (0/1), lg1 (log2 of the four-step column-pass
- * length), tma_col (0: cp.async, 1: TMA column tiles, 2: never the 64-column tiles), cluster (1: units of 2^16 elements shared by a CTA pair through distributed shared memory --
+ * length), tma_col (0: cp.async, 1: TMA column tiles, 2: never the 64- / 32-column tiles), cluster (1: units of 2^16 elements shared by a CTA pair through distributed shared memory --
  * N = 65536 in ONE HBM pass, 16-column units for 4096-point column passes; off by default), ring
  * (landing-ring kernel for 32K-element units: 1 = the 4096-point column pass of four-step plans, the default; 0 = off;
  * 2 = also N = 32768 and the 4096-point row pass, where it does not pay).  For n = 2^24 a line that names lg1 or cluster

@@ -641,6 +641,7 @@ __device__ __forceinline__ void stage_issue(const KernelCtx& c, uint32_t b1_sadd
   constexpr uint32_t R = SS::R, kSteps = SS::kSteps, kTiles = SS::kTiles;
   constexpr bool SW128 = (LM == 1 || LM == 5) && ST == 0;   // 5: column tiles of 64 columns, the same atoms of 64 rows
   constexpr bool SW32 = (LM == 3 || LM == 4) && ST == 0;   // 16-row atoms: LBO = atom stride 32R, SBO = K-group stride 256
+  constexpr bool SW64 = LM == 6 && ST == 0;                // 32-row atoms (column tiles of 32 columns): LBO = 64R, SBO = 512
   constexpr uint32_t S = (LM == 2 && ST == 0) ? 16 * R : SS::S;   // column tiles loaded by TMA are dense: no padding
   constexpr bool kPipe = SS::kPipe;
   constexpr uint32_t idesc = make_idesc_f16(128, 2 * R, /*a_mn=*/1, /*b_mn=*/0);
@@ -655,13 +656,15 @@ __device__ __forceinline__ void stage_issue(const KernelCtx& c, uint32_t b1_sadd
   b1_saddr += zero;
   const uint32_t pa_re = (ST == 0 ? c.a_re : c.s_re) + zero, pa_im = (ST == 0 ? c.a_im : c.s_im) + zero;
   const uint32_t taddr = c.taddr + zero;
-  constexpr uint64_t kSw32 = uint64_t(6) << 61;
+  constexpr uint64_t kSw32 = uint64_t(6) << 61, kSw64 = uint64_t(4) << 61;
   const uint64_t da_re = SW128 ? (make_smem_desc(pa_re, 128 * R, 1024) | kSw128)
+                         : SW64 ? (make_smem_desc(pa_re, 64 * R, 512) | kSw64)
                          : SW32 ? (make_smem_desc(pa_re, 32 * R, 256) | kSw32) : make_smem_desc(pa_re, kKGroupStride, S);
   const uint64_t da_im = SW128 ? (make_smem_desc(pa_im, 128 * R, 1024) | kSw128)
+                         : SW64 ? (make_smem_desc(pa_im, 64 * R, 512) | kSw64)
                          : SW32 ? (make_smem_desc(pa_im, 32 * R, 256) | kSw32) : make_smem_desc(pa_im, kKGroupStride, S);
-  constexpr uint32_t kTileStep = (SW128 || SW32) ? (2 * 128 * R) / 16 : S;   // descriptor address units (16 B) per tile
-  constexpr uint32_t kKStep = SW128 ? 2048 / 16 : SW32 ? 512 / 16 : 16;      // ... per 16-wide K step
+  constexpr uint32_t kTileStep = (SW128 || SW32 || SW64) ? (2 * 128 * R) / 16 : S;   // descriptor address units (16 B) per tile
+  constexpr uint32_t kKStep = SW128 ? 2048 / 16 : SW64 ? 1024 / 16 : SW32 ? 512 / 16 : 16;      // ... per 16-wide K step
   const uint64_t db1 = make_smem_desc(b1_saddr, kKGroupStride, 16 * R);
 #ifdef TFFT_TWO_MATRICES
   const uint64_t db2 = make_smem_desc(b1_saddr + 4 * R * R, kKGroupStride, 16 * R);
@@ -990,10 +993,10 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
 
     // ---------------------------------------------------------------- load phase
     TFFT_TRACE_MARK(0);
-    if constexpr (LM == 2 || LM == 4 || LM == 5) {
-      // per group of W = 8 (16, 64) columns one tile {W columns, R kappa, M rows, 1 batch} per plane, dense: [group][m][kappa][W]
+    if constexpr (LM == 2 || LM == 4 || LM == 5 || LM == 6) {
+      // per group of W = 8 (16, 32, 64) columns one tile {W columns, R kappa, M rows, 1 batch} per plane, dense: [group][m][kappa][W]
       if (tid == 0) {
-        constexpr uint32_t W = LM == 5 ? 64 : LM == 4 ? 16 : 8;
+        constexpr uint32_t W = LM == 5 ? 64 : LM == 6 ? 32 : LM == 4 ? 16 : 8;
         fence_proxy_async_smem();
         mbar_arrive_expect_tx(load_bar, 4u << LOG2E);
         const uint32_t group_bytes = ((2 * W) << P.log2_len) >> CL;   // a cluster CTA loads half of the rows
@@ -1073,8 +1076,8 @@ fft_unit_kernel(const __grid_constant__ UnitPlan P, const __half* __restrict__ i
     const bool pf = !CL && P.prefetch_next && P.b3_shift == 31 && unit + gridDim.x < P.n_units;
     if (pf) {
       const uint32_t un = unit + gridDim.x, nb = un >> P.upb_shift, nu = un & ((1u << P.upb_shift) - 1u);
-      if constexpr (LM == 2 || LM == 4 || LM == 5) {
-        constexpr uint32_t W = LM == 5 ? 64 : LM == 4 ? 16 : 8;
+      if constexpr (LM == 2 || LM == 4 || LM == 5 || LM == 6) {
+        constexpr uint32_t W = LM == 5 ? 64 : LM == 6 ? 32 : LM == 4 ? 16 : 8;
         if (tid == 0)
           for (uint32_t ug = 0; ug < (1u << P.log2_units) / W; ++ug) {
             tma_prefetch_4d_col(&tmap_re, (nu << P.log2_units) + W * ug, nb);

@@ -50,7 +50,9 @@ const ClusterEntry* kernel_cluster_group(int* count) {
 static const KernelEntry g_entries[] = {
 #if TFFT_GROUP == 0
     TFFT_KS(13, 4, 4, 0), TFFT_KSC64(14, 4, 4, 0),                  // L = 2^8
-    TFFT_KS(13, 4, 5, 0), TFFT_KSC(14, 4, 5, 0),                    // 2^9
+    TFFT_KS(13, 4, 5, 0),                                           // 2^9
+    {14, 4, 5, 0, fft_unit_kernel<14, 4, 5, 0, 0>, fft_unit_kernel<14, 4, 5, 0, 3>, fft_unit_kernel<14, 4, 5, 0, 4>,
+     fft_unit_kernel<14, 4, 5, 0, 6>, kThreads},                    //   32 columns per unit: also the 32-column tiles (mode 6)
 #elif TFFT_GROUP == 1
     TFFT_KS(13, 5, 5, 0), TFFT_KSC(14, 5, 5, 0),                    // 2^10
     TFFT_KT(13, 5, 6, 0), TFFT_KTC(14, 5, 6, 0),                    // 2^11

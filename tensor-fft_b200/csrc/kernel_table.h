@@ -17,7 +17,7 @@ struct KernelEntry {
   int log2e, r0, r1, r2;
   KernelFn fn, fn_tma;   // fn_tma: stage-1 operand loaded by TMA (row-mode input)
   KernelFn fn_tma_col;   // column-mode input loaded by TMA column tiles
-  KernelFn fn_tma_col64; // ... by tiles of 64 columns (UnitPlan::tma_load 5; 256-point columns of a 16K-element unit)
+  KernelFn fn_tma_col64; // ... by tiles of 64 / 32 columns (UnitPlan::tma_load 5 / 6; 256- / 512-point columns of a 16K-element unit)
   int threads;
 };
 struct Kernel2Entry {

@@ -171,7 +171,8 @@ KernelFn kernel_for(const UnitPlan& p, int* threads) {
           !(narrow && k.threads == 512)) {
         *threads = k.threads;
         // tma_load 2 / 4: the entry's column-tile kernel; 1 / 3: its row-tile kernel
-        return p.tma_load == 5 ? k.fn_tma_col64 : (p.tma_load == 2 || p.tma_load == 4) ? k.fn_tma_col : (p.tma_load ? k.fn_tma : k.fn);
+        return (p.tma_load == 5 || p.tma_load == 6) ? k.fn_tma_col64
+               : (p.tma_load == 2 || p.tma_load == 4) ? k.fn_tma_col : (p.tma_load ? k.fn_tma : k.fn);
       }
     }
   }
@@ -335,12 +336,12 @@ int make_col_tensor_map(const UnitPlan& plan, const __half* base, int64_t nstrid
                            static_cast<cuuint64_t>(batch_stride) * 2,
                            static_cast<cuuint64_t>(outer_stride > 0 ? outer_stride : batch_stride) * 2};
   // mode 2: 8-column tiles, dense; mode 4: 16-column tiles (whole 32-byte sectors) as SWIZZLE_32B atoms
-  cuuint32_t box[5] = {plan.tma_load == 5 ? 64u : plan.tma_load == 4 ? 16u : 8u, static_cast<cuuint32_t>(R),
+  cuuint32_t box[5] = {plan.tma_load == 5 ? 64u : plan.tma_load == 6 ? 32u : plan.tma_load == 4 ? 16u : 8u, static_cast<cuuint32_t>(R),
                        static_cast<cuuint32_t>(plan.cluster ? M / 2 : plan.ring ? M / 4 : M), 1, 1};   // cluster CTA: one half of m; ring unit: quarters
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, outer > 0 ? 5 : 4, const_cast<__half*>(base), gdim, gstride, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE,
-                      plan.tma_load == 5 ? CU_TENSOR_MAP_SWIZZLE_128B
+                      plan.tma_load == 5 ? CU_TENSOR_MAP_SWIZZLE_128B : plan.tma_load == 6 ? CU_TENSOR_MAP_SWIZZLE_64B
                       : plan.tma_load == 4 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE,
                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? TFFT_OK : TFFT_E_INVALID_ARG;
@@ -995,7 +996,7 @@ int prepare_launch(const tfft_plan_s* p, const Pass& ps, const __half* src_re, c
     const int64_t n_tr = tma_extent ? tma_extent : static_cast<int64_t>(ps.n_units) << plan.log2_units;
     const bool half_box = fn2 != nullptr;   // half-tile boxes: no other kernel may run these maps
     int rc;
-    if (plan.tma_load == 2 || plan.tma_load == 4 || plan.tma_load == 5) {
+    if (plan.tma_load == 2 || plan.tma_load >= 4) {
       const int64_t columns = static_cast<int64_t>(plan.units_per_batch) << plan.log2_units;
       const int64_t batches = (ps.n_units + plan.units_per_batch - 1) / plan.units_per_batch;
       // batched three-pass pass A: one "batch" per transform of the user's batch, in_stride apart

@@ -94,7 +94,10 @@ struct UnitPlan {
   uint32_t ring;                           // 1: landing-ring unit (UnitShape::ring): the unit is loaded as four parts (quarter
   uint32_t ring_c2_step, ring_c3_step;     //   of the stage-1 tiles each); part p starts at tile coordinates (c2, c3) + p * step
   uint32_t prefetch_next;                  // 1: pull the next unit's input into L2 during this unit's stages
-  uint32_t tma_load;                       // 5: column-mode input, >= 64 columns per unit: tiles {64 columns, R kappa, M rows} per
+  uint32_t tma_load;                       // 6: column-mode input, 32 columns per unit: tiles {32 columns, R kappa, M rows} as
+                                           //    SWIZZLE_64B atoms of 32 rows (whole 64-byte pieces): row = (u&31) + 32*m, element
+                                           //    (row, kappa) at (row>>5)*64R + kappa*64 + (row&31)*2, byte-address bits 4-5 ^= bits 7-8
+                                           // 5: column-mode input, >= 64 columns per unit: tiles {64 columns, R kappa, M rows} per
                                            //    64-column group as SWIZZLE_128B atoms (whole 128-byte lines): row = (u&63) +
                                            //    64*(m + M*(u>>6)), element (row, kappa) as in mode 1
                                            // 4: column-mode input, >= 16 columns per unit: tiles {16 columns, R kappa, M rows} per
@@ -264,7 +267,8 @@ inline bool build_unit_plan(const UnitShape& shape, UnitPlan* plan, PlanBuildInf
     info->error = "column-mode TMA load: more than 256 rows per K line"; return false;
   }
   // column mode: tiles of 16 columns (full 32-byte sectors, SWIZZLE_32B atoms) when the unit has >= 16 columns
-  plan->tma_load = shape.tma_load ? (shape.in_mode == kColMode ? ((ups >= 6 && !shape.no_col64 && !cl) ? 5u : ups >= 4 ? 4u : 2u)
+  plan->tma_load = shape.tma_load ? (shape.in_mode == kColMode ? ((ups >= 6 && !shape.no_col64 && !cl) ? 5u
+                                                                  : (ups == 5 && !shape.no_col64 && !cl) ? 6u : ups >= 4 ? 4u : 2u)
                                                                : ((lg - rho[0]) < 6 ? 3u : 1u)) : 0u;
   if (shape.ring) {
     // parts = the top two row bits of the stage-1 operand (natural row order: m, then u)
@@ -345,8 +349,9 @@ inline bool build_unit_plan(const UnitShape& shape, UnitPlan* plan, PlanBuildInf
     if (t == 1) {
       for (int i = 0; i < 3; ++i)
         rb.push_back(shape.in_mode == kRowMode ? LBit{LBit::R, 0, (uint8_t)i} : LBit{LBit::U, 0, (uint8_t)i});
-      if (plan->tma_load == 4 || plan->tma_load == 5) rb.push_back({LBit::U, 0, 3});   // 16 columns = one atom of 16 rows
-      if (plan->tma_load == 5) { rb.push_back({LBit::U, 0, 4}); rb.push_back({LBit::U, 0, 5}); }   // 64 columns = one atom of 64 rows
+      if (plan->tma_load >= 4) rb.push_back({LBit::U, 0, 3});   // 16 columns = one atom of 16 rows
+      if (plan->tma_load >= 5) rb.push_back({LBit::U, 0, 4});   // 32 columns = one atom of 32 rows
+      if (plan->tma_load == 5) rb.push_back({LBit::U, 0, 5});   // 64 columns = one atom of 64 rows
     } else {
       for (int i = 0; i < 3; ++i) rb.push_back({LBit::K, (uint8_t)(t - 1), (uint8_t)i});
     }

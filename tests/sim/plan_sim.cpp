@@ -107,7 +107,19 @@ int plansim_run_ex(int log2_len, int log2_units, int in_mode_flags, int out_mode
     std::vector<double>& sim = pim_[rk];
     const int R0 = 1 << P.log2_radix[0];
     const int64_t Mfull = L / R0, Mloc = Mfull >> (P.cluster ? 1 : 0), m0 = rk * Mloc;   // a cluster CTA loads one half of m
-    if (P.tma_load == 5) {   // column mode, 64-column tiles as SWIZZLE_128B atoms: row = (u&63) + 64*(m + M*(u>>6))
+    if (P.tma_load == 6) {   // column mode, 32-column tiles as SWIZZLE_64B atoms: row = (u&31) + 32*(m + M*(u>>5))
+      const int R = R0;
+      const int64_t U = int64_t(1) << P.log2_units;
+      for (int64_t u = 0; u < U; ++u)
+        for (int64_t m = 0; m < Mloc; ++m)
+          for (int kap = 0; kap < R; ++kap) {
+            const int64_t row = (u & 31) + 32 * (m + Mloc * (u >> 5));
+            uint32_t off = (uint32_t)((row >> 5) * 64 * R + kap * 64 + (row & 31) * 2);
+            off ^= ((off >> 7) & 3u) << 4;
+            const int64_t a = ibase + u + (kap * Mfull + m0 + m) * strides9[1];
+            sre[off / 2] = rh(in_re[a], h); sim[off / 2] = rh(in_im[a], h);
+          }
+    } else if (P.tma_load == 5) {   // column mode, 64-column tiles as SWIZZLE_128B atoms: row = (u&63) + 64*(m + M*(u>>6))
       const int R = R0;
       const int64_t U = int64_t(1) << P.log2_units;
       for (int64_t u = 0; u < U; ++u)
@@ -230,6 +242,10 @@ int plansim_run_ex(int log2_len, int log2_units, int in_mode_flags, int out_mode
             if (t == 1 && (P.tma_load == 3 || P.tma_load == 4)) {
               off = (row >> 4) * 32 * R + kap * 32 + (row & 15) * 2;
               off ^= ((off >> 7) & 1u) << 4;
+            }
+            if (t == 1 && P.tma_load == 6) {
+              off = (row >> 5) * 64 * R + kap * 64 + (row & 31) * 2;
+              off ^= ((off >> 7) & 3u) << 4;
             }
             if (t == 1 && (P.tma_load == 1 || P.tma_load == 5))
               off = (row >> 6) * 128 * R + (kap >> 3) * 1024 + (kap & 7) * 128 + ((((row >> 3) & 7) ^ (kap & 7)) << 4) + (row & 7) * 2;

@@ -183,8 +183,8 @@ def test_in_place_single_pass(lg, b):
     # landing-ring kernel: on by default for the 4096-point column pass (ring=0 switches it off), opt-in (ring=2) for
     # N = 32768 and for the 4096-point row pass of 2^23
     (22, 3, "ring=0"), (15, 5, "ring=2"), (15, 300, "ring=2"), (23, 2, "ring=2"),
-    # column tiles of 16 columns instead of the 64-column tiles of the 256-point column passes
-    (16, 40, "tma_col=2"), (24, 2, "tma_col=2"), (16, 40, "tma_col=0")])
+    # column tiles of 16 columns instead of the 64- / 32-column tiles of the 256- / 512-point column passes
+    (16, 40, "tma_col=2"), (24, 2, "tma_col=2"), (16, 40, "tma_col=0"), (18, 10, "tma_col=2")])
 def test_tuner_knobs_leave_the_result_unchanged(tmp_path, lg, b, knobs):
     """A tuner-file plan (tfft_plan_create_from_file, the reference's CreatePlan(N, file) overload, Plan.h:197-255) with
     non-default kernel knobs: the load path / pipelining / prefetch choices do not change the stages or the DFT matrices;

@@ -69,7 +69,7 @@ def test_predicted_fp16_error_below_reference(sim, lg, ups, ref_level):
 
 
 @pytest.mark.parametrize("lg1,lg2,u1,u2,tma", [(8, 8, 5, 5, 0), (8, 8, 6, 6, 2), (8, 8, 6, 6, 2 | 32), (10, 10, 4, 4, 0), (11, 11, 3, 3, 0),
-                                               (12, 10, 3, 4, 0), (9, 8, 5, 6, 2), (12, 9, 3, 5, 2), (11, 9, 3, 5, 2),
+                                               (12, 10, 3, 4, 0), (9, 8, 5, 6, 2), (9, 8, 5, 6, 2 | 32), (12, 9, 3, 5, 2), (11, 9, 3, 5, 2),
                                                (10, 8, 4, 6, 2)])
 def test_four_step_passes(sim, lg1, lg2, u1, u2, tma):
     """N = N1*N2: column pass (+ exp(-2 pi i k1 n2/N)) then row pass with transposed store."""
