@@ -969,8 +969,10 @@ int prepare_launch(const tfft_plan_s* p, const Pass& ps, const __half* src_re, c
   Kernel2Fn fn2 = plan.ring ? kernel_ring_for(plan) : kernel2_for(plan, allow2);
   if (plan.ring && !fn2) return TFFT_E_UNSUPPORTED;
   const uint32_t smem = (fn2 && !plan.ring) ? smem2_layout(plan).total : ring_fallback ? smem_layout(plan).total : ps.smem;
-  if (ring_fallback && cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            227 * 1024) != cudaSuccess) {
+  // a ring pass runs two different kernels (the ring kernel, and the single-unit kernel for segmented input), but
+  // ensure_pass_on_device opts only the first one it sees in to > 48 KiB of shared memory: do it here for both
+  if (ps.plan.ring && cudaFuncSetAttribute(fn2 ? reinterpret_cast<const void*>(fn2) : reinterpret_cast<const void*>(fn),
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
     cudaGetLastError();
     return TFFT_E_UNSUPPORTED;
   }
