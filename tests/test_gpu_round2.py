@@ -95,7 +95,7 @@ def test_three_pass_preserve_input():
     assert float(torch.linalg.vector_norm(got - want) / torch.linalg.vector_norm(want)) <= GUARD * 6.5e-4
 
 
-@pytest.mark.parametrize("lg,b", [(24, 3), (25, 2)])
+@pytest.mark.parametrize("lg,b", [(24, 3), (25, 2), (26, 2)])
 def test_three_pass_batched_equals_looped(monkeypatch, lg, b):
     """Three-pass plans run the whole batch in three launches (the transform index is an outer level of the unit index);
     the developer knob TFFT_THREEPASS_LOOP runs one transform at a time as in round 1: bit-identical, and every transform
